@@ -1,0 +1,289 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes front end of the CPU oracle (oracle/oracle.cpp) and of the
+unmodified reference Clusterer build (oracle/_ref/libref_cluster.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this package; the
+product path (lidar-processing_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+_LIB = None
+_REF = None
+
+UNKNOWN, GROUND, OBSTACLE = 0, 1, 2
+UNDEFINED = np.iinfo(np.int32).min
+INVALID = -1
+
+
+class SegCfg(C.Structure):
+    """reference: src/segmentation.hpp:48-56"""
+
+    _fields_ = [
+        ("sensor_height_m", C.c_float),
+        ("orthogonal_distance_threshold", C.c_float),
+        ("initial_seed_threshold", C.c_float),
+        ("number_of_iterations", C.c_uint32),
+        ("number_of_planar_partitions", C.c_uint32),
+        ("number_of_lower_point_representatives", C.c_uint32),
+    ]
+
+
+class CluCfg(C.Structure):
+    """reference: src/clustering.hpp:42-48"""
+
+    _fields_ = [
+        ("distance_squared", C.c_float),
+        ("cluster_quality", C.c_float),
+        ("min_cluster_size", C.c_uint32),
+        ("max_cluster_size", C.c_uint32),
+    ]
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so, and oracle/_ref when /root/reference is present (else keep prebuilt)."""
+    lib = HERE / "liboracle.so"
+    srcs = [HERE / "oracle.cpp", HERE / "oracle.h", HERE / "ref_wrap.cpp", HERE / "Makefile"]
+    newest = max(s.stat().st_mtime for s in srcs)
+    need = force or not lib.exists() or lib.stat().st_mtime < newest
+    ref = HERE / "_ref" / "libref_cluster.so"
+    have_reference = Path("/root/reference/src/clustering.cpp").exists()
+    if have_reference and (force or not ref.exists() or ref.stat().st_mtime < newest):
+        need = True
+    if need:
+        subprocess.run(["make", "-s", "-C", str(HERE), "all"], check=True)
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        build()
+        _LIB = C.CDLL(str(HERE / "liboracle.so"))
+        _LIB.oracle_fnv1a64.restype = C.c_uint64
+        _LIB.oracle_canonicalise.restype = C.c_uint32
+    return _LIB
+
+
+def ref_available() -> bool:
+    return (HERE / "_ref" / "libref_cluster.so").exists()
+
+
+def ref() -> C.CDLL:
+    global _REF
+    if _REF is None:
+        build()
+        _REF = C.CDLL(str(HERE / "_ref" / "libref_cluster.so"))
+    return _REF
+
+
+def _f32(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def default_seg_cfg(**kw) -> SegCfg:
+    cfg = SegCfg()
+    lib().oracle_seg_cfg_default(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def default_clu_cfg(**kw) -> CluCfg:
+    cfg = CluCfg()
+    lib().oracle_clu_cfg_default(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def segment(points, cfg: SegCfg | None = None, tie_mode: int = 1, labels_in=None):
+    """Segmenter::segment. Returns dict(labels, ground_idx, obstacle_idx, planes, status)."""
+    pts = _f32(points)
+    n = pts.shape[0]
+    cfg = cfg or default_seg_cfg()
+    labels = np.zeros(n, np.uint32) if labels_in is None else np.ascontiguousarray(labels_in, np.uint32).copy()
+    g = np.zeros(max(n, 1), np.uint32)
+    o = np.zeros(max(n, 1), np.uint32)
+    ng, no = C.c_uint32(0), C.c_uint32(0)
+    P, it = cfg.number_of_planar_partitions, cfg.number_of_iterations
+    planes = np.zeros((max(P, 1), max(it, 1), 4), np.float32)
+    status = np.zeros(max(P, 1), np.int32)
+    rc = lib().oracle_segment(_p(pts, C.c_float), C.c_uint32(n), C.c_uint32(pts.shape[1]), C.byref(cfg),
+                              C.c_int(tie_mode), _p(labels, C.c_uint32), _p(g, C.c_uint32), C.byref(ng),
+                              _p(o, C.c_uint32), C.byref(no), _p(planes, C.c_float), _p(status, C.c_int32))
+    if rc != 0:
+        raise ValueError("oracle_segment: bad configuration")
+    return dict(labels=labels, ground_idx=g[: ng.value].copy(), obstacle_idx=o[: no.value].copy(),
+                planes=planes[:P, :it], status=status[:P])
+
+
+def jacobi_svd3(a):
+    a = np.ascontiguousarray(a, np.float32).reshape(9)
+    v = np.zeros(9, np.float32)
+    sv = np.zeros(3, np.float32)
+    sweeps = lib().oracle_jacobi_svd3(_p(a, C.c_float), _p(v, C.c_float), _p(sv, C.c_float))
+    return v.reshape(3, 3), sv, sweeps
+
+
+def cluster(points, cfg: CluCfg | None = None) -> np.ndarray:
+    pts = _f32(points)
+    m = pts.shape[0]
+    cfg = cfg or default_clu_cfg()
+    labels = np.zeros(max(m, 1), np.int32)
+    lib().oracle_cluster(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), C.byref(cfg),
+                         _p(labels, C.c_int32))
+    return labels[:m]
+
+
+def kd_order(points, mode: int = 0) -> np.ndarray:
+    pts = _f32(points)
+    m = pts.shape[0]
+    order = np.zeros(max(m, 1), np.uint32)
+    lib().oracle_kd_order(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), C.c_int(mode),
+                          _p(order, C.c_uint32))
+    return order[:m]
+
+
+def kd_build(points, mode: int = 0) -> np.ndarray:
+    pts = _f32(points)
+    m = pts.shape[0]
+    slots = np.zeros(max(m, 1), np.uint32)
+    lib().oracle_kd_build(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), C.c_int(mode),
+                          _p(slots, C.c_uint32))
+    return slots[:m]
+
+
+def kd_rank(points, mode: int = 0) -> np.ndarray:
+    order = kd_order(points, mode)
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size, dtype=np.uint32)
+    return rank
+
+
+def cc_roots(points, distance_squared: float = 0.18) -> np.ndarray:
+    pts = _f32(points)
+    m = pts.shape[0]
+    root = np.zeros(max(m, 1), np.uint32)
+    lib().oracle_cc(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), C.c_float(distance_squared),
+                    _p(root, C.c_uint32))
+    return root[:m]
+
+
+def cluster_model(points, rank=None, cfg: CluCfg | None = None):
+    pts = _f32(points)
+    m = pts.shape[0]
+    cfg = cfg or default_clu_cfg()
+    if rank is None:
+        rank = kd_rank(pts, 0)
+    rank = np.ascontiguousarray(rank, np.uint32)
+    labels = np.zeros(max(m, 1), np.int32)
+    stats = np.zeros(8, np.uint64)
+    lib().oracle_cluster_model(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), C.byref(cfg),
+                               _p(rank, C.c_uint32), _p(labels, C.c_int32), _p(stats, C.c_uint64))
+    names = ["seeds", "expansions", "pushes", "max_queue", "components", "max_component", "max_comp_expansions",
+             "hits"]
+    return labels[:m], dict(zip(names, (int(x) for x in stats)))
+
+
+def canonicalise(labels) -> np.ndarray:
+    lab = np.ascontiguousarray(labels, np.int32)
+    out = np.zeros(max(lab.size, 1), np.int32)
+    lib().oracle_canonicalise(_p(lab, C.c_int32), C.c_uint32(lab.size), _p(out, C.c_int32))
+    return out[: lab.size]
+
+
+def fnv1a64(arr) -> int:
+    a = np.ascontiguousarray(arr)
+    return int(lib().oracle_fnv1a64(a.ctypes.data_as(C.c_void_p), C.c_uint64(a.nbytes)))
+
+
+# ---- unmodified reference build (oracle/_ref) ------------------------------------------------
+
+def ref_cluster(points, cfg: CluCfg | None = None) -> np.ndarray:
+    pts = _f32(points)
+    m = pts.shape[0]
+    cfg = cfg or default_clu_cfg()
+    labels = np.zeros(max(m, 1), np.int32)
+    ref().ref_cluster(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), C.c_float(cfg.distance_squared),
+                      C.c_float(cfg.cluster_quality), C.c_uint32(cfg.min_cluster_size),
+                      C.c_uint32(cfg.max_cluster_size), _p(labels, C.c_int32))
+    return labels[:m]
+
+
+def ref_cluster_timed(points, repeats: int = 3):
+    pts = _f32(points)
+    m = pts.shape[0]
+    labels = np.zeros(max(m, 1), np.int32)
+    best, mean = C.c_double(0), C.c_double(0)
+    ref().ref_cluster_timed(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), C.c_uint32(repeats),
+                            _p(labels, C.c_int32), C.byref(best), C.byref(mean))
+    return labels[:m], best.value, mean.value
+
+
+def ref_kd_order(points) -> np.ndarray:
+    pts = _f32(points)
+    m = pts.shape[0]
+    order = np.zeros(max(m, 1), np.uint32)
+    rc = ref().ref_kd_preorder(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), _p(order, C.c_uint32))
+    assert rc == 0
+    return order[:m]
+
+
+def ref_radius_search(points, queries, radius_sqr: float = 0.18, capacity: int | None = None):
+    pts = _f32(points)
+    m = pts.shape[0]
+    q = np.ascontiguousarray(queries, np.uint32)
+    capacity = capacity or max(1, 64 * 1024 * 1024 // 8)
+    offs = np.zeros(q.size + 1, np.uint32)
+    idx = np.zeros(capacity, np.uint32)
+    d2 = np.zeros(capacity, np.float32)
+    rc = ref().ref_radius_search(_p(pts, C.c_float), C.c_uint32(m), C.c_uint32(pts.shape[1]), _p(q, C.c_uint32),
+                                 C.c_uint32(q.size), C.c_float(radius_sqr), _p(offs, C.c_uint32),
+                                 _p(idx, C.c_uint32), _p(d2, C.c_float), C.c_uint32(capacity))
+    assert rc == 0, rc
+    return offs, idx[: offs[-1]].copy(), d2[: offs[-1]].copy()
+
+
+# ---- PCD v0.7 "DATA binary" reader (dataloader.cpp:139 uses pcl::io::loadPCDFile) ------------
+
+def read_pcd(path) -> np.ndarray:
+    """Returns an (N, 4) float32 array x, y, z, intensity."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    pos = 0
+    npts = None
+    fields = None
+    while True:
+        end = raw.index(b"\n", pos)
+        line = raw[pos:end].decode("ascii", "replace").strip()
+        pos = end + 1
+        if line.startswith("FIELDS"):
+            fields = line.split()[1:]
+        elif line.startswith("POINTS"):
+            npts = int(line.split()[1])
+        elif line.startswith("DATA"):
+            assert line.split()[1] == "binary", "only DATA binary is supported"
+            break
+    assert fields == ["x", "y", "z", "intensity"] and npts is not None
+    return np.frombuffer(raw, dtype=np.float32, count=npts * 4, offset=pos).reshape(npts, 4).copy()
+
+
+REFERENCE_DATA = Path(os.environ.get("LIDAR_B200_REFERENCE_DATA", "/root/reference/data"))
+
+
+def reference_frame_paths():
+    if not REFERENCE_DATA.is_dir():
+        return []
+    return sorted(REFERENCE_DATA.glob("*.pcd"))

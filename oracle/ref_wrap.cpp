@@ -1,0 +1,142 @@
+// TEST INFRASTRUCTURE ONLY — C wrapper around the UNMODIFIED reference Clusterer / KDTree.
+// The reference sources are compiled where they lie (/root/reference/src, read-only); nothing is
+// copied. Built by oracle/Makefile into oracle/_ref/libref_cluster.so (git-ignored, travels to the
+// GPU box). Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load it.
+//
+// Wraps: lidar_processing::Clusterer::cluster   (reference src/clustering.cpp:47-125)
+//        lidar_processing::KDTree<float,3>       (reference src/kdtree.hpp:174-225, 292-341)
+#include "clustering.hpp" // from /root/reference/src
+
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+using lidar_processing::Clusterer;
+using lidar_processing::ClusteringConfiguration;
+using lidar_processing::ClusteringLabel;
+
+extern "C"
+{
+
+// points: m records of `stride_floats` floats, xyz first. Returns 0.
+int ref_cluster(const float *points, std::uint32_t m, std::uint32_t stride_floats, float distance_squared,
+                float cluster_quality, std::uint32_t min_cluster_size, std::uint32_t max_cluster_size,
+                std::int32_t *labels_out)
+{
+    pcl::PointCloud<pcl::PointXYZRGBL> cloud; // the type the processor node uses (processor.cpp:158-163)
+    cloud.reserve(m);
+    for (std::uint32_t i = 0; i < m; ++i)
+    {
+        const float *p = points + static_cast<std::size_t>(i) * stride_floats;
+        cloud.emplace_back(p[0], p[1], p[2], 0, 255, 0, 1);
+    }
+    Clusterer clusterer;
+    ClusteringConfiguration cfg;
+    cfg.distance_squared = distance_squared;
+    cfg.cluster_quality = cluster_quality;
+    cfg.min_cluster_size = min_cluster_size;
+    cfg.max_cluster_size = max_cluster_size;
+    clusterer.update_configuration(cfg);
+    std::vector<ClusteringLabel> labels;
+    clusterer.cluster(cloud, labels);
+    if (m)
+        std::memcpy(labels_out, labels.data(), sizeof(std::int32_t) * m);
+    return 0;
+}
+
+// Times `repeats` calls of Clusterer::cluster on a long-lived instance (as the node holds it,
+// processor.cpp:132); returns best and mean milliseconds.
+int ref_cluster_timed(const float *points, std::uint32_t m, std::uint32_t stride_floats, std::uint32_t repeats,
+                      std::int32_t *labels_out, double *best_ms, double *mean_ms)
+{
+    pcl::PointCloud<pcl::PointXYZRGBL> cloud;
+    cloud.reserve(m);
+    for (std::uint32_t i = 0; i < m; ++i)
+    {
+        const float *p = points + static_cast<std::size_t>(i) * stride_floats;
+        cloud.emplace_back(p[0], p[1], p[2], 0, 255, 0, 1);
+    }
+    Clusterer clusterer;
+    std::vector<ClusteringLabel> labels;
+    double best = 1e300, sum = 0.0;
+    for (std::uint32_t r = 0; r < repeats; ++r)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        clusterer.cluster(cloud, labels);
+        const auto t1 = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        best = ms < best ? ms : best;
+        sum += ms;
+    }
+    if (m && labels_out)
+        std::memcpy(labels_out, labels.data(), sizeof(std::int32_t) * m);
+    *best_ms = best;
+    *mean_ms = repeats ? sum / repeats : 0.0;
+    return 0;
+}
+
+// Pre-order rank of every point in the reference k-d tree: one radius_search with a huge radius
+// prunes nothing and therefore returns all nodes in traversal (= pre-) order (kdtree.hpp:292-341).
+int ref_kd_preorder(const float *points, std::uint32_t m, std::uint32_t stride_floats, std::uint32_t *order_out)
+{
+    using namespace lidar_processing;
+    containers::Vector<Point<float, 3>> pts;
+    pts.reserve(m);
+    for (std::uint32_t i = 0; i < m; ++i)
+    {
+        const float *p = points + static_cast<std::size_t>(i) * stride_floats;
+        pts.push_back({p[0], p[1], p[2]});
+    }
+    KDTree<float, 3> tree;
+    tree.reserve(m);
+    tree.rebuild(pts);
+    containers::Vector<KDTree<float, 3>::RetT> neigh;
+    neigh.reserve(m);
+    tree.radius_search(pts[0], 3.0e38F, neigh);
+    if (neigh.size() != m)
+        return 1;
+    for (std::uint32_t i = 0; i < m; ++i)
+        order_out[i] = neigh[i].first; // order_out[rank] = point index
+    return 0;
+}
+
+// radius_search of the reference tree for a list of query point indices; results (index, d2) are
+// concatenated, offsets_out has nq+1 entries. Used to pin neighbour sets / d2 bits / order.
+int ref_radius_search(const float *points, std::uint32_t m, std::uint32_t stride_floats, const std::uint32_t *queries,
+                      std::uint32_t nq, float radius_sqr, std::uint32_t *offsets_out, std::uint32_t *idx_out,
+                      float *d2_out, std::uint32_t capacity)
+{
+    using namespace lidar_processing;
+    containers::Vector<Point<float, 3>> pts;
+    pts.reserve(m);
+    for (std::uint32_t i = 0; i < m; ++i)
+    {
+        const float *p = points + static_cast<std::size_t>(i) * stride_floats;
+        pts.push_back({p[0], p[1], p[2]});
+    }
+    KDTree<float, 3> tree;
+    tree.reserve(m);
+    tree.rebuild(pts);
+    containers::Vector<KDTree<float, 3>::RetT> neigh;
+    std::uint32_t off = 0;
+    offsets_out[0] = 0;
+    for (std::uint32_t q = 0; q < nq; ++q)
+    {
+        tree.radius_search(pts[queries[q]], radius_sqr, neigh);
+        for (const auto &[k, d] : neigh)
+        {
+            if (off >= capacity)
+                return 2;
+            idx_out[off] = k;
+            d2_out[off] = d;
+            ++off;
+        }
+        offsets_out[q + 1] = off;
+    }
+    return 0;
+}
+
+} // extern "C"
