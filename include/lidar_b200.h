@@ -1,0 +1,136 @@
+/* lidar_b200 — C ABI of the B200-native ground-segmentation + Fast-Euclidean-Clustering path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. The C++ classes
+ * lidar_processing::Segmenter / lidar_processing::Clusterer (lidar-processing_b200/include/
+ * segmentation.hpp, clustering.hpp — same public interface as the reference headers) are thin shells
+ * over these entry points; INTEGRATION.md shows the binding a maintainer of the reference adds.
+ *
+ * The library owns pinned host staging buffers, device arenas and CUDA streams. All functions return
+ * 0 on success and a non-zero lidar_b200_status otherwise; lidar_b200_last_error() gives the text.
+ * A context is not thread-safe (the reference classes are used from one executor thread,
+ * reference src/processor.cpp:279); use one context per thread / per GPU.
+ */
+#ifndef LIDAR_B200_H
+#define LIDAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    typedef struct lidar_b200_ctx lidar_b200_ctx;
+
+    typedef enum lidar_b200_status
+    {
+        LIDAR_B200_OK = 0,
+        LIDAR_B200_ERR_CUDA = 1,        /* a CUDA call failed (no analogue in the reference; the C++ shells throw) */
+        LIDAR_B200_ERR_INVALID = 2,     /* bad argument */
+        LIDAR_B200_ERR_UNSUPPORTED = 3, /* configuration outside the supported envelope */
+        LIDAR_B200_ERR_CAPACITY = 4,    /* batch larger than the reserved arenas and growth failed */
+        LIDAR_B200_ERR_INPUT = 5        /* non-finite / out-of-range coordinates (unspecified in the reference) */
+    } lidar_b200_status;
+
+    /* replaces lidar_processing::SegmentationConfiguration (reference src/segmentation.hpp:48-56) */
+    typedef struct lidar_b200_seg_cfg
+    {
+        float sensor_height_m;                          /* 1.73 */
+        float orthogonal_distance_threshold;            /* 0.3  */
+        float initial_seed_threshold;                   /* 0.6  */
+        uint32_t number_of_iterations;                  /* 3    */
+        uint32_t number_of_planar_partitions;           /* 2    */
+        uint32_t number_of_lower_point_representatives; /* 5000 */
+    } lidar_b200_seg_cfg;
+
+    /* replaces lidar_processing::ClusteringConfiguration (reference src/clustering.hpp:42-48) */
+    typedef struct lidar_b200_clu_cfg
+    {
+        float distance_squared;    /* 0.18 */
+        float cluster_quality;     /* 0.5  */
+        uint32_t min_cluster_size; /* 4    */
+        uint32_t max_cluster_size; /* UINT32_MAX */
+    } lidar_b200_clu_cfg;
+
+    /* SegmentationLabel values (reference src/segmentation.hpp:41-46) */
+#define LIDAR_B200_SEG_UNKNOWN 0u
+#define LIDAR_B200_SEG_GROUND 1u
+#define LIDAR_B200_SEG_OBSTACLE 2u
+    /* ClusteringLabel specials (reference src/clustering.hpp:53-54) */
+#define LIDAR_B200_CLU_UNDEFINED INT32_MIN
+#define LIDAR_B200_CLU_INVALID (-1)
+
+    void lidar_b200_seg_cfg_default(lidar_b200_seg_cfg *cfg);
+    void lidar_b200_clu_cfg_default(lidar_b200_clu_cfg *cfg);
+
+    /* replaces Segmenter::Segmenter() / Clusterer::Clusterer() + reserve_memory(200'000)
+     * (reference src/segmentation.cpp:33-60, src/clustering.cpp:27-45). `max_points` is the total
+     * number of points of one batch the arenas are sized for up front (they grow on demand),
+     * `max_frames` the number of frames per batch. Fails when the CUDA library/device is missing —
+     * there is no CPU fallback. */
+    int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lidar_b200_ctx **ctx_out);
+    void lidar_b200_destroy(lidar_b200_ctx *ctx);
+
+    /* replaces Segmenter::reserve_memory / Clusterer::reserve_memory (segmentation.hpp:66, clustering.hpp:61) */
+    int lidar_b200_reserve(lidar_b200_ctx *ctx, uint32_t max_points, uint32_t max_frames);
+
+    /* replaces Segmenter::update_configuration / Clusterer::update_configuration */
+    int lidar_b200_seg_configure(lidar_b200_ctx *ctx, const lidar_b200_seg_cfg *cfg);
+    int lidar_b200_clu_configure(lidar_b200_ctx *ctx, const lidar_b200_clu_cfg *cfg);
+
+    /* replaces Segmenter::segment<PointT> (reference src/segmentation.cpp:311-345).
+     * points: n records, `stride_bytes` apart (16 for PointXYZ, 32 for PointXYZI), x,y,z = the first
+     * three floats of each record. labels_inout: n entries; classified points receive GROUND/OBSTACLE,
+     * all others keep their previous value (the reference's labels.resize() does not reset old
+     * entries, segmentation.cpp:315). ground_idx_out / obstacle_idx_out: capacity n each; original
+     * point indices in the order the reference push_back()s them into ground_cloud / obstacle_cloud. */
+    int lidar_b200_segment(lidar_b200_ctx *ctx, const void *points, uint32_t n, uint32_t stride_bytes,
+                           uint32_t *labels_inout, uint32_t *ground_idx_out, uint32_t *n_ground_out,
+                           uint32_t *obstacle_idx_out, uint32_t *n_obstacle_out);
+
+    /* replaces Clusterer::cluster<PointT> (reference src/clustering.cpp:47-125). labels_out: m int32:
+     * 0..K-1 dense cluster ids, -1 INVALID. */
+    int lidar_b200_cluster(lidar_b200_ctx *ctx, const void *points, uint32_t m, uint32_t stride_bytes,
+                           int32_t *labels_out);
+
+    /* ---- batched frame pipeline: segment + cluster of many independent frames per call ----------
+     * (the throughput path; one call replaces a sequence of Processor::process iterations,
+     * reference src/processor.cpp:150-178, with the obstacle cloud staying on the device).
+     *
+     * stage : host -> pinned staging -> device (asynchronous on the context's stream)
+     * run   : all kernels for the staged batch (asynchronous)
+     * fetch : device -> host results; blocks until they are there.
+     * Frame f of a fetched batch owns [point_offset[f], point_offset[f] + n_points[f]) in the
+     * concatenated output arrays; its obstacle-indexed outputs (obstacle_idx, cluster_labels) use the
+     * same offset with n_obstacle[f] live entries. */
+    int lidar_b200_batch_stage(lidar_b200_ctx *ctx, uint32_t n_frames, const void *const *points,
+                               const uint32_t *n_points, uint32_t stride_bytes);
+    int lidar_b200_batch_run(lidar_b200_ctx *ctx);
+    int lidar_b200_batch_fetch(lidar_b200_ctx *ctx, uint32_t *point_offset_out /* [n_frames] */,
+                               uint32_t *seg_labels_out /* [sum n] */, uint32_t *ground_idx_out /* [sum n] */,
+                               uint32_t *n_ground_out /* [n_frames] */, uint32_t *obstacle_idx_out /* [sum n] */,
+                               uint32_t *n_obstacle_out /* [n_frames] */, int32_t *cluster_labels_out /* [sum n] */,
+                               uint32_t *n_clusters_out /* [n_frames] */);
+    /* waits for the stream; used by benchmarks that keep inputs and outputs resident in HBM */
+    int lidar_b200_sync(lidar_b200_ctx *ctx);
+
+    /* diagnostics */
+    /* plane coefficients (a,b,c,d) of every fit of the last batch: [frame][partition][iteration][4], NaN = no fit;
+     * status per [frame][partition]: 0 ok, 1 "<3 points", 2 "Failed ground segmentation". */
+    int lidar_b200_last_planes(lidar_b200_ctx *ctx, float *planes_out, int32_t *status_out);
+    /* k-d pre-order rank of every point of the last cluster()/batch frame 0 (parity checks) */
+    int lidar_b200_last_kd_rank(lidar_b200_ctx *ctx, uint32_t frame, uint32_t *rank_out, uint32_t capacity);
+    /* component root (smallest member index) of every obstacle point of a frame of the last batch */
+    int lidar_b200_last_cc_root(lidar_b200_ctx *ctx, uint32_t frame, uint32_t *root_out, uint32_t capacity);
+    /* number of kernels launched by this context so far */
+    uint64_t lidar_b200_launch_count(const lidar_b200_ctx *ctx);
+    /* elapsed GPU milliseconds between the start and the end of the last lidar_b200_batch_run (CUDA events) */
+    int lidar_b200_last_run_ms(lidar_b200_ctx *ctx, float *ms_out);
+    const char *lidar_b200_last_error(const lidar_b200_ctx *ctx);
+    const char *lidar_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LIDAR_B200_H */

@@ -1,0 +1,326 @@
+"""lidar_b200 — B200-native ground segmentation + Fast Euclidean Clustering.
+
+Host-side mirror of the reference's operator interface for this path
+(`lidar_processing::Segmenter`, `lidar_processing::Clusterer`; reference src/segmentation.hpp:58-70,
+src/clustering.hpp:50-64) on top of the C ABI in include/lidar_b200.h. The product is the CUDA
+library `liblidar_b200.so` built from csrc/; this module only marshals numpy / torch buffers into
+it. There is no CPU fallback: constructing any class without the built library or without a CUDA
+device raises.
+
+The directory name contains a hyphen, so import it through `__graft_entry__.load_package()` (or
+importlib) under the module name `lidar_processing_b200`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent
+LIB_PATH = HERE / "liblidar_b200.so"
+CSRC = HERE / "csrc"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # the reference build has no FMA contraction; parity depends on it
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+UNKNOWN, GROUND, OBSTACLE = 0, 1, 2
+UNDEFINED = np.iinfo(np.int32).min
+INVALID = -1
+
+_lib = None
+
+
+class LidarB200Error(RuntimeError):
+    pass
+
+
+class SegmentationConfiguration(C.Structure):
+    """reference src/segmentation.hpp:48-56 (same fields, same defaults)"""
+
+    _fields_ = [
+        ("sensor_height_m", C.c_float),
+        ("orthogonal_distance_threshold", C.c_float),
+        ("initial_seed_threshold", C.c_float),
+        ("number_of_iterations", C.c_uint32),
+        ("number_of_planar_partitions", C.c_uint32),
+        ("number_of_lower_point_representatives", C.c_uint32),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.sensor_height_m = 1.73
+        self.orthogonal_distance_threshold = 0.3
+        self.initial_seed_threshold = 0.6
+        self.number_of_iterations = 3
+        self.number_of_planar_partitions = 2
+        self.number_of_lower_point_representatives = 5000
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class ClusteringConfiguration(C.Structure):
+    """reference src/clustering.hpp:42-48 (same fields, same defaults)"""
+
+    _fields_ = [
+        ("distance_squared", C.c_float),
+        ("cluster_quality", C.c_float),
+        ("min_cluster_size", C.c_uint32),
+        ("max_cluster_size", C.c_uint32),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.distance_squared = 0.18
+        self.cluster_quality = 0.5
+        self.min_cluster_size = 4
+        self.max_cluster_size = 0xFFFFFFFF
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "lidar_b200.h"]
+
+
+def build_extension(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc cross-compiles the CUDA library for sm_100a in-tree (no GPU needed to build)."""
+    newest = max(p.stat().st_mtime for p in sources())
+    if not force and LIB_PATH.exists() and LIB_PATH.stat().st_mtime >= newest:
+        return LIB_PATH
+    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB_PATH), str(CSRC / "api.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise LidarB200Error(f"{LIB_PATH} is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(str(LIB_PATH))
+        L.lidar_b200_last_error.restype = C.c_char_p
+        L.lidar_b200_version.restype = C.c_char_p
+        L.lidar_b200_launch_count.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "lidar_b200_seg_cfg_default", "lidar_b200_clu_cfg_default", "lidar_b200_create", "lidar_b200_destroy",
+    "lidar_b200_reserve", "lidar_b200_seg_configure", "lidar_b200_clu_configure", "lidar_b200_segment",
+    "lidar_b200_cluster", "lidar_b200_batch_stage", "lidar_b200_batch_run", "lidar_b200_batch_fetch",
+    "lidar_b200_sync", "lidar_b200_last_planes", "lidar_b200_last_kd_rank", "lidar_b200_last_cc_root",
+    "lidar_b200_launch_count", "lidar_b200_last_run_ms", "lidar_b200_last_error", "lidar_b200_version",
+]
+
+
+def _as_points(points) -> np.ndarray:
+    a = np.asarray(points)
+    if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("points must be (N, >=3) float32: x, y, z first")
+    return a
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Context:
+    """Owns one lidar_b200_ctx (stream, pinned staging, device arenas) on one GPU."""
+
+    def __init__(self, device: int = 0, max_points: int = 200_000, max_frames: int = 1):
+        self._h = C.c_void_p()
+        rc = lib().lidar_b200_create(C.c_int(device), C.c_uint32(max_points), C.c_uint32(max_frames), C.byref(self._h))
+        if rc != 0:
+            raise LidarB200Error(f"lidar_b200_create failed (status {rc}): CUDA device {device} unavailable; "
+                                 "there is no CPU fallback")
+        self.device = device
+        self.seg_cfg = SegmentationConfiguration()
+        self.clu_cfg = ClusteringConfiguration()
+        self._n_points = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().lidar_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = lib().lidar_b200_last_error(self._h)
+            raise LidarB200Error(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+    def reserve(self, max_points: int, max_frames: int = 1):
+        self._check(lib().lidar_b200_reserve(self._h, C.c_uint32(max_points), C.c_uint32(max_frames)), "reserve")
+
+    def seg_configure(self, cfg: SegmentationConfiguration):
+        self._check(lib().lidar_b200_seg_configure(self._h, C.byref(cfg)), "seg_configure")
+        self.seg_cfg = cfg
+
+    def clu_configure(self, cfg: ClusteringConfiguration):
+        self._check(lib().lidar_b200_clu_configure(self._h, C.byref(cfg)), "clu_configure")
+        self.clu_cfg = cfg
+
+    # -- single-frame calls (the reference's per-frame interface) -------------------------------
+    def segment(self, points, labels_inout: np.ndarray | None = None):
+        pts = _as_points(points)
+        n = pts.shape[0]
+        labels = np.zeros(n, np.uint32) if labels_inout is None else labels_inout
+        assert labels.dtype == np.uint32 and labels.size >= n
+        g = np.empty(max(n, 1), np.uint32)
+        o = np.empty(max(n, 1), np.uint32)
+        ng, no = C.c_uint32(0), C.c_uint32(0)
+        self._check(lib().lidar_b200_segment(self._h, pts.ctypes.data_as(C.c_void_p), C.c_uint32(n),
+                                             C.c_uint32(pts.strides[0]), _ptr(labels, C.c_uint32),
+                                             _ptr(g, C.c_uint32), C.byref(ng), _ptr(o, C.c_uint32), C.byref(no)),
+                    "segment")
+        return labels, g[: ng.value].copy(), o[: no.value].copy()
+
+    def cluster(self, points) -> np.ndarray:
+        pts = _as_points(points)
+        m = pts.shape[0]
+        labels = np.full(max(m, 1), UNDEFINED, np.int32)
+        self._check(lib().lidar_b200_cluster(self._h, pts.ctypes.data_as(C.c_void_p), C.c_uint32(m),
+                                             C.c_uint32(pts.strides[0]), _ptr(labels, C.c_int32)), "cluster")
+        return labels[:m]
+
+    # -- batched frame pipeline -----------------------------------------------------------------
+    def batch_stage(self, frames):
+        frames = [_as_points(f) for f in frames]
+        nf = len(frames)
+        strides = {f.strides[0] for f in frames} or {16}
+        if len(strides) != 1:
+            raise ValueError("all frames of a batch must share one point stride")
+        ptrs = (C.c_void_p * max(nf, 1))(*[f.ctypes.data for f in frames])
+        counts = np.array([f.shape[0] for f in frames], np.uint32)
+        self._keep = frames
+        self._n_points = counts
+        self._check(lib().lidar_b200_batch_stage(self._h, C.c_uint32(nf), ptrs, _ptr(counts, C.c_uint32),
+                                                 C.c_uint32(strides.pop())), "batch_stage")
+
+    def batch_run(self):
+        self._check(lib().lidar_b200_batch_run(self._h), "batch_run")
+
+    def sync(self):
+        self._check(lib().lidar_b200_sync(self._h), "sync")
+
+    def batch_fetch(self, want_ground_idx: bool = True):
+        counts = self._n_points
+        nf = counts.size
+        total = int(((counts.astype(np.int64) + 31) & ~31).sum())
+        off = np.zeros(max(nf, 1), np.uint32)
+        seg = np.empty(max(total, 1), np.uint32)
+        gidx = np.empty(max(total, 1), np.uint32) if want_ground_idx else None
+        oidx = np.empty(max(total, 1), np.uint32)
+        clab = np.empty(max(total, 1), np.int32)
+        ng = np.zeros(max(nf, 1), np.uint32)
+        no = np.zeros(max(nf, 1), np.uint32)
+        nc = np.zeros(max(nf, 1), np.uint32)
+        self._check(lib().lidar_b200_batch_fetch(self._h, _ptr(off, C.c_uint32), _ptr(seg, C.c_uint32),
+                                                 _ptr(gidx, C.c_uint32) if want_ground_idx else None,
+                                                 _ptr(ng, C.c_uint32), _ptr(oidx, C.c_uint32), _ptr(no, C.c_uint32),
+                                                 _ptr(clab, C.c_int32), _ptr(nc, C.c_uint32)), "batch_fetch")
+        out = []
+        for f in range(nf):
+            o, n = int(off[f]), int(counts[f])
+            out.append(dict(
+                seg_labels=seg[o:o + n],
+                ground_idx=gidx[o:o + int(ng[f])] if want_ground_idx else None,
+                obstacle_idx=oidx[o:o + int(no[f])],
+                cluster_labels=clab[o:o + int(no[f])],
+                n_clusters=int(nc[f]),
+            ))
+        return out
+
+    def process_batch(self, frames, want_ground_idx: bool = True):
+        self.batch_stage(frames)
+        self.batch_run()
+        return self.batch_fetch(want_ground_idx)
+
+    # -- diagnostics ----------------------------------------------------------------------------
+    def last_planes(self, n_frames: int = 1):
+        P, it = self.seg_cfg.number_of_planar_partitions, self.seg_cfg.number_of_iterations
+        planes = np.zeros((n_frames, P, it, 4), np.float32)
+        status = np.zeros((n_frames, P), np.int32)
+        self._check(lib().lidar_b200_last_planes(self._h, _ptr(planes, C.c_float), _ptr(status, C.c_int32)),
+                    "last_planes")
+        return planes, status
+
+    def last_kd_rank(self, m: int, frame: int = 0) -> np.ndarray:
+        r = np.zeros(max(m, 1), np.uint32)
+        self._check(lib().lidar_b200_last_kd_rank(self._h, C.c_uint32(frame), _ptr(r, C.c_uint32), C.c_uint32(m)),
+                    "last_kd_rank")
+        return r[:m]
+
+    def last_cc_root(self, m: int, frame: int = 0) -> np.ndarray:
+        r = np.zeros(max(m, 1), np.uint32)
+        self._check(lib().lidar_b200_last_cc_root(self._h, C.c_uint32(frame), _ptr(r, C.c_uint32), C.c_uint32(m)),
+                    "last_cc_root")
+        return r[:m]
+
+    def launch_count(self) -> int:
+        return int(lib().lidar_b200_launch_count(self._h))
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float(0)
+        self._check(lib().lidar_b200_last_run_ms(self._h, C.byref(ms)), "last_run_ms")
+        return float(ms.value)
+
+
+class Segmenter:
+    """Mirror of lidar_processing::Segmenter (reference src/segmentation.hpp:58-70)."""
+
+    def __init__(self, device: int = 0, context: Context | None = None):
+        self._ctx = context or Context(device)
+        self._cfg = SegmentationConfiguration()
+
+    def update_configuration(self, configuration: SegmentationConfiguration):
+        self._ctx.seg_configure(configuration)
+        self._cfg = configuration
+
+    def reserve_memory(self, number_of_points: int = 200_000):
+        self._ctx.reserve(number_of_points)
+
+    def segment(self, cloud_in, labels: np.ndarray | None = None):
+        """Returns (labels, ground_cloud, obstacle_cloud). `labels` (uint32, len >= N) is updated in
+        place when given: only classified points are written, like the reference's resize()."""
+        pts = _as_points(cloud_in)
+        labels, gi, oi = self._ctx.segment(pts, labels)
+        return labels, pts[gi], pts[oi]
+
+    def segment_indices(self, cloud_in, labels: np.ndarray | None = None):
+        return self._ctx.segment(_as_points(cloud_in), labels)
+
+
+class Clusterer:
+    """Mirror of lidar_processing::Clusterer (reference src/clustering.hpp:50-64)."""
+
+    UNDEFINED = UNDEFINED
+    INVALID = INVALID
+
+    def __init__(self, device: int = 0, context: Context | None = None):
+        self._ctx = context or Context(device)
+
+    def update_configuration(self, configuration: ClusteringConfiguration):
+        self._ctx.clu_configure(configuration)
+
+    def reserve_memory(self, number_of_points: int = 200_000):
+        self._ctx.reserve(number_of_points)
+
+    def cluster(self, cloud_in) -> np.ndarray:
+        return self._ctx.cluster(cloud_in)

@@ -1,0 +1,750 @@
+// C-ABI layer (include/lidar_b200.h): owns the CUDA stream, pinned staging buffers and device
+// arenas, validates configurations and sequences the kernels of segment.cuh / cluster.cuh /
+// kd_build.cuh / radix_sort.cuh for a batch of frames. No CPU fallback: every entry point either
+// runs the CUDA path or returns an error.
+#include "../../include/lidar_b200.h"
+
+#include "cluster.cuh"
+#include "common.cuh"
+#include "kd_build.cuh"
+#include "radix_sort.cuh"
+#include "segment.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace lb;
+
+namespace
+{
+template <typename T> struct DevBuf
+{
+    T *p{nullptr};
+    size_t n{0};
+};
+
+template <typename T> struct PinBuf
+{
+    T *p{nullptr};
+    size_t n{0};
+};
+
+uint32_t next_pow2(uint32_t v)
+{
+    uint32_t p = 1u;
+    while (p < v)
+        p <<= 1;
+    return p;
+}
+
+uint32_t ceil_log2(uint32_t v)
+{
+    uint32_t b = 0u;
+    while ((1ull << b) < v)
+        ++b;
+    return b;
+}
+} // namespace
+
+struct lidar_b200_ctx
+{
+    int device{0};
+    cudaStream_t stream{nullptr};
+    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr};
+    lidar_b200_seg_cfg seg_cfg{};
+    lidar_b200_clu_cfg clu_cfg{};
+    SegParams seg{};
+    CluParams clu{};
+
+    // reserved capacities
+    uint32_t cap_pts{0}, cap_frames{0}, cap_table{0}, cap_planes{0};
+
+    // pinned host staging
+    PinBuf<float4> h_pts;
+    PinBuf<uint32_t> h_u32[4]; // labels, ground idx, obstacle idx, cluster labels
+    PinBuf<uint32_t> h_meta;   // off, cnt, toff, tcap, n_ground, n_obstacle, n_clusters : 7 * cap_frames
+
+    // device arenas (per point)
+    DevBuf<float4> d_pts, d_spts, d_obs, d_nodes, d_cpts;
+    DevBuf<uint32_t> d_key_a, d_key_b, d_val_a, d_val_b, d_labels, d_gidx, d_oidx, d_slot_of, d_pos_of, d_parent,
+        d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label;
+    DevBuf<int32_t> d_clabels;
+    DevBuf<unsigned long long> d_spill;
+    DevBuf<uint8_t> d_flags, d_seed_valid;
+    // per table slot
+    DevBuf<unsigned long long> d_tkeys;
+    DevBuf<uint32_t> d_tcount;
+    DevBuf<uint4> d_cells;
+    // per frame
+    DevBuf<uint32_t> d_meta; // off, cnt, toff, tcap, n_ground, n_obstacle, n_clusters, cursor : 8 * cap_frames
+    DevBuf<uint32_t> d_err;
+    DevBuf<float> d_planes;
+    DevBuf<int32_t> d_status;
+    DevBuf<uint32_t> d_hist;
+
+    // current batch
+    uint32_t n_frames{0}, total{0}, max_n{0}, max_tcap{0};
+    bool batch_is_cluster_only{false};
+    std::vector<uint32_t> off, cnt;
+
+    uint64_t launches{0};
+    float last_run_ms{0.0f};
+    std::string err;
+
+    uint32_t *m_off() { return d_meta.p; }
+    uint32_t *m_cnt() { return d_meta.p + cap_frames; }
+    uint32_t *m_toff() { return d_meta.p + 2 * static_cast<size_t>(cap_frames); }
+    uint32_t *m_tcap() { return d_meta.p + 3 * static_cast<size_t>(cap_frames); }
+    uint32_t *m_ng() { return d_meta.p + 4 * static_cast<size_t>(cap_frames); }
+    uint32_t *m_no() { return d_meta.p + 5 * static_cast<size_t>(cap_frames); }
+    uint32_t *m_nc() { return d_meta.p + 6 * static_cast<size_t>(cap_frames); }
+    uint32_t *m_cursor() { return d_meta.p + 7 * static_cast<size_t>(cap_frames); }
+};
+
+namespace
+{
+int fail(lidar_b200_ctx *c, int code, const std::string &msg)
+{
+    if (c)
+        c->err = msg;
+    return code;
+}
+
+#define LB_CUDA(c, call)                                                                                              \
+    do                                                                                                                \
+    {                                                                                                                 \
+        const cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess)                                                                                        \
+            return fail((c), LIDAR_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+
+template <typename T> int dev_alloc(lidar_b200_ctx *c, DevBuf<T> &b, size_t n)
+{
+    if (b.n >= n && b.p)
+        return 0;
+    if (b.p)
+        LB_CUDA(c, cudaFree(b.p));
+    b.p = nullptr;
+    b.n = 0;
+    LB_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&b.p), n * sizeof(T)));
+    b.n = n;
+    return 0;
+}
+
+template <typename T> int pin_alloc(lidar_b200_ctx *c, PinBuf<T> &b, size_t n)
+{
+    if (b.n >= n && b.p)
+        return 0;
+    if (b.p)
+        LB_CUDA(c, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.n = 0;
+    LB_CUDA(c, cudaMallocHost(reinterpret_cast<void **>(&b.p), n * sizeof(T)));
+    b.n = n;
+    return 0;
+}
+
+int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
+{
+    LB_CUDA(c, cudaSetDevice(c->device));
+    pts = pts < 1024u ? 1024u : pts;
+    frames = frames < 1u ? 1u : frames;
+    const bool grow_pts = pts > c->cap_pts;
+    const bool grow_frames = frames > c->cap_frames;
+    if (grow_pts || grow_frames)
+        LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (grow_pts)
+    {
+        const size_t n = pts;
+        int rc = 0;
+        rc |= pin_alloc(c, c->h_pts, n);
+        for (auto &h : c->h_u32)
+            rc |= pin_alloc(c, h, n);
+        rc |= dev_alloc(c, c->d_pts, n) | dev_alloc(c, c->d_spts, n) | dev_alloc(c, c->d_obs, n) |
+              dev_alloc(c, c->d_nodes, n) | dev_alloc(c, c->d_cpts, n);
+        DevBuf<uint32_t> *u32s[] = {&c->d_key_a,  &c->d_key_b,  &c->d_val_a,      &c->d_val_b, &c->d_labels,
+                                    &c->d_gidx,   &c->d_oidx,   &c->d_slot_of,    &c->d_pos_of, &c->d_parent,
+                                    &c->d_root,   &c->d_rank,   &c->d_gepos,      &c->d_lepos, &c->d_state,
+                                    &c->d_seed_of, &c->d_member_pos, &c->d_queue, &c->d_seed_label};
+        for (auto *b : u32s)
+            rc |= dev_alloc(c, *b, n);
+        rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_flags, n) |
+              dev_alloc(c, c->d_seed_valid, n);
+        if (rc)
+            return LIDAR_B200_ERR_CUDA;
+        c->cap_pts = pts;
+    }
+    if (grow_frames)
+    {
+        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames)) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)))
+            return LIDAR_B200_ERR_CUDA;
+        c->cap_frames = frames;
+    }
+    // hash-table slots: every frame reserves next_pow2(max(64, 2*n)) <= 4*n + 64 slots
+    const size_t table = 4ull * c->cap_pts + 64ull * c->cap_frames;
+    if (table > c->cap_table)
+    {
+        LB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (dev_alloc(c, c->d_tkeys, table) || dev_alloc(c, c->d_tcount, table) || dev_alloc(c, c->d_cells, table))
+            return LIDAR_B200_ERR_CUDA;
+        c->cap_table = static_cast<uint32_t>(table);
+    }
+    const size_t planes = static_cast<size_t>(c->cap_frames) * c->seg.partitions * c->seg.iterations * 4;
+    if (dev_alloc(c, c->d_planes, planes ? planes : 4) ||
+        dev_alloc(c, c->d_status, static_cast<size_t>(c->cap_frames) * (c->seg.partitions ? c->seg.partitions : 1)))
+        return LIDAR_B200_ERR_CUDA;
+    if (dev_alloc(c, c->d_err, 4))
+        return LIDAR_B200_ERR_CUDA;
+    return 0;
+}
+
+int apply_seg_cfg(lidar_b200_ctx *c, const lidar_b200_seg_cfg &cfg)
+{
+    if (cfg.number_of_planar_partitions == 0u || cfg.number_of_planar_partitions > 4096u)
+        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "number_of_planar_partitions must be in [1, 4096]");
+    if (cfg.number_of_iterations == 0u || cfg.number_of_iterations > 64u)
+        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "number_of_iterations must be in [1, 64]");
+    if (cfg.number_of_lower_point_representatives == 0u || cfg.number_of_lower_point_representatives > kMaxLpr)
+        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "number_of_lower_point_representatives must be in [1, 8192]");
+    if (!std::isfinite(cfg.sensor_height_m) || !std::isfinite(cfg.orthogonal_distance_threshold) ||
+        !std::isfinite(cfg.initial_seed_threshold))
+        return fail(c, LIDAR_B200_ERR_INVALID, "non-finite segmentation configuration");
+    c->seg_cfg = cfg;
+    c->seg.sensor_height_m = cfg.sensor_height_m;
+    c->seg.orthogonal_distance_threshold = cfg.orthogonal_distance_threshold;
+    c->seg.initial_seed_threshold = cfg.initial_seed_threshold;
+    c->seg.iterations = cfg.number_of_iterations;
+    c->seg.partitions = cfg.number_of_planar_partitions;
+    c->seg.lpr = cfg.number_of_lower_point_representatives;
+    return 0;
+}
+
+int apply_clu_cfg(lidar_b200_ctx *c, const lidar_b200_clu_cfg &cfg)
+{
+    if (!(cfg.distance_squared > 0.0f) || !std::isfinite(cfg.distance_squared) || !std::isfinite(cfg.cluster_quality))
+        return fail(c, LIDAR_B200_ERR_INVALID, "distance_squared must be finite and > 0, cluster_quality finite");
+    c->clu_cfg = cfg;
+    c->clu.distance_squared = cfg.distance_squared;
+    // clustering.cpp:66-67: std::pow(1.0 - quality, 2) * distance_squared in double; `dist <= thr`
+    // promotes the float d2. Equivalent float constant: the largest float not above thr.
+    const double thr = std::pow(1.0 - static_cast<double>(cfg.cluster_quality), 2) * static_cast<double>(cfg.distance_squared);
+    float tf = static_cast<float>(thr);
+    if (static_cast<double>(tf) > thr)
+        tf = std::nextafterf(tf, -std::numeric_limits<float>::infinity());
+    c->clu.inner_threshold = tf;
+    c->clu.min_cluster_size = cfg.min_cluster_size;
+    c->clu.max_cluster_size = cfg.max_cluster_size;
+    c->clu.inv_cell = 1.0 / (std::sqrt(static_cast<double>(cfg.distance_squared)) * 1.001);
+    return 0;
+}
+
+uint32_t grid_x(uint32_t n, uint32_t per_block, uint32_t cap)
+{
+    uint32_t g = (n + per_block - 1u) / per_block;
+    g = g < 1u ? 1u : g;
+    return g > cap ? cap : g;
+}
+
+// lays the frames of a batch out, stages the points into pinned memory and starts the upload
+int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const uint32_t *n_points,
+          uint32_t stride_bytes)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    if (stride_bytes < 12u || (stride_bytes & 3u))
+        return fail(c, LIDAR_B200_ERR_INVALID, "stride_bytes must be a multiple of 4 and >= 12");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    uint64_t total = 0;
+    uint32_t max_n = 0;
+    c->off.assign(n_frames, 0u);
+    c->cnt.assign(n_frames, 0u);
+    for (uint32_t f = 0; f < n_frames; ++f)
+    {
+        c->off[f] = static_cast<uint32_t>(total);
+        c->cnt[f] = n_points[f];
+        max_n = n_points[f] > max_n ? n_points[f] : max_n;
+        total += (static_cast<uint64_t>(n_points[f]) + 31u) & ~31ull; // 128-byte aligned frame starts
+        if (n_points[f] && !points[f])
+            return fail(c, LIDAR_B200_ERR_INVALID, "null points pointer");
+    }
+    if (total > 0x7FFFFFFFull)
+        return fail(c, LIDAR_B200_ERR_CAPACITY, "batch exceeds 2^31 points");
+    if (total > c->cap_pts || n_frames > c->cap_frames)
+    {
+        const int rc = reserve(c, total > c->cap_pts ? static_cast<uint32_t>(total) : c->cap_pts,
+                               n_frames > c->cap_frames ? n_frames : c->cap_frames);
+        if (rc)
+            return rc;
+    }
+    // the previous batch may still be reading the staging buffers
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_frames = n_frames;
+    c->total = static_cast<uint32_t>(total);
+    c->max_n = max_n;
+    uint32_t *hm = c->h_meta.p;
+    const size_t F = c->cap_frames;
+    uint32_t toff = 0, max_tcap = 0;
+    for (uint32_t f = 0; f < n_frames; ++f)
+    {
+        hm[f] = c->off[f];
+        hm[F + f] = c->cnt[f];
+        const uint32_t tcap = next_pow2(c->cnt[f] * 2u < 64u ? 64u : c->cnt[f] * 2u);
+        hm[2 * F + f] = toff;
+        hm[3 * F + f] = tcap;
+        toff += tcap;
+        max_tcap = tcap > max_tcap ? tcap : max_tcap;
+    }
+    c->max_tcap = max_tcap;
+    if (dev_alloc(c, c->d_hist, radix_sort_scratch_words(n_frames, max_n)))
+        return LIDAR_B200_ERR_CUDA;
+    for (uint32_t f = 0; f < n_frames; ++f)
+    {
+        float4 *dst = c->h_pts.p + c->off[f];
+        const uint8_t *src = static_cast<const uint8_t *>(points[f]);
+        const uint32_t n = c->cnt[f];
+        if (stride_bytes == 16u)
+            std::memcpy(dst, src, static_cast<size_t>(n) * 16u);
+        else if (stride_bytes >= 16u)
+            for (uint32_t i = 0; i < n; ++i)
+                std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 16u);
+        else
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 12u);
+                dst[i].w = 1.0f;
+            }
+    }
+    if (n_frames)
+        LB_CUDA(c, cudaMemcpyAsync(c->d_meta.p, hm, 4 * F * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (total)
+        LB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, c->h_pts.p, total * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int run_segmentation(lidar_b200_ctx *c)
+{
+    const uint32_t F = c->n_frames;
+    if (F == 0u)
+        return 0;
+    cudaStream_t s = c->stream;
+    LB_CUDA(c, cudaMemsetAsync(c->d_labels.p, 0, static_cast<size_t>(c->total ? c->total : 1) * 4, s));
+    LB_CUDA(c, cudaMemsetAsync(c->m_ng(), 0, 2 * static_cast<size_t>(c->cap_frames) * 4, s)); // n_ground, n_obstacle
+    if (c->max_n == 0u)
+        return 0;
+    const BatchView bv{c->m_off(), c->m_cnt(), F};
+    const dim3 gp(grid_x(c->max_n, 256u, 2048u), F);
+    seg_keys_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, bv, c->d_key_a.p, c->d_val_a.p);
+    ++c->launches;
+    int rl = 0;
+    const int passes = radix_sort_pairs(s, c->d_key_a.p, c->d_val_a.p, c->d_key_b.p, c->d_val_b.p, bv, c->max_n, 32u,
+                                        RadixSortScratch{c->d_hist.p}, &rl);
+    c->launches += rl;
+    const uint32_t *sorted_idx = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
+    seg_gather_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, sorted_idx, bv, c->d_spts.p);
+    ++c->launches;
+    seg_fit_kernel<<<dim3(c->seg.partitions, F), kFitThreads, sizeof(FitSmem), s>>>(c->d_spts.p, bv, c->seg, c->d_flags.p,
+                                                                                    c->d_planes.p, c->d_status.p);
+    ++c->launches;
+    seg_compact_kernel<<<F, 1024, 0, s>>>(c->d_spts.p, c->d_flags.p, bv, c->d_labels.p, c->d_gidx.p, c->d_oidx.p,
+                                          c->d_obs.p, c->m_ng(), c->m_no());
+    ++c->launches;
+    LB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// pts: cloud to cluster (frame-major, same offsets); counts: device array of per-frame sizes
+int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts, uint32_t max_m)
+{
+    const uint32_t F = c->n_frames;
+    if (F == 0u)
+        return 0;
+    cudaStream_t s = c->stream;
+    LB_CUDA(c, cudaMemsetAsync(c->m_nc(), 0, static_cast<size_t>(c->cap_frames) * 4, s));
+    LB_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 4, s));
+    if (max_m == 0u)
+        return 0;
+    const BatchView bv{c->m_off(), counts, F};
+    const TableView tv{c->m_toff(), c->m_tcap()};
+    const dim3 gp(grid_x(max_m, 256u, 2048u), F);
+    const dim3 gt(grid_x(c->max_tcap, 256u, 2048u), F);
+
+    grid_clear_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p);
+    grid_insert_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->clu, c->d_tkeys.p, c->d_tcount.p, c->d_slot_of.p, c->d_err.p);
+    grid_scan_kernel<<<F, 1024, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p, c->d_cells.p);
+    grid_fill_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->d_cells.p, c->d_tcount.p, c->d_slot_of.p, c->d_cpts.p,
+                                        c->d_pos_of.p);
+    cc_init_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
+    cc_union_kernel<<<dim3(grid_x(max_m, 8u, 8192u), F), 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu,
+                                                                      c->d_parent.p);
+    cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_key_a.p, c->d_val_a.p);
+    c->launches += 7;
+    LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
+    int rl = 0;
+    const uint32_t bits = ceil_log2(max_m < 2u ? 2u : max_m);
+    const int passes = radix_sort_pairs(s, c->d_key_a.p, c->d_val_a.p, c->d_key_b.p, c->d_val_b.p, bv, max_m, bits,
+                                        RadixSortScratch{c->d_hist.p}, &rl);
+    c->launches += rl;
+    const uint32_t *member_root = (passes & 1) ? c->d_key_b.p : c->d_key_a.p;
+    const uint32_t *member_idx = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
+
+    c->launches += kd_build_launch(s, pts, bv, max_m, c->d_nodes.p, c->d_gepos.p, c->d_lepos.p, c->d_rank.p);
+
+    replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_state.p,
+                                          c->d_seed_of.p, c->d_member_pos.p, c->m_cursor());
+    const uint32_t claims = (max_m + 31u) / 32u;
+    const uint32_t rctas = grid_x(claims, kReplayWarps, 96u);
+    replay_kernel<<<dim3(rctas, F), kReplayWarps * 32, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, member_root,
+                                                               member_idx, c->d_member_pos.p, c->d_state.p,
+                                                               c->d_seed_of.p, c->d_queue.p, c->d_spill.p,
+                                                               c->d_seed_valid.p, c->m_cursor());
+    label_compact_kernel<<<F, 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
+                                            c->d_clabels.p, c->m_nc());
+    c->launches += 3;
+    LB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+void lidar_b200_seg_cfg_default(lidar_b200_seg_cfg *cfg)
+{
+    cfg->sensor_height_m = 1.73f;
+    cfg->orthogonal_distance_threshold = 0.3f;
+    cfg->initial_seed_threshold = 0.6f;
+    cfg->number_of_iterations = 3u;
+    cfg->number_of_planar_partitions = 2u;
+    cfg->number_of_lower_point_representatives = 5000u;
+}
+
+void lidar_b200_clu_cfg_default(lidar_b200_clu_cfg *cfg)
+{
+    cfg->distance_squared = 0.18f;
+    cfg->cluster_quality = 0.5f;
+    cfg->min_cluster_size = 4u;
+    cfg->max_cluster_size = 0xFFFFFFFFu;
+}
+
+int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lidar_b200_ctx **ctx_out)
+{
+    if (!ctx_out)
+        return LIDAR_B200_ERR_INVALID;
+    *ctx_out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return LIDAR_B200_ERR_CUDA;
+    lidar_b200_ctx *c = new lidar_b200_ctx();
+    c->device = device;
+    lidar_b200_seg_cfg sc;
+    lidar_b200_clu_cfg cc;
+    lidar_b200_seg_cfg_default(&sc);
+    lidar_b200_clu_cfg_default(&cc);
+    apply_seg_cfg(c, sc);
+    apply_clu_cfg(c, cc);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
+        cudaFuncSetAttribute(seg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(FitSmem))) != cudaSuccess ||
+        reserve(c, max_points ? max_points : 200000u, max_frames ? max_frames : 1u) != 0)
+    {
+        lidar_b200_destroy(c);
+        return LIDAR_B200_ERR_CUDA;
+    }
+    *ctx_out = c;
+    return 0;
+}
+
+void lidar_b200_destroy(lidar_b200_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->h_pts.p);
+    for (auto &h : c->h_u32)
+        cudaFreeHost(h.p);
+    cudaFreeHost(c->h_meta.p);
+    void *dev[] = {c->d_pts.p,      c->d_spts.p,   c->d_obs.p,       c->d_nodes.p,  c->d_cpts.p,       c->d_key_a.p,
+                   c->d_key_b.p,    c->d_val_a.p,  c->d_val_b.p,     c->d_labels.p, c->d_gidx.p,       c->d_oidx.p,
+                   c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
+                   c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p,
+                   c->d_clabels.p,  c->d_spill.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
+                   c->d_cells.p,    c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
+    for (void *p : dev)
+        if (p)
+            cudaFree(p);
+    if (c->ev_start)
+        cudaEventDestroy(c->ev_start);
+    if (c->ev_stop)
+        cudaEventDestroy(c->ev_stop);
+    if (c->stream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int lidar_b200_reserve(lidar_b200_ctx *c, uint32_t max_points, uint32_t max_frames)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    return reserve(c, max_points, max_frames);
+}
+
+int lidar_b200_seg_configure(lidar_b200_ctx *c, const lidar_b200_seg_cfg *cfg)
+{
+    if (!c || !cfg)
+        return LIDAR_B200_ERR_INVALID;
+    const int rc = apply_seg_cfg(c, *cfg);
+    if (rc)
+        return rc;
+    return reserve(c, c->cap_pts, c->cap_frames); // plane/status buffers depend on the configuration
+}
+
+int lidar_b200_clu_configure(lidar_b200_ctx *c, const lidar_b200_clu_cfg *cfg)
+{
+    if (!c || !cfg)
+        return LIDAR_B200_ERR_INVALID;
+    return apply_clu_cfg(c, *cfg);
+}
+
+int lidar_b200_batch_stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const uint32_t *n_points,
+                           uint32_t stride_bytes)
+{
+    if (!c || (n_frames && (!points || !n_points)))
+        return LIDAR_B200_ERR_INVALID;
+    c->batch_is_cluster_only = false;
+    return stage(c, n_frames, points, n_points, stride_bytes);
+}
+
+int lidar_b200_batch_run(lidar_b200_ctx *c)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaSetDevice(c->device));
+    LB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    int rc = run_segmentation(c);
+    if (rc)
+        return rc;
+    rc = run_clustering(c, c->d_obs.p, c->m_no(), c->max_n);
+    if (rc)
+        return rc;
+    LB_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+    return 0;
+}
+
+int lidar_b200_sync(lidar_b200_ctx *c)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lidar_b200_batch_fetch(lidar_b200_ctx *c, uint32_t *point_offset_out, uint32_t *seg_labels_out,
+                           uint32_t *ground_idx_out, uint32_t *n_ground_out, uint32_t *obstacle_idx_out,
+                           uint32_t *n_obstacle_out, int32_t *cluster_labels_out, uint32_t *n_clusters_out)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaSetDevice(c->device));
+    const size_t F = c->cap_frames;
+    const size_t bytes = static_cast<size_t>(c->total) * 4;
+    cudaStream_t s = c->stream;
+    if (c->n_frames)
+        LB_CUDA(c, cudaMemcpyAsync(c->h_meta.p + 4 * F, c->m_ng(), 3 * F * 4, cudaMemcpyDeviceToHost, s));
+    if (bytes)
+    {
+        if (seg_labels_out)
+            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[0].p, c->d_labels.p, bytes, cudaMemcpyDeviceToHost, s));
+        if (ground_idx_out)
+            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[1].p, c->d_gidx.p, bytes, cudaMemcpyDeviceToHost, s));
+        if (obstacle_idx_out)
+            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[2].p, c->d_oidx.p, bytes, cudaMemcpyDeviceToHost, s));
+        if (cluster_labels_out)
+            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[3].p, c->d_clabels.p, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    if (cudaEventElapsedTime(&c->last_run_ms, c->ev_start, c->ev_stop) != cudaSuccess)
+    {
+        c->last_run_ms = 0.0f;
+        (void)cudaGetLastError();
+    }
+    {
+        uint32_t e = 0;
+        LB_CUDA(c, cudaMemcpy(&e, c->d_err.p, 4, cudaMemcpyDeviceToHost));
+        if (e)
+            return fail(c, LIDAR_B200_ERR_INPUT, "non-finite or out-of-range point coordinates");
+    }
+    const uint32_t *hm = c->h_meta.p;
+    for (uint32_t f = 0; f < c->n_frames; ++f)
+    {
+        if (point_offset_out)
+            point_offset_out[f] = c->off[f];
+        if (n_ground_out)
+            n_ground_out[f] = hm[4 * F + f];
+        if (n_obstacle_out)
+            n_obstacle_out[f] = hm[5 * F + f];
+        if (n_clusters_out)
+            n_clusters_out[f] = hm[6 * F + f];
+    }
+    if (bytes)
+    {
+        if (seg_labels_out)
+            std::memcpy(seg_labels_out, c->h_u32[0].p, bytes);
+        if (ground_idx_out)
+            std::memcpy(ground_idx_out, c->h_u32[1].p, bytes);
+        if (obstacle_idx_out)
+            std::memcpy(obstacle_idx_out, c->h_u32[2].p, bytes);
+        if (cluster_labels_out)
+            std::memcpy(cluster_labels_out, c->h_u32[3].p, bytes);
+    }
+    return 0;
+}
+
+int lidar_b200_segment(lidar_b200_ctx *c, const void *points, uint32_t n, uint32_t stride_bytes, uint32_t *labels_inout,
+                       uint32_t *ground_idx_out, uint32_t *n_ground_out, uint32_t *obstacle_idx_out,
+                       uint32_t *n_obstacle_out)
+{
+    if (!c || !n_ground_out || !n_obstacle_out || (n && (!points || !labels_inout || !ground_idx_out || !obstacle_idx_out)))
+        return LIDAR_B200_ERR_INVALID;
+    *n_ground_out = 0;
+    *n_obstacle_out = 0;
+    if (n == 0u)
+        return 0; // segmentation.cpp:319-323
+    const void *frames[1] = {points};
+    int rc = stage(c, 1u, frames, &n, stride_bytes);
+    if (rc)
+        return rc;
+    c->batch_is_cluster_only = false;
+    LB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    rc = run_segmentation(c);
+    if (rc)
+        return rc;
+    LB_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+    const size_t F = c->cap_frames;
+    const size_t bytes = static_cast<size_t>(n) * 4;
+    cudaStream_t s = c->stream;
+    LB_CUDA(c, cudaMemcpyAsync(c->h_meta.p + 4 * F, c->m_ng(), 2 * F * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(c->h_u32[0].p, c->d_labels.p, bytes, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(c->h_u32[1].p, c->d_gidx.p, bytes, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(c->h_u32[2].p, c->d_oidx.p, bytes, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    (void)cudaEventElapsedTime(&c->last_run_ms, c->ev_start, c->ev_stop);
+    const uint32_t ng = c->h_meta.p[4 * F], no = c->h_meta.p[5 * F];
+    *n_ground_out = ng;
+    *n_obstacle_out = no;
+    const uint32_t *hl = c->h_u32[0].p;
+    for (uint32_t i = 0; i < n; ++i) // only classified points are written (segmentation.cpp:315, 334, 341)
+        if (hl[i] != LIDAR_B200_SEG_UNKNOWN)
+            labels_inout[i] = hl[i];
+    std::memcpy(ground_idx_out, c->h_u32[1].p, static_cast<size_t>(ng) * 4);
+    std::memcpy(obstacle_idx_out, c->h_u32[2].p, static_cast<size_t>(no) * 4);
+    return 0;
+}
+
+int lidar_b200_cluster(lidar_b200_ctx *c, const void *points, uint32_t m, uint32_t stride_bytes, int32_t *labels_out)
+{
+    if (!c || (m && (!points || !labels_out)))
+        return LIDAR_B200_ERR_INVALID;
+    if (m == 0u)
+        return 0; // clustering.cpp:50-54
+    const void *frames[1] = {points};
+    int rc = stage(c, 1u, frames, &m, stride_bytes);
+    if (rc)
+        return rc;
+    c->batch_is_cluster_only = true;
+    LB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    rc = run_clustering(c, c->d_pts.p, c->m_cnt(), m);
+    if (rc)
+        return rc;
+    LB_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+    LB_CUDA(c, cudaMemcpyAsync(c->h_u32[3].p, c->d_clabels.p, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    (void)cudaEventElapsedTime(&c->last_run_ms, c->ev_start, c->ev_stop);
+    uint32_t e = 0;
+    LB_CUDA(c, cudaMemcpy(&e, c->d_err.p, 4, cudaMemcpyDeviceToHost));
+    if (e)
+        return fail(c, LIDAR_B200_ERR_INPUT, "non-finite or out-of-range point coordinates");
+    std::memcpy(labels_out, c->h_u32[3].p, static_cast<size_t>(m) * 4);
+    return 0;
+}
+
+int lidar_b200_last_planes(lidar_b200_ctx *c, float *planes_out, int32_t *status_out)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t per = static_cast<size_t>(c->seg.partitions) * c->seg.iterations * 4;
+    if (planes_out && c->n_frames)
+        LB_CUDA(c, cudaMemcpy(planes_out, c->d_planes.p, c->n_frames * per * sizeof(float), cudaMemcpyDeviceToHost));
+    if (status_out && c->n_frames)
+        LB_CUDA(c, cudaMemcpy(status_out, c->d_status.p, static_cast<size_t>(c->n_frames) * c->seg.partitions * 4,
+                              cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lidar_b200_last_kd_rank(lidar_b200_ctx *c, uint32_t frame, uint32_t *rank_out, uint32_t capacity)
+{
+    if (!c || frame >= c->n_frames || !rank_out)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t m = 0;
+    LB_CUDA(c, cudaMemcpy(&m, (c->batch_is_cluster_only ? c->m_cnt() : c->m_no()) + frame, 4, cudaMemcpyDeviceToHost));
+    if (m > capacity)
+        return fail(c, LIDAR_B200_ERR_CAPACITY, "rank_out too small");
+    if (m)
+        LB_CUDA(c, cudaMemcpy(rank_out, c->d_rank.p + c->off[frame], static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lidar_b200_last_cc_root(lidar_b200_ctx *c, uint32_t frame, uint32_t *root_out, uint32_t capacity)
+{
+    if (!c || frame >= c->n_frames || !root_out)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t m = 0;
+    LB_CUDA(c, cudaMemcpy(&m, (c->batch_is_cluster_only ? c->m_cnt() : c->m_no()) + frame, 4, cudaMemcpyDeviceToHost));
+    if (m > capacity)
+        return fail(c, LIDAR_B200_ERR_CAPACITY, "root_out too small");
+    if (m)
+        LB_CUDA(c, cudaMemcpy(root_out, c->d_root.p + c->off[frame], static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+uint64_t lidar_b200_launch_count(const lidar_b200_ctx *c)
+{
+    return c ? c->launches : 0;
+}
+
+int lidar_b200_last_run_ms(lidar_b200_ctx *c, float *ms_out)
+{
+    if (!c || !ms_out)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        ms = c->last_run_ms;
+    }
+    *ms_out = ms;
+    return 0;
+}
+
+const char *lidar_b200_last_error(const lidar_b200_ctx *c)
+{
+    return c ? c->err.c_str() : "null context";
+}
+
+const char *lidar_b200_version(void)
+{
+    return "lidar_b200 0.1 (sm_100a)";
+}
+
+} // extern "C"

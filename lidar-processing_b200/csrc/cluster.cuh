@@ -1,0 +1,606 @@
+// Fast Euclidean Clustering kernels (sm_100a). Drop-in for lidar_processing::Clusterer::cluster
+// (reference src/clustering.cpp:47-125) with the k-d tree radius search (src/kdtree.hpp:292-341)
+// replaced by a voxel-hash grid whose cell edge is the cluster tolerance (27-cell neighbour scan).
+//
+// The reference result is NOT the connected components of the radius graph: it is an order-dependent
+// BFS ("remove everything within (1-q)·r of an expanded point, enqueue the annulus") whose outcome
+// depends on the order in which radius_search reports neighbours, i.e. the k-d tree pre-order. The
+// device therefore
+//   1. builds the voxel hash (insert -> scan -> fill),
+//   2. finds the r-connected components with a lock-free union-find (atomicCAS hooking of the
+//      larger root under the smaller + path halving): BFS runs never cross component borders, so
+//      components are independent replay units,
+//   3. replays the reference BFS inside every component with one warp: grid neighbours are tested
+//      with the reference's exact float d², the points that enter the FIFO are ordered by their
+//      k-d pre-order rank (kd_build.cuh), the FIFO is de-duplicated (a duplicate entry is a no-op
+//      when popped in the reference, because the first pop always ends with the point removed),
+//   4. compacts labels: label k = k-th valid seed in ascending seed index (clustering.cpp:113-123).
+#pragma once
+
+#include "common.cuh"
+
+namespace lb
+{
+
+constexpr uint64_t kCellEmpty = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kStRemoved = 1u;
+constexpr uint32_t kStQueued = 2u;
+constexpr uint32_t kSeedUnset = 0xFFFFFFFFu;
+constexpr int kCellBias = 1 << 20;
+constexpr int32_t kLabelUndefined = static_cast<int32_t>(0x80000000u); // Clusterer::UNDEFINED (clustering.hpp:53)
+constexpr int32_t kLabelInvalid = -1;                                   // Clusterer::INVALID   (clustering.hpp:54)
+
+struct CluParams
+{
+    float distance_squared; // ClusteringConfiguration::distance_squared
+    float inner_threshold;  // largest float t with (double)t <= (1-q)^2 * distance_squared (clustering.cpp:66-67)
+    uint32_t min_cluster_size;
+    uint32_t max_cluster_size;
+    double inv_cell; // 1 / (sqrt(distance_squared) * 1.001)
+};
+
+// Per-frame placement of the hash table inside the batch-wide table arrays.
+struct TableView
+{
+    const uint32_t *toff; // [F] first slot
+    const uint32_t *tcap; // [F] reserved slots (power of two)
+};
+
+LB_D uint32_t table_mask(uint32_t m, uint32_t reserved)
+{
+    // effective capacity: smallest power of two >= 2*m (at least 64), never above the reservation
+    uint32_t cap = 64u;
+    while (cap < 2u * m && cap < reserved)
+        cap <<= 1;
+    return cap - 1u;
+}
+
+LB_D uint32_t hash_cell(uint64_t k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return static_cast<uint32_t>(k);
+}
+
+LB_D bool cell_coords(const float4 &p, double inv_cell, int *cx, int *cy, int *cz)
+{
+    const double fx = floor(static_cast<double>(p.x) * inv_cell);
+    const double fy = floor(static_cast<double>(p.y) * inv_cell);
+    const double fz = floor(static_cast<double>(p.z) * inv_cell);
+    const double lim = static_cast<double>(kCellBias - 4);
+    const bool ok = fabs(fx) < lim && fabs(fy) < lim && fabs(fz) < lim; // false for NaN/Inf too
+    *cx = ok ? static_cast<int>(fx) + kCellBias : 0;
+    *cy = ok ? static_cast<int>(fy) + kCellBias : 0;
+    *cz = ok ? static_cast<int>(fz) + kCellBias : 0;
+    return ok;
+}
+
+LB_D uint64_t cell_key(int cx, int cy, int cz)
+{
+    return static_cast<uint64_t>(static_cast<uint32_t>(cx)) | (static_cast<uint64_t>(static_cast<uint32_t>(cy)) << 21) |
+           (static_cast<uint64_t>(static_cast<uint32_t>(cz)) << 42);
+}
+
+// cells[slot] = {key.lo, key.hi, start, count}
+LB_D void cell_lookup(const uint4 *__restrict__ cells, uint32_t mask, uint64_t key, uint32_t *start, uint32_t *count)
+{
+    uint32_t slot = hash_cell(key) & mask;
+    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
+    while (true)
+    {
+        const uint4 c = __ldg(&cells[slot]);
+        if (c.x == klo && c.y == khi)
+        {
+            *start = c.z;
+            *count = c.w;
+            return;
+        }
+        if (c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu)
+        {
+            *start = 0u;
+            *count = 0u;
+            return;
+        }
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_clear_kernel(BatchView bv, TableView tv, unsigned long long *__restrict__ tkeys, uint32_t *__restrict__ tcount)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t cap = table_mask(bv.cnt[f], tv.tcap[f]) + 1u;
+    const uint32_t toff = tv.toff[f];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x)
+    {
+        tkeys[toff + s] = kCellEmpty;
+        tcount[toff + s] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grid_insert_kernel(const float4 *__restrict__ pts, BatchView bv, TableView tv, CluParams prm,
+                   unsigned long long *__restrict__ tkeys, uint32_t *__restrict__ tcount, uint32_t *__restrict__ slot_of,
+                   uint32_t *__restrict__ err)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const uint32_t mask = table_mask(m, tv.tcap[f]);
+    const uint32_t toff = tv.toff[f];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    {
+        const float4 p = pts[off + i];
+        int cx, cy, cz;
+        if (!cell_coords(p, prm.inv_cell, &cx, &cy, &cz))
+            atomicOr(err, 1u); // non-finite or out-of-range coordinate
+        const unsigned long long key = cell_key(cx, cy, cz);
+        uint32_t slot = hash_cell(key) & mask;
+        while (true)
+        {
+            const unsigned long long prev = atomicCAS(&tkeys[toff + slot], kCellEmpty, key);
+            if (prev == kCellEmpty || prev == key)
+                break;
+            slot = (slot + 1u) & mask;
+        }
+        atomicAdd(&tcount[toff + slot], 1u);
+        slot_of[off + i] = slot;
+    }
+}
+
+// One CTA per frame: exclusive scan of the per-slot counts, emits the packed cell records and
+// resets the counts (they become the fill cursors).
+__global__ void __launch_bounds__(1024)
+grid_scan_kernel(BatchView bv, TableView tv, const unsigned long long *__restrict__ tkeys,
+                 uint32_t *__restrict__ tcount, uint4 *__restrict__ cells)
+{
+    constexpr int kPer = 4;
+    __shared__ uint32_t ws[33];
+    const uint32_t f = blockIdx.x;
+    const uint32_t cap = table_mask(bv.cnt[f], tv.tcap[f]) + 1u;
+    const uint32_t toff = tv.toff[f];
+    uint32_t carry = 0u;
+    for (uint32_t base = 0; base < cap; base += 1024 * kPer)
+    {
+        const uint32_t first = base + threadIdx.x * kPer;
+        uint32_t c[kPer];
+        uint32_t sum = 0u;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)
+        {
+            c[k] = (first + k < cap) ? tcount[toff + first + k] : 0u;
+            sum += c[k];
+        }
+        uint32_t total;
+        uint32_t run = carry + block_exclusive_scan<1024>(sum, ws, &total);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)
+        {
+            if (first + k < cap)
+            {
+                const unsigned long long key = tkeys[toff + first + k];
+                cells[toff + first + k] =
+                    make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), run, c[k]);
+                tcount[toff + first + k] = 0u;
+            }
+            run += c[k];
+        }
+        carry += total;
+    }
+}
+
+// cpts[pos] = {x, y, z, bits(index)} grouped by cell; pos_of[index] = pos
+__global__ void __launch_bounds__(256)
+grid_fill_kernel(const float4 *__restrict__ pts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
+                 uint32_t *__restrict__ tcount, const uint32_t *__restrict__ slot_of, float4 *__restrict__ cpts,
+                 uint32_t *__restrict__ pos_of)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const uint32_t toff = tv.toff[f];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t slot = slot_of[off + i];
+        const uint32_t pos = cells[toff + slot].z + atomicAdd(&tcount[toff + slot], 1u);
+        const float4 p = pts[off + i];
+        cpts[off + pos] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
+        pos_of[off + i] = pos;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// union-find over point indices; roots are always the smallest index of their tree
+LB_D uint32_t uf_find(uint32_t *parent, uint32_t x)
+{
+    uint32_t p = __ldcg(&parent[x]);
+    while (p != x)
+    {
+        const uint32_t gp = __ldcg(&parent[p]);
+        if (gp != p)
+            parent[x] = gp; // path halving; only ever points to an ancestor
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+LB_D void uf_unite(uint32_t *parent, uint32_t a, uint32_t b)
+{
+    while (true)
+    {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b)
+            return;
+        if (a < b)
+        {
+            const uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        const uint32_t old = atomicCAS(&parent[a], a, b); // hook the larger root under the smaller
+        if (old == a)
+            return;
+    }
+}
+
+__global__ void __launch_bounds__(256) cc_init_kernel(BatchView bv, uint32_t *__restrict__ parent)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+        parent[off + i] = i;
+}
+
+// One warp per cell-ordered point: lanes probe the 27 neighbour cells, then sweep the flattened
+// candidate list; every pair within the tolerance is united once (from its larger index).
+__global__ void __launch_bounds__(256)
+cc_union_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
+                CluParams prm, uint32_t *__restrict__ parent)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const uint32_t mask = table_mask(m, tv.tcap[f]);
+    const uint4 *tab = cells + tv.toff[f];
+    const float4 *cp = cpts + off;
+    uint32_t *par = parent + off;
+    const uint32_t lane = lane_id();
+    const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t pos = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pos < m; pos += warps_per_grid)
+    {
+        const float4 pj = cp[pos];
+        const uint32_t ij = __float_as_uint(pj.w);
+        int cx, cy, cz;
+        cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
+        uint32_t start = 0u, count = 0u;
+        if (lane < 27u)
+            cell_lookup(tab, mask, cell_key(cx + static_cast<int>(lane % 3u) - 1, cy + static_cast<int>((lane / 3u) % 3u) - 1,
+                                            cz + static_cast<int>(lane / 9u) - 1),
+                        &start, &count);
+        const uint32_t incl = warp_inclusive_scan(count);
+        const uint32_t excl = incl - count;
+        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        for (uint32_t base = 0; base < total; base += 32u)
+        {
+            const uint32_t q = base + lane;
+            uint32_t lo = 0u, hi = 26u;
+#pragma unroll
+            for (int it = 0; it < 5; ++it)
+            {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t v = __shfl_sync(kFullMask, incl, mid);
+                if (v > q)
+                    hi = mid;
+                else
+                    lo = mid + 1u;
+            }
+            const uint32_t c = min(lo, 26u);
+            const uint32_t cstart = __shfl_sync(kFullMask, start, c);
+            const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
+            if (q < total)
+            {
+                const float4 cand = cp[cstart + (q - cexcl)];
+                const uint32_t ik = __float_as_uint(cand.w);
+                if (ik < ij && dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared)
+                    uf_unite(par, ij, ik);
+            }
+        }
+    }
+}
+
+// keys[i] = root of i (component id = smallest member index), vals[i] = i
+__global__ void __launch_bounds__(256)
+cc_flatten_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    {
+        uint32_t x = i;
+        uint32_t p = __ldcg(&parent[off + x]);
+        while (p != x)
+        {
+            x = p;
+            p = __ldcg(&parent[off + x]);
+        }
+        keys[off + i] = x;
+        vals[off + i] = i;
+    }
+}
+
+// state[pos] = rank << 2 (flags clear); seed_of[pos] = unset; member_pos[t] = pos of the t-th member
+__global__ void __launch_bounds__(256)
+replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t *__restrict__ rank_of_point,
+                   const uint32_t *__restrict__ member_idx, const uint32_t *__restrict__ pos_of,
+                   uint32_t *__restrict__ state, uint32_t *__restrict__ seed_of, uint32_t *__restrict__ member_pos,
+                   uint32_t *__restrict__ cursor)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        cursor[f] = 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t idx = __float_as_uint(cpts[off + i].w);
+        state[off + i] = rank_of_point[off + idx] << 2;
+        seed_of[off + i] = kSeedUnset;
+        member_pos[off + i] = pos_of[off + member_idx[off + i]];
+    }
+}
+
+constexpr int kReplayWarps = 4;
+constexpr uint32_t kPushCap = 256u; // per-warp shared push buffer; larger expansions spill to global
+
+// Persistent warps; each claims 32 member slots at a time and replays every component whose first
+// member (= root = smallest index) falls in its claim. grid = (ctas_per_frame, frames).
+__global__ void __launch_bounds__(kReplayWarps * 32)
+replay_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
+              CluParams prm, const uint32_t *__restrict__ member_root, const uint32_t *__restrict__ member_idx,
+              const uint32_t *__restrict__ member_pos, uint32_t *__restrict__ state, uint32_t *__restrict__ seed_of,
+              uint32_t *__restrict__ queue, unsigned long long *__restrict__ push_spill,
+              uint8_t *__restrict__ seed_valid, uint32_t *__restrict__ cursor)
+{
+    __shared__ unsigned long long pbuf_all[kReplayWarps][kPushCap];
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const uint32_t mask = table_mask(m, tv.tcap[f]);
+    const uint4 *tab = cells + tv.toff[f];
+    const float4 *cp = cpts + off;
+    uint32_t *st = state + off;
+    uint32_t *so = seed_of + off;
+    uint32_t *qu = queue + off;
+    unsigned long long *spill = push_spill + off;
+    const uint32_t *mroot = member_root + off;
+    const uint32_t *midx = member_idx + off;
+    const uint32_t *mpos = member_pos + off;
+    const uint32_t lane = lane_id();
+    const uint32_t lt = lanemask_lt();
+    unsigned long long *pbuf = pbuf_all[threadIdx.x >> 5];
+
+    while (true)
+    {
+        uint32_t t0 = 0u;
+        if (lane == 0)
+            t0 = atomicAdd(&cursor[f], 32u);
+        t0 = __shfl_sync(kFullMask, t0, 0);
+        if (t0 >= m)
+            break;
+        const uint32_t tt = t0 + lane;
+        const bool is_start = tt < m && mroot[tt] == midx[tt];
+        uint32_t starts = __ballot_sync(kFullMask, is_start);
+        while (starts)
+        {
+            const uint32_t t_start = t0 + (__ffs(starts) - 1);
+            starts &= starts - 1u;
+            const uint32_t root = mroot[t_start];
+            const uint32_t qbase = t_start; // the component's FIFO lives in queue[t_start, t_start + size)
+
+            uint32_t u = t_start; // next member to examine as a seed candidate (ascending index)
+            while (true)
+            {
+                // find the next member that is not removed (clustering.cpp:70-75)
+                uint32_t seed_t = 0xFFFFFFFFu;
+                bool component_done = false;
+                while (true)
+                {
+                    const uint32_t uu = u + lane;
+                    const bool in_comp = uu < m && mroot[uu] == root;
+                    bool cand = false;
+                    if (in_comp)
+                        cand = (st[mpos[uu]] & kStRemoved) == 0u;
+                    const uint32_t bc = __ballot_sync(kFullMask, cand);
+                    const uint32_t bi = __ballot_sync(kFullMask, in_comp);
+                    if (bc)
+                    {
+                        seed_t = u + (__ffs(bc) - 1);
+                        break;
+                    }
+                    if (bi != kFullMask)
+                    {
+                        component_done = true;
+                        break;
+                    }
+                    u += 32u;
+                }
+                if (component_done)
+                    break;
+                u = seed_t + 1u;
+                const uint32_t seed_idx = midx[seed_t];
+                const uint32_t seed_pos = mpos[seed_t];
+
+                uint32_t head = 0u, tail = 0u, touched = 0u;
+                if (lane == 0)
+                {
+                    qu[qbase] = seed_pos;
+                    st[seed_pos] |= kStQueued;
+                }
+                tail = 1u;
+                __syncwarp();
+
+                while (head < tail) // clustering.cpp:80-111
+                {
+                    const uint32_t j = qu[qbase + head];
+                    ++head;
+                    if (st[j] & kStRemoved)
+                        continue;
+                    const float4 pj = cp[j];
+                    int cx, cy, cz;
+                    cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
+                    uint32_t start = 0u, count = 0u;
+                    if (lane < 27u)
+                        cell_lookup(tab, mask,
+                                    cell_key(cx + static_cast<int>(lane % 3u) - 1, cy + static_cast<int>((lane / 3u) % 3u) - 1,
+                                             cz + static_cast<int>(lane / 9u) - 1),
+                                    &start, &count);
+                    const uint32_t incl = warp_inclusive_scan(count);
+                    const uint32_t excl = incl - count;
+                    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+                    uint32_t np = 0u;
+                    bool spilled = false;
+                    for (uint32_t base = 0; base < total; base += 32u)
+                    {
+                        const uint32_t q = base + lane;
+                        uint32_t lo = 0u, hi = 26u;
+#pragma unroll
+                        for (int it = 0; it < 5; ++it)
+                        {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            const uint32_t v = __shfl_sync(kFullMask, incl, mid);
+                            if (v > q)
+                                hi = mid;
+                            else
+                                lo = mid + 1u;
+                        }
+                        const uint32_t c = min(lo, 26u);
+                        const uint32_t cstart = __shfl_sync(kFullMask, start, c);
+                        const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
+                        bool live = false, push = false;
+                        uint32_t pos = 0u, s = 0u;
+                        if (q < total)
+                        {
+                            pos = cstart + (q - cexcl);
+                            const float4 cand = cp[pos];
+                            s = st[pos];
+                            // KDTree::dist_sqr(target, node) (kdtree.hpp:145-163), inclusive test (kdtree.hpp:314)
+                            const float d2 = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z);
+                            live = d2 <= prm.distance_squared && (s & kStRemoved) == 0u;
+                            if (live)
+                            {
+                                so[pos] = seed_idx; // labels[k] = label (clustering.cpp:99)
+                                if (d2 <= prm.inner_threshold)
+                                    st[pos] = s | kStRemoved; // clustering.cpp:102-105
+                                else if ((s & kStQueued) == 0u)
+                                {
+                                    st[pos] = s | kStQueued; // clustering.cpp:106-109 (first push only)
+                                    push = true;
+                                }
+                            }
+                        }
+                        touched += __popc(__ballot_sync(kFullMask, live)); // indices_.push_back (with multiplicity)
+                        const uint32_t bp = __ballot_sync(kFullMask, push);
+                        const uint32_t nadd = __popc(bp);
+                        if (nadd)
+                        {
+                            if (!spilled && np + nadd > kPushCap)
+                            {
+                                for (uint32_t e = lane; e < np; e += 32u)
+                                    spill[qbase + tail + e] = pbuf[e];
+                                spilled = true;
+                                __syncwarp();
+                            }
+                            if (push)
+                            {
+                                const unsigned long long ent =
+                                    (static_cast<unsigned long long>(s >> 2) << 32) | static_cast<unsigned long long>(pos);
+                                const uint32_t e = np + __popc(bp & lt);
+                                if (spilled)
+                                    spill[qbase + tail + e] = ent;
+                                else
+                                    pbuf[e] = ent;
+                            }
+                            np += nadd;
+                        }
+                    }
+                    __syncwarp();
+                    // the FIFO receives this expansion's pushes in ascending k-d pre-order rank
+                    if (np)
+                    {
+                        const unsigned long long *src = spilled ? (spill + qbase + tail) : pbuf;
+                        for (uint32_t e = lane; e < np; e += 32u)
+                        {
+                            const unsigned long long mine = src[e];
+                            uint32_t dest = 0u;
+                            for (uint32_t x = 0; x < np; ++x)
+                                dest += (src[x] < mine) ? 1u : 0u;
+                            qu[qbase + tail + dest] = static_cast<uint32_t>(mine);
+                        }
+                        tail += np;
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) // clustering.cpp:113-123
+                    seed_valid[off + seed_idx] =
+                        (touched < prm.min_cluster_size || touched > prm.max_cluster_size) ? 0u : 1u;
+            }
+        }
+    }
+}
+
+// One CTA per frame: label k = number of valid seeds with a smaller index (clustering.cpp:68,113-123)
+__global__ void __launch_bounds__(1024)
+label_compact_kernel(BatchView bv, const uint32_t *__restrict__ pos_of, const uint32_t *__restrict__ seed_of,
+                     const uint8_t *__restrict__ seed_valid, uint32_t *__restrict__ seed_label,
+                     int32_t *__restrict__ labels, uint32_t *__restrict__ n_clusters)
+{
+    constexpr int kPer = 4;
+    __shared__ uint32_t ws[33];
+    const uint32_t f = blockIdx.x;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    uint32_t carry = 0u;
+    for (uint32_t base = 0; base < m; base += 1024 * kPer)
+    {
+        const uint32_t first = base + threadIdx.x * kPer;
+        bool is_seed[kPer];
+        uint32_t sum = 0u;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)
+        {
+            const uint32_t i = first + k;
+            is_seed[k] = false;
+            if (i < m)
+                is_seed[k] = seed_of[off + pos_of[off + i]] == i && seed_valid[off + i] != 0u;
+            sum += is_seed[k] ? 1u : 0u;
+        }
+        uint32_t total;
+        uint32_t run = carry + block_exclusive_scan<1024>(sum, ws, &total);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)
+            if (is_seed[k])
+                seed_label[off + first + k] = run++;
+        carry += total;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < m; i += 1024)
+    {
+        const uint32_t s = seed_of[off + pos_of[off + i]];
+        int32_t lab = kLabelUndefined;
+        if (s != kSeedUnset)
+            lab = seed_valid[off + s] ? static_cast<int32_t>(seed_label[off + s]) : kLabelInvalid;
+        labels[off + i] = lab;
+    }
+    if (threadIdx.x == 0)
+        n_clusters[f] = carry;
+}
+
+} // namespace lb

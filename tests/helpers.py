@@ -1,0 +1,71 @@
+"""Shared parity checks: the CUDA path (through the C ABI) against the CPU oracle."""
+from __future__ import annotations
+
+import numpy as np
+
+import oracle as O
+
+FLIP_FRACTION = 1e-3   # north-star tolerance: at most 0.1 % of points may flip ...
+FLIP_BAND_M = 1e-4     # ... and only within 1e-4 m of the decision surface
+
+
+def to_oracle_seg_cfg(cfg):
+    return O.default_seg_cfg(**{n: getattr(cfg, n) for n, _ in cfg._fields_})
+
+
+def to_oracle_clu_cfg(cfg):
+    return O.default_clu_cfg(**{n: getattr(cfg, n) for n, _ in cfg._fields_})
+
+
+def segment_ids(pts, partitions):
+    """partition id of every point under the stable x order (-1 = in no partition)."""
+    n = pts.shape[0]
+    order = np.argsort(pts[:, 0], kind="stable")
+    per = n // partitions
+    seg = np.full(n, -1, np.int64)
+    for s in range(partitions):
+        seg[order[s * per:(s + 1) * per]] = s
+    return seg
+
+
+def check_segmentation(pts, labels, ground_idx, obstacle_idx, seg_cfg=None, labels_in=None):
+    """Returns the number of flipped points after asserting the stated tolerance."""
+    cfg = seg_cfg or O.default_seg_cfg()
+    ref = O.segment(pts, cfg, tie_mode=1, labels_in=labels_in)
+    n = pts.shape[0]
+    assert labels.shape[0] == n
+    diff = np.nonzero(labels != ref["labels"])[0]
+    # structural invariants that hold regardless of float rounding
+    assert np.array_equal(np.sort(np.concatenate([ground_idx, obstacle_idx])),
+                          np.sort(np.concatenate([ref["ground_idx"], ref["obstacle_idx"]])))
+    assert np.all(labels[ground_idx] == O.GROUND) and np.all(labels[obstacle_idx] == O.OBSTACLE)
+    for idx in (ground_idx, obstacle_idx):  # both clouds are x-ascending (segment by segment)
+        assert np.all(np.diff(pts[idx, 0]) >= 0)
+    assert diff.size <= max(0, int(FLIP_FRACTION * n)), f"{diff.size} of {n} labels differ"
+    if diff.size:
+        P = cfg.number_of_planar_partitions
+        seg = segment_ids(pts, P)
+        for i in diff:
+            a, b, c, d = (float(v) for v in ref["planes"][seg[i], -1])
+            x, y, z = (float(v) for v in pts[i, :3])
+            dist = x * a + y * b + z * c - d
+            thr = cfg.orthogonal_distance_threshold * np.sqrt(a * a + b * b + c * c)
+            assert abs(dist - thr) < FLIP_BAND_M, f"point {i} flipped {abs(dist - thr):.3g} m from the decision surface"
+    else:
+        assert np.array_equal(ground_idx, ref["ground_idx"])
+        assert np.array_equal(obstacle_idx, ref["obstacle_idx"])
+    return int(diff.size)
+
+
+def check_clustering(obs_pts, labels, clu_cfg=None, use_ref=True):
+    """Bit-exact: raw labels must equal the oracle's (they are canonical by construction: label k is
+    the k-th valid cluster by smallest member index)."""
+    cfg = clu_cfg or O.default_clu_cfg()
+    want = O.cluster(obs_pts, cfg)
+    assert labels.dtype == np.int32 and labels.shape == want.shape
+    assert np.array_equal(O.canonicalise(labels), O.canonicalise(want)), "canonical cluster partition differs"
+    assert np.array_equal(labels, want), "raw cluster labels differ"
+    if use_ref and O.ref_available():
+        assert np.array_equal(labels, O.ref_cluster(obs_pts, cfg)), "differs from the unmodified reference Clusterer"
+    assert not np.any(labels == O.UNDEFINED)
+    return int(labels.max() + 1) if labels.size else 0

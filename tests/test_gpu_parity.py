@@ -1,0 +1,237 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle (and the unmodified
+reference Clusterer build when oracle/_ref is present). Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle as O
+from tests import helpers as H
+from tests.synth import make_frame, make_stress
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ segmentation
+def test_segment_golden_frames(ctx, golden_frames):
+    for pts in golden_frames:
+        labels, gi, oi = ctx.segment(pts)
+        flips = H.check_segmentation(pts, labels, gi, oi)
+        planes, status = ctx.last_planes(1)
+        ref = O.segment(pts, tie_mode=1)
+        assert np.array_equal(status[0], ref["status"])
+        assert np.allclose(planes[0], ref["planes"], atol=2e-5), (planes[0], ref["planes"])
+        print("flips", flips)
+
+
+def test_segment_point_stride_16_equals_32(ctx, golden_frames):
+    pts = golden_frames[0]
+    a = ctx.segment(pts)                       # 16-byte records (PointXYZ-like: x y z w)
+    wide = np.zeros((pts.shape[0], 8), np.float32)  # 32-byte records (PointXYZI layout)
+    wide[:, :3] = pts[:, :3]
+    wide[:, 3] = 1.0
+    wide[:, 4] = pts[:, 3]
+    b = ctx.segment(wide)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("partitions,iterations,lpr", [(1, 3, 5000), (3, 2, 1000), (5, 1, 64), (2, 4, 8192), (7, 3, 1)])
+def test_segment_configurations(pkg, ctx, synth_small, partitions, iterations, lpr):
+    cfg = pkg.SegmentationConfiguration(number_of_planar_partitions=partitions, number_of_iterations=iterations,
+                                        number_of_lower_point_representatives=lpr)
+    ctx.seg_configure(cfg)
+    try:
+        for pts in (synth_small, synth_small[:10007], synth_small[:10]):
+            labels, gi, oi = ctx.segment(pts)
+            H.check_segmentation(pts, labels, gi, oi, H.to_oracle_seg_cfg(cfg))
+    finally:
+        ctx.seg_configure(pkg.SegmentationConfiguration())
+
+
+def test_segment_edge_cases(pkg, ctx):
+    # empty cloud: early return (segmentation.cpp:319-323)
+    labels, gi, oi = ctx.segment(np.zeros((0, 4), np.float32))
+    assert labels.size == 0 and gi.size == 0 and oi.size == 0
+    # fewer than 3 points per partition: points stay UNKNOWN (segmentation.cpp:225-229)
+    for n in (1, 2, 3, 4, 5):
+        pts = np.array([[i, 0.1 * i, -1.7, 0] for i in range(n)], np.float32)
+        labels, gi, oi = ctx.segment(pts)
+        ref = O.segment(pts, tie_mode=1)
+        assert np.array_equal(labels, ref["labels"]) and np.array_equal(gi, ref["ground_idx"]) and np.array_equal(oi, ref["obstacle_idx"])
+    # perfectly flat cloud: no point exceeds mean + 0.6 -> zero seeds -> "Failed ground segmentation"
+    rng = np.random.default_rng(3)
+    flat = np.zeros((5000, 4), np.float32)
+    flat[:, :2] = rng.uniform(-50, 50, (5000, 2)).astype(np.float32)
+    flat[:, 2] = -1.73
+    labels, gi, oi = ctx.segment(flat)
+    assert gi.size == 0 and oi.size == 5000 and np.all(labels == O.OBSTACLE)
+    _, status = ctx.last_planes(1)
+    assert list(status[0]) == [2, 2]
+    # everything below -1.5*sensor_height: nothing is erased (cutoff index stays 0)
+    deep = flat.copy()
+    deep[:, 2] = -5.0 + rng.uniform(0, 2.0, 5000).astype(np.float32)
+    labels, gi, oi = ctx.segment(deep)
+    H.check_segmentation(deep, labels, gi, oi)
+    # massive x ties (all x equal): the stable order is the original index order
+    ties = make_frame(3, beams=16, azimuth_steps=256).copy()
+    ties[:, 0] = np.float32(1.5)
+    labels, gi, oi = ctx.segment(ties)
+    H.check_segmentation(ties, labels, gi, oi)
+    # -0.0 and +0.0 compare equal in the reference comparator
+    z = make_frame(4, beams=16, azimuth_steps=256).copy()
+    z[::2, 0] = np.float32(0.0)
+    z[1::2, 0] = np.float32(-0.0)
+    labels, gi, oi = ctx.segment(z)
+    H.check_segmentation(z, labels, gi, oi)
+
+
+def test_segment_stale_label_quirk(ctx, synth_small):
+    # odd N with 2 partitions drops the largest-x point; it keeps whatever label the vector held
+    pts = synth_small[:10001]
+    prev = np.full(pts.shape[0], 2, np.uint32)
+    labels, gi, oi = ctx.segment(pts, labels_inout=prev.copy())
+    ref = O.segment(pts, tie_mode=1, labels_in=prev)
+    dropped = np.argsort(pts[:, 0], kind="stable")[-1]
+    assert labels[dropped] == 2 and dropped not in gi and dropped not in oi
+    H.check_segmentation(pts, labels, gi, oi, labels_in=prev)
+    assert ref["labels"][dropped] == 2
+
+
+def test_unsupported_configuration_fails_loudly(pkg, ctx):
+    for bad in (dict(number_of_planar_partitions=0), dict(number_of_iterations=0),
+                dict(number_of_lower_point_representatives=0), dict(number_of_lower_point_representatives=100000)):
+        with pytest.raises(pkg.LidarB200Error):
+            ctx.seg_configure(pkg.SegmentationConfiguration(**bad))
+    with pytest.raises(pkg.LidarB200Error):
+        ctx.clu_configure(pkg.ClusteringConfiguration(distance_squared=0.0))
+    ctx.seg_configure(pkg.SegmentationConfiguration())
+    ctx.clu_configure(pkg.ClusteringConfiguration())
+
+
+# ------------------------------------------------------------------ clustering
+def test_kd_rank_and_components_match_reference(ctx, golden_frames):
+    pts = golden_frames[0]
+    seg = O.segment(pts, tie_mode=1)
+    obs = pts[seg["obstacle_idx"]]
+    labels = ctx.cluster(obs)
+    rank = ctx.last_kd_rank(obs.shape[0])
+    want = O.kd_rank(obs, 0)
+    assert np.array_equal(rank, want), f"{(rank != want).sum()} k-d pre-order ranks differ"
+    if O.ref_available():
+        order = O.ref_kd_order(obs)
+        assert np.array_equal(order[rank], np.arange(obs.shape[0], dtype=np.uint32))
+    assert np.array_equal(ctx.last_cc_root(obs.shape[0]), O.cc_roots(obs))
+    H.check_clustering(obs, labels)
+
+
+def test_cluster_golden_frames(ctx, golden_frames, fingerprints):
+    rows = {r["frame"]: r for r in fingerprints["frames"]}
+    for name, pts in zip(("0000000000.pcd", "0000000077.pcd", "0000000153.pcd"), golden_frames):
+        seg = O.segment(pts, tie_mode=1)
+        obs = pts[seg["obstacle_idx"]]
+        labels = ctx.cluster(obs)
+        k = H.check_clustering(obs, labels)
+        row = rows[name]
+        assert obs.shape[0] == row["n_obstacle"] and k == row["n_clusters"]
+        assert int((labels == -1).sum()) == row["n_invalid"]
+        assert f"{O.fnv1a64(labels):016x}" == row["cluster_labels_fnv"]
+
+
+def test_cluster_input_order_and_stride(ctx, golden_frames):
+    pts = golden_frames[1]
+    seg = O.segment(pts, tie_mode=1)
+    obs = pts[seg["obstacle_idx"]]
+    rng = np.random.default_rng(5)
+    shuffled = obs[rng.permutation(obs.shape[0])]     # arbitrary input order (standalone Clusterer use)
+    H.check_clustering(shuffled, ctx.cluster(shuffled))
+    wide = np.zeros((obs.shape[0], 8), np.float32)     # PointXYZRGBL-like 32-byte records
+    wide[:, :3] = obs[:, :3]
+    assert np.array_equal(ctx.cluster(wide), ctx.cluster(obs))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(min_cluster_size=1), dict(min_cluster_size=10, max_cluster_size=200), dict(cluster_quality=0.0),
+    dict(cluster_quality=1.0), dict(cluster_quality=0.3, distance_squared=0.5), dict(distance_squared=0.02),
+])
+def test_cluster_configurations(pkg, ctx, synth_small, cfg):
+    c = pkg.ClusteringConfiguration(**cfg)
+    ctx.clu_configure(c)
+    try:
+        seg = O.segment(synth_small, tie_mode=1)
+        obs = synth_small[seg["obstacle_idx"]]
+        H.check_clustering(obs, ctx.cluster(obs), H.to_oracle_clu_cfg(c))
+    finally:
+        ctx.clu_configure(pkg.ClusteringConfiguration())
+
+
+def test_cluster_edge_cases(ctx):
+    assert ctx.cluster(np.zeros((0, 4), np.float32)).size == 0
+    one = np.array([[1.0, 2.0, 3.0, 0.0]], np.float32)
+    assert list(ctx.cluster(one)) == [-1]
+    # duplicates and exact-threshold pairs: 0.3^2 + 0.3^2 = 0.18 sits exactly on the inclusive test
+    pts = np.array([[0, 0, 0], [0, 0, 0], [0.3, 0.3, 0], [0.6, 0.6, 0], [0.6, 0.6, 0], [0.9, 0.9, 0.0], [5, 5, 5]], np.float32)
+    H.check_clustering(pts, ctx.cluster(pts))
+    # collinear chain with spacing between r/2 and r: exercises the annulus/FIFO path
+    chain = np.zeros((400, 3), np.float32)
+    chain[:, 0] = np.arange(400, dtype=np.float32) * np.float32(0.3)
+    H.check_clustering(chain, ctx.cluster(chain))
+    # lattice with massive coordinate ties on every axis (k-d tree tie behaviour + heap-select fallback)
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(6), indexing="ij"), -1).reshape(-1, 3)
+    lattice = (g * 0.2).astype(np.float32)
+    H.check_clustering(lattice, ctx.cluster(lattice))
+    rng = np.random.default_rng(11)
+    H.check_clustering(lattice[rng.permutation(lattice.shape[0])], ctx.cluster(lattice[rng.permutation(lattice.shape[0])]))
+    # all points identical
+    same = np.tile(np.array([[1.0, 1.0, 1.0]], np.float32), (100, 1))
+    H.check_clustering(same, ctx.cluster(same))
+
+
+def test_cluster_dense_stress(ctx):
+    pts = make_stress(seed=5, n_blobs=40, blob_pts=250, n_walls=2, wall_len=20.0, wall_height=2.0)
+    H.check_clustering(pts, ctx.cluster(pts), use_ref=True)
+
+
+def test_cluster_rejects_non_finite(pkg, ctx):
+    pts = np.array([[0, 0, 0], [np.nan, 0, 0], [1, 1, 1]], np.float32)
+    with pytest.raises(pkg.LidarB200Error):
+        ctx.cluster(pts)
+
+
+# ------------------------------------------------------------------ fused batch pipeline
+def test_batch_pipeline_ragged(ctx, golden_frames, synth_small):
+    frames = [golden_frames[0], synth_small, np.zeros((0, 4), np.float32), golden_frames[2][:50001], synth_small[:7]]
+    out = ctx.process_batch(frames)
+    assert len(out) == len(frames)
+    for pts, res in zip(frames, out):
+        H.check_segmentation(pts, res["seg_labels"], res["ground_idx"], res["obstacle_idx"])
+        obs = pts[res["obstacle_idx"]]
+        k = H.check_clustering(obs, res["cluster_labels"])
+        assert k == res["n_clusters"]
+    # same frames one by one through the per-frame interface give the same answer
+    for pts, res in zip(frames, out):
+        labels, gi, oi = ctx.segment(pts)
+        assert np.array_equal(labels, res["seg_labels"]) and np.array_equal(oi, res["obstacle_idx"])
+        assert np.array_equal(ctx.cluster(pts[oi]), res["cluster_labels"])
+
+
+def test_batch_is_deterministic(ctx, golden_frames):
+    frames = [golden_frames[1]] * 4
+    a = ctx.process_batch(frames)
+    b = ctx.process_batch(frames)
+    for x, y, z in zip(a, b, a[1:] + a[:1]):
+        for k in ("seg_labels", "obstacle_idx", "cluster_labels"):
+            assert np.array_equal(x[k], y[k]) and np.array_equal(x[k], z[k])
+
+
+def test_mirror_classes(pkg, golden_frames):
+    seg = pkg.Segmenter()
+    clu = pkg.Clusterer()
+    seg.reserve_memory(200_000)
+    clu.reserve_memory(200_000)
+    pts = golden_frames[0]
+    labels, ground, obstacle = seg.segment(pts)
+    assert ground.shape[0] + obstacle.shape[0] == pts.shape[0] - (pts.shape[0] % 2)
+    lab = clu.cluster(obstacle)
+    H.check_clustering(obstacle, lab)
+    assert pkg.Clusterer.INVALID == -1 and pkg.Clusterer.UNDEFINED == np.iinfo(np.int32).min

@@ -1,0 +1,140 @@
+"""CPU tests of the product's host-compilable pieces and of the C-ABI library surface."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def hc(pkg):
+    import __graft_entry__ as ge
+
+    return C.CDLL(str(ge.build_host_checks()))
+
+
+def _nodes(pts):
+    a = np.zeros((len(pts), 4), np.float32)
+    a[:, :3] = pts[:, :3]
+    a[:, 3] = np.arange(len(pts), dtype=np.uint32).view(np.float32)
+    return a
+
+
+def _run(hc, a, first, nth, last, axis, mode, nw=8, cut=48):
+    b = a.copy()
+    hc.hc_nth_element(b.ctypes.data_as(C.c_void_p), first, nth, last, axis, mode, nw, cut)
+    return b.view(np.uint32)
+
+
+def test_nth_element_emulation_matches_libstdcxx(hc):
+    """Product kd_select.h (sequential) and the lane-level model of the cooperative partition must
+    leave exactly the permutation std::nth_element leaves, ties included."""
+    rng = np.random.default_rng(1)
+    for trial in range(1500):
+        n = int(rng.integers(1, 300)) if trial % 3 else int(rng.integers(300, 5000))
+        nvals = int(rng.choice([1, 2, 3, 5, 20, 200, 100000]))
+        a = _nodes(rng.integers(0, nvals, size=(n, 3)).astype(np.float32) / 8)
+        nth = n // 2 if trial % 2 else int(rng.integers(0, n))
+        axis = int(rng.integers(0, 3))
+        lo = int(rng.integers(0, max(1, n // 4))) if trial % 5 == 0 else 0
+        nth = max(nth, lo)
+        want = _run(hc, a, lo, nth, n, axis, 0)
+        assert np.array_equal(_run(hc, a, lo, nth, n, axis, 1), want)
+        assert np.array_equal(_run(hc, a, lo, nth, n, axis, 2, int(rng.choice([1, 8, 32])), int(rng.choice([3, 16, 48]))), want)
+
+
+def test_kd_preorder_rank_of_product_headers(hc, golden_frames):
+    pts = golden_frames[0]
+    obs = pts[O.segment(pts, tie_mode=1)["obstacle_idx"]]
+    want = O.kd_rank(obs, 0)
+    for mode, nw, cut in ((1, 1, 3), (2, 32, 48), (2, 8, 48)):
+        a = _nodes(obs)
+        rank = np.zeros(len(obs), np.uint32)
+        hc.hc_kd_build(a.ctypes.data_as(C.c_void_p), len(obs), mode, nw, cut, rank.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(rank, want)
+
+
+def test_kd_range_at_partitions_the_array(hc):
+    for m in (1, 2, 3, 7, 64, 1000, 46851):
+        for depth in (0, 1, 3, 6):
+            covered = np.zeros(m, np.int32)
+            # nodes at shallower depths + ranges at this depth tile [0, m)
+            for d in range(depth + 1):
+                for path in range(1 << d):
+                    b, e = C.c_uint32(), C.c_uint32()
+                    if hc.hc_range_at(m, d, path, C.byref(b), C.byref(e)):
+                        if d == depth:
+                            covered[b.value:e.value] += 1
+                        else:
+                            covered[b.value + (e.value - b.value) // 2] += 1
+            assert np.all(covered == 1)
+
+
+def test_product_jacobi_equals_oracle_restatement(hc):
+    rng = np.random.default_rng(2)
+    for _ in range(300):
+        m = rng.normal(size=(40, 3)) * rng.uniform(0.01, 30, 3)
+        a = np.cov(m.T).astype(np.float32).reshape(9).copy()
+        v = np.zeros(9, np.float32)
+        sv = np.zeros(3, np.float32)
+        assert hc.hc_jacobi_svd3(a.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), sv.ctypes.data_as(C.c_void_p)) == 1
+        ov, osv, _ = O.jacobi_svd3(a)
+        assert np.array_equal(v.reshape(3, 3).view(np.uint32), ov.view(np.uint32))
+        assert np.array_equal(sv.view(np.uint32), osv.view(np.uint32))
+    bad = np.full(9, np.nan, np.float32)
+    assert hc.hc_jacobi_svd3(bad.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), sv.ctypes.data_as(C.c_void_p)) == 0
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol(pkg):
+    header = (ROOT / "include" / "lidar_b200.h").read_text()
+    declared = set(re.findall(r"\b(lidar_b200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"lidar_b200_ctx", "lidar_b200_status"}
+    assert declared == set(pkg.EXPORTED_SYMBOLS)
+    lib = pkg.lib()
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert b"sm_100a" in lib.lidar_b200_version()
+    cfg = pkg.SegmentationConfiguration()
+    lib.lidar_b200_seg_cfg_default(C.byref(cfg))
+    assert (cfg.number_of_iterations, cfg.number_of_planar_partitions, cfg.number_of_lower_point_representatives) == (3, 2, 5000)
+    assert abs(cfg.sensor_height_m - 1.73) < 1e-6 and abs(cfg.initial_seed_threshold - 0.6) < 1e-6
+    ccfg = pkg.ClusteringConfiguration()
+    lib.lidar_b200_clu_cfg_default(C.byref(ccfg))
+    assert abs(ccfg.distance_squared - 0.18) < 1e-7 and ccfg.min_cluster_size == 4 and ccfg.max_cluster_size == 0xFFFFFFFF
+
+
+def test_no_cpu_fallback_without_a_gpu(pkg):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.LidarB200Error):
+        pkg.Context(device=0)
+    with pytest.raises(pkg.LidarB200Error):
+        pkg.Segmenter()
+
+
+def test_product_never_touches_the_oracle():
+    for p in (ROOT / "lidar-processing_b200").rglob("*"):
+        if p.suffix in {".py", ".cu", ".cuh", ".h", ".hpp", ".cpp"}:
+            text = p.read_text()
+            assert "oracle" not in text.replace("the oracle", "").lower() or p.name == "README.md", p
+
+
+def test_pcd_reader_and_frame_cache_round_trip(tmp_path, golden_frames):
+    from tools.pack_reference_frames import pack, unpack
+
+    pts = golden_frames[0][:1000]
+    path = tmp_path / "f.pcd"
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\n"
+           "TYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 1000\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 1000\nDATA binary\n")
+    path.write_bytes(hdr.encode() + pts.tobytes())
+    back = O.read_pcd(path)
+    assert np.array_equal(back.view(np.uint32), pts.view(np.uint32))
+    pack([path], tmp_path / "c.xz")
+    assert np.array_equal(unpack(tmp_path / "c.xz")[0].view(np.uint32), pts.view(np.uint32))

@@ -1,0 +1,144 @@
+"""CPU tests: the oracle against the committed golden vectors and against the unmodified reference
+Clusterer / KDTree build (oracle/_ref), on real frames and on tie-heavy synthetic clouds."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.synth import make_frame, make_stress
+
+NAMES = ("0000000000.pcd", "0000000077.pcd", "0000000153.pcd")
+
+
+def test_fingerprints_record_full_pinning(fingerprints):
+    p = fingerprints["pinned"]
+    assert p["frames"] == 154
+    assert p["oracle_cluster_eq_ref"] == 154 and p["kd_transcription_eq_ref"] == 154 and p["model_eq_ref"] == 154
+    ns = [r["n"] for r in fingerprints["frames"]]
+    assert min(ns) == 98533 and max(ns) == 124123 and sum(ns) == 18746903
+
+
+def test_oracle_matches_golden_vectors(golden_frames, fingerprints):
+    rows = {r["frame"]: r for r in fingerprints["frames"]}
+    for name, pts in zip(NAMES, golden_frames):
+        row = rows[name]
+        assert pts.shape[0] == row["n"]
+        seg = O.segment(pts, tie_mode=1)
+        assert seg["ground_idx"].size == row["n_ground"] and seg["obstacle_idx"].size == row["n_obstacle"]
+        assert f"{O.fnv1a64(seg['labels']):016x}" == row["seg_labels_fnv"]
+        assert f"{O.fnv1a64(seg['obstacle_idx']):016x}" == row["obstacle_idx_fnv"]
+        obs = pts[seg["obstacle_idx"]]
+        lab = O.cluster(obs)
+        assert f"{O.fnv1a64(lab):016x}" == row["cluster_labels_fnv"]
+        assert int(lab.max() + 1) == row["n_clusters"] and int((lab == -1).sum()) == row["n_invalid"]
+        assert f"{O.fnv1a64(O.kd_order(obs, 1)):016x}" == row["kd_order_fnv"]
+
+
+def test_frame0_matches_survey_probe(golden_frames):
+    # frame 0 has N = 123398, obstacle cloud 46851 points
+    pts = golden_frames[0]
+    seg = O.segment(pts, tie_mode=0)  # std::sort, what the reference compiles to in this container
+    assert pts.shape[0] == 123398 and seg["obstacle_idx"].size == 46851
+    # the plane normal points up and d is negative (sign convention of Eigen's JacobiSVD V)
+    for s in range(2):
+        a, b, c, d = seg["planes"][s, -1]
+        assert c > 0.99 and d < -1.5
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+def test_oracle_cluster_equals_unmodified_reference(golden_frames):
+    pts = golden_frames[2]
+    obs = pts[O.segment(pts, tie_mode=1)["obstacle_idx"]]
+    ref = O.ref_cluster(obs)
+    assert np.array_equal(O.cluster(obs), ref)
+    assert np.array_equal(O.ref_kd_order(obs), O.kd_order(obs, 0))
+    assert np.array_equal(O.ref_kd_order(obs), O.kd_order(obs, 1))
+    model, stats = O.cluster_model(obs, O.kd_rank(obs, 1))
+    assert np.array_equal(model, ref)
+    assert stats["components"] > 100 and stats["expansions"] > 1000
+    # sandwich invariant CC(r/2) ⊑ reference ⊑ CC(r)   (SURVEY.md finding 4)
+    outer = O.cc_roots(obs, 0.18)
+    inner = O.cc_roots(obs, 0.25 * 0.18)
+    valid = ref >= 0
+    for lab, root in ((ref[valid], outer[valid]),):
+        first = {}
+        for l, r in zip(lab, root):
+            assert first.setdefault(int(l), int(r)) == int(r)  # a reference cluster never spans two r-components
+    first = {}
+    for r, l in zip(inner, ref):
+        assert first.setdefault(int(r), int(l)) == int(l)      # an r/2-component is never split
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["synth", "stress", "lattice", "ties", "random"])
+def test_oracle_vs_reference_on_synthetic(case):
+    rng = np.random.default_rng(17)
+    if case == "synth":
+        f = make_frame(21, beams=32, azimuth_steps=512)
+        pts = f[O.segment(f, tie_mode=1)["obstacle_idx"]]
+    elif case == "stress":
+        pts = make_stress(seed=9, n_blobs=30, blob_pts=200, n_walls=2, wall_len=10.0, wall_height=2.0)
+    elif case == "lattice":
+        g = np.stack(np.meshgrid(np.arange(10), np.arange(10), np.arange(5), indexing="ij"), -1).reshape(-1, 3)
+        pts = (g * 0.2).astype(np.float32)[rng.permutation(500)]
+    elif case == "ties":
+        pts = (rng.integers(0, 6, (3000, 3)) * 0.25).astype(np.float32)
+    else:
+        pts = rng.uniform(-5, 5, (5000, 3)).astype(np.float32)
+    for cfg in (O.default_clu_cfg(), O.default_clu_cfg(cluster_quality=0.2, min_cluster_size=2),
+                O.default_clu_cfg(distance_squared=0.5, max_cluster_size=50)):
+        ref = O.ref_cluster(pts, cfg)
+        assert np.array_equal(O.cluster(pts, cfg), ref)
+        assert np.array_equal(O.kd_order(pts, 1), O.ref_kd_order(pts))
+        model, _ = O.cluster_model(pts, O.kd_rank(pts, 1), cfg)
+        assert np.array_equal(model, ref)
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+def test_radius_search_sets_and_d2_bits(golden_frames):
+    # what the reference's own test pins (test/test_kdtree.cpp:97-187): neighbour sets and d2 vs brute force
+    pts = golden_frames[0][:20000]
+    q = np.arange(0, 20000, 97, dtype=np.uint32)
+    offs, idx, d2 = O.ref_radius_search(pts, q, 0.18)
+    p3 = pts[:, :3]
+    for k, qi in enumerate(q):
+        diff = p3[qi] - p3
+        bf = (diff[:, 0] * diff[:, 0]) + ((diff[:, 1] * diff[:, 1]) + ((diff[:, 2] * diff[:, 2]) + np.float32(0)))
+        want = np.nonzero(bf <= np.float32(0.18))[0]
+        got = idx[offs[k]:offs[k + 1]]
+        assert np.array_equal(np.sort(got), want)
+        assert np.array_equal(d2[offs[k]:offs[k + 1]].view(np.uint32), bf[got].astype(np.float32).view(np.uint32))
+
+
+def test_jacobi_restatement_against_numpy(golden_frames):
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        m = rng.normal(size=(50, 3)) * rng.uniform(0.01, 30, 3)
+        a = np.cov(m.T).astype(np.float32)
+        v, sv, sweeps = O.jacobi_svd3(a)
+        w, q = np.linalg.eigh(a.astype(np.float64))
+        assert 0 < sweeps < 20
+        assert np.allclose(np.sort(sv)[::-1], sv) and np.allclose(sv, w[::-1], rtol=2e-4, atol=1e-6)
+        assert abs(abs(float(v[:, 2] @ q[:, 0])) - 1.0) < 1e-3  # col 2 = smallest-eigenvalue direction
+    # ground-like covariance: the normal comes out with positive z
+    v, sv, _ = O.jacobi_svd3(np.array([[96, 3, 0.5], [3, 27, 0.2], [0.5, 0.2, 0.0124]], np.float32))
+    assert v[2, 2] > 0.99
+
+
+def test_segmentation_paths():
+    cfg = O.default_seg_cfg()
+    empty = O.segment(np.zeros((0, 4), np.float32), cfg)
+    assert empty["labels"].size == 0 and empty["ground_idx"].size == 0
+    two = O.segment(np.array([[0, 0, -1.7, 0], [1, 0, -1.7, 0]], np.float32), cfg)
+    assert list(two["status"]) == [1, 1] and np.all(two["labels"] == O.UNKNOWN)
+    flat = np.zeros((100, 4), np.float32)
+    flat[:, 0] = np.arange(100)
+    flat[:, 2] = -1.73
+    res = O.segment(flat, cfg)
+    assert list(res["status"]) == [2, 2] and np.all(res["labels"] == O.OBSTACLE)
+    with pytest.raises(ValueError):
+        O.segment(flat, O.default_seg_cfg(number_of_planar_partitions=0))
+    f = make_frame(2, beams=16, azimuth_steps=256)
+    odd = f[: f.shape[0] - 1 + (f.shape[0] & 1)]
+    prev = np.full(odd.shape[0], 7, np.uint32)
+    res = O.segment(odd, cfg, labels_in=prev)
+    assert (res["labels"] == 7).sum() == 1  # the dropped point keeps the stale label
