@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ground segmentation + Fast Euclidean Clustering.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over the whole workload (BASELINE.json configs[1]: the
+reference's 154-frame data/*.pcd sequence, ~121.7k points per frame; when the frame cache is not on
+the box a synthetic 64-beam sequence of the same shape — BASELINE.json configs[4] generator — is
+used and named in config.workload). Metric: frames/s (whole job, all GPUs).
+
+  value         device-resident: frames already in HBM, K passes of all kernels, timed with CUDA
+                events recorded on the library's own stream (max over ranks)
+  e2e           same metric through the public host API (host buffers -> pinned staging -> H2D ->
+                kernels -> D2H -> host arrays every step), wall clock around the calls
+  roofline      dominant stage's kernel time vs the algorithmic bytes of SURVEY.md §8(d)
+  cpu_baseline  the reference's CPU path on this box's host cores (rank 0, N=1), bounded sample
+  --impl reference   times only that CPU path (restated Segmenter + UNMODIFIED reference Clusterer
+                from oracle/_ref; this is the one place besides tests/smoke that executes oracle/)
+
+Multi-GPU: one process per GPU (torchrun), frames are independent so every rank processes its own
+copy of the per-GPU workload with no collective on the data path ("weak" scaling); NCCL is used only
+for the barrier and the max-over-ranks of the timings.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "frames/s seg+cluster (154-frame HDL-64E sequence, ~121.7k pts/frame)"
+HBM_FALLBACK_GBS = 6650.0
+
+
+def load_workload(max_frames: int | None = None):
+    cache = ROOT / "data_cache" / "frames_mm.xz"
+    if cache.exists():
+        from tools.pack_reference_frames import unpack
+
+        frames = unpack(cache)
+        name = "kitti154: reference data/*.pcd sequence (154 frames, 98.5k-124.1k pts, lossless cache)"
+    else:
+        from tests.synth import make_frame
+
+        distinct = [make_frame(1000 + i) for i in range(22)]
+        frames = [distinct[i % len(distinct)] for i in range(154)]
+        name = "synth64x154: 154 synthetic 64-beam frames (22 distinct scenes cycled), reference data cache absent"
+    if max_frames:
+        frames = frames[:max_frames]
+    return frames, name
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(frames, threads: int, n_sample: int):
+    import oracle as O
+
+    sample = [frames[i % len(frames)] for i in range(n_sample)]
+    res = O.ref_pipeline_run(sample, threads)
+    return res, sample
+
+
+def run_reference(args, frames, workload):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    import oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = min(len(frames), max(32, 2 * threads))
+    kind = "reference" if O.ref_available() else "port"
+    times = []
+    for it in range(args.warmup + args.steps):
+        res, _ = cpu_reference_run(frames, threads, n_sample)
+        if it >= args.warmup:
+            times.append(res["wall_s"])
+    total = sum(times)
+    fps = n_sample * args.steps / total
+    pts = sum(frames[i % len(frames)].shape[0] for i in range(n_sample))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "real" if workload.startswith("kitti") else "synthetic",
+        "config": {"workload": workload, "sample": f"{n_sample} frames per step"},
+        "mpts_per_s": pts * args.steps / total / 1e6,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": f"{n_sample} frames/step on {threads} std::threads: restated Segmenter "
+                                   "(Eigen/PCL absent) + unmodified reference Clusterer (oracle/_ref); TBB absent so "
+                                   "the reference's par sorts run serially"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="use only the first N frames of the workload (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    frames, workload = load_workload(args.frames or None)
+    if args.impl == "reference":
+        run_reference(args, frames, workload)
+        return
+
+    import torch
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pkg = ge.load_package()
+    nf = len(frames)
+    total_pts = int(sum(f.shape[0] for f in frames))
+    padded = int(sum((f.shape[0] + 31) & ~31 for f in frames))
+    ctx = pkg.Context(device=local_rank, max_points=padded, max_frames=nf)
+    ctx.set_profiling(True)
+
+    # ---- device-resident throughput (`value`) -------------------------------------------------
+    ctx.batch_stage(frames)  # inputs resident in HBM before the timed region
+    for _ in range(args.warmup):
+        ctx.batch_run()
+        ctx.sync()
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler.start()
+    gpu_ms, stage_acc = [], {}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.batch_run()
+        ctx.sync()
+        gpu_ms.append(ctx.last_run_ms())
+        for k, v in ctx.last_stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    res = ctx.batch_fetch()
+    n_obstacle = int(sum(r["obstacle_idx"].size for r in res))
+    n_clusters = int(sum(r["n_clusters"] for r in res))
+    dev_ms_total = max_over_ranks(sum(gpu_ms))
+    value = world * nf * args.steps / (dev_ms_total / 1e3)
+
+    # ---- end to end through the host API ------------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        ctx.process_batch(frames)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.process_batch(frames)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_fps = world * nf * args.steps / e2e_s
+    h2d = padded * 16 + 4 * 4 * nf
+    d2h = 4 * padded * 4 + 3 * 4 * nf
+
+    # ---- p50 per-frame latency, one frame in flight (submit -> labels on host) ------------------
+    lat = []
+    if rank == 0:
+        for f in frames[: min(nf, 48)]:
+            t1 = time.perf_counter()
+            ctx.process_batch([f])
+            lat.append(1e3 * (time.perf_counter() - t1))
+        lat = lat[4:] if len(lat) > 8 else lat
+
+    # ---- roofline of the dominant stage ------------------------------------------------------
+    peak, peak_src = hbm_peak()
+    algo_bytes = 16 * total_pts + 4 * total_pts + 4 * n_obstacle  # B = 16N + 4N + 4M per frame
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "n/a"
+    dom_ms = stage_ms.get(dom, 0.0)
+    achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": dom, "kernel_ms_per_step": dom_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": algo_bytes,
+                "whole_path_achieved_GBs": algo_bytes / (dev_ms_total / args.steps / 1e3) / 1e9,
+                "stage_ms_per_step": stage_ms}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle as O  # CPU baseline leg only
+
+        threads = os.cpu_count() or 1
+        n_sample = min(len(frames), max(32, 2 * threads))
+        r1, _ = cpu_reference_run(frames, 1, min(12, n_sample))
+        rN, _ = cpu_reference_run(frames, threads, n_sample)
+        cpu = {"value": n_sample / rN["wall_s"], "unit": "frames/s", "cores": threads,
+               "kind": "reference" if O.ref_available() else "port",
+               "sample": f"{n_sample} frames on {threads} std::threads (restated Segmenter + unmodified reference "
+                         f"Clusterer, TBB absent); 1-thread latency p50 {statistics.median(r1['per_frame_ms']):.1f} ms/frame "
+                         f"over {len(r1['per_frame_ms'])} frames",
+               "one_thread_ms_per_frame_p50": statistics.median(r1["per_frame_ms"])}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "real" if workload.startswith("kitti") else "synthetic",
+        "config": {"workload": workload, "frames_per_step_per_gpu": nf, "points_per_step_per_gpu": total_pts,
+                   "l2": "inputs larger than L2 (%.0f MB of points per step)" % (padded * 16 / 1e6),
+                   "parallelism": f"frame-sharded x{world}, no collective"},
+        "mpts_per_s": world * total_pts * args.steps / (dev_ms_total / 1e3) / 1e6,
+        "latency_ms": {"p50": statistics.median(lat) if lat else None,
+                       "p95": sorted(lat)[int(0.95 * (len(lat) - 1))] if lat else None, "frames": len(lat),
+                       "what": "one frame in flight, host buffers in, labels on host out"},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "results": {"obstacle_points_per_step": n_obstacle, "clusters_per_step": n_clusters,
+                    "wall_s_resident_region": wall_resident},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,11 @@ extern "C"
     uint64_t lidar_b200_launch_count(const lidar_b200_ctx *ctx);
     /* elapsed GPU milliseconds between the start and the end of the last lidar_b200_batch_run (CUDA events) */
     int lidar_b200_last_run_ms(lidar_b200_ctx *ctx, float *ms_out);
+    /* per-stage GPU times of the last run, measured with CUDA events on the context's stream when
+     * profiling is enabled. 9 stages: x-sort | gather+fit | compact | voxel grid | union-find |
+     * component sort | k-d order | replay | label compaction. */
+    int lidar_b200_set_profiling(lidar_b200_ctx *ctx, int enabled);
+    int lidar_b200_last_stage_ms(lidar_b200_ctx *ctx, float *ms_out /* [9] */, uint32_t capacity);
     const char *lidar_b200_last_error(const lidar_b200_ctx *ctx);
     const char *lidar_b200_version(void);
 

@@ -119,6 +119,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_cluster", "lidar_b200_batch_stage", "lidar_b200_batch_run", "lidar_b200_batch_fetch",
     "lidar_b200_sync", "lidar_b200_last_planes", "lidar_b200_last_kd_rank", "lidar_b200_last_cc_root",
     "lidar_b200_launch_count", "lidar_b200_last_run_ms", "lidar_b200_last_error", "lidar_b200_version",
+    "lidar_b200_set_profiling", "lidar_b200_last_stage_ms",
 ]
 
 
@@ -186,7 +187,7 @@ class Context:
         o = np.empty(max(n, 1), np.uint32)
         ng, no = C.c_uint32(0), C.c_uint32(0)
         self._check(lib().lidar_b200_segment(self._h, pts.ctypes.data_as(C.c_void_p), C.c_uint32(n),
-                                             C.c_uint32(pts.strides[0]), _ptr(labels, C.c_uint32),
+                                             C.c_uint32(pts.shape[1] * 4), _ptr(labels, C.c_uint32),
                                              _ptr(g, C.c_uint32), C.byref(ng), _ptr(o, C.c_uint32), C.byref(no)),
                     "segment")
         return labels, g[: ng.value].copy(), o[: no.value].copy()
@@ -196,14 +197,14 @@ class Context:
         m = pts.shape[0]
         labels = np.full(max(m, 1), UNDEFINED, np.int32)
         self._check(lib().lidar_b200_cluster(self._h, pts.ctypes.data_as(C.c_void_p), C.c_uint32(m),
-                                             C.c_uint32(pts.strides[0]), _ptr(labels, C.c_int32)), "cluster")
+                                             C.c_uint32(pts.shape[1] * 4), _ptr(labels, C.c_int32)), "cluster")
         return labels[:m]
 
     # -- batched frame pipeline -----------------------------------------------------------------
     def batch_stage(self, frames):
         frames = [_as_points(f) for f in frames]
         nf = len(frames)
-        strides = {f.strides[0] for f in frames} or {16}
+        strides = {f.shape[1] * 4 for f in frames} or {16}
         if len(strides) != 1:
             raise ValueError("all frames of a batch must share one point stride")
         ptrs = (C.c_void_p * max(nf, 1))(*[f.ctypes.data for f in frames])
@@ -272,6 +273,17 @@ class Context:
         self._check(lib().lidar_b200_last_cc_root(self._h, C.c_uint32(frame), _ptr(r, C.c_uint32), C.c_uint32(m)),
                     "last_cc_root")
         return r[:m]
+
+    STAGES = ("x_sort", "gather_fit", "compact", "voxel_grid", "union_find", "component_sort", "kd_order", "replay",
+              "label_compact")
+
+    def set_profiling(self, enabled: bool):
+        self._check(lib().lidar_b200_set_profiling(self._h, C.c_int(1 if enabled else 0)), "set_profiling")
+
+    def last_stage_ms(self) -> dict:
+        ms = (C.c_float * 9)()
+        self._check(lib().lidar_b200_last_stage_ms(self._h, ms, C.c_uint32(9)), "last_stage_ms")
+        return dict(zip(self.STAGES, (float(v) for v in ms)))
 
     def launch_count(self) -> int:
         return int(lib().lidar_b200_launch_count(self._h))

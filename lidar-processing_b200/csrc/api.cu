@@ -91,6 +91,12 @@ struct lidar_b200_ctx
     bool batch_is_cluster_only{false};
     std::vector<uint32_t> off, cnt;
 
+    // optional per-stage CUDA-event timing (lidar_b200_set_profiling)
+    static constexpr int kStages = 10;
+    bool profiling{false};
+    cudaEvent_t ev_stage[kStages + 1]{};
+    int n_stage_marks{0};
+
     uint64_t launches{0};
     float last_run_ms{0.0f};
     std::string err;
@@ -242,6 +248,17 @@ int apply_clu_cfg(lidar_b200_ctx *c, const lidar_b200_clu_cfg &cfg)
     return 0;
 }
 
+// stage boundaries: 0 begin | 1 x-sort | 2 gather+fit | 3 compact | 4 voxel grid | 5 union-find |
+// 6 component sort | 7 k-d order | 8 replay | 9 label compaction
+int mark(lidar_b200_ctx *c, int idx)
+{
+    if (!c->profiling)
+        return 0;
+    LB_CUDA(c, cudaEventRecord(c->ev_stage[idx], c->stream));
+    c->n_stage_marks = idx + 1;
+    return 0;
+}
+
 uint32_t grid_x(uint32_t n, uint32_t per_block, uint32_t cap)
 {
     uint32_t g = (n + per_block - 1u) / per_block;
@@ -337,6 +354,7 @@ int run_segmentation(lidar_b200_ctx *c)
         return 0;
     const BatchView bv{c->m_off(), c->m_cnt(), F};
     const dim3 gp(grid_x(c->max_n, 256u, 2048u), F);
+    mark(c, 0);
     seg_keys_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, bv, c->d_key_a.p, c->d_val_a.p);
     ++c->launches;
     int rl = 0;
@@ -344,14 +362,17 @@ int run_segmentation(lidar_b200_ctx *c)
                                         RadixSortScratch{c->d_hist.p}, &rl);
     c->launches += rl;
     const uint32_t *sorted_idx = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
+    mark(c, 1);
     seg_gather_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, sorted_idx, bv, c->d_spts.p);
     ++c->launches;
     seg_fit_kernel<<<dim3(c->seg.partitions, F), kFitThreads, sizeof(FitSmem), s>>>(c->d_spts.p, bv, c->seg, c->d_flags.p,
                                                                                     c->d_planes.p, c->d_status.p);
     ++c->launches;
+    mark(c, 2);
     seg_compact_kernel<<<F, 1024, 0, s>>>(c->d_spts.p, c->d_flags.p, bv, c->d_labels.p, c->d_gidx.p, c->d_oidx.p,
                                           c->d_obs.p, c->m_ng(), c->m_no());
     ++c->launches;
+    mark(c, 3);
     LB_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -371,17 +392,21 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     const TableView tv{c->m_toff(), c->m_tcap()};
     const dim3 gp(grid_x(max_m, 256u, 2048u), F);
     const dim3 gt(grid_x(c->max_tcap, 256u, 2048u), F);
+    if (c->batch_is_cluster_only)
+        mark(c, 3);
 
     grid_clear_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p);
     grid_insert_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->clu, c->d_tkeys.p, c->d_tcount.p, c->d_slot_of.p, c->d_err.p);
     grid_scan_kernel<<<F, 1024, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p, c->d_cells.p);
     grid_fill_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->d_cells.p, c->d_tcount.p, c->d_slot_of.p, c->d_cpts.p,
                                         c->d_pos_of.p);
+    mark(c, 4);
     cc_init_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
     cc_union_kernel<<<dim3(grid_x(max_m, 8u, 8192u), F), 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu,
                                                                       c->d_parent.p);
     cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_key_a.p, c->d_val_a.p);
     c->launches += 7;
+    mark(c, 5);
     LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
     int rl = 0;
     const uint32_t bits = ceil_log2(max_m < 2u ? 2u : max_m);
@@ -391,8 +416,10 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     const uint32_t *member_root = (passes & 1) ? c->d_key_b.p : c->d_key_a.p;
     const uint32_t *member_idx = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
 
+    mark(c, 6);
     c->launches += kd_build_launch(s, pts, bv, max_m, c->d_nodes.p, c->d_gepos.p, c->d_lepos.p, c->d_rank.p);
 
+    mark(c, 7);
     replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_state.p,
                                           c->d_seed_of.p, c->d_member_pos.p, c->m_cursor());
     const uint32_t claims = (max_m + 31u) / 32u;
@@ -401,9 +428,11 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
                                                                member_idx, c->d_member_pos.p, c->d_state.p,
                                                                c->d_seed_of.p, c->d_queue.p, c->d_spill.p,
                                                                c->d_seed_valid.p, c->m_cursor());
+    mark(c, 8);
     label_compact_kernel<<<F, 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
                                             c->d_clabels.p, c->m_nc());
     c->launches += 3;
+    mark(c, 9);
     LB_CUDA(c, cudaGetLastError());
     return 0;
 }
@@ -449,6 +478,12 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     apply_clu_cfg(c, cc);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
+        [&]() {
+            for (auto &e : c->ev_stage)
+                if (cudaEventCreate(&e) != cudaSuccess)
+                    return true;
+            return false;
+        }() ||
         cudaFuncSetAttribute(seg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(FitSmem))) != cudaSuccess ||
         reserve(c, max_points ? max_points : 200000u, max_frames ? max_frames : 1u) != 0)
@@ -480,6 +515,9 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     for (void *p : dev)
         if (p)
             cudaFree(p);
+    for (auto &e : c->ev_stage)
+        if (e)
+            cudaEventDestroy(e);
     if (c->ev_start)
         cudaEventDestroy(c->ev_start);
     if (c->ev_stop)
@@ -734,6 +772,33 @@ int lidar_b200_last_run_ms(lidar_b200_ctx *c, float *ms_out)
         ms = c->last_run_ms;
     }
     *ms_out = ms;
+    return 0;
+}
+
+int lidar_b200_set_profiling(lidar_b200_ctx *c, int enabled)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    c->profiling = enabled != 0;
+    c->n_stage_marks = 0;
+    return 0;
+}
+
+int lidar_b200_last_stage_ms(lidar_b200_ctx *c, float *ms_out, uint32_t capacity)
+{
+    if (!c || !ms_out || capacity < static_cast<uint32_t>(lidar_b200_ctx::kStages - 1))
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i + 1 < lidar_b200_ctx::kStages; ++i)
+    {
+        ms_out[i] = 0.0f;
+        if (c->profiling && i + 1 < c->n_stage_marks &&
+            cudaEventElapsedTime(&ms_out[i], c->ev_stage[i], c->ev_stage[i + 1]) != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            ms_out[i] = 0.0f;
+        }
+    }
     return 0;
 }
 

@@ -256,6 +256,24 @@ def ref_radius_search(points, queries, radius_sqr: float = 0.18, capacity: int |
     return offs, idx[: offs[-1]].copy(), d2[: offs[-1]].copy()
 
 
+def ref_pipeline_run(frames, nthreads: int = 1):
+    """CPU baseline: restated Segmenter + unmodified reference Clusterer on `nthreads` threads.
+    Returns dict(per_frame_ms, wall_s, n_obstacle, n_clusters)."""
+    frames = [_f32(f) for f in frames]
+    nf = len(frames)
+    strides = {f.shape[1] for f in frames}
+    assert len(strides) == 1
+    ptrs = (C.POINTER(C.c_float) * nf)(*[_p(f, C.c_float) for f in frames])
+    counts = np.array([f.shape[0] for f in frames], np.uint32)
+    ms = np.zeros(nf, np.float64)
+    wall = C.c_double(0)
+    nobs = np.zeros(nf, np.uint32)
+    ncl = np.zeros(nf, np.uint32)
+    ref().ref_pipeline_run(ptrs, _p(counts, C.c_uint32), C.c_uint32(nf), C.c_uint32(strides.pop()), C.c_uint32(nthreads),
+                           _p(ms, C.c_double), C.byref(wall), _p(nobs, C.c_uint32), _p(ncl, C.c_uint32))
+    return dict(per_frame_ms=ms, wall_s=wall.value, n_obstacle=nobs, n_clusters=ncl)
+
+
 # ---- PCD v0.7 "DATA binary" reader (dataloader.cpp:139 uses pcl::io::loadPCDFile) ------------
 
 def read_pcd(path) -> np.ndarray:

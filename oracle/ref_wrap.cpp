@@ -6,6 +6,7 @@
 // Wraps: lidar_processing::Clusterer::cluster   (reference src/clustering.cpp:47-125)
 //        lidar_processing::KDTree<float,3>       (reference src/kdtree.hpp:174-225, 292-341)
 #include "clustering.hpp" // from /root/reference/src
+#include "oracle.h"     // restated Segmenter (segmentation.cpp needs Eigen + PCL, absent here)
 
 #include <chrono>
 #include <cstdint>
@@ -136,6 +137,66 @@ int ref_radius_search(const float *points, std::uint32_t m, std::uint32_t stride
         }
         offsets_out[q + 1] = off;
     }
+    return 0;
+}
+
+// CPU baseline for the whole hot path, the way BASELINE.md §3 asks for it: restated Segmenter
+// (std::sort tie order, i.e. what the reference compiles to in this container) followed by the
+// UNMODIFIED reference Clusterer on the resulting obstacle cloud (processor.cpp:150-178). One
+// long-lived Clusterer per thread (processor.cpp:129-132), frames dealt round-robin to `nthreads`
+// std::threads. per_frame_ms[f] = segment + cluster time of frame f on its thread.
+int ref_pipeline_run(const float *const *frames, const std::uint32_t *counts, std::uint32_t nframes,
+                     std::uint32_t stride_floats, std::uint32_t nthreads, double *per_frame_ms, double *wall_s,
+                     std::uint32_t *n_obstacle_out, std::uint32_t *n_clusters_out)
+{
+    nthreads = nthreads ? nthreads : 1U;
+    oracle_seg_cfg seg_cfg;
+    oracle_seg_cfg_default(&seg_cfg);
+    auto worker = [&](std::uint32_t tid) {
+        Clusterer clusterer;
+        std::vector<ClusteringLabel> cluster_labels;
+        std::vector<std::uint32_t> seg_labels, ground_idx, obstacle_idx;
+        pcl::PointCloud<pcl::PointXYZRGBL> obstacle_cloud;
+        for (std::uint32_t f = tid; f < nframes; f += nthreads)
+        {
+            const std::uint32_t n = counts[f];
+            const float *pts = frames[f];
+            const auto t0 = std::chrono::steady_clock::now();
+            seg_labels.assign(n, 0U);
+            ground_idx.resize(n ? n : 1U);
+            obstacle_idx.resize(n ? n : 1U);
+            std::uint32_t ng = 0, no = 0;
+            oracle_segment(pts, n, stride_floats, &seg_cfg, 0, seg_labels.data(), ground_idx.data(), &ng,
+                           obstacle_idx.data(), &no, nullptr, nullptr);
+            obstacle_cloud.clear();
+            obstacle_cloud.reserve(no);
+            for (std::uint32_t k = 0; k < no; ++k)
+            {
+                const float *p = pts + static_cast<std::size_t>(obstacle_idx[k]) * stride_floats;
+                obstacle_cloud.emplace_back(p[0], p[1], p[2], 0, 255, 0, 1);
+            }
+            clusterer.cluster(obstacle_cloud, cluster_labels);
+            const auto t1 = std::chrono::steady_clock::now();
+            per_frame_ms[f] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+            if (n_obstacle_out)
+                n_obstacle_out[f] = no;
+            if (n_clusters_out)
+            {
+                std::int32_t mx = -1;
+                for (const auto l : cluster_labels)
+                    mx = l > mx ? l : mx;
+                n_clusters_out[f] = static_cast<std::uint32_t>(mx + 1);
+            }
+        }
+    };
+    const auto w0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (std::uint32_t t = 1; t < nthreads; ++t)
+        threads.emplace_back(worker, t);
+    worker(0U);
+    for (auto &t : threads)
+        t.join();
+    *wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
     return 0;
 }
 
