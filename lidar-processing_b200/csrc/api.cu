@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -71,7 +72,7 @@ struct lidar_b200_ctx
     // device arenas (per point)
     DevBuf<float4> d_pts, d_spts, d_obs, d_nodes, d_cpts;
     DevBuf<uint32_t> d_key_a, d_key_b, d_val_a, d_val_b, d_labels, d_gidx, d_oidx, d_slot_of, d_pos_of, d_parent,
-        d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label;
+        d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label, d_comp_size;
     DevBuf<int32_t> d_clabels;
     DevBuf<unsigned long long> d_spill;
     DevBuf<uint8_t> d_flags, d_seed_valid;
@@ -97,6 +98,7 @@ struct lidar_b200_ctx
     cudaEvent_t ev_stage[kStages + 1]{};
     int n_stage_marks{0};
 
+    uint32_t sm_count{148}, replay_ctas_per_sm{12};
     uint64_t launches{0};
     float last_run_ms{0.0f};
     std::string err;
@@ -175,7 +177,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
         DevBuf<uint32_t> *u32s[] = {&c->d_key_a,  &c->d_key_b,  &c->d_val_a,      &c->d_val_b, &c->d_labels,
                                     &c->d_gidx,   &c->d_oidx,   &c->d_slot_of,    &c->d_pos_of, &c->d_parent,
                                     &c->d_root,   &c->d_rank,   &c->d_gepos,      &c->d_lepos, &c->d_state,
-                                    &c->d_seed_of, &c->d_member_pos, &c->d_queue, &c->d_seed_label};
+                                    &c->d_seed_of, &c->d_member_pos, &c->d_queue, &c->d_seed_label, &c->d_comp_size};
         for (auto *b : u32s)
             rc |= dev_alloc(c, *b, n);
         rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_flags, n) |
@@ -186,7 +188,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
     }
     if (grow_frames)
     {
-        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames)) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)))
+        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames) + 8) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)))
             return LIDAR_B200_ERR_CUDA;
         c->cap_frames = frames;
     }
@@ -401,11 +403,15 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     grid_fill_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->d_cells.p, c->d_tcount.p, c->d_slot_of.p, c->d_cpts.p,
                                         c->d_pos_of.p);
     mark(c, 4);
-    cc_init_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
-    cc_union_kernel<<<dim3(grid_x(max_m, 8u, 8192u), F), 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu,
-                                                                      c->d_parent.p);
-    cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_key_a.p, c->d_val_a.p);
-    c->launches += 7;
+    cc_init_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_comp_size.p);
+    {
+        const dim3 gl(grid_x(max_m, 32u, 2368u), F); // each warp walks several points
+        cc_link_kernel<true><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p);
+        cc_compress_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
+        cc_link_kernel<false><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p);
+    }
+    cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_key_a.p, c->d_val_a.p, c->d_comp_size.p);
+    c->launches += 9;
     mark(c, 5);
     LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
     int rl = 0;
@@ -423,11 +429,11 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_state.p,
                                           c->d_seed_of.p, c->d_member_pos.p, c->m_cursor());
     const uint32_t claims = (max_m + 31u) / 32u;
-    const uint32_t rctas = grid_x(claims, kReplayWarps, 96u);
-    replay_kernel<<<dim3(rctas, F), kReplayWarps * 32, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, member_root,
-                                                               member_idx, c->d_member_pos.p, c->d_state.p,
-                                                               c->d_seed_of.p, c->d_queue.p, c->d_spill.p,
-                                                               c->d_seed_valid.p, c->m_cursor());
+    // persistent grid: a fixed number of CTAs per SM walks the flat (frame, claim) work list
+    const uint32_t rctas = grid_x(claims * F, kReplayWarps, c->sm_count * c->replay_ctas_per_sm);
+    replay_kernel<<<rctas, kReplayWarps * 32, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx,
+                                                      c->d_member_pos.p, c->d_comp_size.p, c->d_state.p, c->d_seed_of.p,
+                                                      c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->m_cursor(), claims);
     mark(c, 8);
     label_compact_kernel<<<F, 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
                                             c->d_clabels.p, c->m_nc());
@@ -491,6 +497,17 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
         lidar_b200_destroy(c);
         return LIDAR_B200_ERR_CUDA;
     }
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+            c->sm_count = static_cast<uint32_t>(sms);
+        if (const char *e = std::getenv("LIDAR_B200_REPLAY_CTAS_PER_SM"))
+        {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 16)
+                c->replay_ctas_per_sm = static_cast<uint32_t>(v);
+        }
+    }
     *ctx_out = c;
     return 0;
 }
@@ -509,7 +526,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     void *dev[] = {c->d_pts.p,      c->d_spts.p,   c->d_obs.p,       c->d_nodes.p,  c->d_cpts.p,       c->d_key_a.p,
                    c->d_key_b.p,    c->d_val_a.p,  c->d_val_b.p,     c->d_labels.p, c->d_gidx.p,       c->d_oidx.p,
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
-                   c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p,
+                   c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
                    c->d_cells.p,    c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
     for (void *p : dev)

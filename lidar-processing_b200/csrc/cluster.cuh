@@ -249,20 +249,32 @@ LB_D void uf_unite(uint32_t *parent, uint32_t a, uint32_t b)
     }
 }
 
-__global__ void __launch_bounds__(256) cc_init_kernel(BatchView bv, uint32_t *__restrict__ parent)
+__global__ void __launch_bounds__(256)
+cc_init_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict__ comp_size)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    {
         parent[off + i] = i;
+        comp_size[off + i] = 0u;
+    }
 }
 
-// One warp per cell-ordered point: lanes probe the 27 neighbour cells, then sweep the flattened
-// candidate list; every pair within the tolerance is united once (from its larger index).
+// One warp per cell-ordered point. Every unordered pair of points in the same or in adjacent cells
+// is visited exactly once: a point scans its own cell (partners with a smaller index only) and the
+// 13 neighbour cells that follow it in (dz, dy, dx) lexicographic order.
+//   kSample = true : Afforest-style sampling pass — link to the first two partners found, which
+//                    already merges most of every component;
+//   kSample = false: full pass. parent[] was flattened in between, so for nearly every pair both
+//                    (L1-cached) parent reads agree and the pair is skipped without touching the
+//                    union-find. Stale cached parents are safe for that test: a node reachable
+//                    through old pointers stays in the same set forever.
+template <bool kSample>
 __global__ void __launch_bounds__(256)
-cc_union_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
-                CluParams prm, uint32_t *__restrict__ parent)
+cc_link_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
+               CluParams prm, uint32_t *__restrict__ parent)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
@@ -273,6 +285,9 @@ cc_union_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, con
     uint32_t *par = parent + off;
     const uint32_t lane = lane_id();
     const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    // lane l < 14 -> neighbour offset number 13 + l of the 27 (index 13 is the cell itself)
+    const uint32_t nb = 13u + lane;
+    const int ox = static_cast<int>(nb % 3u) - 1, oy = static_cast<int>((nb / 3u) % 3u) - 1, oz = static_cast<int>(nb / 9u) - 1;
     for (uint32_t pos = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pos < m; pos += warps_per_grid)
     {
         const float4 pj = cp[pos];
@@ -280,19 +295,21 @@ cc_union_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, con
         int cx, cy, cz;
         cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
         uint32_t start = 0u, count = 0u;
-        if (lane < 27u)
-            cell_lookup(tab, mask, cell_key(cx + static_cast<int>(lane % 3u) - 1, cy + static_cast<int>((lane / 3u) % 3u) - 1,
-                                            cz + static_cast<int>(lane / 9u) - 1),
-                        &start, &count);
+        if (lane < 14u)
+            cell_lookup(tab, mask, cell_key(cx + ox, cy + oy, cz + oz), &start, &count);
+        const uint32_t own_end = __shfl_sync(kFullMask, start + count, 0); // candidates below this are in pj's cell
+        const uint32_t own_start = __shfl_sync(kFullMask, start, 0);
         const uint32_t incl = warp_inclusive_scan(count);
         const uint32_t excl = incl - count;
         const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+        uint32_t ri = par[ij];
+        uint32_t linked = 0u;
         for (uint32_t base = 0; base < total; base += 32u)
         {
             const uint32_t q = base + lane;
-            uint32_t lo = 0u, hi = 26u;
+            uint32_t lo = 0u, hi = 13u;
 #pragma unroll
-            for (int it = 0; it < 5; ++it)
+            for (int it = 0; it < 4; ++it)
             {
                 const uint32_t mid = (lo + hi) >> 1;
                 const uint32_t v = __shfl_sync(kFullMask, incl, mid);
@@ -301,23 +318,67 @@ cc_union_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, con
                 else
                     lo = mid + 1u;
             }
-            const uint32_t c = min(lo, 26u);
+            const uint32_t c = min(lo, 13u);
             const uint32_t cstart = __shfl_sync(kFullMask, start, c);
             const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
+            bool hit = false;
+            uint32_t ik = 0u;
             if (q < total)
             {
-                const float4 cand = cp[cstart + (q - cexcl)];
-                const uint32_t ik = __float_as_uint(cand.w);
-                if (ik < ij && dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared)
+                const uint32_t cpos = cstart + (q - cexcl);
+                const float4 cand = cp[cpos];
+                ik = __float_as_uint(cand.w);
+                const bool own = cpos >= own_start && cpos < own_end && c == 0u;
+                hit = (!own || ik < ij) &&
+                      dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared;
+            }
+            if (kSample)
+            {
+                // link the first two partners only
+                const uint32_t bh = __ballot_sync(kFullMask, hit);
+                const uint32_t before = linked + __popc(bh & lanemask_lt());
+                if (hit && before < 2u)
                     uf_unite(par, ij, ik);
+                linked += __popc(bh);
+                if (linked >= 2u)
+                    break;
+            }
+            else if (hit)
+            {
+                const uint32_t pk = par[ik];
+                if (pk != ri)
+                {
+                    uf_unite(par, ij, ik);
+                    ri = __ldcg(&par[ij]);
+                }
             }
         }
     }
 }
 
-// keys[i] = root of i (component id = smallest member index), vals[i] = i
+// parent[i] = root(i), in place
+__global__ void __launch_bounds__(256) cc_compress_kernel(BatchView bv, uint32_t *__restrict__ parent)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    {
+        uint32_t x = i;
+        uint32_t p = __ldcg(&parent[off + x]);
+        while (p != x)
+        {
+            x = p;
+            p = __ldcg(&parent[off + x]);
+        }
+        parent[off + i] = x;
+    }
+}
+
+// keys[i] = root of i (component id = smallest member index), vals[i] = i; comp_size[root] = members
 __global__ void __launch_bounds__(256)
-cc_flatten_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+cc_flatten_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                  uint32_t *__restrict__ comp_size)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
@@ -333,6 +394,10 @@ cc_flatten_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restr
         }
         keys[off + i] = x;
         vals[off + i] = i;
+        // warp-aggregated count per root (neighbouring indices mostly share a component)
+        const uint32_t peers = __match_any_sync(__activemask(), x);
+        if ((peers & lanemask_lt()) == 0u)
+            atomicAdd(&comp_size[off + x], static_cast<uint32_t>(__popc(peers)));
     }
 }
 
@@ -346,8 +411,8 @@ replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        cursor[f] = 0u;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2)
+        cursor[threadIdx.x] = 0u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
         const uint32_t idx = __float_as_uint(cpts[off + i].w);
@@ -358,45 +423,57 @@ replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t
 }
 
 constexpr int kReplayWarps = 4;
-constexpr uint32_t kPushCap = 256u; // per-warp shared push buffer; larger expansions spill to global
+constexpr uint32_t kPushCap = 256u;   // per-warp shared push buffer; larger expansions spill to global
+constexpr uint32_t kBigComponent = 96u; // components with at least this many members are replayed first
 
-// Persistent warps; each claims 32 member slots at a time and replays every component whose first
-// member (= root = smallest index) falls in its claim. grid = (ctas_per_frame, frames).
+// Persistent warps over a flat work list of (frame, 32 member slots) claims, walked twice: the first
+// walk replays only the big components — their BFS chains are the critical path, so they must start
+// at time zero — the second walk replays everything else around them. A warp replays every
+// component whose first member (= root = smallest index) falls into its claim.
 __global__ void __launch_bounds__(kReplayWarps * 32)
 replay_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
               CluParams prm, const uint32_t *__restrict__ member_root, const uint32_t *__restrict__ member_idx,
-              const uint32_t *__restrict__ member_pos, uint32_t *__restrict__ state, uint32_t *__restrict__ seed_of,
-              uint32_t *__restrict__ queue, unsigned long long *__restrict__ push_spill,
-              uint8_t *__restrict__ seed_valid, uint32_t *__restrict__ cursor)
+              const uint32_t *__restrict__ member_pos, const uint32_t *__restrict__ comp_size,
+              uint32_t *__restrict__ state, uint32_t *__restrict__ seed_of, uint32_t *__restrict__ queue,
+              unsigned long long *__restrict__ push_spill, uint8_t *__restrict__ seed_valid,
+              uint32_t *__restrict__ cursor, uint32_t claims_per_frame)
 {
     __shared__ unsigned long long pbuf_all[kReplayWarps][kPushCap];
-    const uint32_t f = blockIdx.y;
-    const uint32_t m = bv.cnt[f];
-    const uint32_t off = bv.off[f];
-    const uint32_t mask = table_mask(m, tv.tcap[f]);
-    const uint4 *tab = cells + tv.toff[f];
-    const float4 *cp = cpts + off;
-    uint32_t *st = state + off;
-    uint32_t *so = seed_of + off;
-    uint32_t *qu = queue + off;
-    unsigned long long *spill = push_spill + off;
-    const uint32_t *mroot = member_root + off;
-    const uint32_t *midx = member_idx + off;
-    const uint32_t *mpos = member_pos + off;
     const uint32_t lane = lane_id();
     const uint32_t lt = lanemask_lt();
     unsigned long long *pbuf = pbuf_all[threadIdx.x >> 5];
+    const uint32_t total_claims = claims_per_frame * bv.frames;
 
+    for (uint32_t phase = 0; phase < 2u; ++phase)
     while (true)
     {
-        uint32_t t0 = 0u;
+        uint32_t w = 0u;
         if (lane == 0)
-            t0 = atomicAdd(&cursor[f], 32u);
-        t0 = __shfl_sync(kFullMask, t0, 0);
-        if (t0 >= m)
+            w = atomicAdd(&cursor[phase], 1u);
+        w = __shfl_sync(kFullMask, w, 0);
+        if (w >= total_claims)
             break;
+        const uint32_t f = w / claims_per_frame;
+        const uint32_t t0 = (w - f * claims_per_frame) * 32u;
+        const uint32_t m = bv.cnt[f];
+        if (t0 >= m)
+            continue;
+        const uint32_t off = bv.off[f];
+        const uint32_t mask = table_mask(m, tv.tcap[f]);
+        const uint4 *tab = cells + tv.toff[f];
+        const float4 *cp = cpts + off;
+        uint32_t *st = state + off;
+        uint32_t *so = seed_of + off;
+        uint32_t *qu = queue + off;
+        unsigned long long *spill = push_spill + off;
+        const uint32_t *mroot = member_root + off;
+        const uint32_t *midx = member_idx + off;
+        const uint32_t *mpos = member_pos + off;
+
         const uint32_t tt = t0 + lane;
-        const bool is_start = tt < m && mroot[tt] == midx[tt];
+        bool is_start = tt < m && mroot[tt] == midx[tt];
+        if (is_start)
+            is_start = (comp_size[off + midx[tt]] >= kBigComponent) == (phase == 0u);
         uint32_t starts = __ballot_sync(kFullMask, is_start);
         while (starts)
         {
