@@ -1,0 +1,73 @@
+// Drop-in replacement for the reference's src/clustering.hpp (YevgeniyEngineer/LiDAR-Processing):
+// same namespace, label alias, configuration struct, class name, constants, public member functions
+// and explicit instantiations (reference src/clustering.hpp:38-91). src/polygonization.hpp includes
+// this header for ClusteringLabel (polygonization.hpp:26,71) and keeps compiling. The body runs on a
+// B200 through the C ABI in include/lidar_b200.h; there is no CPU implementation behind it.
+#ifndef LIDAR_PROCESSING__CLUSTERING_HPP
+#define LIDAR_PROCESSING__CLUSTERING_HPP
+
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+
+#include <cstdint>
+#include <limits>
+#include <vector>
+
+struct lidar_b200_ctx;
+
+namespace lidar_processing
+{
+using ClusteringLabel = std::int32_t;
+
+struct ClusteringConfiguration final
+{
+    float distance_squared{0.18F};
+    float cluster_quality{0.5F};
+    std::uint32_t min_cluster_size{4U};
+    std::uint32_t max_cluster_size{std::numeric_limits<std::uint32_t>::max()};
+};
+
+class Clusterer final
+{
+  public:
+    static constexpr ClusteringLabel UNDEFINED{std::numeric_limits<std::int32_t>::lowest()};
+    static constexpr ClusteringLabel INVALID{-1};
+
+    Clusterer();
+    ~Clusterer();
+    Clusterer(const Clusterer &) = delete;
+    Clusterer &operator=(const Clusterer &) = delete;
+
+    void update_configuration(const ClusteringConfiguration &configuration);
+
+    void reserve_memory(std::uint32_t number_of_points = 200'000U);
+
+    // Same contract as the reference (src/clustering.cpp:47-125): labels.assign(n, UNDEFINED), then
+    // every point receives a dense cluster id 0..K-1 or INVALID. The partition is bit-identical to
+    // the reference's for the same cloud in the same point order. Throws std::runtime_error on a
+    // CUDA failure or non-finite coordinates.
+    template <typename PointT>
+    void cluster(const pcl::PointCloud<PointT> &cloud_in, std::vector<ClusteringLabel> &labels);
+
+  private:
+    lidar_b200_ctx *context_{nullptr};
+    ClusteringConfiguration configuration_{};
+};
+
+extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZ> &cloud_in,
+                                        std::vector<ClusteringLabel> &labels);
+
+extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZI> &cloud_in,
+                                        std::vector<ClusteringLabel> &labels);
+
+extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZL> &cloud_in,
+                                        std::vector<ClusteringLabel> &labels);
+
+extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZRGB> &cloud_in,
+                                        std::vector<ClusteringLabel> &labels);
+
+extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZRGBL> &cloud_in,
+                                        std::vector<ClusteringLabel> &labels);
+} // namespace lidar_processing
+
+#endif // LIDAR_PROCESSING__CLUSTERING_HPP

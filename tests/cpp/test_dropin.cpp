@@ -1,0 +1,102 @@
+// C++ parity harness for the drop-in classes: does what Processor::process does around the hot path
+// (reference src/processor.cpp:150-195) with the replacement Segmenter / Clusterer headers, then
+// dumps the results for tests/test_gpu_dropin.py to compare with the oracle.
+//   usage: test_dropin <points.f32 (N x 4 floats)> <out_prefix>
+#include "clustering.hpp"
+#include "segmentation.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include <vector>
+
+using namespace lidar_processing;
+
+template <typename T> void dump(const std::string &path, const std::vector<T> &v)
+{
+    std::ofstream f(path, std::ios::binary);
+    f.write(reinterpret_cast<const char *>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+}
+
+int main(int argc, char **argv)
+{
+    if (argc != 3)
+        return 2;
+    std::ifstream in(argv[1], std::ios::binary | std::ios::ate);
+    const std::size_t bytes = static_cast<std::size_t>(in.tellg());
+    in.seekg(0);
+    std::vector<float> raw(bytes / 4);
+    in.read(reinterpret_cast<char *>(raw.data()), static_cast<std::streamsize>(bytes));
+    const std::size_t n = raw.size() / 4;
+
+    pcl::PointCloud<pcl::PointXYZI> cloud_in;
+    for (std::size_t i = 0; i < n; ++i)
+        cloud_in.emplace_back(raw[i * 4 + 0], raw[i * 4 + 1], raw[i * 4 + 2], raw[i * 4 + 3]);
+
+    try
+    {
+        Segmenter segmenter;
+        Clusterer clusterer;
+        std::vector<SegmentationLabel> segmentation_labels;
+        pcl::PointCloud<pcl::PointXYZI> ground_points, obstacle_points;
+        // twice, like consecutive callbacks reusing the member vectors (processor.cpp:126-132)
+        for (int rep = 0; rep < 2; ++rep)
+            segmenter.segment(cloud_in, segmentation_labels, ground_points, obstacle_points);
+
+        pcl::PointCloud<pcl::PointXYZRGBL> obstacle_cloud; // processor.cpp:158-163
+        obstacle_cloud.reserve(obstacle_points.size());
+        for (const auto &p : obstacle_points)
+            obstacle_cloud.emplace_back(p.x, p.y, p.z, 0, 255, 0, 1);
+
+        std::vector<ClusteringLabel> cluster_labels;
+        clusterer.cluster(obstacle_cloud, cluster_labels);
+        for (const auto label : cluster_labels)
+            if (label == Clusterer::UNDEFINED)
+                throw std::runtime_error("Undefined label found (clustering)"); // processor.cpp:186-189
+
+        std::vector<std::uint32_t> seg(segmentation_labels.size());
+        for (std::size_t i = 0; i < seg.size(); ++i)
+            seg[i] = static_cast<std::uint32_t>(segmentation_labels[i]);
+        std::vector<float> ground_xyz, obstacle_xyz;
+        for (const auto &p : ground_points)
+            ground_xyz.insert(ground_xyz.end(), {p.x, p.y, p.z, p.intensity});
+        for (const auto &p : obstacle_points)
+            obstacle_xyz.insert(obstacle_xyz.end(), {p.x, p.y, p.z, p.intensity});
+        const std::string prefix = argv[2];
+        dump(prefix + ".seg.u32", seg);
+        dump(prefix + ".ground.f32", ground_xyz);
+        dump(prefix + ".obstacle.f32", obstacle_xyz);
+        dump(prefix + ".clusters.i32", cluster_labels);
+
+        // configuration errors surface as exceptions, empty clouds are fine
+        bool threw = false;
+        try
+        {
+            SegmentationConfiguration bad;
+            bad.number_of_planar_partitions = 0U;
+            segmenter.update_configuration(bad);
+        }
+        catch (const std::invalid_argument &)
+        {
+            threw = true;
+        }
+        pcl::PointCloud<pcl::PointXYZ> empty_in, g, o;
+        std::vector<SegmentationLabel> l;
+        segmenter.segment(empty_in, l, g, o);
+        std::vector<ClusteringLabel> cl;
+        clusterer.cluster(empty_in, cl);
+        if (!threw || !l.empty() || !cl.empty())
+            return 3;
+        std::printf("ok %zu points, %zu ground, %zu obstacle, %d clusters\n", n, ground_points.size(),
+                    obstacle_points.size(),
+                    cluster_labels.empty() ? 0 : 1 + *std::max_element(cluster_labels.begin(), cluster_labels.end()));
+    }
+    catch (const std::exception &e)
+    {
+        std::cerr << "exception: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}
