@@ -201,6 +201,12 @@ def main():
         return float(t.item())
 
     pkg = ge.load_package()
+    from lidar_processing_b200 import sharding
+
+    # the job is world x (workload) frames, split into contiguous blocks, one per rank; frame id i
+    # uses workload frame i mod len(workload), so every rank holds the same amount of work (weak scaling)
+    mine = sharding.shard_frames(world * len(frames), rank, world)
+    frames = [frames[i % len(frames)] for i in mine]
     nf = len(frames)
     total_pts = int(sum(f.shape[0] for f in frames))
     padded = int(sum((f.shape[0] + 31) & ~31 for f in frames))

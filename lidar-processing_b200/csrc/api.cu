@@ -70,15 +70,15 @@ struct lidar_b200_ctx
     PinBuf<uint32_t> h_meta;   // off, cnt, toff, tcap, n_ground, n_obstacle, n_clusters : 7 * cap_frames
 
     // device arenas (per point)
-    DevBuf<float4> d_pts, d_spts, d_obs, d_nodes, d_cpts;
+    DevBuf<float4> d_pts, d_spts, d_obs, d_nodes, d_cpts, d_rpts;
     DevBuf<uint32_t> d_key_a, d_key_b, d_val_a, d_val_b, d_labels, d_gidx, d_oidx, d_slot_of, d_pos_of, d_parent,
-        d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label, d_comp_size;
+        d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label, d_comp_size, d_pslot;
     DevBuf<int32_t> d_clabels;
     DevBuf<unsigned long long> d_spill;
     DevBuf<uint8_t> d_flags, d_seed_valid;
     // per table slot
     DevBuf<unsigned long long> d_tkeys;
-    DevBuf<uint32_t> d_tcount;
+    DevBuf<uint32_t> d_tcount, d_tlive;
     DevBuf<uint4> d_cells;
     // per frame
     DevBuf<uint32_t> d_meta; // off, cnt, toff, tcap, n_ground, n_obstacle, n_clusters, cursor : 8 * cap_frames
@@ -173,11 +173,11 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
         for (auto &h : c->h_u32)
             rc |= pin_alloc(c, h, n);
         rc |= dev_alloc(c, c->d_pts, n) | dev_alloc(c, c->d_spts, n) | dev_alloc(c, c->d_obs, n) |
-              dev_alloc(c, c->d_nodes, n) | dev_alloc(c, c->d_cpts, n);
+              dev_alloc(c, c->d_nodes, n) | dev_alloc(c, c->d_cpts, n) | dev_alloc(c, c->d_rpts, n);
         DevBuf<uint32_t> *u32s[] = {&c->d_key_a,  &c->d_key_b,  &c->d_val_a,      &c->d_val_b, &c->d_labels,
                                     &c->d_gidx,   &c->d_oidx,   &c->d_slot_of,    &c->d_pos_of, &c->d_parent,
                                     &c->d_root,   &c->d_rank,   &c->d_gepos,      &c->d_lepos, &c->d_state,
-                                    &c->d_seed_of, &c->d_member_pos, &c->d_queue, &c->d_seed_label, &c->d_comp_size};
+                                    &c->d_seed_of, &c->d_member_pos, &c->d_queue, &c->d_seed_label, &c->d_comp_size, &c->d_pslot};
         for (auto *b : u32s)
             rc |= dev_alloc(c, *b, n);
         rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_flags, n) |
@@ -197,7 +197,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
     if (table > c->cap_table)
     {
         LB_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (dev_alloc(c, c->d_tkeys, table) || dev_alloc(c, c->d_tcount, table) || dev_alloc(c, c->d_cells, table))
+        if (dev_alloc(c, c->d_tkeys, table) || dev_alloc(c, c->d_tcount, table) || dev_alloc(c, c->d_tlive, table) || dev_alloc(c, c->d_cells, table))
             return LIDAR_B200_ERR_CUDA;
         c->cap_table = static_cast<uint32_t>(table);
     }
@@ -410,7 +410,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
         cc_compress_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
         cc_link_kernel<false><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p);
     }
-    cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_key_a.p, c->d_val_a.p, c->d_comp_size.p);
+    cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_pos_of.p, c->d_key_a.p, c->d_val_a.p, c->d_comp_size.p);
     c->launches += 9;
     mark(c, 5);
     LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
@@ -426,18 +426,20 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     c->launches += kd_build_launch(s, pts, bv, max_m, c->d_nodes.p, c->d_gepos.p, c->d_lepos.p, c->d_rank.p);
 
     mark(c, 7);
-    replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_state.p,
-                                          c->d_seed_of.p, c->d_member_pos.p, c->m_cursor());
+    replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_slot_of.p,
+                                          c->d_rpts.p, c->d_seed_of.p, c->d_member_pos.p, c->d_pslot.p, c->m_cursor());
+    replay_live_init_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_cells.p, c->d_tlive.p);
     const uint32_t claims = (max_m + 31u) / 32u;
     // persistent grid: a fixed number of CTAs per SM walks the flat (frame, claim) work list
     const uint32_t rctas = grid_x(claims * F, kReplayWarps, c->sm_count * c->replay_ctas_per_sm);
-    replay_kernel<<<rctas, kReplayWarps * 32, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx,
-                                                      c->d_member_pos.p, c->d_comp_size.p, c->d_state.p, c->d_seed_of.p,
-                                                      c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->m_cursor(), claims);
+    replay_kernel<<<rctas, kReplayWarps * 32, 0, s>>>(c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx,
+                                                      c->d_member_pos.p, c->d_comp_size.p, c->d_pslot.p, c->d_tlive.p,
+                                                      c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
+                                                      c->m_cursor(), claims);
     mark(c, 8);
     label_compact_kernel<<<F, 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
                                             c->d_clabels.p, c->m_nc());
-    c->launches += 3;
+    c->launches += 4;
     mark(c, 9);
     LB_CUDA(c, cudaGetLastError());
     return 0;
@@ -526,7 +528,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     void *dev[] = {c->d_pts.p,      c->d_spts.p,   c->d_obs.p,       c->d_nodes.p,  c->d_cpts.p,       c->d_key_a.p,
                    c->d_key_b.p,    c->d_val_a.p,  c->d_val_b.p,     c->d_labels.p, c->d_gidx.p,       c->d_oidx.p,
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
-                   c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p,
+                   c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
                    c->d_cells.p,    c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
     for (void *p : dev)

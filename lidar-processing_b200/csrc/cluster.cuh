@@ -214,7 +214,7 @@ grid_fill_kernel(const float4 *__restrict__ pts, BatchView bv, TableView tv, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// union-find over point indices; roots are always the smallest index of their tree
+// lock-free union-find; roots are always the smallest id of their tree
 LB_D uint32_t uf_find(uint32_t *parent, uint32_t x)
 {
     uint32_t p = __ldcg(&parent[x]);
@@ -262,15 +262,19 @@ cc_init_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict
     }
 }
 
-// One warp per cell-ordered point. Every unordered pair of points in the same or in adjacent cells
-// is visited exactly once: a point scans its own cell (partners with a smaller index only) and the
-// 13 neighbour cells that follow it in (dz, dy, dx) lexicographic order.
+// Union-find runs in CELL-ORDER space: parent[pos], roots are the smallest pos of their tree.
+//
+// One warp per point (cell order, so neighbouring warps share cells and cache lines). Every
+// unordered pair of points in the same or in adjacent cells is visited exactly once: a point pairs
+// with the points of its own cell that precede it and with the 13 neighbour cells that follow its
+// cell in (dz, dy, dx) lexicographic order.
 //   kSample = true : Afforest-style sampling pass — link to the first two partners found, which
 //                    already merges most of every component;
-//   kSample = false: full pass. parent[] was flattened in between, so for nearly every pair both
-//                    (L1-cached) parent reads agree and the pair is skipped without touching the
-//                    union-find. Stale cached parents are safe for that test: a node reachable
-//                    through old pointers stays in the same set forever.
+//   kSample = false: full pass. parent[] was flattened in between, so for nearly every candidate the
+//                    (coalesced, L1-cached) parent read equals the point's own and the pair is
+//                    skipped before the candidate's coordinates are even loaded. Stale cached
+//                    parents are safe for that test: a node reachable through old pointers stays in
+//                    the same set forever.
 template <bool kSample>
 __global__ void __launch_bounds__(256)
 cc_link_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
@@ -285,24 +289,24 @@ cc_link_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, cons
     uint32_t *par = parent + off;
     const uint32_t lane = lane_id();
     const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    // lane l < 14 -> neighbour offset number 13 + l of the 27 (index 13 is the cell itself)
+    // lane l < 14 -> neighbour offset number 13 + l of the 27 (number 13 is the cell itself)
     const uint32_t nb = 13u + lane;
     const int ox = static_cast<int>(nb % 3u) - 1, oy = static_cast<int>((nb / 3u) % 3u) - 1, oz = static_cast<int>(nb / 9u) - 1;
     for (uint32_t pos = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pos < m; pos += warps_per_grid)
     {
         const float4 pj = cp[pos];
-        const uint32_t ij = __float_as_uint(pj.w);
         int cx, cy, cz;
         cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
         uint32_t start = 0u, count = 0u;
         if (lane < 14u)
             cell_lookup(tab, mask, cell_key(cx + ox, cy + oy, cz + oz), &start, &count);
-        const uint32_t own_end = __shfl_sync(kFullMask, start + count, 0); // candidates below this are in pj's cell
-        const uint32_t own_start = __shfl_sync(kFullMask, start, 0);
+        // own cell: only the points that precede pos (a cell is a contiguous run of pos)
+        if (lane == 0u)
+            count = pos - start;
         const uint32_t incl = warp_inclusive_scan(count);
         const uint32_t excl = incl - count;
         const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-        uint32_t ri = par[ij];
+        uint32_t ri = par[pos];
         uint32_t linked = 0u;
         for (uint32_t base = 0; base < total; base += 32u)
         {
@@ -321,42 +325,41 @@ cc_link_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, cons
             const uint32_t c = min(lo, 13u);
             const uint32_t cstart = __shfl_sync(kFullMask, start, c);
             const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
-            bool hit = false;
-            uint32_t ik = 0u;
-            if (q < total)
-            {
-                const uint32_t cpos = cstart + (q - cexcl);
-                const float4 cand = cp[cpos];
-                ik = __float_as_uint(cand.w);
-                const bool own = cpos >= own_start && cpos < own_end && c == 0u;
-                hit = (!own || ik < ij) &&
-                      dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared;
-            }
+            const bool valid = q < total;
+            const uint32_t cpos = cstart + (q - cexcl);
             if (kSample)
             {
-                // link the first two partners only
+                bool hit = false;
+                if (valid)
+                {
+                    const float4 cand = cp[cpos];
+                    hit = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared;
+                }
                 const uint32_t bh = __ballot_sync(kFullMask, hit);
-                const uint32_t before = linked + __popc(bh & lanemask_lt());
-                if (hit && before < 2u)
-                    uf_unite(par, ij, ik);
+                if (hit && linked + __popc(bh & lanemask_lt()) < 2u)
+                    uf_unite(par, pos, cpos);
                 linked += __popc(bh);
                 if (linked >= 2u)
                     break;
             }
-            else if (hit)
+            else if (valid)
             {
-                const uint32_t pk = par[ik];
+                const uint32_t pk = par[cpos];
                 if (pk != ri)
                 {
-                    uf_unite(par, ij, ik);
-                    ri = __ldcg(&par[ij]);
+                    const float4 cand = cp[cpos];
+                    if (dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared)
+                    {
+                        uf_unite(par, pos, cpos);
+                        ri = __ldcg(&par[pos]);
+                    }
                 }
             }
         }
     }
 }
 
-// parent[i] = root(i), in place
+// parent[pos] = root(pos), in place
 __global__ void __launch_bounds__(256) cc_compress_kernel(BatchView bv, uint32_t *__restrict__ parent)
 {
     const uint32_t f = blockIdx.y;
@@ -375,17 +378,18 @@ __global__ void __launch_bounds__(256) cc_compress_kernel(BatchView bv, uint32_t
     }
 }
 
-// keys[i] = root of i (component id = smallest member index), vals[i] = i; comp_size[root] = members
+// For point index i: keys[i] = component id (root pos) of i, vals[i] = i; comp_size[root pos] = members.
+// A stable sort by key then lists every component's members in ascending index order.
 __global__ void __launch_bounds__(256)
-cc_flatten_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                  uint32_t *__restrict__ comp_size)
+cc_flatten_kernel(BatchView bv, const uint32_t *__restrict__ parent, const uint32_t *__restrict__ pos_of,
+                  uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ comp_size)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
-        uint32_t x = i;
+        uint32_t x = pos_of[off + i];
         uint32_t p = __ldcg(&parent[off + x]);
         while (p != x)
         {
@@ -401,12 +405,15 @@ cc_flatten_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restr
     }
 }
 
-// state[pos] = rank << 2 (flags clear); seed_of[pos] = unset; member_pos[t] = pos of the t-th member
+// Replay working set, in cell order: rpts[pos] = {x, y, z, bits(state)} with state = rank << 2 | flags,
+// so one 16-byte load brings a candidate's coordinates, its k-d pre-order rank and its removed /
+// queued flags. seed_of[pos] = unset; member_pos[t] = pos of the t-th member; pslot[pos] = hash slot
+// of the point's cell; tlive[slot] = points of the cell that are not removed yet.
 __global__ void __launch_bounds__(256)
 replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t *__restrict__ rank_of_point,
                    const uint32_t *__restrict__ member_idx, const uint32_t *__restrict__ pos_of,
-                   uint32_t *__restrict__ state, uint32_t *__restrict__ seed_of, uint32_t *__restrict__ member_pos,
-                   uint32_t *__restrict__ cursor)
+                   const uint32_t *__restrict__ slot_of, float4 *__restrict__ rpts, uint32_t *__restrict__ seed_of,
+                   uint32_t *__restrict__ member_pos, uint32_t *__restrict__ pslot, uint32_t *__restrict__ cursor)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
@@ -415,28 +422,92 @@ replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t
         cursor[threadIdx.x] = 0u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
-        const uint32_t idx = __float_as_uint(cpts[off + i].w);
-        state[off + i] = rank_of_point[off + idx] << 2;
+        const float4 p = cpts[off + i];
+        const uint32_t idx = __float_as_uint(p.w);
+        rpts[off + i] = make_float4(p.x, p.y, p.z, __uint_as_float(rank_of_point[off + idx] << 2));
         seed_of[off + i] = kSeedUnset;
+        pslot[off + i] = slot_of[off + idx];
         member_pos[off + i] = pos_of[off + member_idx[off + i]];
     }
 }
 
+// tlive[slot] = cells[slot].count
+__global__ void __launch_bounds__(256)
+replay_live_init_kernel(BatchView bv, TableView tv, const uint4 *__restrict__ cells, uint32_t *__restrict__ tlive)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t cap = table_mask(bv.cnt[f], tv.tcap[f]) + 1u;
+    const uint32_t toff = tv.toff[f];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x)
+        tlive[toff + s] = cells[toff + s].w;
+}
+
 constexpr int kReplayWarps = 4;
-constexpr uint32_t kPushCap = 256u;   // per-warp shared push buffer; larger expansions spill to global
+constexpr uint32_t kPushCap = 256u;     // per-warp shared push buffer; larger expansions spill to global
 constexpr uint32_t kBigComponent = 96u; // components with at least this many members are replayed first
+
+// like cell_lookup, also returning the slot (0xFFFFFFFF when the cell does not exist)
+LB_D uint32_t cell_lookup_slot(const uint4 *__restrict__ cells, uint32_t mask, uint64_t key, uint32_t *start,
+                               uint32_t *count)
+{
+    uint32_t slot = hash_cell(key) & mask;
+    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
+    while (true)
+    {
+        const uint4 c = __ldg(&cells[slot]);
+        if (c.x == klo && c.y == khi)
+        {
+            *start = c.z;
+            *count = c.w;
+            return slot;
+        }
+        if (c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu)
+        {
+            *start = 0u;
+            *count = 0u;
+            return 0xFFFFFFFFu;
+        }
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// Replay-time lookup: cells[slot].w carries a "dead" flag in its top bit, set by the warp that removed
+// the cell's last live point (a dead cell cannot contribute, clustering.cpp:94-97). Read through L2
+// (other warps set flags concurrently); a stale "alive" only costs a wasted scan.
+LB_D void cell_lookup_live(const uint4 *cells, uint32_t mask, uint64_t key, uint32_t *start, uint32_t *count)
+{
+    uint32_t slot = hash_cell(key) & mask;
+    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
+    while (true)
+    {
+        const uint4 c = __ldcg(&cells[slot]);
+        if (c.x == klo && c.y == khi)
+        {
+            *start = c.z;
+            *count = (c.w & 0x80000000u) ? 0u : c.w;
+            return;
+        }
+        if (c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu)
+        {
+            *start = 0u;
+            *count = 0u;
+            return;
+        }
+        slot = (slot + 1u) & mask;
+    }
+}
 
 // Persistent warps over a flat work list of (frame, 32 member slots) claims, walked twice: the first
 // walk replays only the big components — their BFS chains are the critical path, so they must start
 // at time zero — the second walk replays everything else around them. A warp replays every
-// component whose first member (= root = smallest index) falls into its claim.
+// component whose first member falls into its claim.
 __global__ void __launch_bounds__(kReplayWarps * 32)
-replay_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
+replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *__restrict__ cells,
               CluParams prm, const uint32_t *__restrict__ member_root, const uint32_t *__restrict__ member_idx,
               const uint32_t *__restrict__ member_pos, const uint32_t *__restrict__ comp_size,
-              uint32_t *__restrict__ state, uint32_t *__restrict__ seed_of, uint32_t *__restrict__ queue,
-              unsigned long long *__restrict__ push_spill, uint8_t *__restrict__ seed_valid,
-              uint32_t *__restrict__ cursor, uint32_t claims_per_frame)
+              const uint32_t *__restrict__ pslot_all, uint32_t *__restrict__ tlive_all, uint32_t *__restrict__ seed_of,
+              uint32_t *__restrict__ queue, unsigned long long *__restrict__ push_spill,
+              uint8_t *__restrict__ seed_valid, uint32_t *__restrict__ cursor, uint32_t claims_per_frame)
 {
     __shared__ unsigned long long pbuf_all[kReplayWarps][kPushCap];
     const uint32_t lane = lane_id();
@@ -460,9 +531,13 @@ replay_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const
             continue;
         const uint32_t off = bv.off[f];
         const uint32_t mask = table_mask(m, tv.tcap[f]);
-        const uint4 *tab = cells + tv.toff[f];
-        const float4 *cp = cpts + off;
-        uint32_t *st = state + off;
+        uint4 *tab = cells + tv.toff[f];
+        uint32_t *tabw = reinterpret_cast<uint32_t *>(tab) + 3; // count/flag word of a slot
+        uint32_t *tlive = tlive_all + tv.toff[f];
+        float4 *rp = rpts_all + off;
+        // the state word of a point is the .w lane of its float4
+        uint32_t *stw = reinterpret_cast<uint32_t *>(rp) + 3;
+        const uint32_t *pslot = pslot_all + off;
         uint32_t *so = seed_of + off;
         uint32_t *qu = queue + off;
         unsigned long long *spill = push_spill + off;
@@ -471,9 +546,9 @@ replay_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const
         const uint32_t *mpos = member_pos + off;
 
         const uint32_t tt = t0 + lane;
-        bool is_start = tt < m && mroot[tt] == midx[tt];
+        bool is_start = tt < m && (tt == 0u || mroot[tt] != mroot[tt - 1u]);
         if (is_start)
-            is_start = (comp_size[off + midx[tt]] >= kBigComponent) == (phase == 0u);
+            is_start = (comp_size[off + mroot[tt]] >= kBigComponent) == (phase == 0u);
         uint32_t starts = __ballot_sync(kFullMask, is_start);
         while (starts)
         {
@@ -494,7 +569,7 @@ replay_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const
                     const bool in_comp = uu < m && mroot[uu] == root;
                     bool cand = false;
                     if (in_comp)
-                        cand = (st[mpos[uu]] & kStRemoved) == 0u;
+                        cand = (stw[4u * mpos[uu]] & kStRemoved) == 0u;
                     const uint32_t bc = __ballot_sync(kFullMask, cand);
                     const uint32_t bi = __ballot_sync(kFullMask, in_comp);
                     if (bc)
@@ -519,107 +594,196 @@ replay_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const
                 if (lane == 0)
                 {
                     qu[qbase] = seed_pos;
-                    st[seed_pos] |= kStQueued;
+                    stw[4u * seed_pos] |= kStQueued;
                 }
                 tail = 1u;
                 __syncwarp();
 
                 while (head < tail) // clustering.cpp:80-111
                 {
-                    const uint32_t j = qu[qbase + head];
-                    ++head;
-                    if (st[j] & kStRemoved)
+                    // Pop: look at the next 32 FIFO entries at once. Entries that are already removed
+                    // are no-ops in the reference (clustering.cpp:85-88) and nothing between here and
+                    // the first live entry can change any state, so jump straight to it.
+                    const uint32_t e_look = head + lane;
+                    uint32_t qj = 0u;
+                    float4 pe = make_float4(0.f, 0.f, 0.f, __uint_as_float(kStRemoved));
+                    if (e_look < tail)
+                    {
+                        qj = qu[qbase + e_look];
+                        pe = rp[qj];
+                    }
+                    const uint32_t alive = __ballot_sync(kFullMask, (__float_as_uint(pe.w) & kStRemoved) == 0u);
+                    if (alive == 0u)
+                    {
+                        head = min(tail, head + 32u);
                         continue;
-                    const float4 pj = cp[j];
+                    }
+                    const int first = __ffs(alive) - 1;
+                    head += static_cast<uint32_t>(first) + 1u;
+                    float4 pj;
+                    pj.x = __shfl_sync(kFullMask, pe.x, first);
+                    pj.y = __shfl_sync(kFullMask, pe.y, first);
+                    pj.z = __shfl_sync(kFullMask, pe.z, first);
+                    pj.w = 0.f;
+
                     int cx, cy, cz;
                     cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
                     uint32_t start = 0u, count = 0u;
                     if (lane < 27u)
-                        cell_lookup(tab, mask,
-                                    cell_key(cx + static_cast<int>(lane % 3u) - 1, cy + static_cast<int>((lane / 3u) % 3u) - 1,
-                                             cz + static_cast<int>(lane / 9u) - 1),
-                                    &start, &count);
+                    {
+                        cell_lookup_live(tab, mask,
+                                         cell_key(cx + static_cast<int>(lane % 3u) - 1,
+                                                  cy + static_cast<int>((lane / 3u) % 3u) - 1,
+                                                  cz + static_cast<int>(lane / 9u) - 1),
+                                         &start, &count);
+                    }
                     const uint32_t incl = warp_inclusive_scan(count);
                     const uint32_t excl = incl - count;
                     const uint32_t total = __shfl_sync(kFullMask, incl, 31);
                     uint32_t np = 0u;
                     bool spilled = false;
-                    for (uint32_t base = 0; base < total; base += 32u)
+                    for (uint32_t base = 0; base < total; base += 64u)
                     {
-                        const uint32_t q = base + lane;
-                        uint32_t lo = 0u, hi = 26u;
+                        // two batches of 32 candidates per trip: both loads are in flight together
+                        uint32_t pos2[2];
+                        float4 cand2[2];
+                        bool valid2[2];
 #pragma unroll
-                        for (int it = 0; it < 5; ++it)
+                        for (int h = 0; h < 2; ++h)
                         {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            const uint32_t v = __shfl_sync(kFullMask, incl, mid);
-                            if (v > q)
-                                hi = mid;
-                            else
-                                lo = mid + 1u;
-                        }
-                        const uint32_t c = min(lo, 26u);
-                        const uint32_t cstart = __shfl_sync(kFullMask, start, c);
-                        const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
-                        bool live = false, push = false;
-                        uint32_t pos = 0u, s = 0u;
-                        if (q < total)
-                        {
-                            pos = cstart + (q - cexcl);
-                            const float4 cand = cp[pos];
-                            s = st[pos];
-                            // KDTree::dist_sqr(target, node) (kdtree.hpp:145-163), inclusive test (kdtree.hpp:314)
-                            const float d2 = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z);
-                            live = d2 <= prm.distance_squared && (s & kStRemoved) == 0u;
-                            if (live)
+                            const uint32_t q = base + 32u * h + lane;
+                            uint32_t lo = 0u, hi = 26u;
+#pragma unroll
+                            for (int it = 0; it < 5; ++it)
                             {
-                                so[pos] = seed_idx; // labels[k] = label (clustering.cpp:99)
-                                if (d2 <= prm.inner_threshold)
-                                    st[pos] = s | kStRemoved; // clustering.cpp:102-105
-                                else if ((s & kStQueued) == 0u)
+                                const uint32_t mid = (lo + hi) >> 1;
+                                const uint32_t v = __shfl_sync(kFullMask, incl, mid);
+                                if (v > q)
+                                    hi = mid;
+                                else
+                                    lo = mid + 1u;
+                            }
+                            const uint32_t c = min(lo, 26u);
+                            const uint32_t cstart = __shfl_sync(kFullMask, start, c);
+                            const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
+                            valid2[h] = q < total;
+                            pos2[h] = cstart + (q - cexcl);
+                            cand2[h] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kStRemoved));
+                            if (valid2[h])
+                                cand2[h] = rp[pos2[h]];
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                        {
+                            if (h == 1 && base + 32u >= total)
+                                break;
+                            const uint32_t pos = pos2[h];
+                            const float4 cand = cand2[h];
+                            const uint32_t sw = __float_as_uint(cand.w);
+                            bool live = false, push = false, removed_now = false;
+                            if (valid2[h] && (sw & kStRemoved) == 0u) // removed points are skipped (clustering.cpp:94-97)
+                            {
+                                // KDTree::dist_sqr(target, node) (kdtree.hpp:145-163), inclusive test (kdtree.hpp:314)
+                                const float d2 = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z);
+                                live = d2 <= prm.distance_squared;
+                                if (live)
                                 {
-                                    st[pos] = s | kStQueued; // clustering.cpp:106-109 (first push only)
-                                    push = true;
+                                    so[pos] = seed_idx; // labels[k] = label (clustering.cpp:99)
+                                    if (d2 <= prm.inner_threshold)
+                                    {
+                                        stw[4u * pos] = sw | kStRemoved; // clustering.cpp:102-105
+                                        removed_now = true;
+                                    }
+                                    else if ((sw & kStQueued) == 0u)
+                                    {
+                                        stw[4u * pos] = sw | kStQueued; // clustering.cpp:106-109 (first push only)
+                                        push = true;
+                                    }
                                 }
                             }
-                        }
-                        touched += __popc(__ballot_sync(kFullMask, live)); // indices_.push_back (with multiplicity)
-                        const uint32_t bp = __ballot_sync(kFullMask, push);
-                        const uint32_t nadd = __popc(bp);
-                        if (nadd)
-                        {
-                            if (!spilled && np + nadd > kPushCap)
+                            touched += __popc(__ballot_sync(kFullMask, live)); // indices_.push_back (with multiplicity)
+                            if (__any_sync(kFullMask, removed_now))
                             {
-                                for (uint32_t e = lane; e < np; e += 32u)
-                                    spill[qbase + tail + e] = pbuf[e];
-                                spilled = true;
-                                __syncwarp();
+                                // one atomic per cell: candidates arrive cell by cell, so equal slots are neighbours.
+                                // The warp that removes a cell's last live point flags the cell as dead.
+                                const uint32_t sl = removed_now ? pslot[pos] : 0xFFFFFFFFu;
+                                const uint32_t peers = __match_any_sync(kFullMask, sl);
+                                if (removed_now && (peers & lt) == 0u)
+                                {
+                                    const uint32_t k = static_cast<uint32_t>(__popc(peers));
+                                    if (atomicSub(&tlive[sl], k) == k)
+                                        atomicOr(&tabw[4u * sl], 0x80000000u);
+                                }
                             }
-                            if (push)
+                            const uint32_t bp = __ballot_sync(kFullMask, push);
+                            const uint32_t nadd = __popc(bp);
+                            if (nadd)
                             {
-                                const unsigned long long ent =
-                                    (static_cast<unsigned long long>(s >> 2) << 32) | static_cast<unsigned long long>(pos);
-                                const uint32_t e = np + __popc(bp & lt);
-                                if (spilled)
-                                    spill[qbase + tail + e] = ent;
-                                else
-                                    pbuf[e] = ent;
+                                if (!spilled && np + nadd > kPushCap)
+                                {
+                                    for (uint32_t e = lane; e < np; e += 32u)
+                                        spill[qbase + tail + e] = pbuf[e];
+                                    spilled = true;
+                                    __syncwarp();
+                                }
+                                if (push)
+                                {
+                                    const unsigned long long ent = (static_cast<unsigned long long>(sw >> 2) << 32) |
+                                                                   static_cast<unsigned long long>(pos);
+                                    const uint32_t e = np + __popc(bp & lt);
+                                    if (spilled)
+                                        spill[qbase + tail + e] = ent;
+                                    else
+                                        pbuf[e] = ent;
+                                }
+                                np += nadd;
                             }
-                            np += nadd;
                         }
                     }
                     __syncwarp();
                     // the FIFO receives this expansion's pushes in ascending k-d pre-order rank
                     if (np)
                     {
-                        const unsigned long long *src = spilled ? (spill + qbase + tail) : pbuf;
-                        for (uint32_t e = lane; e < np; e += 32u)
+                        if (!spilled && np > 32u)
                         {
-                            const unsigned long long mine = src[e];
-                            uint32_t dest = 0u;
-                            for (uint32_t x = 0; x < np; ++x)
-                                dest += (src[x] < mine) ? 1u : 0u;
-                            qu[qbase + tail + dest] = static_cast<uint32_t>(mine);
+                            // bitonic sort in the warp's shared buffer
+                            uint32_t n2 = 64u;
+                            while (n2 < np)
+                                n2 <<= 1;
+                            for (uint32_t e = np + lane; e < n2; e += 32u)
+                                pbuf[e] = 0xFFFFFFFFFFFFFFFFull;
+                            __syncwarp();
+                            for (uint32_t kk = 2u; kk <= n2; kk <<= 1)
+                                for (uint32_t jj = kk >> 1; jj > 0u; jj >>= 1)
+                                {
+                                    for (uint32_t t = lane; t < (n2 >> 1); t += 32u)
+                                    {
+                                        const uint32_t i0 = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u));
+                                        const uint32_t i1 = i0 | jj;
+                                        const unsigned long long a = pbuf[i0], b = pbuf[i1];
+                                        const bool asc = (i0 & kk) == 0u;
+                                        if ((a > b) == asc)
+                                        {
+                                            pbuf[i0] = b;
+                                            pbuf[i1] = a;
+                                        }
+                                    }
+                                    __syncwarp();
+                                }
+                            for (uint32_t e = lane; e < np; e += 32u)
+                                qu[qbase + tail + e] = static_cast<uint32_t>(pbuf[e]);
+                        }
+                        else
+                        {
+                            const unsigned long long *src = spilled ? (spill + qbase + tail) : pbuf;
+                            for (uint32_t e = lane; e < np; e += 32u)
+                            {
+                                const unsigned long long mine = src[e];
+                                uint32_t dest = 0u;
+                                for (uint32_t x = 0; x < np; ++x)
+                                    dest += (src[x] < mine) ? 1u : 0u;
+                                qu[qbase + tail + dest] = static_cast<uint32_t>(mine);
+                            }
                         }
                         tail += np;
                     }

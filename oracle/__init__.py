@@ -49,12 +49,12 @@ class CluCfg(C.Structure):
 def build(force: bool = False) -> None:
     """Compile liboracle.so, and oracle/_ref when /root/reference is present (else keep prebuilt)."""
     lib = HERE / "liboracle.so"
-    srcs = [HERE / "oracle.cpp", HERE / "oracle.h", HERE / "ref_wrap.cpp", HERE / "Makefile"]
-    newest = max(s.stat().st_mtime for s in srcs)
-    need = force or not lib.exists() or lib.stat().st_mtime < newest
+    lib_deps = [HERE / "oracle.cpp", HERE / "oracle.h", HERE / "Makefile"]
     ref = HERE / "_ref" / "libref_cluster.so"
+    ref_deps = lib_deps + [HERE / "ref_wrap.cpp"]
+    need = force or not lib.exists() or lib.stat().st_mtime < max(s.stat().st_mtime for s in lib_deps)
     have_reference = Path("/root/reference/src/clustering.cpp").exists()
-    if have_reference and (force or not ref.exists() or ref.stat().st_mtime < newest):
+    if have_reference and (force or not ref.exists() or ref.stat().st_mtime < max(s.stat().st_mtime for s in ref_deps)):
         need = True
     if need:
         subprocess.run(["make", "-s", "-C", str(HERE), "all"], check=True)
