@@ -164,10 +164,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="use only the first N frames of the workload (debug)")
+    ap.add_argument("--frame-offset", type=int, default=0, help="skip the first N frames (debug / profiling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
-    frames, workload = load_workload(args.frames or None)
+    frames, workload = load_workload(None)
+    if args.frame_offset or args.frames:
+        frames = frames[args.frame_offset:][: (args.frames or None)]
     if args.impl == "reference":
         run_reference(args, frames, workload)
         return

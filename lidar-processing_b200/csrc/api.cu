@@ -406,12 +406,13 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     cc_init_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_comp_size.p);
     {
         const dim3 gl(grid_x(max_m, 32u, 2368u), F); // each warp walks several points
-        cc_link_kernel<true><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p);
+        cc_link_kernel<true><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p, c->d_tlive.p);
         cc_compress_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
-        cc_link_kernel<false><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p);
+        cc_cell_parent_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_cells.p, c->d_parent.p, c->d_tlive.p); // d_tlive doubles as cell_parent
+        cc_link_kernel<false><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p, c->d_tlive.p);
     }
     cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_pos_of.p, c->d_key_a.p, c->d_val_a.p, c->d_comp_size.p);
-    c->launches += 9;
+    c->launches += 10;
     mark(c, 5);
     LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
     int rl = 0;

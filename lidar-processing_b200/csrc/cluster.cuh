@@ -108,6 +108,31 @@ LB_D void cell_lookup(const uint4 *__restrict__ cells, uint32_t mask, uint64_t k
     }
 }
 
+// like cell_lookup, also returning the slot (0xFFFFFFFF when the cell does not exist)
+LB_D uint32_t cell_lookup_slot(const uint4 *__restrict__ cells, uint32_t mask, uint64_t key, uint32_t *start,
+                               uint32_t *count)
+{
+    uint32_t slot = hash_cell(key) & mask;
+    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
+    while (true)
+    {
+        const uint4 c = __ldg(&cells[slot]);
+        if (c.x == klo && c.y == khi)
+        {
+            *start = c.z;
+            *count = c.w;
+            return slot;
+        }
+        if (c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu)
+        {
+            *start = 0u;
+            *count = 0u;
+            return 0xFFFFFFFFu;
+        }
+        slot = (slot + 1u) & mask;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 grid_clear_kernel(BatchView bv, TableView tv, unsigned long long *__restrict__ tkeys, uint32_t *__restrict__ tcount)
@@ -278,35 +303,44 @@ cc_init_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict
 template <bool kSample>
 __global__ void __launch_bounds__(256)
 cc_link_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
-               CluParams prm, uint32_t *__restrict__ parent)
+               CluParams prm, uint32_t *__restrict__ parent, const uint32_t *__restrict__ cell_parent)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
     const uint32_t mask = table_mask(m, tv.tcap[f]);
     const uint4 *tab = cells + tv.toff[f];
+    const uint32_t *cpar = cell_parent + tv.toff[f];
     const float4 *cp = cpts + off;
     uint32_t *par = parent + off;
     const uint32_t lane = lane_id();
     const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    // lane l < 14 -> neighbour offset number 13 + l of the 27 (number 13 is the cell itself)
-    const uint32_t nb = 13u + lane;
+    // Full pass: lane l < 14 -> neighbour offset number 13 + l of the 27 (number 13 is the cell itself).
+    // Sampling pass: only the cell itself and its +x, +y, +z face neighbours (numbers 13, 14, 16, 22).
+    const uint32_t n_lookups = kSample ? 4u : 14u;
+    const uint32_t nb = kSample ? (lane == 0u ? 13u : (lane == 1u ? 14u : (lane == 2u ? 16u : 22u))) : 13u + lane;
     const int ox = static_cast<int>(nb % 3u) - 1, oy = static_cast<int>((nb / 3u) % 3u) - 1, oz = static_cast<int>(nb / 9u) - 1;
     for (uint32_t pos = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pos < m; pos += warps_per_grid)
     {
         const float4 pj = cp[pos];
+        uint32_t ri = par[pos];
         int cx, cy, cz;
         cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
         uint32_t start = 0u, count = 0u;
-        if (lane < 14u)
-            cell_lookup(tab, mask, cell_key(cx + ox, cy + oy, cz + oz), &start, &count);
-        // own cell: only the points that precede pos (a cell is a contiguous run of pos)
-        if (lane == 0u)
-            count = pos - start;
+        if (lane < n_lookups)
+        {
+            const uint32_t slot = cell_lookup_slot(tab, mask, cell_key(cx + ox, cy + oy, cz + oz), &start, &count);
+            // own cell: only the points that precede pos (a cell is a contiguous run of pos)
+            if (lane == 0u)
+                count = pos - start;
+            // a cell whose points all carried parent p when parent[] was flattened, p being this
+            // point's parent too, lies in this point's set already: skip it without reading a point
+            if (!kSample && count != 0u && cpar[slot] == ri)
+                count = 0u;
+        }
         const uint32_t incl = warp_inclusive_scan(count);
         const uint32_t excl = incl - count;
         const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-        uint32_t ri = par[pos];
         uint32_t linked = 0u;
         for (uint32_t base = 0; base < total; base += 32u)
         {
@@ -378,6 +412,34 @@ __global__ void __launch_bounds__(256) cc_compress_kernel(BatchView bv, uint32_t
     }
 }
 
+// cell_parent[slot] = the common parent of all points of the cell, or 0xFFFFFFFF when they differ
+// (or the slot is empty). Run right after cc_compress_kernel. One thread per slot; cells are short.
+__global__ void __launch_bounds__(256)
+cc_cell_parent_kernel(BatchView bv, TableView tv, const uint4 *__restrict__ cells, const uint32_t *__restrict__ parent,
+                      uint32_t *__restrict__ cell_parent)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t cap = table_mask(bv.cnt[f], tv.tcap[f]) + 1u;
+    const uint32_t toff = tv.toff[f];
+    const uint32_t off = bv.off[f];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x)
+    {
+        const uint4 c = cells[toff + s];
+        uint32_t common = 0xFFFFFFFFu;
+        if (c.w != 0u && !(c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu))
+        {
+            common = parent[off + c.z];
+            for (uint32_t k = 1; k < c.w; ++k)
+                if (parent[off + c.z + k] != common)
+                {
+                    common = 0xFFFFFFFFu;
+                    break;
+                }
+        }
+        cell_parent[toff + s] = common;
+    }
+}
+
 // For point index i: keys[i] = component id (root pos) of i, vals[i] = i; comp_size[root pos] = members.
 // A stable sort by key then lists every component's members in ascending index order.
 __global__ void __launch_bounds__(256)
@@ -445,31 +507,7 @@ replay_live_init_kernel(BatchView bv, TableView tv, const uint4 *__restrict__ ce
 constexpr int kReplayWarps = 4;
 constexpr uint32_t kPushCap = 256u;     // per-warp shared push buffer; larger expansions spill to global
 constexpr uint32_t kBigComponent = 96u; // components with at least this many members are replayed first
-
-// like cell_lookup, also returning the slot (0xFFFFFFFF when the cell does not exist)
-LB_D uint32_t cell_lookup_slot(const uint4 *__restrict__ cells, uint32_t mask, uint64_t key, uint32_t *start,
-                               uint32_t *count)
-{
-    uint32_t slot = hash_cell(key) & mask;
-    const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
-    while (true)
-    {
-        const uint4 c = __ldg(&cells[slot]);
-        if (c.x == klo && c.y == khi)
-        {
-            *start = c.z;
-            *count = c.w;
-            return slot;
-        }
-        if (c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu)
-        {
-            *start = 0u;
-            *count = 0u;
-            return 0xFFFFFFFFu;
-        }
-        slot = (slot + 1u) & mask;
-    }
-}
+constexpr int kReplayUnroll = 4;        // candidate batches whose loads are issued together
 
 // Replay-time lookup: cells[slot].w carries a "dead" flag in its top bit, set by the warp that removed
 // the cell's last live point (a dead cell cannot contribute, clustering.cpp:94-97). Read through L2
@@ -642,14 +680,15 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
                     const uint32_t total = __shfl_sync(kFullMask, incl, 31);
                     uint32_t np = 0u;
                     bool spilled = false;
-                    for (uint32_t base = 0; base < total; base += 64u)
+                    uint32_t pend_slot = 0xFFFFFFFFu, pend_k = 0u, pend_old = 0u;
+                    for (uint32_t base = 0; base < total; base += 32u * kReplayUnroll)
                     {
-                        // two batches of 32 candidates per trip: both loads are in flight together
-                        uint32_t pos2[2];
-                        float4 cand2[2];
-                        bool valid2[2];
+                        // several batches of 32 candidates per trip: their loads are in flight together
+                        uint32_t pos2[kReplayUnroll];
+                        float4 cand2[kReplayUnroll];
+                        bool valid2[kReplayUnroll];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
+                        for (int h = 0; h < kReplayUnroll; ++h)
                         {
                             const uint32_t q = base + 32u * h + lane;
                             uint32_t lo = 0u, hi = 26u;
@@ -673,9 +712,9 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
                                 cand2[h] = rp[pos2[h]];
                         }
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
+                        for (int h = 0; h < kReplayUnroll; ++h)
                         {
-                            if (h == 1 && base + 32u >= total)
+                            if (h > 0 && base + 32u * h >= total)
                                 break;
                             const uint32_t pos = pos2[h];
                             const float4 cand = cand2[h];
@@ -708,11 +747,15 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
                                 // The warp that removes a cell's last live point flags the cell as dead.
                                 const uint32_t sl = removed_now ? pslot[pos] : 0xFFFFFFFFu;
                                 const uint32_t peers = __match_any_sync(kFullMask, sl);
+                                // resolve the previous batch's counter first: its round trip is over by now
+                                if (pend_slot != 0xFFFFFFFFu && pend_old == pend_k)
+                                    atomicOr(&tabw[4u * pend_slot], 0x80000000u);
+                                pend_slot = 0xFFFFFFFFu;
                                 if (removed_now && (peers & lt) == 0u)
                                 {
-                                    const uint32_t k = static_cast<uint32_t>(__popc(peers));
-                                    if (atomicSub(&tlive[sl], k) == k)
-                                        atomicOr(&tabw[4u * sl], 0x80000000u);
+                                    pend_k = static_cast<uint32_t>(__popc(peers));
+                                    pend_slot = sl;
+                                    pend_old = atomicSub(&tlive[sl], pend_k);
                                 }
                             }
                             const uint32_t bp = __ballot_sync(kFullMask, push);
@@ -740,6 +783,8 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
                             }
                         }
                     }
+                    if (pend_slot != 0xFFFFFFFFu && pend_old == pend_k)
+                        atomicOr(&tabw[4u * pend_slot], 0x80000000u);
                     __syncwarp();
                     // the FIFO receives this expansion's pushes in ascending k-d pre-order rank
                     if (np)
