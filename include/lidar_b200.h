@@ -1,7 +1,7 @@
 /* lidar_b200 — C ABI of the B200-native ground-segmentation + Fast-Euclidean-Clustering path.
  *
  * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. The C++ classes
- * lidar_processing::Segmenter / lidar_processing::Clusterer (lidar-processing_b200/include/
+ * lidar_processing::Segmenter / lidar_processing::Clusterer (lidar-processing_b200/dropin/
  * segmentation.hpp, clustering.hpp — same public interface as the reference headers) are thin shells
  * over these entry points; INTEGRATION.md shows the binding a maintainer of the reference adds.
  *
@@ -111,8 +111,44 @@ extern "C"
                                uint32_t *n_ground_out /* [n_frames] */, uint32_t *obstacle_idx_out /* [sum n] */,
                                uint32_t *n_obstacle_out /* [n_frames] */, int32_t *cluster_labels_out /* [sum n] */,
                                uint32_t *n_clusters_out /* [n_frames] */);
+    /* fetch split in two: _fetch_async enqueues the device -> host copies behind the kernels and returns;
+     * _wait blocks until the results are in the caller's arrays (lidar_b200_batch_fetch = both). The
+     * arrays must stay valid until _wait (or the next _stage on this context, which waits first). */
+    int lidar_b200_batch_fetch_async(lidar_b200_ctx *ctx, uint32_t *point_offset_out, uint32_t *seg_labels_out,
+                                     uint32_t *ground_idx_out, uint32_t *n_ground_out, uint32_t *obstacle_idx_out,
+                                     uint32_t *n_obstacle_out, int32_t *cluster_labels_out, uint32_t *n_clusters_out);
+    int lidar_b200_batch_wait(lidar_b200_ctx *ctx);
     /* waits for the stream; used by benchmarks that keep inputs and outputs resident in HBM */
     int lidar_b200_sync(lidar_b200_ctx *ctx);
+
+    /* Page-locked host memory for clouds and result arrays — the zero-copy counterpart of the
+     * caller-owned cloud_in_ / label vectors of the reference (src/processor.cpp:123-126). Every entry
+     * point accepts ordinary (pageable) host pointers and stages them through the library's own pinned
+     * buffers; when a point array with 16-byte records or a result array lives in memory obtained here
+     * (or from cudaMallocHost / cudaHostRegister) the copy engines read / write it directly and the
+     * staging pass disappears. */
+    int lidar_b200_host_alloc(void **ptr_out, uint64_t bytes);
+    void lidar_b200_host_free(void *ptr);
+
+    /* ---- frame pipeline: `depth` contexts on one GPU used round-robin, so that the upload of chunk
+     * k+1, the kernels of chunk k and the download of chunk k-1 overlap. _submit = stage + run +
+     * fetch_async of one chunk of frames on the next slot; the results of a chunk are complete once
+     * `depth` further chunks have been submitted or after _drain. Same array conventions as the
+     * batch calls; one host thread per pipe. */
+    typedef struct lidar_b200_pipe lidar_b200_pipe;
+    int lidar_b200_pipe_create(int device, uint32_t depth, uint32_t max_points, uint32_t max_frames,
+                               lidar_b200_pipe **pipe_out);
+    void lidar_b200_pipe_destroy(lidar_b200_pipe *pipe);
+    int lidar_b200_pipe_seg_configure(lidar_b200_pipe *pipe, const lidar_b200_seg_cfg *cfg);
+    int lidar_b200_pipe_clu_configure(lidar_b200_pipe *pipe, const lidar_b200_clu_cfg *cfg);
+    int lidar_b200_pipe_submit(lidar_b200_pipe *pipe, uint32_t n_frames, const void *const *points,
+                               const uint32_t *n_points, uint32_t stride_bytes, uint32_t *point_offset_out,
+                               uint32_t *seg_labels_out, uint32_t *ground_idx_out, uint32_t *n_ground_out,
+                               uint32_t *obstacle_idx_out, uint32_t *n_obstacle_out, int32_t *cluster_labels_out,
+                               uint32_t *n_clusters_out);
+    int lidar_b200_pipe_drain(lidar_b200_pipe *pipe);
+    uint64_t lidar_b200_pipe_launch_count(const lidar_b200_pipe *pipe);
+    const char *lidar_b200_pipe_last_error(const lidar_b200_pipe *pipe);
 
     /* diagnostics */
     /* plane coefficients (a,b,c,d) of every fit of the last batch: [frame][partition][iteration][4], NaN = no fit;

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import subprocess
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -109,6 +110,9 @@ def lib() -> C.CDLL:
         L.lidar_b200_last_error.restype = C.c_char_p
         L.lidar_b200_version.restype = C.c_char_p
         L.lidar_b200_launch_count.restype = C.c_uint64
+        L.lidar_b200_pipe_launch_count.restype = C.c_uint64
+        L.lidar_b200_pipe_last_error.restype = C.c_char_p
+        L.lidar_b200_host_free.restype = None
         _lib = L
     return _lib
 
@@ -119,8 +123,41 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_cluster", "lidar_b200_batch_stage", "lidar_b200_batch_run", "lidar_b200_batch_fetch",
     "lidar_b200_sync", "lidar_b200_last_planes", "lidar_b200_last_kd_rank", "lidar_b200_last_cc_root",
     "lidar_b200_launch_count", "lidar_b200_last_run_ms", "lidar_b200_last_error", "lidar_b200_version",
-    "lidar_b200_set_profiling", "lidar_b200_last_stage_ms",
+    "lidar_b200_set_profiling", "lidar_b200_last_stage_ms", "lidar_b200_batch_fetch_async", "lidar_b200_batch_wait",
+    "lidar_b200_host_alloc", "lidar_b200_host_free", "lidar_b200_pipe_create", "lidar_b200_pipe_destroy",
+    "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
+    "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error",
 ]
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array in page-locked host memory (lidar_b200_host_alloc): clouds and result arrays kept
+    there are read / written by the copy engines directly, without a staging pass."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    rc = lib().lidar_b200_host_alloc(C.byref(ptr), C.c_uint64(max(nbytes, 1)))
+    if rc != 0 or not ptr.value:
+        raise LidarB200Error(f"lidar_b200_host_alloc({nbytes}) failed (status {rc})")
+    buf = (C.c_byte * max(nbytes, 1)).from_address(ptr.value)
+    weakref.finalize(buf, lib().lidar_b200_host_free, C.c_void_p(ptr.value))
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def pin_frames(frames):
+    """Copies a list of (N, 4) float32 clouds into one page-locked arena; returns the list of views."""
+    frames = [_as_points(f) for f in frames]
+    if any(f.shape[1] != 4 for f in frames):
+        raise ValueError("pin_frames expects 16-byte records (N, 4) float32")
+    total = sum(f.shape[0] for f in frames)
+    arena = pinned_empty((max(total, 1), 4), np.float32)
+    out, pos = [], 0
+    for f in frames:
+        v = arena[pos:pos + f.shape[0]]
+        v[...] = f
+        out.append(v)
+        pos += f.shape[0]
+    return out
 
 
 def _as_points(points) -> np.ndarray:
@@ -292,6 +329,95 @@ class Context:
         ms = C.c_float(0)
         self._check(lib().lidar_b200_last_run_ms(self._h, C.byref(ms)), "last_run_ms")
         return float(ms.value)
+
+
+class FramePipeline:
+    """Throughput path: a job of independent frames is cut into chunks that rotate through `depth`
+    contexts (lidar_b200_pipe_*), so uploads, kernels and downloads of neighbouring chunks overlap.
+    Results are written into one page-locked arena owned by the pipeline and returned as views: they
+    stay valid until the next process() call."""
+
+    def __init__(self, device: int = 0, depth: int = 3, chunk_frames: int = 22, max_points_per_chunk: int = 0):
+        self._h = C.c_void_p()
+        self.depth, self.chunk_frames = depth, chunk_frames
+        rc = lib().lidar_b200_pipe_create(C.c_int(device), C.c_uint32(depth),
+                                          C.c_uint32(max_points_per_chunk or 130_000 * chunk_frames),
+                                          C.c_uint32(chunk_frames), C.byref(self._h))
+        if rc != 0:
+            raise LidarB200Error(f"lidar_b200_pipe_create failed (status {rc}): CUDA device {device} unavailable; "
+                                 "there is no CPU fallback")
+        self._arena = None
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().lidar_b200_pipe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = lib().lidar_b200_pipe_last_error(self._h)
+            raise LidarB200Error(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+    def seg_configure(self, cfg: SegmentationConfiguration):
+        self._check(lib().lidar_b200_pipe_seg_configure(self._h, C.byref(cfg)), "pipe_seg_configure")
+
+    def clu_configure(self, cfg: ClusteringConfiguration):
+        self._check(lib().lidar_b200_pipe_clu_configure(self._h, C.byref(cfg)), "pipe_clu_configure")
+
+    def launch_count(self) -> int:
+        return int(lib().lidar_b200_pipe_launch_count(self._h))
+
+    def process(self, frames, want_ground_idx: bool = True):
+        frames = [_as_points(f) for f in frames]
+        nf = len(frames)
+        strides = {f.shape[1] * 4 for f in frames} or {16}
+        if len(strides) != 1:
+            raise ValueError("all frames of a job must share one point stride")
+        stride = strides.pop()
+        counts = np.array([f.shape[0] for f in frames], np.uint32)
+        padded = (counts.astype(np.int64) + 31) & ~31
+        chunks = [(a, min(a + self.chunk_frames, nf)) for a in range(0, nf, self.chunk_frames)]
+        total = int(padded.sum())
+        if self._arena is None or self._arena[0].size < max(total, 1) or self._arena[4].size < max(nf, 1):
+            self._arena = (pinned_empty(max(total, 1), np.uint32), pinned_empty(max(total, 1), np.uint32),
+                           pinned_empty(max(total, 1), np.uint32), pinned_empty(max(total, 1), np.int32),
+                           pinned_empty((4, max(nf, 1)), np.uint32))
+        seg, gidx, oidx, clab, meta = self._arena
+        u32, i32 = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+
+        def at(a, pos, t):
+            return C.cast(C.c_void_p(a.ctypes.data + 4 * pos), t)
+
+        base = 0
+        bases = []
+        for a, b in chunks:
+            n = b - a
+            ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames[a:b]])
+            mrow = lambda r: C.cast(C.c_void_p(meta.ctypes.data + 4 * (r * meta.shape[1] + a)), u32)  # noqa: E731
+            self._check(lib().lidar_b200_pipe_submit(
+                self._h, C.c_uint32(n), ptrs, _ptr(counts[a:b], C.c_uint32), C.c_uint32(stride), mrow(0),
+                at(seg, base, u32), at(gidx, base, u32) if want_ground_idx else None, mrow(1), at(oidx, base, u32),
+                mrow(2), at(clab, base, i32), mrow(3)), "pipe_submit")
+            bases.append(base)
+            base += int(padded[a:b].sum())
+        self._check(lib().lidar_b200_pipe_drain(self._h), "pipe_drain")
+        self.h2d_bytes = int(counts.astype(np.int64).sum()) * 16 + 16 * nf
+        self.d2h_bytes = (4 if want_ground_idx else 3) * total * 4 + 12 * nf + 4 * len(chunks)
+        out = []
+        for (a, b), cb in zip(chunks, bases):
+            for f in range(a, b):
+                o, n = cb + int(meta[0, f]), int(counts[f])
+                ng, no = int(meta[1, f]), int(meta[2, f])
+                out.append(dict(seg_labels=seg[o:o + n], ground_idx=gidx[o:o + ng] if want_ground_idx else None,
+                                obstacle_idx=oidx[o:o + no], cluster_labels=clab[o:o + no], n_clusters=int(meta[3, f])))
+        return out
 
 
 class Segmenter:

@@ -68,6 +68,7 @@ struct lidar_b200_ctx
     PinBuf<float4> h_pts;
     PinBuf<uint32_t> h_u32[4]; // labels, ground idx, obstacle idx, cluster labels
     PinBuf<uint32_t> h_meta;   // off, cnt, toff, tcap, n_ground, n_obstacle, n_clusters : 7 * cap_frames
+    PinBuf<uint32_t> h_err;    // device error flag of the batch being fetched
 
     // device arenas (per point)
     DevBuf<float4> d_pts, d_spts, d_obs, d_nodes, d_cpts, d_rpts;
@@ -98,6 +99,15 @@ struct lidar_b200_ctx
     cudaEvent_t ev_stage[kStages + 1]{};
     int n_stage_marks{0};
 
+    // outstanding asynchronous fetch (lidar_b200_batch_fetch_async .. lidar_b200_batch_wait)
+    struct FetchReq
+    {
+        bool pending{false};
+        uint32_t *point_offset{nullptr}, *n_ground{nullptr}, *n_obstacle{nullptr}, *n_clusters{nullptr};
+        void *out[4]{nullptr, nullptr, nullptr, nullptr}; // seg labels, ground idx, obstacle idx, cluster labels
+        bool direct[4]{false, false, false, false};       // destination is page-locked: DMA went straight into it
+    } fetch;
+
     uint32_t sm_count{148}, replay_ctas_per_sm{12};
     uint64_t launches{0};
     float last_run_ms{0.0f};
@@ -120,6 +130,21 @@ int fail(lidar_b200_ctx *c, int code, const std::string &msg)
     if (c)
         c->err = msg;
     return code;
+}
+
+// true when `p` is page-locked host memory known to CUDA (lidar_b200_host_alloc, cudaMallocHost,
+// cudaHostRegister): the copy engines can then read / write it directly, no staging pass needed
+bool is_pinned(const void *p)
+{
+    if (!p)
+        return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
 }
 
 #define LB_CUDA(c, call)                                                                                              \
@@ -205,7 +230,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
     if (dev_alloc(c, c->d_planes, planes ? planes : 4) ||
         dev_alloc(c, c->d_status, static_cast<size_t>(c->cap_frames) * (c->seg.partitions ? c->seg.partitions : 1)))
         return LIDAR_B200_ERR_CUDA;
-    if (dev_alloc(c, c->d_err, 4))
+    if (dev_alloc(c, c->d_err, 4) || pin_alloc(c, c->h_err, 4))
         return LIDAR_B200_ERR_CUDA;
     return 0;
 }
@@ -268,6 +293,8 @@ uint32_t grid_x(uint32_t n, uint32_t per_block, uint32_t cap)
     return g > cap ? cap : g;
 }
 
+int finish_fetch(lidar_b200_ctx *c);
+
 // lays the frames of a batch out, stages the points into pinned memory and starts the upload
 int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const uint32_t *n_points,
           uint32_t stride_bytes)
@@ -277,6 +304,12 @@ int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const
     if (stride_bytes < 12u || (stride_bytes & 3u))
         return fail(c, LIDAR_B200_ERR_INVALID, "stride_bytes must be a multiple of 4 and >= 12");
     LB_CUDA(c, cudaSetDevice(c->device));
+    if (c->fetch.pending) // complete the batch this context still owes before its bookkeeping is reused
+    {
+        const int rc = finish_fetch(c);
+        if (rc)
+            return rc;
+    }
     uint64_t total = 0;
     uint32_t max_n = 0;
     c->off.assign(n_frames, 0u);
@@ -320,27 +353,36 @@ int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const
     c->max_tcap = max_tcap;
     if (dev_alloc(c, c->d_hist, radix_sort_scratch_words(n_frames, max_n)))
         return LIDAR_B200_ERR_CUDA;
-    for (uint32_t f = 0; f < n_frames; ++f)
-    {
-        float4 *dst = c->h_pts.p + c->off[f];
-        const uint8_t *src = static_cast<const uint8_t *>(points[f]);
-        const uint32_t n = c->cnt[f];
-        if (stride_bytes == 16u)
-            std::memcpy(dst, src, static_cast<size_t>(n) * 16u);
-        else if (stride_bytes >= 16u)
-            for (uint32_t i = 0; i < n; ++i)
-                std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 16u);
-        else
-            for (uint32_t i = 0; i < n; ++i)
-            {
-                std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 12u);
-                dst[i].w = 1.0f;
-            }
-    }
     if (n_frames)
         LB_CUDA(c, cudaMemcpyAsync(c->d_meta.p, hm, 4 * F * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    if (total)
-        LB_CUDA(c, cudaMemcpyAsync(c->d_pts.p, c->h_pts.p, total * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    // one upload per frame, issued as soon as the frame is staged: the DMA of frame f overlaps the
+    // staging pass of frame f+1. Page-locked 16-byte records need no staging pass at all.
+    for (uint32_t f = 0; f < n_frames; ++f)
+    {
+        const uint32_t n = c->cnt[f];
+        if (n == 0u)
+            continue;
+        const uint8_t *src = static_cast<const uint8_t *>(points[f]);
+        const void *from = src;
+        if (!(stride_bytes == 16u && is_pinned(src)))
+        {
+            float4 *dst = c->h_pts.p + c->off[f];
+            if (stride_bytes == 16u)
+                std::memcpy(dst, src, static_cast<size_t>(n) * 16u);
+            else if (stride_bytes >= 16u)
+                for (uint32_t i = 0; i < n; ++i)
+                    std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 16u);
+            else
+                for (uint32_t i = 0; i < n; ++i)
+                {
+                    std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 12u);
+                    dst[i].w = 1.0f;
+                }
+            from = dst;
+        }
+        LB_CUDA(c, cudaMemcpyAsync(c->d_pts.p + c->off[f], from, static_cast<size_t>(n) * sizeof(float4),
+                                   cudaMemcpyHostToDevice, c->stream));
+    }
     return 0;
 }
 
@@ -446,6 +488,41 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     return 0;
 }
 
+// completes an asynchronous fetch: waits for the stream, un-stages the results that could not be
+// written by DMA directly and reports the per-frame counts
+int finish_fetch(lidar_b200_ctx *c)
+{
+    lidar_b200_ctx::FetchReq &r = c->fetch;
+    r.pending = false;
+    LB_CUDA(c, cudaSetDevice(c->device));
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (cudaEventElapsedTime(&c->last_run_ms, c->ev_start, c->ev_stop) != cudaSuccess)
+    {
+        c->last_run_ms = 0.0f;
+        (void)cudaGetLastError();
+    }
+    if (c->h_err.p[0])
+        return fail(c, LIDAR_B200_ERR_INPUT, "non-finite or out-of-range point coordinates");
+    const size_t F = c->cap_frames;
+    const uint32_t *hm = c->h_meta.p;
+    for (uint32_t f = 0; f < c->n_frames; ++f)
+    {
+        if (r.point_offset)
+            r.point_offset[f] = c->off[f];
+        if (r.n_ground)
+            r.n_ground[f] = hm[4 * F + f];
+        if (r.n_obstacle)
+            r.n_obstacle[f] = hm[5 * F + f];
+        if (r.n_clusters)
+            r.n_clusters[f] = hm[6 * F + f];
+    }
+    const size_t bytes = static_cast<size_t>(c->total) * 4;
+    for (int k = 0; k < 4; ++k)
+        if (bytes && r.out[k] && !r.direct[k])
+            std::memcpy(r.out[k], c->h_u32[k].p, bytes);
+    return 0;
+}
+
 } // namespace
 
 extern "C"
@@ -526,6 +603,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     for (auto &h : c->h_u32)
         cudaFreeHost(h.p);
     cudaFreeHost(c->h_meta.p);
+    cudaFreeHost(c->h_err.p);
     void *dev[] = {c->d_pts.p,      c->d_spts.p,   c->d_obs.p,       c->d_nodes.p,  c->d_cpts.p,       c->d_key_a.p,
                    c->d_key_b.p,    c->d_val_a.p,  c->d_val_b.p,     c->d_labels.p, c->d_gidx.p,       c->d_oidx.p,
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
@@ -604,65 +682,64 @@ int lidar_b200_sync(lidar_b200_ctx *c)
     return 0;
 }
 
-int lidar_b200_batch_fetch(lidar_b200_ctx *c, uint32_t *point_offset_out, uint32_t *seg_labels_out,
-                           uint32_t *ground_idx_out, uint32_t *n_ground_out, uint32_t *obstacle_idx_out,
-                           uint32_t *n_obstacle_out, int32_t *cluster_labels_out, uint32_t *n_clusters_out)
+int lidar_b200_batch_fetch_async(lidar_b200_ctx *c, uint32_t *point_offset_out, uint32_t *seg_labels_out,
+                                 uint32_t *ground_idx_out, uint32_t *n_ground_out, uint32_t *obstacle_idx_out,
+                                 uint32_t *n_obstacle_out, int32_t *cluster_labels_out, uint32_t *n_clusters_out)
 {
     if (!c)
         return LIDAR_B200_ERR_INVALID;
+    if (c->fetch.pending)
+    {
+        const int rc = finish_fetch(c);
+        if (rc)
+            return rc;
+    }
     LB_CUDA(c, cudaSetDevice(c->device));
     const size_t F = c->cap_frames;
     const size_t bytes = static_cast<size_t>(c->total) * 4;
     cudaStream_t s = c->stream;
+    lidar_b200_ctx::FetchReq &r = c->fetch;
+    r.point_offset = point_offset_out;
+    r.n_ground = n_ground_out;
+    r.n_obstacle = n_obstacle_out;
+    r.n_clusters = n_clusters_out;
+    r.out[0] = seg_labels_out;
+    r.out[1] = ground_idx_out;
+    r.out[2] = obstacle_idx_out;
+    r.out[3] = cluster_labels_out;
+    const void *dev[4] = {c->d_labels.p, c->d_gidx.p, c->d_oidx.p, c->d_clabels.p};
     if (c->n_frames)
         LB_CUDA(c, cudaMemcpyAsync(c->h_meta.p + 4 * F, c->m_ng(), 3 * F * 4, cudaMemcpyDeviceToHost, s));
-    if (bytes)
+    LB_CUDA(c, cudaMemcpyAsync(c->h_err.p, c->d_err.p, 4, cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < 4; ++k)
     {
-        if (seg_labels_out)
-            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[0].p, c->d_labels.p, bytes, cudaMemcpyDeviceToHost, s));
-        if (ground_idx_out)
-            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[1].p, c->d_gidx.p, bytes, cudaMemcpyDeviceToHost, s));
-        if (obstacle_idx_out)
-            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[2].p, c->d_oidx.p, bytes, cudaMemcpyDeviceToHost, s));
-        if (cluster_labels_out)
-            LB_CUDA(c, cudaMemcpyAsync(c->h_u32[3].p, c->d_clabels.p, bytes, cudaMemcpyDeviceToHost, s));
+        r.direct[k] = false;
+        if (!bytes || !r.out[k])
+            continue;
+        r.direct[k] = is_pinned(r.out[k]); // page-locked destination: the copy engine writes it directly
+        LB_CUDA(c, cudaMemcpyAsync(r.direct[k] ? r.out[k] : static_cast<void *>(c->h_u32[k].p), dev[k], bytes,
+                                   cudaMemcpyDeviceToHost, s));
     }
-    LB_CUDA(c, cudaStreamSynchronize(s));
-    if (cudaEventElapsedTime(&c->last_run_ms, c->ev_start, c->ev_stop) != cudaSuccess)
-    {
-        c->last_run_ms = 0.0f;
-        (void)cudaGetLastError();
-    }
-    {
-        uint32_t e = 0;
-        LB_CUDA(c, cudaMemcpy(&e, c->d_err.p, 4, cudaMemcpyDeviceToHost));
-        if (e)
-            return fail(c, LIDAR_B200_ERR_INPUT, "non-finite or out-of-range point coordinates");
-    }
-    const uint32_t *hm = c->h_meta.p;
-    for (uint32_t f = 0; f < c->n_frames; ++f)
-    {
-        if (point_offset_out)
-            point_offset_out[f] = c->off[f];
-        if (n_ground_out)
-            n_ground_out[f] = hm[4 * F + f];
-        if (n_obstacle_out)
-            n_obstacle_out[f] = hm[5 * F + f];
-        if (n_clusters_out)
-            n_clusters_out[f] = hm[6 * F + f];
-    }
-    if (bytes)
-    {
-        if (seg_labels_out)
-            std::memcpy(seg_labels_out, c->h_u32[0].p, bytes);
-        if (ground_idx_out)
-            std::memcpy(ground_idx_out, c->h_u32[1].p, bytes);
-        if (obstacle_idx_out)
-            std::memcpy(obstacle_idx_out, c->h_u32[2].p, bytes);
-        if (cluster_labels_out)
-            std::memcpy(cluster_labels_out, c->h_u32[3].p, bytes);
-    }
+    r.pending = true;
     return 0;
+}
+
+int lidar_b200_batch_wait(lidar_b200_ctx *c)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    if (!c->fetch.pending)
+        return 0;
+    return finish_fetch(c);
+}
+
+int lidar_b200_batch_fetch(lidar_b200_ctx *c, uint32_t *point_offset_out, uint32_t *seg_labels_out,
+                           uint32_t *ground_idx_out, uint32_t *n_ground_out, uint32_t *obstacle_idx_out,
+                           uint32_t *n_obstacle_out, int32_t *cluster_labels_out, uint32_t *n_clusters_out)
+{
+    const int rc = lidar_b200_batch_fetch_async(c, point_offset_out, seg_labels_out, ground_idx_out, n_ground_out,
+                                                obstacle_idx_out, n_obstacle_out, cluster_labels_out, n_clusters_out);
+    return rc ? rc : lidar_b200_batch_wait(c);
 }
 
 int lidar_b200_segment(lidar_b200_ctx *c, const void *points, uint32_t n, uint32_t stride_bytes, uint32_t *labels_inout,
@@ -723,11 +800,10 @@ int lidar_b200_cluster(lidar_b200_ctx *c, const void *points, uint32_t m, uint32
         return rc;
     LB_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
     LB_CUDA(c, cudaMemcpyAsync(c->h_u32[3].p, c->d_clabels.p, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost, c->stream));
+    LB_CUDA(c, cudaMemcpyAsync(c->h_err.p, c->d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
     LB_CUDA(c, cudaStreamSynchronize(c->stream));
     (void)cudaEventElapsedTime(&c->last_run_ms, c->ev_start, c->ev_stop);
-    uint32_t e = 0;
-    LB_CUDA(c, cudaMemcpy(&e, c->d_err.p, 4, cudaMemcpyDeviceToHost));
-    if (e)
+    if (c->h_err.p[0])
         return fail(c, LIDAR_B200_ERR_INPUT, "non-finite or out-of-range point coordinates");
     std::memcpy(labels_out, c->h_u32[3].p, static_cast<size_t>(m) * 4);
     return 0;
@@ -830,6 +906,151 @@ const char *lidar_b200_last_error(const lidar_b200_ctx *c)
 const char *lidar_b200_version(void)
 {
     return "lidar_b200 0.1 (sm_100a)";
+}
+
+int lidar_b200_host_alloc(void **ptr_out, uint64_t bytes)
+{
+    if (!ptr_out)
+        return LIDAR_B200_ERR_INVALID;
+    *ptr_out = nullptr;
+    if (cudaHostAlloc(ptr_out, bytes ? bytes : 1u, cudaHostAllocPortable) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        *ptr_out = nullptr;
+        return LIDAR_B200_ERR_CUDA;
+    }
+    return 0;
+}
+
+void lidar_b200_host_free(void *ptr)
+{
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess)
+        (void)cudaGetLastError();
+}
+
+// ---- frame pipeline: `depth` contexts used round-robin, so that the upload of chunk k+1, the
+// kernels of chunk k and the download of chunk k-1 overlap (three engines, independent streams)
+struct lidar_b200_pipe
+{
+    std::vector<lidar_b200_ctx *> slots;
+    uint32_t next{0};
+    std::string err;
+};
+
+int lidar_b200_pipe_create(int device, uint32_t depth, uint32_t max_points, uint32_t max_frames, lidar_b200_pipe **pipe_out)
+{
+    if (!pipe_out || depth == 0u || depth > 16u)
+        return LIDAR_B200_ERR_INVALID;
+    *pipe_out = nullptr;
+    lidar_b200_pipe *p = new lidar_b200_pipe();
+    for (uint32_t i = 0; i < depth; ++i)
+    {
+        lidar_b200_ctx *c = nullptr;
+        const int rc = lidar_b200_create(device, max_points, max_frames, &c);
+        if (rc)
+        {
+            lidar_b200_pipe_destroy(p);
+            return rc;
+        }
+        p->slots.push_back(c);
+    }
+    *pipe_out = p;
+    return 0;
+}
+
+void lidar_b200_pipe_destroy(lidar_b200_pipe *p)
+{
+    if (!p)
+        return;
+    for (lidar_b200_ctx *c : p->slots)
+        lidar_b200_destroy(c);
+    delete p;
+}
+
+int lidar_b200_pipe_seg_configure(lidar_b200_pipe *p, const lidar_b200_seg_cfg *cfg)
+{
+    if (!p)
+        return LIDAR_B200_ERR_INVALID;
+    for (lidar_b200_ctx *c : p->slots)
+    {
+        const int rc = lidar_b200_seg_configure(c, cfg);
+        if (rc)
+        {
+            p->err = c->err;
+            return rc;
+        }
+    }
+    return 0;
+}
+
+int lidar_b200_pipe_clu_configure(lidar_b200_pipe *p, const lidar_b200_clu_cfg *cfg)
+{
+    if (!p)
+        return LIDAR_B200_ERR_INVALID;
+    for (lidar_b200_ctx *c : p->slots)
+    {
+        const int rc = lidar_b200_clu_configure(c, cfg);
+        if (rc)
+        {
+            p->err = c->err;
+            return rc;
+        }
+    }
+    return 0;
+}
+
+int lidar_b200_pipe_submit(lidar_b200_pipe *p, uint32_t n_frames, const void *const *points, const uint32_t *n_points,
+                           uint32_t stride_bytes, uint32_t *point_offset_out, uint32_t *seg_labels_out,
+                           uint32_t *ground_idx_out, uint32_t *n_ground_out, uint32_t *obstacle_idx_out,
+                           uint32_t *n_obstacle_out, int32_t *cluster_labels_out, uint32_t *n_clusters_out)
+{
+    if (!p || p->slots.empty())
+        return LIDAR_B200_ERR_INVALID;
+    lidar_b200_ctx *c = p->slots[p->next];
+    p->next = (p->next + 1u) % static_cast<uint32_t>(p->slots.size());
+    // staging completes the chunk this slot still owes (its results are in caller memory afterwards)
+    int rc = lidar_b200_batch_stage(c, n_frames, points, n_points, stride_bytes);
+    if (!rc)
+        rc = lidar_b200_batch_run(c);
+    if (!rc)
+        rc = lidar_b200_batch_fetch_async(c, point_offset_out, seg_labels_out, ground_idx_out, n_ground_out,
+                                          obstacle_idx_out, n_obstacle_out, cluster_labels_out, n_clusters_out);
+    if (rc)
+        p->err = c->err;
+    return rc;
+}
+
+int lidar_b200_pipe_drain(lidar_b200_pipe *p)
+{
+    if (!p)
+        return LIDAR_B200_ERR_INVALID;
+    int first = 0;
+    const uint32_t k = static_cast<uint32_t>(p->slots.size());
+    for (uint32_t i = 0; i < k; ++i) // oldest chunk first
+    {
+        lidar_b200_ctx *c = p->slots[(p->next + i) % k];
+        const int rc = lidar_b200_batch_wait(c);
+        if (rc && !first)
+        {
+            first = rc;
+            p->err = c->err;
+        }
+    }
+    return first;
+}
+
+uint64_t lidar_b200_pipe_launch_count(const lidar_b200_pipe *p)
+{
+    uint64_t n = 0;
+    if (p)
+        for (const lidar_b200_ctx *c : p->slots)
+            n += c->launches;
+    return n;
+}
+
+const char *lidar_b200_pipe_last_error(const lidar_b200_pipe *p)
+{
+    return p ? p->err.c_str() : "null pipe";
 }
 
 } // extern "C"

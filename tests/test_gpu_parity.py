@@ -241,3 +241,46 @@ def test_mirror_classes(pkg, golden_frames):
     lab = clu.cluster(obstacle)
     H.check_clustering(obstacle, lab)
     assert pkg.Clusterer.INVALID == -1 and pkg.Clusterer.UNDEFINED == np.iinfo(np.int32).min
+
+
+# ------------------------------------------------------------------ frame pipeline / page-locked buffers
+def test_pipeline_matches_batch_and_oracle(pkg, ctx, golden_frames, synth_small):
+    frames = [golden_frames[0], synth_small, np.zeros((0, 4), np.float32), golden_frames[2][:50001], synth_small[:7],
+              golden_frames[1], synth_small[:10001]]
+    want = ctx.process_batch(frames)
+    pipe = pkg.FramePipeline(device=0, depth=2, chunk_frames=2)   # 4 chunks through 2 slots: slots are reused
+    try:
+        for src in (frames, pkg.pin_frames(frames)):               # pageable (staged) and page-locked (direct DMA)
+            for _ in range(2):                                    # arena reuse across jobs
+                got = pipe.process(src)
+                assert len(got) == len(frames)
+                for w, g in zip(want, got):
+                    for k in ("seg_labels", "ground_idx", "obstacle_idx", "cluster_labels"):
+                        assert np.array_equal(w[k], g[k]), k
+                    assert w["n_clusters"] == g["n_clusters"]
+        pts, res = frames[0], got[0]
+        H.check_segmentation(pts, res["seg_labels"], res["ground_idx"], res["obstacle_idx"])
+        H.check_clustering(pts[res["obstacle_idx"]], res["cluster_labels"])
+        assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0 and pipe.launch_count() > 0
+    finally:
+        pipe.close()
+
+
+def test_pinned_buffers_single_frame_calls(pkg, ctx, golden_frames):
+    pts = pkg.pin_frames([golden_frames[1]])[0]
+    a = ctx.segment(pts)
+    b = ctx.segment(golden_frames[1])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    obs = pkg.pin_frames([golden_frames[1][a[2]]])[0]
+    assert np.array_equal(ctx.cluster(obs), ctx.cluster(golden_frames[1][a[2]]))
+
+
+def test_pipeline_reports_bad_input(pkg):
+    pipe = pkg.FramePipeline(device=0, depth=2, chunk_frames=1)
+    try:
+        bad = np.array([[0, 0, 0, 0], [np.inf, 0, 3, 0], [1, 1, 5, 0], [2, 2, 2, 0], [3, 3, 3, 0], [1, 2, 3, 0]], np.float32)
+        with pytest.raises(pkg.LidarB200Error):
+            pipe.process([bad, bad])
+    finally:
+        pipe.close()
