@@ -158,6 +158,11 @@ extern "C"
     int lidar_b200_last_kd_rank(lidar_b200_ctx *ctx, uint32_t frame, uint32_t *rank_out, uint32_t capacity);
     /* component root (smallest member index) of every obstacle point of a frame of the last batch */
     int lidar_b200_last_cc_root(lidar_b200_ctx *ctx, uint32_t frame, uint32_t *root_out, uint32_t capacity);
+    /* per-component counters of the CTA-per-component replay of the last run (development aid; needs
+     * LIDAR_B200_REPLAY_STATS=1 in the environment when the context is created). 8 words per job:
+     * frame, members, kilo-cycles, rounds, direct rounds, entries taken, seeds, candidates scanned. */
+    int lidar_b200_last_replay_stats(lidar_b200_ctx *ctx, uint32_t *stats_out, uint32_t capacity_jobs,
+                                     uint32_t *n_jobs_out);
     /* number of kernels launched by this context so far */
     uint64_t lidar_b200_launch_count(const lidar_b200_ctx *ctx);
     /* elapsed GPU milliseconds between the start and the end of the last lidar_b200_batch_run (CUDA events) */

@@ -127,6 +127,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_host_alloc", "lidar_b200_host_free", "lidar_b200_pipe_create", "lidar_b200_pipe_destroy",
     "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
     "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error",
+    "lidar_b200_last_replay_stats",
 ]
 
 
@@ -324,6 +325,14 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().lidar_b200_launch_count(self._h))
+
+    def last_replay_stats(self, capacity: int = 65536) -> np.ndarray:
+        """(jobs, 8) uint32: frame, members, kilo-cycles, rounds, direct rounds, entries taken, seeds, candidates."""
+        out = np.zeros((capacity, 8), np.uint32)
+        n = C.c_uint32(0)
+        self._check(lib().lidar_b200_last_replay_stats(self._h, _ptr(out, C.c_uint32), C.c_uint32(capacity), C.byref(n)),
+                    "last_replay_stats")
+        return out[: min(n.value, capacity)]
 
     def last_run_ms(self) -> float:
         ms = C.c_float(0)

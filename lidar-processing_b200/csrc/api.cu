@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kd_build.cuh"
 #include "radix_sort.cuh"
+#include "replay_cta.cuh"
 #include "segment.cuh"
 
 #include <cmath>
@@ -55,7 +56,8 @@ struct lidar_b200_ctx
 {
     int device{0};
     cudaStream_t stream{nullptr};
-    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr};
+    cudaStream_t stream_big{nullptr}; // the CTA-per-component replay runs beside the warp-per-component one
+    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_fork{nullptr}, ev_join{nullptr};
     lidar_b200_seg_cfg seg_cfg{};
     lidar_b200_clu_cfg clu_cfg{};
     SegParams seg{};
@@ -81,6 +83,9 @@ struct lidar_b200_ctx
     DevBuf<unsigned long long> d_tkeys;
     DevBuf<uint32_t> d_tcount, d_tlive;
     DevBuf<uint4> d_cells;
+    DevBuf<uint2> d_biglist; // {frame, first member} of every component replayed by a whole CTA
+    DevBuf<uint32_t> d_job_stats; // optional per-job counters of the CTA replay (LIDAR_B200_REPLAY_STATS=1)
+    bool want_job_stats{false};
     // per frame
     DevBuf<uint32_t> d_meta; // off, cnt, toff, tcap, n_ground, n_obstacle, n_clusters, cursor : 8 * cap_frames
     DevBuf<uint32_t> d_err;
@@ -108,7 +113,7 @@ struct lidar_b200_ctx
         bool direct[4]{false, false, false, false};       // destination is page-locked: DMA went straight into it
     } fetch;
 
-    uint32_t sm_count{148}, replay_ctas_per_sm{12};
+    uint32_t sm_count{148}, replay_ctas_per_sm{12}, replay_big_ctas_per_sm{2};
     uint64_t launches{0};
     float last_run_ms{0.0f};
     std::string err;
@@ -206,7 +211,9 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
         for (auto *b : u32s)
             rc |= dev_alloc(c, *b, n);
         rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_flags, n) |
-              dev_alloc(c, c->d_seed_valid, n);
+              dev_alloc(c, c->d_seed_valid, n) | dev_alloc(c, c->d_biglist, kBigBuckets * (n / kCtaComponentMin + 1u));
+        if (c->want_job_stats)
+            rc |= dev_alloc(c, c->d_job_stats, 8u * (n / kCtaComponentMin + 1u));
         if (rc)
             return LIDAR_B200_ERR_CUDA;
         c->cap_pts = pts;
@@ -272,6 +279,13 @@ int apply_clu_cfg(lidar_b200_ctx *c, const lidar_b200_clu_cfg &cfg)
     c->clu.min_cluster_size = cfg.min_cluster_size;
     c->clu.max_cluster_size = cfg.max_cluster_size;
     c->clu.inv_cell = 1.0 / (std::sqrt(static_cast<double>(cfg.distance_squared)) * 1.001);
+    c->clu.cta_min_members = 256u;
+    if (const char *e = std::getenv("LIDAR_B200_CTA_MIN_MEMBERS"))
+    {
+        const long v = std::atol(e);
+        if (v >= static_cast<long>(kCtaComponentMin))
+            c->clu.cta_min_members = static_cast<uint32_t>(v);
+    }
     return 0;
 }
 
@@ -472,6 +486,19 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_slot_of.p,
                                           c->d_rpts.p, c->d_seed_of.p, c->d_member_pos.p, c->d_pslot.p, c->m_cursor());
     replay_live_init_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_cells.p, c->d_tlive.p);
+    // components of at least kCtaComponent members: one CTA each (speculative rounds, CTA-wide scans),
+    // started first on a second stream so that the longest BFS chains begin at time zero
+    uint32_t *big_count = c->m_cursor() + 3; // kBigBuckets counters
+    const uint32_t bucket_capacity = c->cap_pts / kCtaComponentMin + 1u;
+    replay_biglist_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->clu.cta_min_members, c->d_biglist.p,
+                                             bucket_capacity, big_count);
+    LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
+    LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
+    replay_cta_kernel<<<c->sm_count * c->replay_big_ctas_per_sm, kCtaThreads, sizeof(CtaSmem), c->stream_big>>>(
+        c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
+        c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p, bucket_capacity, big_count,
+        c->m_cursor() + 2, c->d_job_stats.p);
+    LB_CUDA(c, cudaEventRecord(c->ev_join, c->stream_big));
     const uint32_t claims = (max_m + 31u) / 32u;
     // persistent grid: a fixed number of CTAs per SM walks the flat (frame, claim) work list
     const uint32_t rctas = grid_x(claims * F, kReplayWarps, c->sm_count * c->replay_ctas_per_sm);
@@ -479,10 +506,11 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
                                                       c->d_member_pos.p, c->d_comp_size.p, c->d_pslot.p, c->d_tlive.p,
                                                       c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
                                                       c->m_cursor(), claims);
+    LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join, 0));
     mark(c, 8);
     label_compact_kernel<<<F, 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
                                             c->d_clabels.p, c->m_nc());
-    c->launches += 4;
+    c->launches += 6;
     mark(c, 9);
     LB_CUDA(c, cudaGetLastError());
     return 0;
@@ -556,6 +584,7 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
         return LIDAR_B200_ERR_CUDA;
     lidar_b200_ctx *c = new lidar_b200_ctx();
     c->device = device;
+    c->want_job_stats = std::getenv("LIDAR_B200_REPLAY_STATS") != nullptr;
     lidar_b200_seg_cfg sc;
     lidar_b200_clu_cfg cc;
     lidar_b200_seg_cfg_default(&sc);
@@ -563,7 +592,10 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     apply_seg_cfg(c, sc);
     apply_clu_cfg(c, cc);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_big, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         [&]() {
             for (auto &e : c->ev_stage)
                 if (cudaEventCreate(&e) != cudaSuccess)
@@ -572,6 +604,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
         }() ||
         cudaFuncSetAttribute(seg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(FitSmem))) != cudaSuccess ||
+        cudaFuncSetAttribute(replay_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(CtaSmem))) != cudaSuccess ||
         reserve(c, max_points ? max_points : 200000u, max_frames ? max_frames : 1u) != 0)
     {
         lidar_b200_destroy(c);
@@ -587,6 +621,12 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
             if (v >= 1 && v <= 16)
                 c->replay_ctas_per_sm = static_cast<uint32_t>(v);
         }
+        if (const char *e = std::getenv("LIDAR_B200_REPLAY_BIG_CTAS_PER_SM"))
+        {
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 4)
+                c->replay_big_ctas_per_sm = static_cast<uint32_t>(v);
+        }
     }
     *ctx_out = c;
     return 0;
@@ -597,6 +637,8 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     if (!c)
         return;
     cudaSetDevice(c->device);
+    if (c->stream_big)
+        cudaStreamSynchronize(c->stream_big);
     if (c->stream)
         cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_pts.p);
@@ -609,7 +651,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
+                   c->d_cells.p,    c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -620,6 +662,12 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
         cudaEventDestroy(c->ev_start);
     if (c->ev_stop)
         cudaEventDestroy(c->ev_stop);
+    if (c->ev_fork)
+        cudaEventDestroy(c->ev_fork);
+    if (c->ev_join)
+        cudaEventDestroy(c->ev_join);
+    if (c->stream_big)
+        cudaStreamDestroy(c->stream_big);
     if (c->stream)
         cudaStreamDestroy(c->stream);
     delete c;
@@ -848,6 +896,26 @@ int lidar_b200_last_cc_root(lidar_b200_ctx *c, uint32_t frame, uint32_t *root_ou
         return fail(c, LIDAR_B200_ERR_CAPACITY, "root_out too small");
     if (m)
         LB_CUDA(c, cudaMemcpy(root_out, c->d_root.p + c->off[frame], static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lidar_b200_last_replay_stats(lidar_b200_ctx *c, uint32_t *stats_out, uint32_t capacity_jobs, uint32_t *n_jobs_out)
+{
+    if (!c || !n_jobs_out)
+        return LIDAR_B200_ERR_INVALID;
+    *n_jobs_out = 0;
+    if (!c->d_job_stats.p)
+        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "set LIDAR_B200_REPLAY_STATS=1 before creating the context");
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t nb[kBigBuckets];
+    LB_CUDA(c, cudaMemcpy(nb, c->m_cursor() + 3, sizeof(nb), cudaMemcpyDeviceToHost));
+    uint32_t n = 0;
+    for (uint32_t b = 0; b < kBigBuckets; ++b)
+        n += nb[b];
+    *n_jobs_out = n;
+    n = n < capacity_jobs ? n : capacity_jobs;
+    if (n && stats_out)
+        LB_CUDA(c, cudaMemcpy(stats_out, c->d_job_stats.p, static_cast<size_t>(n) * 32, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -37,6 +37,7 @@ struct CluParams
     uint32_t min_cluster_size;
     uint32_t max_cluster_size;
     double inv_cell; // 1 / (sqrt(distance_squared) * 1.001)
+    uint32_t cta_min_members; // components of at least this many members are replayed by a whole CTA (replay_cta.cuh)
 };
 
 // Per-frame placement of the hash table inside the batch-wide table arrays.
@@ -480,8 +481,8 @@ replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2)
-        cursor[threadIdx.x] = 0u;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8)
+        cursor[threadIdx.x] = 0u; // warp-path phases 0/1, CTA-path cursor, CTA-path job counts per size bucket
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
         const float4 p = cpts[off + i];
@@ -507,28 +508,33 @@ replay_live_init_kernel(BatchView bv, TableView tv, const uint4 *__restrict__ ce
 constexpr int kReplayWarps = 4;
 constexpr uint32_t kPushCap = 256u;     // per-warp shared push buffer; larger expansions spill to global
 constexpr uint32_t kBigComponent = 96u; // components with at least this many members are replayed first
+constexpr uint32_t kCtaComponentMin = 128u; // smallest permitted CluParams::cta_min_members (sizes the job list)
 constexpr int kReplayUnroll = 4;        // candidate batches whose loads are issued together
 
-// Replay-time lookup: cells[slot].w carries a "dead" flag in its top bit, set by the warp that removed
-// the cell's last live point (a dead cell cannot contribute, clustering.cpp:94-97). Read through L2
-// (other warps set flags concurrently); a stale "alive" only costs a wasted scan.
-LB_D void cell_lookup_live(const uint4 *cells, uint32_t mask, uint64_t key, uint32_t *start, uint32_t *count)
+// Replay-time lookup: tlive[slot] counts the points of the cell that are not removed yet (decremented
+// with fire-and-forget atomics by whoever removes a point); a cell without live points cannot
+// contribute (clustering.cpp:94-97) and reports count 0. A stale non-zero only costs a wasted scan.
+LB_D void cell_lookup_alive(const uint4 *cells, const uint32_t *tlive, uint32_t mask, uint64_t key, uint32_t *start,
+                            uint32_t *count, uint32_t *slot_out)
 {
     uint32_t slot = hash_cell(key) & mask;
     const uint32_t klo = static_cast<uint32_t>(key), khi = static_cast<uint32_t>(key >> 32);
     while (true)
     {
-        const uint4 c = __ldcg(&cells[slot]);
+        const uint4 c = __ldg(&cells[slot]);
+        const uint32_t live = __ldcg(&tlive[slot]);
         if (c.x == klo && c.y == khi)
         {
             *start = c.z;
-            *count = (c.w & 0x80000000u) ? 0u : c.w;
+            *count = live ? c.w : 0u;
+            *slot_out = slot;
             return;
         }
         if (c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu)
         {
             *start = 0u;
             *count = 0u;
+            *slot_out = 0u;
             return;
         }
         slot = (slot + 1u) & mask;
@@ -540,7 +546,7 @@ LB_D void cell_lookup_live(const uint4 *cells, uint32_t mask, uint64_t key, uint
 // at time zero — the second walk replays everything else around them. A warp replays every
 // component whose first member falls into its claim.
 __global__ void __launch_bounds__(kReplayWarps * 32)
-replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *__restrict__ cells,
+replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
               CluParams prm, const uint32_t *__restrict__ member_root, const uint32_t *__restrict__ member_idx,
               const uint32_t *__restrict__ member_pos, const uint32_t *__restrict__ comp_size,
               const uint32_t *__restrict__ pslot_all, uint32_t *__restrict__ tlive_all, uint32_t *__restrict__ seed_of,
@@ -569,8 +575,7 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
             continue;
         const uint32_t off = bv.off[f];
         const uint32_t mask = table_mask(m, tv.tcap[f]);
-        uint4 *tab = cells + tv.toff[f];
-        uint32_t *tabw = reinterpret_cast<uint32_t *>(tab) + 3; // count/flag word of a slot
+        const uint4 *tab = cells + tv.toff[f];
         uint32_t *tlive = tlive_all + tv.toff[f];
         float4 *rp = rpts_all + off;
         // the state word of a point is the .w lane of its float4
@@ -586,7 +591,10 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
         const uint32_t tt = t0 + lane;
         bool is_start = tt < m && (tt == 0u || mroot[tt] != mroot[tt - 1u]);
         if (is_start)
-            is_start = (comp_size[off + mroot[tt]] >= kBigComponent) == (phase == 0u);
+        {
+            const uint32_t size = comp_size[off + mroot[tt]];
+            is_start = size < prm.cta_min_members && (size >= kBigComponent) == (phase == 0u);
+        }
         uint32_t starts = __ballot_sync(kFullMask, is_start);
         while (starts)
         {
@@ -669,18 +677,18 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
                     uint32_t start = 0u, count = 0u;
                     if (lane < 27u)
                     {
-                        cell_lookup_live(tab, mask,
-                                         cell_key(cx + static_cast<int>(lane % 3u) - 1,
-                                                  cy + static_cast<int>((lane / 3u) % 3u) - 1,
-                                                  cz + static_cast<int>(lane / 9u) - 1),
-                                         &start, &count);
+                        uint32_t slot_unused;
+                        cell_lookup_alive(tab, tlive, mask,
+                                          cell_key(cx + static_cast<int>(lane % 3u) - 1,
+                                                   cy + static_cast<int>((lane / 3u) % 3u) - 1,
+                                                   cz + static_cast<int>(lane / 9u) - 1),
+                                          &start, &count, &slot_unused);
                     }
                     const uint32_t incl = warp_inclusive_scan(count);
                     const uint32_t excl = incl - count;
                     const uint32_t total = __shfl_sync(kFullMask, incl, 31);
                     uint32_t np = 0u;
                     bool spilled = false;
-                    uint32_t pend_slot = 0xFFFFFFFFu, pend_k = 0u, pend_old = 0u;
                     for (uint32_t base = 0; base < total; base += 32u * kReplayUnroll)
                     {
                         // several batches of 32 candidates per trip: their loads are in flight together
@@ -743,20 +751,11 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
                             touched += __popc(__ballot_sync(kFullMask, live)); // indices_.push_back (with multiplicity)
                             if (__any_sync(kFullMask, removed_now))
                             {
-                                // one atomic per cell: candidates arrive cell by cell, so equal slots are neighbours.
-                                // The warp that removes a cell's last live point flags the cell as dead.
+                                // one fire-and-forget atomic per cell: candidates arrive cell by cell, so equal slots are neighbours
                                 const uint32_t sl = removed_now ? pslot[pos] : 0xFFFFFFFFu;
                                 const uint32_t peers = __match_any_sync(kFullMask, sl);
-                                // resolve the previous batch's counter first: its round trip is over by now
-                                if (pend_slot != 0xFFFFFFFFu && pend_old == pend_k)
-                                    atomicOr(&tabw[4u * pend_slot], 0x80000000u);
-                                pend_slot = 0xFFFFFFFFu;
                                 if (removed_now && (peers & lt) == 0u)
-                                {
-                                    pend_k = static_cast<uint32_t>(__popc(peers));
-                                    pend_slot = sl;
-                                    pend_old = atomicSub(&tlive[sl], pend_k);
-                                }
+                                    atomicSub(&tlive[sl], static_cast<uint32_t>(__popc(peers)));
                             }
                             const uint32_t bp = __ballot_sync(kFullMask, push);
                             const uint32_t nadd = __popc(bp);
@@ -783,8 +782,6 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, uint4 *
                             }
                         }
                     }
-                    if (pend_slot != 0xFFFFFFFFu && pend_old == pend_k)
-                        atomicOr(&tabw[4u * pend_slot], 0x80000000u);
                     __syncwarp();
                     // the FIFO receives this expansion's pushes in ascending k-d pre-order rank
                     if (np)

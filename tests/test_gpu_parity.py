@@ -284,3 +284,37 @@ def test_pipeline_reports_bad_input(pkg):
             pipe.process([bad, bad])
     finally:
         pipe.close()
+
+
+def test_cluster_cta_path_extremes(ctx):
+    """Shapes that drive the CTA-per-component replay through its rare branches: > 4096 pushes from one
+    expansion (global-memory sort), record overflow with round halving, direct rounds with the large
+    push buffer, and long thin chains (speculative rounds whose entries remove each other)."""
+    rng = np.random.default_rng(23)
+    # 6000 points on a 0.3 m shell around the seed: one expansion pushes all of them
+    v = rng.normal(size=(6000, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    shell = np.concatenate([np.zeros((1, 3)), 0.3 * v]).astype(np.float32)
+    H.check_clustering(shell, ctx.cluster(shell))
+    # solid dense ball, 1 mm quantised (ties): thousands of candidates per expansion
+    ball = rng.normal(size=(9000, 3)) * 0.25
+    ball = (np.round(ball * 1000) / 1000).astype(np.float32)
+    H.check_clustering(ball, ctx.cluster(ball))
+    # long thin chain, about 6 points per expansion, random input order
+    t = np.sort(rng.uniform(0, 120, 3000))
+    chain = np.stack([t, 0.05 * np.sin(t), 0.02 * rng.normal(size=t.size)], 1).astype(np.float32)
+    chain = chain[rng.permutation(chain.shape[0])]
+    H.check_clustering(chain, ctx.cluster(chain))
+    # a sheet: wide frontier, many live entries per round
+    g = np.stack(np.meshgrid(np.arange(80), np.arange(80), indexing="ij"), -1).reshape(-1, 2) * 0.07
+    sheet = np.concatenate([g, 0.01 * rng.normal(size=(g.shape[0], 1))], 1).astype(np.float32)
+    H.check_clustering(sheet, ctx.cluster(sheet))
+    # min/max cluster size with multiplicity on a CTA-sized component
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    ctx.clu_configure(pkg.ClusteringConfiguration(min_cluster_size=10, max_cluster_size=20000))
+    try:
+        for pts in (sheet, chain, ball):
+            H.check_clustering(pts, ctx.cluster(pts), H.to_oracle_clu_cfg(pkg.ClusteringConfiguration(min_cluster_size=10, max_cluster_size=20000)))
+    finally:
+        ctx.clu_configure(pkg.ClusteringConfiguration())
