@@ -77,7 +77,7 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_key_a, d_key_b, d_val_a, d_val_b, d_labels, d_gidx, d_oidx, d_slot_of, d_pos_of, d_parent,
         d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label, d_comp_size, d_pslot;
     DevBuf<int32_t> d_clabels;
-    DevBuf<unsigned long long> d_spill;
+    DevBuf<unsigned long long> d_spill, d_pkey;
     DevBuf<uint8_t> d_flags, d_seed_valid;
     // per table slot
     DevBuf<unsigned long long> d_tkeys;
@@ -210,7 +210,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
                                     &c->d_seed_of, &c->d_member_pos, &c->d_queue, &c->d_seed_label, &c->d_comp_size, &c->d_pslot};
         for (auto *b : u32s)
             rc |= dev_alloc(c, *b, n);
-        rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_flags, n) |
+        rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_pkey, n) | dev_alloc(c, c->d_flags, n) |
               dev_alloc(c, c->d_seed_valid, n) | dev_alloc(c, c->d_biglist, kBigBuckets * (n / kCtaComponentMin + 1u));
         if (c->want_job_stats)
             rc |= dev_alloc(c, c->d_job_stats, 8u * (n / kCtaComponentMin + 1u));
@@ -484,7 +484,8 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
 
     mark(c, 7);
     replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_slot_of.p,
-                                          c->d_rpts.p, c->d_seed_of.p, c->d_member_pos.p, c->d_pslot.p, c->m_cursor());
+                                          c->d_rpts.p, c->d_seed_of.p, c->d_member_pos.p, c->d_pslot.p, c->m_cursor(), tv,
+                                          c->d_cells.p, c->d_pkey.p);
     replay_live_init_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_cells.p, c->d_tlive.p);
     // components of at least kCtaComponent members: one CTA each (speculative rounds, CTA-wide scans),
     // started first on a second stream so that the longest BFS chains begin at time zero
@@ -494,9 +495,9 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
                                              bucket_capacity, big_count);
     LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
     LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
-    replay_cta_kernel<<<c->sm_count * c->replay_big_ctas_per_sm, kCtaThreads, sizeof(CtaSmem), c->stream_big>>>(
+    replay_cta_kernel<<<c->sm_count * c->replay_big_ctas_per_sm, kCtaThreads, 0, c->stream_big>>>(
         c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
-        c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p, bucket_capacity, big_count,
+        c->d_pkey.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p, bucket_capacity, big_count,
         c->m_cursor() + 2, c->d_job_stats.p);
     LB_CUDA(c, cudaEventRecord(c->ev_join, c->stream_big));
     const uint32_t claims = (max_m + 31u) / 32u;
@@ -604,8 +605,6 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
         }() ||
         cudaFuncSetAttribute(seg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(FitSmem))) != cudaSuccess ||
-        cudaFuncSetAttribute(replay_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(sizeof(CtaSmem))) != cudaSuccess ||
         reserve(c, max_points ? max_points : 200000u, max_frames ? max_frames : 1u) != 0)
     {
         lidar_b200_destroy(c);
@@ -650,7 +649,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_key_b.p,    c->d_val_a.p,  c->d_val_b.p,     c->d_labels.p, c->d_gidx.p,       c->d_oidx.p,
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
-                   c->d_clabels.p,  c->d_spill.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
+                   c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
                    c->d_cells.p,    c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
     for (void *p : dev)
         if (p)

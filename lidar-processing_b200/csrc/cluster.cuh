@@ -470,13 +470,14 @@ cc_flatten_kernel(BatchView bv, const uint32_t *__restrict__ parent, const uint3
 
 // Replay working set, in cell order: rpts[pos] = {x, y, z, bits(state)} with state = rank << 2 | flags,
 // so one 16-byte load brings a candidate's coordinates, its k-d pre-order rank and its removed /
-// queued flags. seed_of[pos] = unset; member_pos[t] = pos of the t-th member; pslot[pos] = hash slot
+// queued flags. pkey[pos] = key of the point's cell (neighbour keys are one 64-bit add away). seed_of[pos] = unset; member_pos[t] = pos of the t-th member; pslot[pos] = hash slot
 // of the point's cell; tlive[slot] = points of the cell that are not removed yet.
 __global__ void __launch_bounds__(256)
 replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t *__restrict__ rank_of_point,
                    const uint32_t *__restrict__ member_idx, const uint32_t *__restrict__ pos_of,
                    const uint32_t *__restrict__ slot_of, float4 *__restrict__ rpts, uint32_t *__restrict__ seed_of,
-                   uint32_t *__restrict__ member_pos, uint32_t *__restrict__ pslot, uint32_t *__restrict__ cursor)
+                   uint32_t *__restrict__ member_pos, uint32_t *__restrict__ pslot, uint32_t *__restrict__ cursor,
+                   TableView tv, const uint4 *__restrict__ cells, unsigned long long *__restrict__ pkey)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
@@ -489,7 +490,10 @@ replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t
         const uint32_t idx = __float_as_uint(p.w);
         rpts[off + i] = make_float4(p.x, p.y, p.z, __uint_as_float(rank_of_point[off + idx] << 2));
         seed_of[off + i] = kSeedUnset;
-        pslot[off + i] = slot_of[off + idx];
+        const uint32_t slot = slot_of[off + idx];
+        pslot[off + i] = slot;
+        const uint4 cell = cells[tv.toff[f] + slot];
+        pkey[off + i] = static_cast<unsigned long long>(cell.x) | (static_cast<unsigned long long>(cell.y) << 32);
         member_pos[off + i] = pos_of[off + member_idx[off + i]];
     }
 }

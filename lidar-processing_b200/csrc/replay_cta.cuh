@@ -9,16 +9,16 @@
 //  * speculative rounds — the next kW live FIFO entries are expanded TOGETHER against the state at
 //    the start of the round (window read, 27-cell lookups and candidate tests of all entries run in
 //    parallel across the CTA, one L2 round trip each), then the sequential semantics are restored
-//    in closed form:
+//    in closed form, from geometry alone (all entries' coordinates sit in shared memory):
 //        applied(k)      = entry k is not within the inner radius of an applied entry j < k
+//                          (otherwise j removed it: the reference pops it and moves on)
 //        removed_before  = some applied j < k holds the candidate within its inner radius
 //        queued_before   = queued at round start, or some applied j < k holds it in its annulus
-//    (per-candidate masks collected in a shared-memory hash). A record {candidate, entry k} then
-//    acts exactly like the reference's loop body at clustering.cpp:94-109; the round's pushes enter
-//    the FIFO ordered by (entry, k-d pre-order rank), i.e. in the reference's order. Warp k owns
-//    entry k: lookups, candidate tests, record resolution and the rank sort of its pushes are
-//    warp-local, the CTA meets at five barriers per round.
-//  * direct rounds — an entry with more candidates or hits than a warp's buffers hold (a dense
+//    With these three predicates a candidate of entry k is treated exactly like the reference's
+//    loop body at clustering.cpp:94-109 treats it; the round's pushes enter the FIFO ordered by
+//    (entry, k-d pre-order rank), i.e. in the reference's order. Warp k owns entry k (lookups,
+//    candidate tests, rank sort of its pushes); entries that are not applied cost nothing.
+//  * direct rounds — an entry with more candidates than a warp's buffers hold (a dense
 //    neighbourhood, thousands of candidates) is expanded alone by all 256 threads, its pushes are
 //    sorted by a CTA-wide bitonic network in shared memory.
 //
@@ -34,9 +34,7 @@ namespace lb
 constexpr int kCtaThreads = 256;
 constexpr uint32_t kCtaW = 8u;             // FIFO entries expanded per speculative round = warps per CTA
 constexpr uint32_t kRing = 1024u;          // FIFO entries mirrored in shared memory (power of two)
-constexpr uint32_t kEntryCandCap = 1024u;  // candidates of one entry in a speculative round
-constexpr uint32_t kEntryRecCap = 128u;    // hit records of one entry in a speculative round
-constexpr uint32_t kHashCap = 2048u;       // slots of the per-round candidate hash (power of two, >= 2 x records)
+constexpr uint32_t kEntryCandCap = 512u;   // candidates (hence pushes) of one entry in a speculative round
 constexpr uint32_t kDirectPushCap = 4096u; // pushes of a direct round kept in shared memory
 constexpr int kCtaUnroll = 4;
 
@@ -45,27 +43,19 @@ struct __align__(16) CtaSmem
     uint32_t ring[kRing];
     union
     {
-        struct
-        {
-            uint4 rec[kCtaW][kEntryRecCap];               // {pos, state word at load, cell slot << 1 | inner, hash slot}
-            unsigned long long pbuf[kCtaW][kEntryRecCap]; // pushes of entry k: rank << 31 | pos
-            uint8_t owner[kCtaW][kEntryCandCap];          // candidate number -> neighbour cell (0..26)
-        } b;
-        unsigned long long dpush[kDirectPushCap]; // direct round: pushes of the single entry
+        unsigned long long pbuf[kCtaW][kEntryCandCap]; // speculative round: pushes of entry k, rank << 31 | pos
+        unsigned long long dpush[kDirectPushCap];      // direct round: pushes of the single entry
     } u;
-    uint32_t hkey[kHashCap];  // pos + 1, 0 = empty
-    uint32_t hmask[kHashCap]; // bits 0..7: entries holding the point within the inner radius; 8..15: annulus
-    float4 ent[kCtaW];        // entry coordinates (w = state word)
-    uint32_t ent_widx[kCtaW]; // window index of the entry
-    uint32_t close[kCtaW];    // bit j: entry j < k lies within the inner radius of entry k
-    uint32_t nrec[kCtaW], np[kCtaW];
+    uint8_t owner[kCtaW][kEntryCandCap]; // candidate number -> neighbour cell (0..26)
+    float4 ent[kCtaW];                   // entry coordinates (w = state word)
+    unsigned long long ent_key[kCtaW];   // cell key of the entry
+    uint32_t ent_widx[kCtaW];            // window index of the entry
+    uint32_t tk[kCtaW], np[kCtaW];       // candidates / pushes of entry k
     uint32_t dstart[27], dexcl[27], dincl[27], dslot[27]; // neighbour cells of entry 0 (direct round)
     uint32_t wcnt[8];
-    uint32_t n_push, dense, claim, found;
+    uint32_t n_push, claim, found;
 };
-static_assert(sizeof(unsigned long long) * kDirectPushCap <=
-                  sizeof(uint4) * kCtaW * kEntryRecCap + 8u * kCtaW * kEntryRecCap + kCtaW * kEntryCandCap,
-              "direct push buffer must fit the speculative-round buffers it overlays");
+static_assert(sizeof(CtaSmem) <= 48u * 1024u, "static shared memory");
 
 // Sorts n 64-bit keys ascending with the whole CTA; works on shared or global memory. Bitonic network
 // in its "flip" form: every compare-exchange moves the smaller key to the lower index, so the slots
@@ -143,13 +133,13 @@ __global__ void __launch_bounds__(kCtaThreads)
 replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
                   CluParams prm, const uint32_t *__restrict__ member_root, const uint32_t *__restrict__ member_idx,
                   const uint32_t *__restrict__ member_pos, const uint32_t *__restrict__ comp_size,
-                  uint32_t *__restrict__ tlive_all, uint32_t *__restrict__ seed_of, uint32_t *__restrict__ queue,
+                  const unsigned long long *__restrict__ pkey_all, uint32_t *__restrict__ tlive_all,
+                  uint32_t *__restrict__ seed_of, uint32_t *__restrict__ queue,
                   unsigned long long *__restrict__ push_spill, uint8_t *__restrict__ seed_valid,
                   const uint2 *__restrict__ biglist, uint32_t bucket_capacity, const uint32_t *__restrict__ big_count,
                   uint32_t *__restrict__ cursor, uint32_t *__restrict__ job_stats /* optional: 8 words per job, see lidar_b200_last_replay_stats */)
 {
-    extern __shared__ __align__(16) unsigned char cta_smem_raw[];
-    CtaSmem &sm = *reinterpret_cast<CtaSmem *>(cta_smem_raw);
+    __shared__ CtaSmem sm;
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
@@ -164,12 +154,6 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
         }
     }
     const uint32_t n_big = bucket_end[kBigBuckets - 1u];
-
-    for (uint32_t i = tid; i < kHashCap; i += kCtaThreads)
-    {
-        sm.hkey[i] = 0u;
-        sm.hmask[i] = 0u;
-    }
 
     while (true)
     {
@@ -192,6 +176,7 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
         const uint4 *tab = cells + tv.toff[f];
         uint32_t *tlive = tlive_all + tv.toff[f];
         float4 *rp = rpts_all + off;
+        const unsigned long long *pkey = pkey_all + off;
         uint32_t *stw = reinterpret_cast<uint32_t *>(rp) + 3; // state word = .w of the point record
         uint32_t *so = seed_of + off;
         uint32_t *qu = queue + off + t_start; // the component's FIFO
@@ -204,6 +189,7 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
 
         const long long job_t0 = clock64();
         uint32_t st_rounds = 0u, st_direct = 0u, st_taken = 0u, st_seeds = 0u, st_cands = 0u;
+        long long tA = 0, tBC = 0, tEF = 0, tmark = 0;
         uint32_t u = t_start; // next member to examine as a seed candidate (ascending index, clustering.cpp:70-75)
         while (true)
         {
@@ -247,19 +233,20 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
             while (head < tail) // clustering.cpp:80-111
             {
                 // ---- A: window of the next 256 FIFO entries, the first kCtaW live ones are taken
+                tmark = clock64();
                 const uint32_t e = head + tid;
                 float4 pe = make_float4(0.f, 0.f, 0.f, __uint_as_float(kStRemoved));
+                unsigned long long pk = 0ull;
                 if (e < tail)
                 {
                     const uint32_t qpos = (tail - e <= kRing) ? sm.ring[e & (kRing - 1u)] : __ldcg(&qu[e]);
                     pe = __ldcg(&rp[qpos]);
+                    pk = __ldg(&pkey[qpos]);
                 }
                 const bool alive = (__float_as_uint(pe.w) & kStRemoved) == 0u;
                 const uint32_t ba = __ballot_sync(kFullMask, alive);
                 if (lane == 0)
                     sm.wcnt[warp] = __popc(ba);
-                if (tid == 0)
-                    sm.dense = 0u;
                 __syncthreads();
                 uint32_t before = 0u, total_alive = 0u;
 #pragma unroll
@@ -279,39 +266,55 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                 if (alive && arank < kCtaW)
                 {
                     sm.ent[arank] = pe;
+                    sm.ent_key[arank] = pk;
                     sm.ent_widx[arank] = tid;
                 }
                 const uint32_t n_take = min(kCtaW, total_alive);
                 __syncthreads();
                 ++st_rounds;
                 st_taken += n_take;
+                { const long long t = clock64(); tA += t - tmark; tmark = t; }
 
-                // ---- B + C: warp k expands entry k against the state at the start of the round
-                uint32_t my_nrec = 0u;
-                if (warp < n_take)
+                // ---- which entries are really expanded: lane p < 28 tests the pair (j, k), j < k; every warp
+                // derives the same mask. close bits of entry k sit at bit k(k-1)/2 + j.
+                uint32_t applied = 0u;
                 {
-                    const float4 pj = sm.ent[warp];
+                    const uint32_t k = lane >= 21u ? 7u : lane >= 15u ? 6u : lane >= 10u ? 5u : lane >= 6u ? 4u : lane >= 3u ? 3u : lane >= 1u ? 2u : 1u;
+                    const uint32_t j = lane - ((k * (k - 1u)) >> 1);
                     bool cl = false;
-                    if (lane < warp)
+                    if (lane < 28u && k < n_take)
                     {
-                        const float4 po = sm.ent[lane];
-                        cl = dist_sqr_ref(po.x, po.y, po.z, pj.x, pj.y, pj.z) <= prm.inner_threshold;
+                        const float4 pa = sm.ent[j], pb = sm.ent[k];
+                        cl = dist_sqr_ref(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) <= prm.inner_threshold;
                     }
-                    const uint32_t close = __ballot_sync(kFullMask, cl);
-                    uint32_t start = 0u, count = 0u, slot = 0u;
+                    const uint32_t pm = __ballot_sync(kFullMask, cl);
+                    for (uint32_t kk = 0; kk < n_take; ++kk)
+                    {
+                        const uint32_t closebits = (pm >> ((kk * (kk - 1u)) >> 1)) & ((1u << kk) - 1u);
+                        if ((closebits & applied) == 0u)
+                            applied |= 1u << kk;
+                    }
+                }
+
+                // ---- B: warp k looks up the 27 cells of entry k (applied entries only)
+                const bool mine = warp < n_take && ((applied >> warp) & 1u);
+                uint32_t start = 0u, count = 0u, slot = 0u, incl = 0u, excl = 0u, T = 0u;
+                float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mine)
+                {
+                    pj = sm.ent[warp];
                     if (lane < 27u)
                     {
-                        int cx, cy, cz;
-                        cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
-                        cell_lookup_alive(tab, tlive, mask,
-                                          cell_key(cx + static_cast<int>(lane % 3u) - 1,
-                                                   cy + static_cast<int>((lane / 3u) % 3u) - 1,
-                                                   cz + static_cast<int>(lane / 9u) - 1),
-                                          &start, &count, &slot);
+                        // neighbour key = own key + (dx, dy, dz) in the packed 21-bit fields (biased, no borrow)
+                        const long long dk = static_cast<long long>(static_cast<int>(lane % 3u) - 1) +
+                                             (static_cast<long long>(static_cast<int>((lane / 3u) % 3u) - 1) << 21) +
+                                             (static_cast<long long>(static_cast<int>(lane / 9u) - 1) << 42);
+                        cell_lookup_alive(tab, tlive, mask, sm.ent_key[warp] + static_cast<unsigned long long>(dk), &start,
+                                          &count, &slot);
                     }
-                    const uint32_t incl = warp_inclusive_scan(count);
-                    const uint32_t excl = incl - count;
-                    const uint32_t T = __shfl_sync(kFullMask, incl, 31);
+                    incl = warp_inclusive_scan(count);
+                    excl = incl - count;
+                    T = __shfl_sync(kFullMask, incl, 31);
                     st_cands += T;
                     if (warp == 0u && lane < 27u)
                     {
@@ -320,10 +323,27 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                         sm.dincl[lane] = incl;
                         sm.dslot[lane] = slot;
                     }
-                    bool dense = T > kEntryCandCap;
-                    if (!dense)
+                }
+                if (lane == 0)
+                    sm.tk[warp] = T;
+                __syncthreads();
+                // entries from the first dense one on wait for a later round; a dense FIRST entry is expanded alone
+                uint32_t n_use = n_take;
+#pragma unroll
+                for (uint32_t v = kCtaW; v-- > 0u;)
+                    if (v < n_take && sm.tk[v] > kEntryCandCap)
+                        n_use = v;
+                { const long long t = clock64(); tBC += t - tmark; tmark = t; }
+                uint32_t np_total = 0u;
+
+                if (n_use != 0u)
+                {
+                    // ---- C: warp k treats the candidates of entry k like the loop body of clustering.cpp:94-109
+                    uint32_t my_np = 0u;
+                    if (mine && warp < n_use)
                     {
-                        uint8_t *own = sm.u.b.owner[warp];
+                        const uint32_t earlier = applied & ((1u << warp) - 1u);
+                        uint8_t *own = sm.owner[warp];
                         for (uint32_t i = 0; i < count; ++i)
                             own[excl + i] = static_cast<uint8_t>(lane);
                         __syncwarp();
@@ -352,96 +372,46 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                                     break;
                                 const float4 cand = cand2[h];
                                 const uint32_t sw = __float_as_uint(cand.w);
-                                bool hit = false, inner = false;
+                                bool push = false;
                                 if ((sw & kStRemoved) == 0u) // removed points are skipped (clustering.cpp:94-97)
                                 {
                                     // KDTree::dist_sqr(target, node) (kdtree.hpp:145-163), inclusive test (kdtree.hpp:314)
                                     const float d2 = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z);
-                                    hit = d2 <= prm.distance_squared;
-                                    inner = d2 <= prm.inner_threshold;
-                                }
-                                const uint32_t bh = __ballot_sync(kFullMask, hit);
-                                const uint32_t idx = my_nrec + __popc(bh & lt);
-                                if (hit && idx < kEntryRecCap)
-                                {
-                                    const uint32_t pos = pos2[h];
-                                    uint32_t hs = (pos * 2654435761u) >> 21; // 11 bits
-                                    while (true)
+                                    if (d2 <= prm.distance_squared)
                                     {
-                                        const uint32_t old = atomicCAS(&sm.hkey[hs], 0u, pos + 1u);
-                                        if (old == 0u || old == pos + 1u)
-                                            break;
-                                        hs = (hs + 1u) & (kHashCap - 1u);
+                                        // what the entries expanded earlier in this round did to the candidate
+                                        bool removed_before = false, queued_before = (sw & kStQueued) != 0u;
+                                        for (uint32_t em = earlier; em; em &= em - 1u)
+                                        {
+                                            const float4 po = sm.ent[__ffs(em) - 1];
+                                            const float dj = dist_sqr_ref(po.x, po.y, po.z, cand.x, cand.y, cand.z);
+                                            removed_before |= dj <= prm.inner_threshold;
+                                            queued_before |= dj <= prm.distance_squared;
+                                        }
+                                        if (!removed_before)
+                                        {
+                                            const uint32_t pos = pos2[h];
+                                            so[pos] = seed_idx; // labels[k] = label (clustering.cpp:99)
+                                            ++touched;          // indices_.push_back (with multiplicity)
+                                            if (d2 <= prm.inner_threshold)
+                                            {
+                                                atomicOr(&stw[4u * pos], kStRemoved); // clustering.cpp:102-105
+                                                atomicSub(&tlive[slot2[h]], 1u);
+                                            }
+                                            else if (!queued_before)
+                                            {
+                                                atomicOr(&stw[4u * pos], kStQueued); // clustering.cpp:106-109 (first push only)
+                                                push = true;
+                                            }
+                                        }
                                     }
-                                    atomicOr(&sm.hmask[hs], (inner ? 1u : 0x100u) << warp);
-                                    sm.u.b.rec[warp][idx] = make_uint4(pos, sw, (slot2[h] << 1) | (inner ? 1u : 0u), hs);
                                 }
-                                my_nrec += __popc(bh);
+                                const uint32_t bp = __ballot_sync(kFullMask, push);
+                                if (push)
+                                    sm.u.pbuf[warp][my_np + __popc(bp & lt)] =
+                                        (static_cast<unsigned long long>(sw >> 2) << 31) | static_cast<unsigned long long>(pos2[h]);
+                                my_np += __popc(bp);
                             }
-                        }
-                        dense = my_nrec > kEntryRecCap;
-                    }
-                    if (lane == 0)
-                    {
-                        sm.close[warp] = close;
-                        sm.nrec[warp] = min(my_nrec, kEntryRecCap);
-                        if (dense)
-                            atomicOr(&sm.dense, 1u << warp);
-                    }
-                }
-                else if (lane == 0)
-                    sm.nrec[warp] = 0u;
-                __syncthreads();
-
-                // entries from the first dense one on wait for a later round; a dense FIRST entry is expanded alone
-                const uint32_t dense_mask = sm.dense;
-                const uint32_t n_use = dense_mask ? min(n_take, static_cast<uint32_t>(__ffs(dense_mask)) - 1u) : n_take;
-                uint32_t np_total = 0u;
-
-                if (n_use != 0u)
-                {
-                    // ---- D: which entries are really expanded (every thread derives the same mask)
-                    uint32_t applied = 0u;
-                    for (uint32_t k = 0; k < n_use; ++k)
-                        if ((sm.close[k] & applied) == 0u)
-                            applied |= 1u << k;
-                    // ---- E: every record of an applied entry acts like the loop body of clustering.cpp:94-109
-                    uint32_t my_np = 0u;
-                    const uint32_t nrec = sm.nrec[warp];
-                    if (warp < n_use && ((applied >> warp) & 1u))
-                    {
-                        const uint32_t earlier = applied & ((1u << warp) - 1u);
-                        for (uint32_t base = 0; base < nrec; base += 32u)
-                        {
-                            const uint32_t r = base + lane;
-                            bool push = false;
-                            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-                            if (r < nrec)
-                            {
-                                rec = sm.u.b.rec[warp][r];
-                                const uint32_t hm = sm.hmask[rec.w];
-                                if ((hm & 0xFFu & earlier) == 0u) // not removed by an earlier entry of this round
-                                {
-                                    const uint32_t pos = rec.x;
-                                    so[pos] = seed_idx; // labels[k] = label (clustering.cpp:99)
-                                    ++touched;          // indices_.push_back (with multiplicity)
-                                    if (rec.z & 1u)
-                                    {
-                                        atomicOr(&stw[4u * pos], kStRemoved); // clustering.cpp:102-105
-                                        atomicSub(&tlive[rec.z >> 1], 1u);
-                                    }
-                                    else if ((rec.y & kStQueued) == 0u && ((hm >> 8) & earlier) == 0u)
-                                    {
-                                        atomicOr(&stw[4u * pos], kStQueued); // clustering.cpp:106-109 (first push only)
-                                        push = true;
-                                    }
-                                }
-                            }
-                            const uint32_t bp = __ballot_sync(kFullMask, push);
-                            if (push)
-                                sm.u.b.pbuf[warp][my_np + __popc(bp & lt)] =
-                                    (static_cast<unsigned long long>(rec.y >> 2) << 31) | static_cast<unsigned long long>(rec.x);
-                            my_np += __popc(bp);
                         }
                     }
                     if (lane == 0)
@@ -458,20 +428,13 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                     }
                     for (uint32_t e2 = lane; e2 < my_np; e2 += 32u)
                     {
-                        const unsigned long long mine = sm.u.b.pbuf[warp][e2];
+                        const unsigned long long key = sm.u.pbuf[warp][e2];
                         uint32_t dest = 0u;
                         for (uint32_t x = 0; x < my_np; ++x)
-                            dest += sm.u.b.pbuf[warp][x] < mine ? 1u : 0u;
-                        const uint32_t pos = static_cast<uint32_t>(mine) & 0x7FFFFFFFu;
+                            dest += sm.u.pbuf[warp][x] < key ? 1u : 0u;
+                        const uint32_t pos = static_cast<uint32_t>(key) & 0x7FFFFFFFu;
                         qu[tail + pre + dest] = pos;
                         sm.ring[(tail + pre + dest) & (kRing - 1u)] = pos;
-                    }
-                    // the hash goes back to all-empty for the next round
-                    for (uint32_t r = lane; r < nrec; r += 32u)
-                    {
-                        const uint32_t hs = sm.u.b.rec[warp][r].w;
-                        sm.hkey[hs] = 0u;
-                        sm.hmask[hs] = 0u;
                     }
                     head += sm.ent_widx[n_use - 1u] + 1u;
                 }
@@ -479,20 +442,11 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                 {
                     // ---- direct round: entry 0 alone, all 256 threads, acting on the loaded state at once
                     ++st_direct;
-                    {
-                        const uint32_t nrec = sm.nrec[warp];
-                        for (uint32_t r = lane; r < nrec; r += 32u)
-                        {
-                            const uint32_t hs = sm.u.b.rec[warp][r].w;
-                            sm.hkey[hs] = 0u;
-                            sm.hmask[hs] = 0u;
-                        }
-                    }
                     if (tid == 0)
                         sm.n_push = 0u;
-                    __syncthreads(); // the push buffer overlays the records
-                    const float4 pj = sm.ent[0];
-                    const uint32_t T = sm.dincl[26];
+                    __syncthreads();
+                    pj = sm.ent[0];
+                    T = sm.dincl[26];
                     for (uint32_t base = 0; base < T; base += kCtaThreads * kCtaUnroll)
                     {
                         uint32_t pos2[kCtaUnroll], ci2[kCtaUnroll];
@@ -611,6 +565,7 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                 }
                 tail += np_total;
                 __syncthreads();
+                { const long long t = clock64(); tEF += t - tmark; tmark = t; }
             }
             // ---- seed finished: cluster size test with multiplicity (clustering.cpp:113-123)
             touched = warp_reduce_add(touched);
@@ -635,9 +590,9 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
             js[2] = static_cast<uint32_t>((clock64() - job_t0) >> 10);
             js[3] = st_rounds;
             js[4] = st_direct;
-            js[5] = st_taken;
-            js[6] = st_seeds;
-            js[7] = st_cands; // warp 0's share (entry 0 of every round)
+            js[5] = static_cast<uint32_t>(tA >> 10);
+            js[6] = static_cast<uint32_t>(tBC >> 10);
+            js[7] = static_cast<uint32_t>(tEF >> 10);
         }
     }
 }
