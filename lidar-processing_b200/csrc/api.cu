@@ -83,6 +83,8 @@ struct lidar_b200_ctx
     DevBuf<unsigned long long> d_tkeys;
     DevBuf<uint32_t> d_tcount, d_tlive;
     DevBuf<uint4> d_cells;
+    DevBuf<uint32_t> d_nbr;  // 27 neighbour cell ids per cell (rows live at cell-start positions)
+    DevBuf<uint2> d_cinfo;   // {points, common parent} per cell
     DevBuf<uint2> d_biglist; // {frame, first member} of every component replayed by a whole CTA
     DevBuf<uint32_t> d_job_stats; // optional per-job counters of the CTA replay (LIDAR_B200_REPLAY_STATS=1)
     bool want_job_stats{false};
@@ -211,7 +213,8 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
         for (auto *b : u32s)
             rc |= dev_alloc(c, *b, n);
         rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_pkey, n) | dev_alloc(c, c->d_flags, n) |
-              dev_alloc(c, c->d_seed_valid, n) | dev_alloc(c, c->d_biglist, kBigBuckets * (n / kCtaComponentMin + 1u));
+              dev_alloc(c, c->d_seed_valid, n) | dev_alloc(c, c->d_nbr, 27u * n) | dev_alloc(c, c->d_cinfo, n) |
+              dev_alloc(c, c->d_biglist, kBigBuckets * (n / kCtaComponentMin + 1u));
         if (c->want_job_stats)
             rc |= dev_alloc(c, c->d_job_stats, 8u * (n / kCtaComponentMin + 1u));
         if (rc)
@@ -457,18 +460,20 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     grid_insert_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->clu, c->d_tkeys.p, c->d_tcount.p, c->d_slot_of.p, c->d_err.p);
     grid_scan_kernel<<<F, 1024, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p, c->d_cells.p);
     grid_fill_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->d_cells.p, c->d_tcount.p, c->d_slot_of.p, c->d_cpts.p,
-                                        c->d_pos_of.p);
+                                        c->d_pos_of.p, c->d_state.p /* cell_of */);
     mark(c, 4);
     cc_init_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_comp_size.p);
     {
-        const dim3 gl(grid_x(max_m, 32u, 2368u), F); // each warp walks several points
-        cc_link_kernel<true><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p, c->d_tlive.p);
+        const uint32_t *cell_of = c->d_state.p;
+        cc_nbr_kernel<<<dim3(grid_x(max_m, 256u, 2048u), F), 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->d_slot_of.p,
+                                                                          cell_of, c->d_nbr.p, c->d_cinfo.p);
+        cc_sample_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->clu, cell_of, c->d_nbr.p, c->d_cinfo.p, c->d_parent.p);
         cc_compress_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
-        cc_cell_parent_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_cells.p, c->d_parent.p, c->d_tlive.p); // d_tlive doubles as cell_parent
-        cc_link_kernel<false><<<gl, 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->clu, c->d_parent.p, c->d_tlive.p);
+        cc_cell_parent_kernel<<<gp, 256, 0, s>>>(bv, cell_of, c->d_parent.p, c->d_cinfo.p);
+        cc_link_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->clu, cell_of, c->d_nbr.p, c->d_cinfo.p, c->d_parent.p);
     }
     cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_pos_of.p, c->d_key_a.p, c->d_val_a.p, c->d_comp_size.p);
-    c->launches += 10;
+    c->launches += 11;
     mark(c, 5);
     LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
     int rl = 0;
@@ -650,7 +655,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);

@@ -219,11 +219,12 @@ grid_scan_kernel(BatchView bv, TableView tv, const unsigned long long *__restric
     }
 }
 
-// cpts[pos] = {x, y, z, bits(index)} grouped by cell; pos_of[index] = pos
+// cpts[pos] = {x, y, z, bits(index)} grouped by cell; pos_of[index] = pos; cell_of[pos] = first pos of
+// the point's cell — the id under which the cell is known to the union-find kernels
 __global__ void __launch_bounds__(256)
 grid_fill_kernel(const float4 *__restrict__ pts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
                  uint32_t *__restrict__ tcount, const uint32_t *__restrict__ slot_of, float4 *__restrict__ cpts,
-                 uint32_t *__restrict__ pos_of)
+                 uint32_t *__restrict__ pos_of, uint32_t *__restrict__ cell_of)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
@@ -232,10 +233,12 @@ grid_fill_kernel(const float4 *__restrict__ pts, BatchView bv, TableView tv, con
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
         const uint32_t slot = slot_of[off + i];
-        const uint32_t pos = cells[toff + slot].z + atomicAdd(&tcount[toff + slot], 1u);
+        const uint32_t first = cells[toff + slot].z;
+        const uint32_t pos = first + atomicAdd(&tcount[toff + slot], 1u);
         const float4 p = pts[off + i];
         cpts[off + pos] = make_float4(p.x, p.y, p.z, __uint_as_float(i));
         pos_of[off + i] = pos;
+        cell_of[off + pos] = first;
     }
 }
 
@@ -288,106 +291,175 @@ cc_init_kernel(BatchView bv, uint32_t *__restrict__ parent, uint32_t *__restrict
     }
 }
 
-// Union-find runs in CELL-ORDER space: parent[pos], roots are the smallest pos of their tree.
-//
-// One warp per point (cell order, so neighbouring warps share cells and cache lines). Every
-// unordered pair of points in the same or in adjacent cells is visited exactly once: a point pairs
-// with the points of its own cell that precede it and with the 13 neighbour cells that follow its
-// cell in (dz, dy, dx) lexicographic order.
-//   kSample = true : Afforest-style sampling pass — link to the first two partners found, which
-//                    already merges most of every component;
-//   kSample = false: full pass. parent[] was flattened in between, so for nearly every candidate the
-//                    (coalesced, L1-cached) parent read equals the point's own and the pair is
-//                    skipped before the candidate's coordinates are even loaded. Stale cached
-//                    parents are safe for that test: a node reachable through old pointers stays in
-//                    the same set forever.
-template <bool kSample>
+// Union-find runs in CELL-ORDER space: parent[pos], roots are the smallest pos of their tree. A cell is
+// a contiguous run of pos and is named by its first pos (cell id); per cell:
+//   nbr[cid * 27 + k]  = id of the neighbour cell number k = (dz+1)*9 + (dy+1)*3 + (dx+1), or kNoCell
+//   cinfo[cid]         = {points in the cell, common parent of all its points after the last
+//                         flattening or kNoCell when they differ}
+// The neighbour table is built once per frame (27 hash probes per CELL instead of per point).
+constexpr uint32_t kNoCell = 0xFFFFFFFFu;
+
+// One warp per 32 consecutive pos: for every cell that starts among them, lanes 0..26 probe the hash.
 __global__ void __launch_bounds__(256)
-cc_link_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
-               CluParams prm, uint32_t *__restrict__ parent, const uint32_t *__restrict__ cell_parent)
+cc_nbr_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
+              const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ cell_of, uint32_t *__restrict__ nbr,
+              uint2 *__restrict__ cinfo)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
     const uint32_t mask = table_mask(m, tv.tcap[f]);
     const uint4 *tab = cells + tv.toff[f];
-    const uint32_t *cpar = cell_parent + tv.toff[f];
-    const float4 *cp = cpts + off;
-    uint32_t *par = parent + off;
     const uint32_t lane = lane_id();
     const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    // Full pass: lane l < 14 -> neighbour offset number 13 + l of the 27 (number 13 is the cell itself).
-    // Sampling pass: only the cell itself and its +x, +y, +z face neighbours (numbers 13, 14, 16, 22).
-    const uint32_t n_lookups = kSample ? 4u : 14u;
-    const uint32_t nb = kSample ? (lane == 0u ? 13u : (lane == 1u ? 14u : (lane == 2u ? 16u : 22u))) : 13u + lane;
-    const int ox = static_cast<int>(nb % 3u) - 1, oy = static_cast<int>((nb / 3u) % 3u) - 1, oz = static_cast<int>(nb / 9u) - 1;
-    for (uint32_t pos = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pos < m; pos += warps_per_grid)
+    const long long dk = static_cast<long long>(static_cast<int>(lane % 3u) - 1) +
+                         (static_cast<long long>(static_cast<int>((lane / 3u) % 3u) - 1) << 21) +
+                         (static_cast<long long>(static_cast<int>(lane / 9u) - 1) << 42);
+    for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; base < m; base += warps_per_grid * 32u)
+    {
+        const uint32_t pos = base + lane;
+        uint32_t slot = 0u;
+        bool is_start = false;
+        if (pos < m)
+        {
+            is_start = cell_of[off + pos] == pos;
+            if (is_start)
+                slot = slot_of[off + __float_as_uint(cpts[off + pos].w)];
+        }
+        uint32_t starts = __ballot_sync(kFullMask, is_start);
+        while (starts)
+        {
+            const int src = __ffs(starts) - 1;
+            starts &= starts - 1u;
+            const uint32_t cslot = __shfl_sync(kFullMask, slot, src);
+            const uint32_t cid = base + static_cast<uint32_t>(src);
+            const uint4 own = tab[cslot];
+            if (lane < 27u)
+            {
+                const unsigned long long key =
+                    (static_cast<unsigned long long>(own.x) | (static_cast<unsigned long long>(own.y) << 32)) +
+                    static_cast<unsigned long long>(dk);
+                uint32_t nstart, ncount;
+                cell_lookup(tab, mask, key, &nstart, &ncount);
+                nbr[(static_cast<size_t>(off) + cid) * 27u + lane] = ncount ? nstart : kNoCell;
+            }
+            if (lane == 0)
+                cinfo[off + cid] = make_uint2(own.w, kNoCell);
+        }
+    }
+}
+
+// Afforest-style sampling pass, one thread per point: link to the first point of the own cell that is
+// within reach (star-shaped trees), then to the first point within reach in each of the +x, +y, +z
+// face neighbours. This already merges most of every component.
+__global__ void __launch_bounds__(256)
+cc_sample_kernel(const float4 *__restrict__ cpts, BatchView bv, CluParams prm, const uint32_t *__restrict__ cell_of,
+                 const uint32_t *__restrict__ nbr, const uint2 *__restrict__ cinfo, uint32_t *__restrict__ parent)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const float4 *cp = cpts + off;
+    uint32_t *par = parent + off;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < m; pos += gridDim.x * blockDim.x)
+    {
+        const float4 pj = cp[pos];
+        const uint32_t cid = cell_of[off + pos];
+        for (uint32_t q = cid; q < pos; ++q)
+        {
+            const float4 cand = cp[q];
+            if (dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared)
+            {
+                uf_unite(par, pos, q);
+                break;
+            }
+        }
+        const uint32_t *row = nbr + (static_cast<size_t>(off) + cid) * 27u;
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+        {
+            const uint32_t n = row[t == 0 ? 14 : (t == 1 ? 16 : 22)];
+            if (n == kNoCell)
+                continue;
+            const uint32_t cnt = cinfo[off + n].x;
+            for (uint32_t q = n; q < n + cnt; ++q)
+            {
+                const float4 cand = cp[q];
+                if (dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared)
+                {
+                    uf_unite(par, pos, q);
+                    break;
+                }
+            }
+        }
+    }
+}
+
+// cinfo[cid].y = the common parent of all points of the cell, or kNoCell when they differ. Run right
+// after cc_compress_kernel. One thread per point, only cell starts work; cells are short.
+__global__ void __launch_bounds__(256)
+cc_cell_parent_kernel(BatchView bv, const uint32_t *__restrict__ cell_of, const uint32_t *__restrict__ parent,
+                      uint2 *__restrict__ cinfo)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < m; pos += gridDim.x * blockDim.x)
+    {
+        if (cell_of[off + pos] != pos)
+            continue;
+        const uint32_t cnt = cinfo[off + pos].x;
+        uint32_t common = parent[off + pos];
+        for (uint32_t k = 1; k < cnt; ++k)
+            if (parent[off + pos + k] != common)
+            {
+                common = kNoCell;
+                break;
+            }
+        cinfo[off + pos].y = common;
+    }
+}
+
+// Full pass, one thread per point. Every unordered pair of points in the same or in adjacent cells is
+// visited exactly once: a point pairs with the points of its own cell that precede it and with the 13
+// neighbour cells that follow its cell in (dz, dy, dx) lexicographic order. parent[] was flattened
+// after the sampling pass, so nearly every neighbour cell carries this point's parent as its common
+// parent and is skipped without touching a point; in the remaining cells a candidate whose (cached)
+// parent equals the point's own is skipped before its coordinates are loaded. Stale cached parents
+// are safe for that test: a node reachable through old pointers stays in the same set forever.
+__global__ void __launch_bounds__(256)
+cc_link_kernel(const float4 *__restrict__ cpts, BatchView bv, CluParams prm, const uint32_t *__restrict__ cell_of,
+               const uint32_t *__restrict__ nbr, const uint2 *__restrict__ cinfo, uint32_t *__restrict__ parent)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const float4 *cp = cpts + off;
+    uint32_t *par = parent + off;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < m; pos += gridDim.x * blockDim.x)
     {
         const float4 pj = cp[pos];
         uint32_t ri = par[pos];
-        int cx, cy, cz;
-        cell_coords(pj, prm.inv_cell, &cx, &cy, &cz);
-        uint32_t start = 0u, count = 0u;
-        if (lane < n_lookups)
+        const uint32_t cid = cell_of[off + pos];
+        const uint32_t *row = nbr + (static_cast<size_t>(off) + cid) * 27u;
+        for (uint32_t k = 13u; k < 27u; ++k)
         {
-            const uint32_t slot = cell_lookup_slot(tab, mask, cell_key(cx + ox, cy + oy, cz + oz), &start, &count);
-            // own cell: only the points that precede pos (a cell is a contiguous run of pos)
-            if (lane == 0u)
-                count = pos - start;
-            // a cell whose points all carried parent p when parent[] was flattened, p being this
-            // point's parent too, lies in this point's set already: skip it without reading a point
-            if (!kSample && count != 0u && cpar[slot] == ri)
-                count = 0u;
-        }
-        const uint32_t incl = warp_inclusive_scan(count);
-        const uint32_t excl = incl - count;
-        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-        uint32_t linked = 0u;
-        for (uint32_t base = 0; base < total; base += 32u)
-        {
-            const uint32_t q = base + lane;
-            uint32_t lo = 0u, hi = 13u;
-#pragma unroll
-            for (int it = 0; it < 4; ++it)
+            const uint32_t n = k == 13u ? cid : row[k];
+            if (n == kNoCell)
+                continue;
+            const uint2 ci = cinfo[off + n];
+            if (ci.y == ri)
+                continue;
+            const uint32_t end = k == 13u ? pos : n + ci.x; // own cell: only the points that precede pos
+            for (uint32_t q = n; q < end; ++q)
             {
-                const uint32_t mid = (lo + hi) >> 1;
-                const uint32_t v = __shfl_sync(kFullMask, incl, mid);
-                if (v > q)
-                    hi = mid;
-                else
-                    lo = mid + 1u;
-            }
-            const uint32_t c = min(lo, 13u);
-            const uint32_t cstart = __shfl_sync(kFullMask, start, c);
-            const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
-            const bool valid = q < total;
-            const uint32_t cpos = cstart + (q - cexcl);
-            if (kSample)
-            {
-                bool hit = false;
-                if (valid)
+                if (par[q] == ri)
+                    continue;
+                const float4 cand = cp[q];
+                if (dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared)
                 {
-                    const float4 cand = cp[cpos];
-                    hit = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared;
-                }
-                const uint32_t bh = __ballot_sync(kFullMask, hit);
-                if (hit && linked + __popc(bh & lanemask_lt()) < 2u)
-                    uf_unite(par, pos, cpos);
-                linked += __popc(bh);
-                if (linked >= 2u)
-                    break;
-            }
-            else if (valid)
-            {
-                const uint32_t pk = par[cpos];
-                if (pk != ri)
-                {
-                    const float4 cand = cp[cpos];
-                    if (dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z) <= prm.distance_squared)
-                    {
-                        uf_unite(par, pos, cpos);
-                        ri = __ldcg(&par[pos]);
-                    }
+                    uf_unite(par, pos, q);
+                    ri = __ldcg(&par[pos]);
                 }
             }
         }
@@ -410,34 +482,6 @@ __global__ void __launch_bounds__(256) cc_compress_kernel(BatchView bv, uint32_t
             p = __ldcg(&parent[off + x]);
         }
         parent[off + i] = x;
-    }
-}
-
-// cell_parent[slot] = the common parent of all points of the cell, or 0xFFFFFFFF when they differ
-// (or the slot is empty). Run right after cc_compress_kernel. One thread per slot; cells are short.
-__global__ void __launch_bounds__(256)
-cc_cell_parent_kernel(BatchView bv, TableView tv, const uint4 *__restrict__ cells, const uint32_t *__restrict__ parent,
-                      uint32_t *__restrict__ cell_parent)
-{
-    const uint32_t f = blockIdx.y;
-    const uint32_t cap = table_mask(bv.cnt[f], tv.tcap[f]) + 1u;
-    const uint32_t toff = tv.toff[f];
-    const uint32_t off = bv.off[f];
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x)
-    {
-        const uint4 c = cells[toff + s];
-        uint32_t common = 0xFFFFFFFFu;
-        if (c.w != 0u && !(c.x == 0xFFFFFFFFu && c.y == 0xFFFFFFFFu))
-        {
-            common = parent[off + c.z];
-            for (uint32_t k = 1; k < c.w; ++k)
-                if (parent[off + c.z + k] != common)
-                {
-                    common = 0xFFFFFFFFu;
-                    break;
-                }
-        }
-        cell_parent[toff + s] = common;
     }
 }
 
