@@ -57,7 +57,7 @@ struct lidar_b200_ctx
     int device{0};
     cudaStream_t stream{nullptr};
     cudaStream_t stream_big{nullptr}; // the CTA-per-component replay runs beside the warp-per-component one
-    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_fork{nullptr}, ev_join{nullptr};
+    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_fork{nullptr}, ev_join{nullptr}, ev_kd{nullptr};
     lidar_b200_seg_cfg seg_cfg{};
     lidar_b200_clu_cfg clu_cfg{};
     SegParams seg{};
@@ -456,6 +456,13 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     if (c->batch_is_cluster_only)
         mark(c, 3);
 
+    // The k-d pre-order ranks depend on the cloud only: they are built on the second stream while this
+    // one builds the voxel grid and the components (stage 'kd_order' below is what is left to wait for).
+    LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
+    LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
+    c->launches += kd_build_launch(c->stream_big, pts, bv, max_m, c->d_nodes.p, c->d_gepos.p, c->d_lepos.p, c->d_rank.p);
+    LB_CUDA(c, cudaEventRecord(c->ev_kd, c->stream_big));
+
     grid_clear_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p);
     grid_insert_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->clu, c->d_tkeys.p, c->d_tcount.p, c->d_slot_of.p, c->d_err.p);
     grid_scan_kernel<<<F, 1024, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p, c->d_cells.p);
@@ -485,7 +492,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     const uint32_t *member_idx = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
 
     mark(c, 6);
-    c->launches += kd_build_launch(s, pts, bv, max_m, c->d_nodes.p, c->d_gepos.p, c->d_lepos.p, c->d_rank.p);
+    LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_kd, 0)); // k-d order built on the second stream meanwhile
 
     mark(c, 7);
     replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_slot_of.p,
@@ -602,6 +609,7 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_kd, cudaEventDisableTiming) != cudaSuccess ||
         [&]() {
             for (auto &e : c->ev_stage)
                 if (cudaEventCreate(&e) != cudaSuccess)
@@ -670,6 +678,8 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
         cudaEventDestroy(c->ev_fork);
     if (c->ev_join)
         cudaEventDestroy(c->ev_join);
+    if (c->ev_kd)
+        cudaEventDestroy(c->ev_kd);
     if (c->stream_big)
         cudaStreamDestroy(c->stream_big);
     if (c->stream)
