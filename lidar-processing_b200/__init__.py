@@ -355,7 +355,7 @@ class FramePipeline:
         if rc != 0:
             raise LidarB200Error(f"lidar_b200_pipe_create failed (status {rc}): CUDA device {device} unavailable; "
                                  "there is no CPU fallback")
-        self._arena = None
+        self._arenas = {}
         self.h2d_bytes = self.d2h_bytes = 0
 
     def close(self):
@@ -383,7 +383,11 @@ class FramePipeline:
     def launch_count(self) -> int:
         return int(lib().lidar_b200_pipe_launch_count(self._h))
 
-    def process(self, frames, want_ground_idx: bool = True):
+    def submit(self, frames, want_ground_idx: bool = True, arena: int = 0):
+        """Enqueues a job (all its chunks) without waiting; returns a handle for results(). Jobs submitted
+        back to back keep the copy engines and the SMs busy across job boundaries; a job's results are
+        complete after drain() (or once `depth` later chunks have been submitted). Use a different
+        `arena` index for consecutive jobs whose results must stay readable meanwhile."""
         frames = [_as_points(f) for f in frames]
         nf = len(frames)
         strides = {f.shape[1] * 4 for f in frames} or {16}
@@ -394,11 +398,13 @@ class FramePipeline:
         padded = (counts.astype(np.int64) + 31) & ~31
         chunks = [(a, min(a + self.chunk_frames, nf)) for a in range(0, nf, self.chunk_frames)]
         total = int(padded.sum())
-        if self._arena is None or self._arena[0].size < max(total, 1) or self._arena[4].size < max(nf, 1):
-            self._arena = (pinned_empty(max(total, 1), np.uint32), pinned_empty(max(total, 1), np.uint32),
-                           pinned_empty(max(total, 1), np.uint32), pinned_empty(max(total, 1), np.int32),
-                           pinned_empty((4, max(nf, 1)), np.uint32))
-        seg, gidx, oidx, clab, meta = self._arena
+        ar = self._arenas.get(arena)
+        if ar is None or ar[0].size < max(total, 1) or ar[4].shape[1] < max(nf, 1):
+            ar = (pinned_empty(max(total, 1), np.uint32), pinned_empty(max(total, 1), np.uint32),
+                  pinned_empty(max(total, 1), np.uint32), pinned_empty(max(total, 1), np.int32),
+                  pinned_empty((4, max(nf, 1)), np.uint32))
+            self._arenas[arena] = ar
+        seg, gidx, oidx, clab, meta = ar
         u32, i32 = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
 
         def at(a, pos, t):
@@ -416,17 +422,30 @@ class FramePipeline:
                 mrow(2), at(clab, base, i32), mrow(3)), "pipe_submit")
             bases.append(base)
             base += int(padded[a:b].sum())
-        self._check(lib().lidar_b200_pipe_drain(self._h), "pipe_drain")
         self.h2d_bytes = int(counts.astype(np.int64).sum()) * 16 + 16 * nf
         self.d2h_bytes = (4 if want_ground_idx else 3) * total * 4 + 12 * nf + 4 * len(chunks)
+        return dict(frames=frames, counts=counts, chunks=chunks, bases=bases, arena=arena, want_ground_idx=want_ground_idx)
+
+    def drain(self):
+        self._check(lib().lidar_b200_pipe_drain(self._h), "pipe_drain")
+
+    def results(self, job):
+        """Per-frame result views of a drained job (valid until its arena is reused)."""
+        seg, gidx, oidx, clab, meta = self._arenas[job["arena"]]
+        counts, want = job["counts"], job["want_ground_idx"]
         out = []
-        for (a, b), cb in zip(chunks, bases):
+        for (a, b), cb in zip(job["chunks"], job["bases"]):
             for f in range(a, b):
                 o, n = cb + int(meta[0, f]), int(counts[f])
                 ng, no = int(meta[1, f]), int(meta[2, f])
-                out.append(dict(seg_labels=seg[o:o + n], ground_idx=gidx[o:o + ng] if want_ground_idx else None,
+                out.append(dict(seg_labels=seg[o:o + n], ground_idx=gidx[o:o + ng] if want else None,
                                 obstacle_idx=oidx[o:o + no], cluster_labels=clab[o:o + no], n_clusters=int(meta[3, f])))
         return out
+
+    def process(self, frames, want_ground_idx: bool = True):
+        job = self.submit(frames, want_ground_idx)
+        self.drain()
+        return self.results(job)
 
 
 class Segmenter:
