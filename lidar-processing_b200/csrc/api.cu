@@ -430,9 +430,14 @@ int run_segmentation(lidar_b200_ctx *c)
                                                                                     c->d_planes.p, c->d_status.p);
     ++c->launches;
     mark(c, 2);
-    seg_compact_kernel<<<F, 1024, 0, s>>>(c->d_spts.p, c->d_flags.p, bv, c->d_labels.p, c->d_gidx.p, c->d_oidx.p,
-                                          c->d_obs.p, c->m_ng(), c->m_no());
-    ++c->launches;
+    {
+        const uint32_t tiles = grid_x(c->max_n, kCompactTile, 0xFFFFu);
+        unsigned long long *tile_counts = reinterpret_cast<unsigned long long *>(c->d_hist.p);
+        seg_compact_count_kernel<<<dim3(tiles, F), 1024, 0, s>>>(c->d_flags.p, bv, tiles, tile_counts);
+        seg_compact_kernel<<<dim3(tiles, F), 1024, 0, s>>>(c->d_spts.p, c->d_flags.p, bv, tiles, tile_counts, c->d_labels.p,
+                                                           c->d_gidx.p, c->d_oidx.p, c->d_obs.p, c->m_ng(), c->m_no());
+    }
+    c->launches += 2;
     mark(c, 3);
     LB_CUDA(c, cudaGetLastError());
     return 0;
@@ -465,7 +470,12 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
 
     grid_clear_kernel<<<gt, 256, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p);
     grid_insert_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->clu, c->d_tkeys.p, c->d_tcount.p, c->d_slot_of.p, c->d_err.p);
-    grid_scan_kernel<<<F, 1024, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p, c->d_cells.p);
+    {
+        const uint32_t tiles = grid_x(c->max_tcap, kScanTile, 0xFFFFu);
+        unsigned long long *tile_counts = reinterpret_cast<unsigned long long *>(c->d_hist.p);
+        grid_scan_count_kernel<<<dim3(tiles, F), 1024, 0, s>>>(bv, tv, c->d_tcount.p, tiles, tile_counts);
+        grid_scan_kernel<<<dim3(tiles, F), 1024, 0, s>>>(bv, tv, c->d_tkeys.p, c->d_tcount.p, c->d_cells.p, tiles, tile_counts);
+    }
     grid_fill_kernel<<<gp, 256, 0, s>>>(pts, bv, tv, c->d_cells.p, c->d_tcount.p, c->d_slot_of.p, c->d_cpts.p,
                                         c->d_pos_of.p, c->d_state.p /* cell_of */);
     mark(c, 4);
@@ -480,7 +490,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
         cc_link_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->clu, cell_of, c->d_nbr.p, c->d_cinfo.p, c->d_parent.p);
     }
     cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_pos_of.p, c->d_key_a.p, c->d_val_a.p, c->d_comp_size.p);
-    c->launches += 11;
+    c->launches += 12;
     mark(c, 5);
     LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
     int rl = 0;
@@ -521,9 +531,17 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
                                                       c->m_cursor(), claims);
     LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join, 0));
     mark(c, 8);
-    label_compact_kernel<<<F, 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
-                                            c->d_clabels.p, c->m_nc());
-    c->launches += 6;
+    {
+        const uint32_t tiles = grid_x(max_m, kLabelTile, 0xFFFFu);
+        unsigned long long *tile_counts = reinterpret_cast<unsigned long long *>(c->d_hist.p);
+        label_count_kernel<<<dim3(tiles, F), 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, tiles,
+                                                           tile_counts);
+        label_number_kernel<<<dim3(tiles, F), 1024, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, tiles,
+                                                            tile_counts, c->d_seed_label.p, c->m_nc());
+        label_assign_kernel<<<gp, 256, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
+                                               c->d_clabels.p);
+    }
+    c->launches += 8;
     mark(c, 9);
     LB_CUDA(c, cudaGetLastError());
     return 0;

@@ -178,44 +178,66 @@ grid_insert_kernel(const float4 *__restrict__ pts, BatchView bv, TableView tv, C
     }
 }
 
-// One CTA per frame: exclusive scan of the per-slot counts, emits the packed cell records and
-// resets the counts (they become the fill cursors).
+// Exclusive scan of the per-slot counts in tiles of 4096 slots (grid = (tiles, frames)): pass 1 sums
+// every tile, pass 2 adds the sums of the preceding tiles, emits the packed cell records and resets
+// the counts (they become the fill cursors).
+constexpr int kScanPer = 4;
+constexpr uint32_t kScanTile = 1024u * kScanPer;
+
 __global__ void __launch_bounds__(1024)
-grid_scan_kernel(BatchView bv, TableView tv, const unsigned long long *__restrict__ tkeys,
-                 uint32_t *__restrict__ tcount, uint4 *__restrict__ cells)
+grid_scan_count_kernel(BatchView bv, TableView tv, const uint32_t *__restrict__ tcount, uint32_t max_tiles,
+                       unsigned long long *__restrict__ tile_counts)
 {
-    constexpr int kPer = 4;
-    __shared__ uint32_t ws[33];
-    const uint32_t f = blockIdx.x;
+    __shared__ unsigned long long ws64[33];
+    const uint32_t f = blockIdx.y;
     const uint32_t cap = table_mask(bv.cnt[f], tv.tcap[f]) + 1u;
     const uint32_t toff = tv.toff[f];
-    uint32_t carry = 0u;
-    for (uint32_t base = 0; base < cap; base += 1024 * kPer)
+    const uint32_t first = blockIdx.x * kScanTile + threadIdx.x * kScanPer;
+    unsigned long long sum = 0ull;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k)
+        sum += (first + k < cap) ? tcount[toff + first + k] : 0u;
+    sum = block_reduce_add64<1024>(sum, ws64);
+    if (threadIdx.x == 0)
+        tile_counts[static_cast<size_t>(f) * max_tiles + blockIdx.x] = sum;
+}
+
+__global__ void __launch_bounds__(1024)
+grid_scan_kernel(BatchView bv, TableView tv, const unsigned long long *__restrict__ tkeys,
+                 uint32_t *__restrict__ tcount, uint4 *__restrict__ cells, uint32_t max_tiles,
+                 const unsigned long long *__restrict__ tile_counts)
+{
+    __shared__ uint32_t ws[33];
+    __shared__ unsigned long long ws64[33];
+    const uint32_t f = blockIdx.y;
+    const uint32_t cap = table_mask(bv.cnt[f], tv.tcap[f]) + 1u;
+    const uint32_t toff = tv.toff[f];
+    const uint32_t base = blockIdx.x * kScanTile;
+    if (base >= cap)
+        return;
+    const uint32_t before =
+        static_cast<uint32_t>(tile_prefix64<1024>(tile_counts + static_cast<size_t>(f) * max_tiles, blockIdx.x, ws64));
+    const uint32_t first = base + threadIdx.x * kScanPer;
+    uint32_t cnt[kScanPer];
+    uint32_t sum = 0u;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k)
     {
-        const uint32_t first = base + threadIdx.x * kPer;
-        uint32_t c[kPer];
-        uint32_t sum = 0u;
+        cnt[k] = (first + k < cap) ? tcount[toff + first + k] : 0u;
+        sum += cnt[k];
+    }
+    uint32_t total;
+    uint32_t run = before + block_exclusive_scan<1024>(sum, ws, &total);
 #pragma unroll
-        for (int k = 0; k < kPer; ++k)
+    for (int k = 0; k < kScanPer; ++k)
+    {
+        if (first + k < cap)
         {
-            c[k] = (first + k < cap) ? tcount[toff + first + k] : 0u;
-            sum += c[k];
+            const unsigned long long key = tkeys[toff + first + k];
+            cells[toff + first + k] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), run, cnt[k]);
+            tcount[toff + first + k] = 0u;
         }
-        uint32_t total;
-        uint32_t run = carry + block_exclusive_scan<1024>(sum, ws, &total);
-#pragma unroll
-        for (int k = 0; k < kPer; ++k)
-        {
-            if (first + k < cap)
-            {
-                const unsigned long long key = tkeys[toff + first + k];
-                cells[toff + first + k] =
-                    make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), run, c[k]);
-                tcount[toff + first + k] = 0u;
-            }
-            run += c[k];
-        }
-        carry += total;
+        run += cnt[k];
     }
 }
 
@@ -887,42 +909,80 @@ replay_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, const u
     }
 }
 
-// One CTA per frame: label k = number of valid seeds with a smaller index (clustering.cpp:68,113-123)
-__global__ void __launch_bounds__(1024)
-label_compact_kernel(BatchView bv, const uint32_t *__restrict__ pos_of, const uint32_t *__restrict__ seed_of,
-                     const uint8_t *__restrict__ seed_valid, uint32_t *__restrict__ seed_label,
-                     int32_t *__restrict__ labels, uint32_t *__restrict__ n_clusters)
+// label k = number of valid seeds with a smaller index (clustering.cpp:68,113-123), in tiles of 4096
+// points (grid = (tiles, frames)): count the valid seeds per tile, number them, then label every point.
+constexpr int kLabelPer = 4;
+constexpr uint32_t kLabelTile = 1024u * kLabelPer;
+
+LB_D bool label_is_valid_seed(uint32_t i, uint32_t off, const uint32_t *pos_of, const uint32_t *seed_of,
+                              const uint8_t *seed_valid)
 {
-    constexpr int kPer = 4;
-    __shared__ uint32_t ws[33];
-    const uint32_t f = blockIdx.x;
+    return seed_of[off + pos_of[off + i]] == i && seed_valid[off + i] != 0u;
+}
+
+__global__ void __launch_bounds__(1024)
+label_count_kernel(BatchView bv, const uint32_t *__restrict__ pos_of, const uint32_t *__restrict__ seed_of,
+                   const uint8_t *__restrict__ seed_valid, uint32_t max_tiles, unsigned long long *__restrict__ tile_counts)
+{
+    __shared__ unsigned long long ws64[33];
+    const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
-    uint32_t carry = 0u;
-    for (uint32_t base = 0; base < m; base += 1024 * kPer)
+    const uint32_t first = blockIdx.x * kLabelTile + threadIdx.x * kLabelPer;
+    unsigned long long sum = 0ull;
+#pragma unroll
+    for (int k = 0; k < kLabelPer; ++k)
+        if (first + k < m && label_is_valid_seed(first + k, off, pos_of, seed_of, seed_valid))
+            ++sum;
+    sum = block_reduce_add64<1024>(sum, ws64);
+    if (threadIdx.x == 0)
+        tile_counts[static_cast<size_t>(f) * max_tiles + blockIdx.x] = sum;
+}
+
+__global__ void __launch_bounds__(1024)
+label_number_kernel(BatchView bv, const uint32_t *__restrict__ pos_of, const uint32_t *__restrict__ seed_of,
+                    const uint8_t *__restrict__ seed_valid, uint32_t max_tiles,
+                    const unsigned long long *__restrict__ tile_counts, uint32_t *__restrict__ seed_label,
+                    uint32_t *__restrict__ n_clusters)
+{
+    __shared__ uint32_t ws[33];
+    __shared__ unsigned long long ws64[33];
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const uint32_t base = blockIdx.x * kLabelTile;
+    if (base >= m && blockIdx.x != 0u)
+        return;
+    const uint32_t before =
+        static_cast<uint32_t>(tile_prefix64<1024>(tile_counts + static_cast<size_t>(f) * max_tiles, blockIdx.x, ws64));
+    const uint32_t first = base + threadIdx.x * kLabelPer;
+    bool is_seed[kLabelPer];
+    uint32_t sum = 0u;
+#pragma unroll
+    for (int k = 0; k < kLabelPer; ++k)
     {
-        const uint32_t first = base + threadIdx.x * kPer;
-        bool is_seed[kPer];
-        uint32_t sum = 0u;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k)
-        {
-            const uint32_t i = first + k;
-            is_seed[k] = false;
-            if (i < m)
-                is_seed[k] = seed_of[off + pos_of[off + i]] == i && seed_valid[off + i] != 0u;
-            sum += is_seed[k] ? 1u : 0u;
-        }
-        uint32_t total;
-        uint32_t run = carry + block_exclusive_scan<1024>(sum, ws, &total);
-#pragma unroll
-        for (int k = 0; k < kPer; ++k)
-            if (is_seed[k])
-                seed_label[off + first + k] = run++;
-        carry += total;
+        is_seed[k] = first + k < m && label_is_valid_seed(first + k, off, pos_of, seed_of, seed_valid);
+        sum += is_seed[k] ? 1u : 0u;
     }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < m; i += 1024)
+    uint32_t total;
+    uint32_t run = before + block_exclusive_scan<1024>(sum, ws, &total);
+#pragma unroll
+    for (int k = 0; k < kLabelPer; ++k)
+        if (is_seed[k])
+            seed_label[off + first + k] = run++;
+    if (threadIdx.x == 0 && base + kLabelTile >= m)
+        n_clusters[f] = before + total;
+}
+
+__global__ void __launch_bounds__(256)
+label_assign_kernel(BatchView bv, const uint32_t *__restrict__ pos_of, const uint32_t *__restrict__ seed_of,
+                    const uint8_t *__restrict__ seed_valid, const uint32_t *__restrict__ seed_label,
+                    int32_t *__restrict__ labels)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
         const uint32_t s = seed_of[off + pos_of[off + i]];
         int32_t lab = kLabelUndefined;
@@ -930,8 +990,6 @@ label_compact_kernel(BatchView bv, const uint32_t *__restrict__ pos_of, const ui
             lab = seed_valid[off + s] ? static_cast<int32_t>(seed_label[off + s]) : kLabelInvalid;
         labels[off + i] = lab;
     }
-    if (threadIdx.x == 0)
-        n_clusters[f] = carry;
 }
 
 } // namespace lb

@@ -139,6 +139,37 @@ template <int NT> LB_D uint32_t block_exclusive_scan(uint32_t v, uint32_t *ws, u
     return ws[warp] + incl - v;
 }
 
+// Sum of one 64-bit value per thread across a CTA of NT threads; every thread gets the total.
+// `ws64` is NT/32 + 1 words of shared memory. Two __syncthreads(); safe to call repeatedly.
+template <int NT> LB_D unsigned long long block_reduce_add64(unsigned long long v, unsigned long long *ws64)
+{
+    constexpr int NW = NT / 32;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v += __shfl_xor_sync(kFullMask, v, d);
+    __syncthreads(); // protect ws64 from a previous call's readers
+    if (lane_id() == 0)
+        ws64[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = 0ull;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        t += ws64[w];
+    return t;
+}
+
+// Tiled scans: a frame is cut into tiles of one CTA each; pass 1 stores one packed 64-bit count per
+// tile, pass 2 starts from the sum of the counts of the preceding tiles of its frame.
+template <int NT>
+LB_D unsigned long long tile_prefix64(const unsigned long long *__restrict__ tile_counts, uint32_t tile,
+                                      unsigned long long *ws64)
+{
+    unsigned long long v = 0ull;
+    for (uint32_t t = threadIdx.x; t < tile; t += NT)
+        v += tile_counts[t];
+    return block_reduce_add64<NT>(v, ws64);
+}
+
 // The reference build has no FMA contraction (x86-64 baseline, no -march; CMakeLists.txt has no
 // arch flags), so squared distances and plane distances are formed with explicit round-to-nearest
 // multiplies and adds. kdtree.hpp:145-163: d0 + (d1 + (d2 + 0)).

@@ -520,61 +520,86 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stable compaction, one CTA per frame. Output order = x-sorted order, i.e. partition 0 then 1 ...,
-// exactly the push_back order of segmentation.cpp:331-343.
+// Stable compaction in tiles of 4096 points (grid = (tiles, frames)): pass 1 counts ground / obstacle
+// points per tile, pass 2 adds the counts of the preceding tiles and writes. Output order = x-sorted
+// order, i.e. partition 0 then 1 ..., exactly the push_back order of segmentation.cpp:331-343.
+constexpr int kCompactPer = 4;
+constexpr uint32_t kCompactTile = 1024u * kCompactPer;
+
 __global__ void __launch_bounds__(1024)
-seg_compact_kernel(const float4 *__restrict__ spts, const uint8_t *__restrict__ flags, BatchView bv,
-                   uint32_t *__restrict__ labels, uint32_t *__restrict__ ground_idx, uint32_t *__restrict__ obstacle_idx,
-                   float4 *__restrict__ obstacle_pts, uint32_t *__restrict__ n_ground, uint32_t *__restrict__ n_obstacle)
+seg_compact_count_kernel(const uint8_t *__restrict__ flags, BatchView bv, uint32_t max_tiles,
+                         unsigned long long *__restrict__ tile_counts)
 {
-    constexpr int kPer = 4;
-    __shared__ uint32_t ws[33];
-    const uint32_t f = blockIdx.x;
+    __shared__ unsigned long long ws64[33];
+    const uint32_t f = blockIdx.y;
     const uint32_t n = bv.cnt[f];
     const uint32_t off = bv.off[f];
-    uint32_t gbase = 0u, obase = 0u;
-    for (uint32_t base = 0; base < n; base += 1024 * kPer)
+    const uint32_t first = blockIdx.x * kCompactTile + threadIdx.x * kCompactPer;
+    unsigned long long packed = 0ull; // ground count in the low word, obstacle count in the high word
+#pragma unroll
+    for (int k = 0; k < kCompactPer; ++k)
     {
-        const uint32_t first = base + threadIdx.x * kPer;
-        uint8_t fl[kPer];
-        uint32_t packed = 0u; // ground count in low 16 bits, obstacle count in high 16 bits
-#pragma unroll
-        for (int k = 0; k < kPer; ++k)
-        {
-            fl[k] = (first + k < n) ? flags[off + first + k] : 0u;
-            packed += (fl[k] == 1u ? 1u : 0u) + (fl[k] == 2u ? 0x10000u : 0u);
-        }
-        uint32_t total;
-        uint32_t ex = block_exclusive_scan<1024>(packed, ws, &total);
-        uint32_t g = gbase + (ex & 0xFFFFu);
-        uint32_t o = obase + (ex >> 16);
-#pragma unroll
-        for (int k = 0; k < kPer; ++k)
-        {
-            if (fl[k] == 0u)
-                continue;
-            const float4 p = spts[off + first + k];
-            const uint32_t orig = __float_as_uint(p.w);
-            if (fl[k] == 1u)
-            {
-                ground_idx[off + g++] = orig;
-                labels[off + orig] = kSegGround;
-            }
-            else
-            {
-                obstacle_idx[off + o] = orig;
-                obstacle_pts[off + o] = p;
-                ++o;
-                labels[off + orig] = kSegObstacle;
-            }
-        }
-        gbase += total & 0xFFFFu;
-        obase += total >> 16;
+        const uint8_t fl = (first + k < n) ? flags[off + first + k] : 0u;
+        packed += (fl == 1u ? 1ull : 0ull) + (fl == 2u ? (1ull << 32) : 0ull);
     }
+    const unsigned long long total = block_reduce_add64<1024>(packed, ws64);
     if (threadIdx.x == 0)
+        tile_counts[static_cast<size_t>(f) * max_tiles + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+seg_compact_kernel(const float4 *__restrict__ spts, const uint8_t *__restrict__ flags, BatchView bv, uint32_t max_tiles,
+                   const unsigned long long *__restrict__ tile_counts, uint32_t *__restrict__ labels,
+                   uint32_t *__restrict__ ground_idx, uint32_t *__restrict__ obstacle_idx,
+                   float4 *__restrict__ obstacle_pts, uint32_t *__restrict__ n_ground, uint32_t *__restrict__ n_obstacle)
+{
+    __shared__ uint32_t ws[33];
+    __shared__ unsigned long long ws64[33];
+    const uint32_t f = blockIdx.y;
+    const uint32_t n = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    const uint32_t base = blockIdx.x * kCompactTile;
+    if (base >= n && !(blockIdx.x == 0u))
+        return;
+    const unsigned long long before = tile_prefix64<1024>(tile_counts + static_cast<size_t>(f) * max_tiles, blockIdx.x, ws64);
+    const uint32_t first = base + threadIdx.x * kCompactPer;
+    uint8_t fl[kCompactPer];
+    uint32_t packed = 0u; // ground count in low 16 bits, obstacle count in high 16 bits (<= 4096 each)
+#pragma unroll
+    for (int k = 0; k < kCompactPer; ++k)
     {
-        n_ground[f] = gbase;
-        n_obstacle[f] = obase;
+        fl[k] = (first + k < n) ? flags[off + first + k] : 0u;
+        packed += (fl[k] == 1u ? 1u : 0u) + (fl[k] == 2u ? 0x10000u : 0u);
+    }
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan<1024>(packed, ws, &total);
+    uint32_t g = static_cast<uint32_t>(before) + (ex & 0xFFFFu);
+    uint32_t o = static_cast<uint32_t>(before >> 32) + (ex >> 16);
+#pragma unroll
+    for (int k = 0; k < kCompactPer; ++k)
+    {
+        if (fl[k] == 0u)
+            continue;
+        const float4 p = spts[off + first + k];
+        const uint32_t orig = __float_as_uint(p.w);
+        if (fl[k] == 1u)
+        {
+            ground_idx[off + g++] = orig;
+            labels[off + orig] = kSegGround;
+        }
+        else
+        {
+            obstacle_idx[off + o] = orig;
+            obstacle_pts[off + o] = p;
+            ++o;
+            labels[off + orig] = kSegObstacle;
+        }
+    }
+    // the tile that holds the frame's last point (tile 0 of an empty frame) publishes the totals
+    if (threadIdx.x == 0 && (base + kCompactTile >= n))
+    {
+        n_ground[f] = static_cast<uint32_t>(before) + (total & 0xFFFFu);
+        n_obstacle[f] = static_cast<uint32_t>(before >> 32) + (total >> 16);
     }
 }
 

@@ -28,8 +28,16 @@ def segment_ids(pts, partitions):
     return seg
 
 
-def check_segmentation(pts, labels, ground_idx, obstacle_idx, seg_cfg=None, labels_in=None):
-    """Returns the number of flipped points after asserting the stated tolerance."""
+def check_segmentation(pts, labels, ground_idx, obstacle_idx, seg_cfg=None, labels_in=None, device_planes=None,
+                       surface_gap_m=2 * FLIP_BAND_M):
+    """Returns the number of flipped points after asserting the stated tolerance. A flipped point must
+    lie within FLIP_BAND_M of the decision surface of the oracle's plane. When `device_planes`
+    ([partition][iteration][4]) is given the criterion is instead that the point lies between the
+    oracle's and the device's decision surfaces and that these are at most `surface_gap_m` apart at
+    that point: for partitions of several 100k points the oracle's sequential float32 sums (relative
+    error ~ sqrt(n)·eps) tilt its plane by ~1e-5 rad against the device's double-precision moments,
+    i.e. a few 1e-4 m at a 60 m lever arm (the reference's Eigen GEMM order is a third, unknowable,
+    rounding)."""
     cfg = seg_cfg or O.default_seg_cfg()
     ref = O.segment(pts, cfg, tie_mode=1, labels_in=labels_in)
     n = pts.shape[0]
@@ -50,7 +58,13 @@ def check_segmentation(pts, labels, ground_idx, obstacle_idx, seg_cfg=None, labe
             x, y, z = (float(v) for v in pts[i, :3])
             dist = x * a + y * b + z * c - d
             thr = cfg.orthogonal_distance_threshold * np.sqrt(a * a + b * b + c * c)
-            assert abs(dist - thr) < FLIP_BAND_M, f"point {i} flipped {abs(dist - thr):.3g} m from the decision surface"
+            gap = abs(dist - thr)
+            if device_planes is not None:
+                a, b, c, d = (float(v) for v in device_planes[seg[i], -1])
+                gap += abs(x * a + y * b + z * c - d - cfg.orthogonal_distance_threshold * np.sqrt(a * a + b * b + c * c))
+                assert gap < surface_gap_m, f"point {i}: decision surfaces {gap:.3g} m apart"
+                continue
+            assert gap < FLIP_BAND_M, f"point {i} flipped {gap:.3g} m from the decision surface"
     else:
         assert np.array_equal(ground_idx, ref["ground_idx"])
         assert np.array_equal(obstacle_idx, ref["obstacle_idx"])
