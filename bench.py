@@ -60,6 +60,30 @@ def load_workload(max_frames: int | None = None):
     return frames, name
 
 
+def check_fingerprints(results, frame_ids, workload):
+    """Bit-exact check of the timed run's own outputs against the committed per-frame fingerprints
+    (tests/golden/fingerprints.json: oracle segmentation + UNMODIFIED reference Clusterer, made in the
+    build container by tests/golden/make_golden.py). numpy only - no oracle code runs here."""
+    fp = ROOT / "tests" / "golden" / "fingerprints.json"
+    if not workload.startswith("kitti") or not fp.exists():
+        return None
+    from tools.checksums import mix64
+
+    rows = json.loads(fp.read_text())["frames"]
+    if "cluster_labels_mix64" not in rows[0]:
+        return None
+    out = {"frames_checked": 0, "seg_labels_equal": 0, "obstacle_order_equal": 0, "cluster_labels_equal": 0}
+    for r, fid in zip(results, frame_ids):
+        row = rows[fid % len(rows)]
+        out["frames_checked"] += 1
+        out["seg_labels_equal"] += int(mix64(r["seg_labels"]) == row["seg_labels_mix64"])
+        out["obstacle_order_equal"] += int(mix64(r["obstacle_idx"]) == row["obstacle_idx_mix64"])
+        out["cluster_labels_equal"] += int(mix64(r["cluster_labels"]) == row["cluster_labels_mix64"])
+    out["what"] = ("outputs of the timed resident run vs committed fingerprints of the oracle segmentation + unmodified "
+                   "reference Clusterer (raw labels, bit-exact)")
+    return out
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -211,6 +235,7 @@ def main():
     # the job is world x (workload) frames, split into contiguous blocks, one per rank; frame id i
     # uses workload frame i mod len(workload), so every rank holds the same amount of work (weak scaling)
     mine = sharding.shard_frames(world * len(frames), rank, world)
+    frame_ids = [args.frame_offset + (i % len(frames)) for i in mine]  # index into the 154-frame sequence
     frames = [frames[i % len(frames)] for i in mine]
     nf = len(frames)
     total_pts = int(sum(f.shape[0] for f in frames))
@@ -242,6 +267,7 @@ def main():
     res = ctx.batch_fetch()
     n_obstacle = int(sum(r["obstacle_idx"].size for r in res))
     n_clusters = int(sum(r["n_clusters"] for r in res))
+    parity = check_fingerprints(res, frame_ids, workload) if rank == 0 else None
     dev_ms_total = max_over_ranks(sum(gpu_ms))
     value = world * nf * args.steps / (dev_ms_total / 1e3)
 
@@ -339,6 +365,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "results": {"obstacle_points_per_step": n_obstacle, "clusters_per_step": n_clusters,
                     "wall_s_resident_region": wall_resident},
     }

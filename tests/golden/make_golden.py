@@ -6,7 +6,7 @@ Run in the build container (needs /root/reference):
 
 Outputs (committed):
   tests/golden/frames_0_77_153.xz   three reference frames, lossless (tools/pack_reference_frames.py format)
-  tests/golden/fingerprints.json    per-frame counts + FNV-1a fingerprints for all 154 frames:
+  tests/golden/fingerprints.json    per-frame counts + FNV-1a and numpy-only mix64 (tools/checksums.py) fingerprints for all 154 frames:
         segmentation  = oracle restatement (stable x order)          [parity unpinned at the Eigen boundary]
         clustering    = UNMODIFIED reference Clusterer (oracle/_ref)  on that obstacle cloud
     and, for every frame, the result of pinning the oracle against the reference build:
@@ -23,6 +23,7 @@ ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import oracle as O  # noqa: E402
 from tools.pack_reference_frames import pack  # noqa: E402
+from tools.checksums import mix64  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
 
@@ -56,6 +57,8 @@ def main():
             n_clusters=int(ref_lab.max() + 1) if ref_lab.size else 0, n_invalid=int((ref_lab == -1).sum()),
             cluster_labels_fnv=f"{O.fnv1a64(ref_lab):016x}", kd_order_fnv=f"{O.fnv1a64(ref_order):016x}",
             replay=stats,
+            seg_labels_mix64=mix64(seg["labels"]), obstacle_idx_mix64=mix64(seg["obstacle_idx"]),
+            ground_idx_mix64=mix64(seg["ground_idx"]), cluster_labels_mix64=mix64(ref_lab),
         ))
         if i % 10 == 0:
             print(i, rows[-1]["frame"], rows[-1]["n_obstacle"], rows[-1]["n_clusters"], pinned, flush=True)

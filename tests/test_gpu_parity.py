@@ -357,3 +357,38 @@ def test_config4_merged_multi_lidar_1m(ctx):
     assert np.unique(pairs[:, 0]).size == pairs.shape[0]          # an r/2-component is never split
     again = ctx.cluster(obs)
     assert np.array_equal(again, lab)
+
+
+@pytest.mark.gpu
+def test_all_154_reference_frames_bit_exact(pkg, fingerprints):
+    """North-star target: bit-exact cluster partition on all 154 repo frames. The frames travel to the
+    GPU box as data_cache/frames_mm.xz (tools/pack_reference_frames.py, lossless); the expected values
+    are the committed fingerprints of the oracle segmentation + UNMODIFIED reference Clusterer."""
+    from pathlib import Path
+
+    from tools.checksums import mix64
+    from tools.pack_reference_frames import unpack
+
+    cache = Path(__file__).resolve().parent.parent / "data_cache" / "frames_mm.xz"
+    if not cache.exists():
+        pytest.skip("data_cache/frames_mm.xz not on this box (run tools/pack_reference_frames.py in the build container)")
+    frames = unpack(cache)
+    rows = fingerprints["frames"]
+    assert len(frames) == len(rows) == 154
+    big = pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames))
+    try:
+        res = big.process_batch(frames)
+    finally:
+        big.close()
+    bad = []
+    for i, (r, row) in enumerate(zip(res, rows)):
+        ok = (r["seg_labels"].shape[0] == row["n"] and r["obstacle_idx"].size == row["n_obstacle"]
+              and mix64(r["seg_labels"]) == row["seg_labels_mix64"]
+              and mix64(r["obstacle_idx"]) == row["obstacle_idx_mix64"]
+              and mix64(r["ground_idx"]) == row["ground_idx_mix64"]
+              and r["n_clusters"] == row["n_clusters"]
+              and int((r["cluster_labels"] == -1).sum()) == row["n_invalid"]
+              and mix64(r["cluster_labels"]) == row["cluster_labels_mix64"])
+        if not ok:
+            bad.append(i)
+    assert not bad, f"frames differing from the reference fingerprints: {bad}"

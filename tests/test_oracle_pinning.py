@@ -142,3 +142,21 @@ def test_segmentation_paths():
     prev = np.full(odd.shape[0], 7, np.uint32)
     res = O.segment(odd, cfg, labels_in=prev)
     assert (res["labels"] == 7).sum() == 1  # the dropped point keeps the stale label
+
+
+def test_mix64_fingerprints_match_oracle_on_golden_frames(golden_frames, fingerprints):
+    """The numpy-only mix64 fingerprints (used on the GPU box for all 154 frames) agree with the oracle
+    and the unmodified reference Clusterer on the three committed frames."""
+    from tools.checksums import mix64
+
+    rows = {r["frame"]: r for r in fingerprints["frames"]}
+    for name, pts in zip(("0000000000.pcd", "0000000077.pcd", "0000000153.pcd"), golden_frames):
+        seg = O.segment(pts, tie_mode=1)
+        row = rows[name]
+        assert mix64(seg["labels"]) == row["seg_labels_mix64"]
+        assert mix64(seg["obstacle_idx"]) == row["obstacle_idx_mix64"]
+        assert mix64(seg["ground_idx"]) == row["ground_idx_mix64"]
+        lab = O.ref_cluster(pts[seg["obstacle_idx"]]) if O.ref_available() else O.cluster(pts[seg["obstacle_idx"]])
+        assert mix64(lab) == row["cluster_labels_mix64"]
+    assert mix64(np.array([], np.int32)) == f"{0:016x}"
+    assert mix64(np.array([1, 2], np.int32)) != mix64(np.array([2, 1], np.int32))

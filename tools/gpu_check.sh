@@ -26,8 +26,11 @@ launches)
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline ${NCU_BENCH_ARGS:---frames 16} > gpurun_out/ncu_bench.log 2>&1
   echo "launches exit: $?"; wc -l gpurun_out/launches.csv ;;
 ncu)
-  timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-replay_kernel} -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} \
-     -f -o gpurun_out/prof_${NCU_KERNEL:-replay_kernel} python bench.py --steps 1 --warmup 1 --no-cpu-baseline ${NCU_BENCH_ARGS:---frames 16} > gpurun_out/ncu_full.log 2>&1
-  echo "ncu exit: $?"; ls -la gpurun_out/*.ncu-rep ;;
+  for k in ${NCU_KERNELS:-replay_cta_kernel}; do
+  timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"^${k}" -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} \
+     -f -o gpurun_out/prof_${k} python bench.py --steps 1 --warmup 1 --no-cpu-baseline ${NCU_BENCH_ARGS:---frames 16} > gpurun_out/ncu_full_${k}.log 2>&1
+  echo "ncu $k exit: $?"
+  done
+  ls -la gpurun_out/*.ncu-rep ;;
 esac
 done
