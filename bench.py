@@ -72,15 +72,18 @@ def check_fingerprints(results, frame_ids, workload):
     rows = json.loads(fp.read_text())["frames"]
     if "cluster_labels_mix64" not in rows[0]:
         return None
-    out = {"frames_checked": 0, "seg_labels_equal": 0, "obstacle_order_equal": 0, "cluster_labels_equal": 0}
+    out = {"frames_checked": 0, "seg_labels_equal": 0, "same_obstacle_cloud": 0, "cluster_labels_equal_on_same_obstacle_cloud": 0}
     for r, fid in zip(results, frame_ids):
         row = rows[fid % len(rows)]
         out["frames_checked"] += 1
         out["seg_labels_equal"] += int(mix64(r["seg_labels"]) == row["seg_labels_mix64"])
-        out["obstacle_order_equal"] += int(mix64(r["obstacle_idx"]) == row["obstacle_idx_mix64"])
-        out["cluster_labels_equal"] += int(mix64(r["cluster_labels"]) == row["cluster_labels_mix64"])
-    out["what"] = ("outputs of the timed resident run vs committed fingerprints of the oracle segmentation + unmodified "
-                   "reference Clusterer (raw labels, bit-exact)")
+        same = mix64(r["obstacle_idx"]) == row["obstacle_idx_mix64"]
+        out["same_obstacle_cloud"] += int(same)
+        out["cluster_labels_equal_on_same_obstacle_cloud"] += int(same and mix64(r["cluster_labels"]) == row["cluster_labels_mix64"])
+    out["what"] = ("outputs of the timed resident run vs committed fingerprints (oracle segmentation + unmodified reference "
+                   "Clusterer, raw labels, bit-exact). Frames whose ground mask differs from the oracle's by a few points "
+                   "inside the stated 1e-4 m band feed a different obstacle cloud to the clusterer; those are checked "
+                   "against the reference on their own cloud by tests/test_gpu_parity.py::test_all_154_reference_frames")
     return out
 
 
@@ -95,48 +98,93 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions: an in-process NVML thread
+    (nvidia_ml_py, one sample every ~4 ms); `nvidia-smi -lms` is the fallback when NVML cannot load."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []  # (perf_counter, sm_mhz, reasons bitmask)
+        self.windows = []  # timed regions [(t0, t1)]
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            why = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            why = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((time.perf_counter(), mhz, why))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+
+            self.source = "nvml"
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            pass
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                     "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def pump():
+                for line in proc.stdout:
+                    parts = [x.strip() for x in line.split(",")]
+                    try:
+                        mhz, self.sm_max = float(parts[0]), float(parts[1])
+                    except (ValueError, IndexError):
+                        continue
+                    why = 0
+                    for (_, bit), val in zip(self.REASONS, parts[2:6]):
+                        if val.lower().startswith("active"):
+                            why |= bit
+                    self.samples.append((time.perf_counter(), mhz, why))
+                    if self._stop.is_set():
+                        break
+                proc.terminate()
+
+            self.source = "nvidia-smi"
+            self._thread = threading.Thread(target=pump, daemon=True)
+            self._thread.start()
+            t_end = time.perf_counter() + 5.0
+            while not self.samples and time.perf_counter() < t_end:
+                time.sleep(0.05)  # nvidia-smi needs a moment before its first line
+        except Exception:
+            self.source = None
+
+    def window(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)]
+        used = inside or self.samples
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        why = 0
+        for s_ in used:
+            why |= s_[2]
+        return {"sm_mhz": statistics.median(s_[1] for s_ in used), "sm_max_mhz": self.sm_max,
+                "reasons": [name for name, bit in self.REASONS if why & bit], "samples": len(used),
+                "samples_inside_timed_regions": len(inside), "source": self.source}
 
 
 def cpu_reference_run(frames, threads: int, n_sample: int):
@@ -184,7 +232,7 @@ def run_reference(args, frames, workload):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="use only the first N frames of the workload (debug)")
@@ -244,14 +292,14 @@ def main():
     ctx.set_profiling(True)
 
     # ---- device-resident throughput (`value`) -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     ctx.batch_stage(frames)  # inputs resident in HBM before the timed region
     for _ in range(args.warmup):
         ctx.batch_run()
         ctx.sync()
-    sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
     barrier()
-    sampler.start()
     gpu_ms, stage_acc = [], {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -262,7 +310,7 @@ def main():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     barrier()
     wall_resident = time.perf_counter() - t0
-    clocks = sampler.stop()
+    sampler.window(t0, t0 + wall_resident)
     launches = ctx.launch_count() - launches0
     res = ctx.batch_fetch()
     n_obstacle = int(sum(r["obstacle_idx"].size for r in res))
@@ -291,7 +339,9 @@ def main():
             job = pipe.submit(src, arena=s_ % 2)
         pipe.drain()
         barrier()
-        return max_over_ranks(time.perf_counter() - t0), pipe.results(job)
+        t1 = time.perf_counter()
+        sampler.window(t0, t1)
+        return max_over_ranks(t1 - t0), pipe.results(job)
 
     pipe_launches0 = pipe.launch_count()
     e2e_s, e2e_out = e2e_run(pinned_frames)
@@ -302,6 +352,7 @@ def main():
                    for a, b in zip(e2e_out, res))
     e2e_pageable_s, _ = e2e_run(frames)
     e2e_pageable_fps = world * nf * args.steps / e2e_pageable_s
+    clocks = sampler.stop()
 
     # ---- p50 per-frame latency, one frame in flight (submit -> labels on host) ------------------
     lat = []
@@ -319,8 +370,17 @@ def main():
     dom = max(stage_ms, key=stage_ms.get) if stage_ms else "n/a"
     dom_ms = stage_ms.get(dom, 0.0)
     achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(dom)
+        if t:
+            traffic = t["dram_bytes"] / t["frames_in_capture"] * nf
+            traffic_src = (f"{t['kernel']}: {t['dram_bytes']} B DRAM read+write in a {t['frames_in_capture']}-frame ncu capture "
+                           f"({t['capture']}), scaled per frame to this launch's {nf} frames")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": dom, "kernel_ms_per_step": dom_ms, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": dom, "kernel_ms_per_step": dom_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_step": algo_bytes,
                 "whole_path_achieved_GBs": algo_bytes / (dev_ms_total / args.steps / 1e3) / 1e9,
                 "stage_ms_per_step": stage_ms}

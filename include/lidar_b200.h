@@ -121,6 +121,24 @@ extern "C"
     /* waits for the stream; used by benchmarks that keep inputs and outputs resident in HBM */
     int lidar_b200_sync(lidar_b200_ctx *ctx);
 
+    /* ---- per-cluster point compaction on the device (the step right after Clusterer::cluster in the
+     * reference's caller): replaces the host loop of Processor::process that splits the obstacle cloud
+     * by label, skips INVALID points and erases empty clouds (reference src/processor.cpp:180-200).
+     *
+     * _group_clusters: enqueue behind the last lidar_b200_batch_run / lidar_b200_cluster of this context.
+     * _fetch_clusters: blocks; per frame f (O = point_offset[f], K = n_clusters[f]):
+     *   cluster_offset_out[O + f + k], k = 0..K : CSR offsets, cluster k owns grouped points
+     *       [O + offset[k], O + offset[k+1]); offset[K] = number of points in a valid cluster
+     *   cluster_points_out : 4 floats per point = pcl::PointXYZ(x, y, z) records (data[3] = 1.0f), in
+     *       ascending obstacle-cloud index inside a cluster = the reference's emplace_back order
+     *   cluster_point_idx_out : the obstacle-cloud index of every grouped point (optional, may be NULL)
+     * Array sizes: n_clusters_out [n_frames], cluster_offset_out [sum n + n_frames],
+     * cluster_points_out [sum n][4], cluster_point_idx_out [sum n] (sum n over the padded frame slots,
+     * i.e. point_offset of the last frame + its n). */
+    int lidar_b200_batch_group_clusters(lidar_b200_ctx *ctx);
+    int lidar_b200_batch_fetch_clusters(lidar_b200_ctx *ctx, uint32_t *n_clusters_out, uint32_t *cluster_offset_out,
+                                        float *cluster_points_out, uint32_t *cluster_point_idx_out);
+
     /* Page-locked host memory for clouds and result arrays — the zero-copy counterpart of the
      * caller-owned cloud_in_ / label vectors of the reference (src/processor.cpp:123-126). Every entry
      * point accepts ordinary (pageable) host pointers and stages them through the library's own pinned
@@ -129,6 +147,16 @@ extern "C"
      * staging pass disappears. */
     int lidar_b200_host_alloc(void **ptr_out, uint64_t bytes);
     void lidar_b200_host_free(void *ptr);
+
+    /* PCD v0.7 reader (host code): replaces pcl::io::loadPCDFile + Dataloader::convert on the feeding side
+     * (reference src/dataloader.cpp:87-126, 139). Writes records `stride_bytes` apart: 16 = packed
+     * (x, y, z, intensity); 32 = the pcl::PointXYZI / PointCloud2 wire layout the processor node receives
+     * (x 0, y 4, z 8, 1.0f 12, intensity 16; conversions.cpp:62-85). Both are accepted as they are by
+     * lidar_b200_segment / _batch_stage / _pipe_submit. DATA binary and DATA ascii; fields x y z required,
+     * intensity optional (0), other fields skipped. points_out == NULL only reports *n_points_out.
+     * error_out (optional) receives the reason on failure. Needs no CUDA device. */
+    int lidar_b200_pcd_read(const char *path, void *points_out, uint64_t capacity_points, uint32_t stride_bytes,
+                            uint64_t *n_points_out, char *error_out, uint32_t error_capacity);
 
     /* ---- frame pipeline: `depth` contexts on one GPU used round-robin, so that the upload of chunk
      * k+1, the kernels of chunk k and the download of chunk k-1 overlap. _submit = stage + run +

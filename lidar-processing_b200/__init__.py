@@ -127,7 +127,8 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_host_alloc", "lidar_b200_host_free", "lidar_b200_pipe_create", "lidar_b200_pipe_destroy",
     "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
     "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error",
-    "lidar_b200_last_replay_stats",
+    "lidar_b200_last_replay_stats", "lidar_b200_batch_group_clusters", "lidar_b200_batch_fetch_clusters",
+    "lidar_b200_pcd_read",
 ]
 
 
@@ -172,6 +173,21 @@ def _as_points(points) -> np.ndarray:
 
 def _ptr(a: np.ndarray, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def read_pcd(path, stride_bytes: int = 16) -> np.ndarray:
+    """PCD v0.7 file -> (N, 4) float32 x, y, z, intensity (stride 16) or (N, 8) float32 in the 32-byte
+    pcl::PointXYZI wire layout (reference src/dataloader.cpp:87-126, 139). Host code of the library."""
+    n = C.c_uint64(0)
+    err = C.create_string_buffer(256)
+    path_b = str(path).encode()
+    if lib().lidar_b200_pcd_read(path_b, None, C.c_uint64(0), C.c_uint32(stride_bytes), C.byref(n), err, C.c_uint32(256)):
+        raise LidarB200Error(f"read_pcd({path}): {err.value.decode()}")
+    out = np.zeros((max(int(n.value), 1), stride_bytes // 4), np.float32)
+    if lib().lidar_b200_pcd_read(path_b, out.ctypes.data_as(C.c_void_p), C.c_uint64(n.value), C.c_uint32(stride_bytes),
+                                 C.byref(n), err, C.c_uint32(256)):
+        raise LidarB200Error(f"read_pcd({path}): {err.value.decode()}")
+    return out[:int(n.value)]
 
 
 class Context:
@@ -285,6 +301,40 @@ class Context:
                 n_clusters=int(nc[f]),
             ))
         return out
+
+    def batch_clusters(self):
+        """Per-cluster point compaction on the device (reference src/processor.cpp:180-200) of the last
+        batch_run / cluster call. Returns, per frame, dict(offsets[K+1], points[n_valid,4], point_idx[n_valid]):
+        cluster k = points[offsets[k]:offsets[k+1]] in ascending obstacle-cloud index."""
+        counts = self._n_points
+        nf = counts.size
+        padded = ((counts.astype(np.int64) + 31) & ~31)
+        total = int(padded.sum())
+        off = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64) if nf else np.zeros(0, np.int64)
+        nc = np.zeros(max(nf, 1), np.uint32)
+        goff = np.zeros(max(total + nf, 1), np.uint32)
+        gpts = np.zeros((max(total, 1), 4), np.float32)
+        gidx = np.zeros(max(total, 1), np.uint32)
+        self._check(lib().lidar_b200_batch_group_clusters(self._h), "batch_group_clusters")
+        self._check(lib().lidar_b200_batch_fetch_clusters(self._h, _ptr(nc, C.c_uint32), _ptr(goff, C.c_uint32),
+                                                          _ptr(gpts, C.c_float), _ptr(gidx, C.c_uint32)), "batch_fetch_clusters")
+        out = []
+        for f in range(nf):
+            o, k = int(off[f]), int(nc[f])
+            offsets = goff[o + f:o + f + k + 1]
+            nv = int(offsets[k]) if offsets.size else 0
+            out.append(dict(offsets=offsets, points=gpts[o:o + nv], point_idx=gidx[o:o + nv], n_clusters=k))
+        return out
+
+    def cluster_and_split(self, points):
+        """Clusterer::cluster followed by the device-side split (single frame)."""
+        pts = _as_points(points)
+        labels = self.cluster(pts)
+        if pts.shape[0] == 0:
+            return labels, dict(offsets=np.zeros(1, np.uint32), points=np.zeros((0, 4), np.float32),
+                                point_idx=np.zeros(0, np.uint32), n_clusters=0)
+        self._n_points = np.array([pts.shape[0]], np.uint32)
+        return labels, self.batch_clusters()[0]
 
     def process_batch(self, frames, want_ground_idx: bool = True):
         self.batch_stage(frames)

@@ -6,7 +6,9 @@
 
 #include "cluster.cuh"
 #include "common.cuh"
+#include "group.cuh"
 #include "kd_build.cuh"
+#include "pcd_io.h"
 #include "radix_sort.cuh"
 #include "replay_cta.cuh"
 #include "segment.cuh"
@@ -98,6 +100,12 @@ struct lidar_b200_ctx
     // current batch
     uint32_t n_frames{0}, total{0}, max_n{0}, max_tcap{0};
     bool batch_is_cluster_only{false};
+    // what the last run_clustering worked on (input of lidar_b200_batch_group_clusters)
+    const float4 *clu_pts{nullptr};
+    const uint32_t *clu_counts{nullptr};
+    uint32_t clu_max_m{0};
+    bool grouped{false};
+    DevBuf<uint32_t> d_goff; // CSR offsets of the grouped clusters: frame f at [off[f] + f, off[f] + f + K_f]
     std::vector<uint32_t> off, cnt;
 
     // optional per-stage CUDA-event timing (lidar_b200_set_profiling)
@@ -115,7 +123,7 @@ struct lidar_b200_ctx
         bool direct[4]{false, false, false, false};       // destination is page-locked: DMA went straight into it
     } fetch;
 
-    uint32_t sm_count{148}, replay_ctas_per_sm{12}, replay_big_ctas_per_sm{2};
+    uint32_t sm_count{148}, replay_ctas_per_sm{12}, replay_big_ctas_per_sm{3};
     uint64_t launches{0};
     float last_run_ms{0.0f};
     std::string err;
@@ -424,9 +432,10 @@ int run_segmentation(lidar_b200_ctx *c)
     c->launches += rl;
     const uint32_t *sorted_idx = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
     mark(c, 1);
-    seg_gather_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, sorted_idx, bv, c->d_spts.p);
+    uint32_t *zkeys = c->d_key_a.p; // the sort's key buffers are free again; the order lives in val_a / val_b
+    seg_gather_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, sorted_idx, bv, c->d_spts.p, zkeys);
     ++c->launches;
-    seg_fit_kernel<<<dim3(c->seg.partitions, F), kFitThreads, sizeof(FitSmem), s>>>(c->d_spts.p, bv, c->seg, c->d_flags.p,
+    seg_fit_kernel<<<dim3(c->seg.partitions, F), kFitThreads, sizeof(FitSmem), s>>>(c->d_spts.p, zkeys, bv, c->seg, c->d_flags.p,
                                                                                     c->d_planes.p, c->d_status.p);
     ++c->launches;
     mark(c, 2);
@@ -452,6 +461,10 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     cudaStream_t s = c->stream;
     LB_CUDA(c, cudaMemsetAsync(c->m_nc(), 0, static_cast<size_t>(c->cap_frames) * 4, s));
     LB_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 4, s));
+    c->clu_pts = pts;
+    c->clu_counts = counts;
+    c->clu_max_m = max_m;
+    c->grouped = false;
     if (max_m == 0u)
         return 0;
     const BatchView bv{c->m_off(), counts, F};
@@ -517,10 +530,22 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
                                              bucket_capacity, big_count);
     LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
     LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
-    replay_cta_kernel<<<c->sm_count * c->replay_big_ctas_per_sm, kCtaThreads, 0, c->stream_big>>>(
-        c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
-        c->d_pkey.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p, bucket_capacity, big_count,
-        c->m_cursor() + 2, c->d_job_stats.p);
+    {
+        const uint32_t per_sm = c->replay_big_ctas_per_sm;
+        const uint32_t grid = c->sm_count * per_sm;
+#define LB_LAUNCH_REPLAY_CTA(MINB)                                                                                     \
+    replay_cta_kernel<MINB><<<grid, kCtaThreads, 0, c->stream_big>>>(                                                  \
+        c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,       \
+        c->d_pkey.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p,      \
+        bucket_capacity, big_count, c->m_cursor() + 2, c->d_job_stats.p)
+        if (per_sm >= 4u)
+            LB_LAUNCH_REPLAY_CTA(4);
+        else if (per_sm == 3u)
+            LB_LAUNCH_REPLAY_CTA(3);
+        else
+            LB_LAUNCH_REPLAY_CTA(2);
+#undef LB_LAUNCH_REPLAY_CTA
+    }
     LB_CUDA(c, cudaEventRecord(c->ev_join, c->stream_big));
     const uint32_t claims = (max_m + 31u) / 32u;
     // persistent grid: a fixed number of CTAs per SM walks the flat (frame, claim) work list
@@ -681,7 +706,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -889,6 +914,63 @@ int lidar_b200_cluster(lidar_b200_ctx *c, const void *points, uint32_t m, uint32
     return 0;
 }
 
+int lidar_b200_batch_group_clusters(lidar_b200_ctx *c)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    if (!c->clu_pts && c->n_frames)
+        return fail(c, LIDAR_B200_ERR_INVALID, "group_clusters: no clustering result on this context");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t F = c->n_frames;
+    if (dev_alloc(c, c->d_goff, static_cast<size_t>(c->cap_pts) + c->cap_frames + 1u))
+        return LIDAR_B200_ERR_CUDA;
+    cudaStream_t s = c->stream;
+    c->grouped = true;
+    if (F == 0u)
+        return 0;
+    LB_CUDA(c, cudaMemsetAsync(c->d_goff.p, 0, (static_cast<size_t>(c->total) + F) * 4, s));
+    const uint32_t max_m = c->clu_max_m;
+    if (max_m == 0u)
+        return 0;
+    const BatchView bv{c->m_off(), c->clu_counts, F};
+    const dim3 gp(grid_x(max_m, 256u, 2048u), F);
+    // every per-point scratch array of the clustering stage is free again once the labels are out
+    group_keys_kernel<<<gp, 256, 0, s>>>(bv, c->d_clabels.p, c->m_nc(), c->d_key_a.p, c->d_val_a.p);
+    int rl = 0;
+    const int passes = radix_sort_pairs(s, c->d_key_a.p, c->d_val_a.p, c->d_key_b.p, c->d_val_b.p, bv, max_m,
+                                        ceil_log2(max_m + 1u), RadixSortScratch{c->d_hist.p}, &rl);
+    const uint32_t *skeys = (passes & 1) ? c->d_key_b.p : c->d_key_a.p;
+    const uint32_t *svals = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
+    group_emit_kernel<<<gp, 256, 0, s>>>(c->clu_pts, bv, skeys, svals, c->m_nc(), c->d_nodes.p /* grouped points */,
+                                         c->d_queue.p /* grouped source indices */, c->d_goff.p);
+    c->launches += 2 + rl;
+    LB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int lidar_b200_batch_fetch_clusters(lidar_b200_ctx *c, uint32_t *n_clusters_out, uint32_t *cluster_offset_out,
+                                    float *cluster_points_out, uint32_t *cluster_point_idx_out)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    if (!c->grouped)
+        return fail(c, LIDAR_B200_ERR_INVALID, "fetch_clusters: call lidar_b200_batch_group_clusters first");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t F = c->n_frames;
+    const size_t total = c->total;
+    if (F && n_clusters_out)
+        LB_CUDA(c, cudaMemcpyAsync(n_clusters_out, c->m_nc(), static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
+    if (F && cluster_offset_out)
+        LB_CUDA(c, cudaMemcpyAsync(cluster_offset_out, c->d_goff.p, (total + F) * 4, cudaMemcpyDeviceToHost, s));
+    if (total && cluster_points_out)
+        LB_CUDA(c, cudaMemcpyAsync(cluster_points_out, c->d_nodes.p, total * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    if (total && cluster_point_idx_out)
+        LB_CUDA(c, cudaMemcpyAsync(cluster_point_idx_out, c->d_queue.p, total * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
 int lidar_b200_last_planes(lidar_b200_ctx *c, float *planes_out, int32_t *status_out)
 {
     if (!c)
@@ -1006,6 +1088,18 @@ const char *lidar_b200_last_error(const lidar_b200_ctx *c)
 const char *lidar_b200_version(void)
 {
     return "lidar_b200 0.1 (sm_100a)";
+}
+
+int lidar_b200_pcd_read(const char *path, void *points_out, uint64_t capacity_points, uint32_t stride_bytes,
+                        uint64_t *n_points_out, char *error_out, uint32_t error_capacity)
+{
+    const std::string err = pcd_read(path, points_out, capacity_points, stride_bytes, n_points_out);
+    if (error_out && error_capacity)
+    {
+        std::strncpy(error_out, err.c_str(), error_capacity - 1u);
+        error_out[error_capacity - 1u] = '\0';
+    }
+    return err.empty() ? LIDAR_B200_OK : LIDAR_B200_ERR_INVALID;
 }
 
 int lidar_b200_host_alloc(void **ptr_out, uint64_t bytes)

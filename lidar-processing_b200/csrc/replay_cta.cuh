@@ -129,7 +129,10 @@ replay_biglist_kernel(BatchView bv, const uint32_t *__restrict__ member_root, co
     }
 }
 
-__global__ void __launch_bounds__(kCtaThreads)
+// MINB = CTAs per SM the register allocation is capped for (99 / 80 / 64 registers for 2 / 3 / 4): the kernel
+// waits on CTA barriers most of the time, so more resident CTAs per SM hide each other's round latency.
+template <int MINB>
+__global__ void __launch_bounds__(kCtaThreads, MINB)
 replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
                   CluParams prm, const uint32_t *__restrict__ member_root, const uint32_t *__restrict__ member_idx,
                   const uint32_t *__restrict__ member_pos, const uint32_t *__restrict__ comp_size,

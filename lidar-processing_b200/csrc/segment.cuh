@@ -23,6 +23,7 @@ constexpr uint32_t kSegGround = 1u;
 constexpr uint32_t kSegObstacle = 2u;
 
 constexpr int kFitThreads = 1024;
+constexpr int kFitUnroll = 4; // independent loads in flight per thread in every pass of seg_fit
 constexpr uint32_t kMaxLpr = 8192u; // number_of_lower_point_representatives supported by the in-smem sort
 
 struct SegParams
@@ -52,7 +53,7 @@ seg_keys_kernel(const float4 *__restrict__ pts, BatchView bv, uint32_t *__restri
 
 __global__ void __launch_bounds__(256)
 seg_gather_kernel(const float4 *__restrict__ pts, const uint32_t *__restrict__ sorted_idx, BatchView bv,
-                  float4 *__restrict__ spts)
+                  float4 *__restrict__ spts, uint32_t *__restrict__ zkeys)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t n = bv.cnt[f];
@@ -62,6 +63,7 @@ seg_gather_kernel(const float4 *__restrict__ pts, const uint32_t *__restrict__ s
         const uint32_t idx = sorted_idx[off + r];
         const float4 p = __ldg(&pts[off + idx]);
         spts[off + r] = make_float4(p.x, p.y, p.z, __uint_as_float(idx));
+        zkeys[off + r] = float_to_ordered(p.z); // 4-byte keys for the selection passes of seg_fit (coalesced)
     }
 }
 
@@ -212,7 +214,8 @@ LB_D bool fit_is_ground(const float4 &p, const PlaneF &pl)
 // grid = (partitions, frames), kFitThreads threads, dynamic smem = sizeof(FitSmem)
 // status: 0 ok, 1 "<3 points" (points stay UNKNOWN), 2 "Failed ground segmentation" (all OBSTACLE)
 __global__ void __launch_bounds__(kFitThreads, 1)
-seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uint8_t *__restrict__ flags,
+seg_fit_kernel(const float4 *__restrict__ spts, const uint32_t *__restrict__ zkeys, BatchView bv, SegParams prm,
+               uint8_t *__restrict__ flags,
                float *__restrict__ planes_out, int32_t *__restrict__ status_out)
 {
     extern __shared__ __align__(16) unsigned char fit_smem_raw[];
@@ -228,6 +231,7 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
     const uint32_t hi = lo + per;
     const uint32_t tid = threadIdx.x;
     const float4 *seg = spts + off;
+    const uint32_t *zk = zkeys + off;
     uint8_t *fl = flags + off;
     float *planes = planes_out + (static_cast<size_t>(f) * P + s) * prm.iterations * 4;
     int32_t *status = status_out + static_cast<size_t>(f) * P + s;
@@ -257,18 +261,27 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
         sm.hist[i] = 0u;
     __syncthreads();
     uint32_t cnt_above = 0u, kmax = 0u;
-    for (uint32_t base = lo; base < hi; base += kFitThreads)
+    for (uint32_t base = lo; base < hi; base += kFitThreads * kFitUnroll)
     {
-        const uint32_t i = base + tid;
-        const bool valid = i < hi;
-        uint32_t k = 0u;
-        if (valid)
+        uint32_t k[kFitUnroll];
+        bool valid[kFitUnroll];
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
         {
-            k = float_to_ordered(seg[i].z);
-            cnt_above += (k > kmin) ? 1u : 0u;
-            kmax = max(kmax, k);
+            const uint32_t i = base + h * kFitThreads + tid;
+            valid[h] = i < hi;
+            k[h] = valid[h] ? __ldg(&zk[i]) : 0u;
         }
-        fit_hist_add(sm, valid, k >> 20);
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
+        {
+            if (valid[h])
+            {
+                cnt_above += (k[h] > kmin) ? 1u : 0u;
+                kmax = max(kmax, k[h]);
+            }
+            fit_hist_add(sm, valid[h], k[h] >> 20);
+        }
     }
     cnt_above = warp_reduce_add(cnt_above);
     kmax = warp_reduce_max(kmax);
@@ -331,17 +344,24 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
     for (uint32_t i = tid; i < 4096u; i += kFitThreads)
         sm.hist[i] = 0u;
     __syncthreads();
-    for (uint32_t base = lo; base < hi; base += kFitThreads)
+    for (uint32_t base = lo; base < hi; base += kFitThreads * kFitUnroll)
     {
-        const uint32_t i = base + tid;
-        bool valid = i < hi;
-        uint32_t k = 0u;
-        if (valid)
+        uint32_t k[kFitUnroll];
+        bool valid[kFitUnroll];
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
         {
-            k = float_to_ordered(seg[i].z);
-            valid = (!use_kmin || k > kmin) && (k >> 20) == b1;
+            const uint32_t i = base + h * kFitThreads + tid;
+            valid[h] = i < hi;
+            k[h] = valid[h] ? __ldg(&zk[i]) : 0u;
         }
-        fit_hist_add(sm, valid, (k >> 8) & 0xFFFu);
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
+        {
+            const bool v = valid[h] && (!use_kmin || k[h] > kmin) && (k[h] >> 20) == b1;
+            if (__any_sync(kFullMask, v)) // most warps hold no key of the selected bin
+                fit_hist_add(sm, v, (k[h] >> 8) & 0xFFFu);
+        }
     }
     __syncthreads();
     uint32_t b2, before2;
@@ -353,17 +373,24 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
         sm.hist[i] = 0u;
     __syncthreads();
     const uint32_t prefix24 = (b1 << 12) | b2;
-    for (uint32_t base = lo; base < hi; base += kFitThreads)
+    for (uint32_t base = lo; base < hi; base += kFitThreads * kFitUnroll)
     {
-        const uint32_t i = base + tid;
-        bool valid = i < hi;
-        uint32_t k = 0u;
-        if (valid)
+        uint32_t k[kFitUnroll];
+        bool valid[kFitUnroll];
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
         {
-            k = float_to_ordered(seg[i].z);
-            valid = (!use_kmin || k > kmin) && (k >> 8) == prefix24;
+            const uint32_t i = base + h * kFitThreads + tid;
+            valid[h] = i < hi;
+            k[h] = valid[h] ? __ldg(&zk[i]) : 0u;
         }
-        fit_hist_add(sm, valid, k & 0xFFu);
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
+        {
+            const bool v = valid[h] && (!use_kmin || k[h] > kmin) && (k[h] >> 8) == prefix24;
+            if (__any_sync(kFullMask, v))
+                fit_hist_add(sm, v, k[h] & 0xFFu);
+        }
     }
     __syncthreads();
     uint32_t b3, before3;
@@ -373,7 +400,7 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
     const uint32_t c_less = n_lpr - remaining; // included keys strictly below T  (<= lpr - 1 < kMaxLpr)
 
     // gather the keys below T, sort them ascending (bitonic in smem)
-    uint32_t n_pad = 1u;
+    uint32_t n_pad = 256u; // at least one warp chunk
     while (n_pad < c_less)
         n_pad <<= 1;
     if (tid == 0)
@@ -381,50 +408,100 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
     for (uint32_t i = tid; i < n_pad; i += kFitThreads)
         sm.buf[i] = 0xFFFFFFFFu;
     __syncthreads();
-    for (uint32_t base = lo; base < hi; base += kFitThreads)
+    for (uint32_t base = lo; base < hi; base += kFitThreads * kFitUnroll)
     {
-        const uint32_t i = base + tid;
-        bool take = false;
-        uint32_t k = 0u;
-        if (i < hi)
+        uint32_t k[kFitUnroll];
+        bool valid[kFitUnroll];
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
         {
-            k = float_to_ordered(seg[i].z);
-            take = (!use_kmin || k > kmin) && k < kT;
+            const uint32_t i = base + h * kFitThreads + tid;
+            valid[h] = i < hi;
+            k[h] = valid[h] ? __ldg(&zk[i]) : 0u;
         }
-        const uint32_t ballot = __ballot_sync(kFullMask, take);
-        uint32_t wbase = 0u;
-        if (lane_id() == 0 && ballot)
-            wbase = atomicAdd(&sm.u[5], static_cast<uint32_t>(__popc(ballot)));
-        wbase = __shfl_sync(kFullMask, wbase, 0);
-        if (take)
-            sm.buf[wbase + __popc(ballot & lanemask_lt())] = k;
+#pragma unroll
+        for (int h = 0; h < kFitUnroll; ++h)
+        {
+            const bool take = valid[h] && (!use_kmin || k[h] > kmin) && k[h] < kT;
+            const uint32_t ballot = __ballot_sync(kFullMask, take);
+            if (ballot == 0u)
+                continue;
+            uint32_t wbase = 0u;
+            if (lane_id() == 0)
+                wbase = atomicAdd(&sm.u[5], static_cast<uint32_t>(__popc(ballot)));
+            wbase = __shfl_sync(kFullMask, wbase, 0);
+            if (take)
+                sm.buf[wbase + __popc(ballot & lanemask_lt())] = k[h];
+        }
     }
     __syncthreads();
-    for (uint32_t kk = 2u; kk <= n_pad; kk <<= 1)
-        for (uint32_t j = kk >> 1; j > 0u; j >>= 1)
-        {
-            for (uint32_t i = tid; i < n_pad; i += kFitThreads)
+    // Bitonic sort in shared memory. Warp w owns elements [256 w, 256 w + 256): every compare-exchange with
+    // j < 256 stays inside one warp's chunk and needs only __syncwarp; only the 15 stages with j >= 256 are
+    // CTA-wide (76 of the 91 stages of an 8192-key sort run without a CTA barrier).
+    {
+        const uint32_t lane = lane_id();
+        const uint32_t chunk = (tid >> 5) * 256u;
+        auto exchange = [&](uint32_t i, uint32_t j, uint32_t kk) {
+            const uint32_t ixj = i | j;
+            const uint32_t a = sm.buf[i];
+            const uint32_t b = sm.buf[ixj];
+            const bool asc = (i & kk) == 0u;
+            if ((a > b) == asc)
             {
-                const uint32_t ixj = i ^ j;
-                if (ixj > i)
+                sm.buf[i] = b;
+                sm.buf[ixj] = a;
+            }
+        };
+        auto warp_stages = [&](uint32_t kk, uint32_t j_first) {
+            if (chunk < n_pad)
+                for (uint32_t j = j_first; j > 0u; j >>= 1)
                 {
-                    const uint32_t a = sm.buf[i];
-                    const uint32_t b = sm.buf[ixj];
-                    const bool asc = (i & kk) == 0u;
-                    if ((a > b) == asc)
+#pragma unroll
+                    for (uint32_t r = 0; r < 4u; ++r)
                     {
-                        sm.buf[i] = b;
-                        sm.buf[ixj] = a;
+                        const uint32_t t = lane + 32u * r; // pair number inside the chunk
+                        exchange(chunk + (((t & ~(j - 1u)) << 1) | (t & (j - 1u))), j, kk);
                     }
+                    __syncwarp();
                 }
+        };
+        for (uint32_t kk = 2u; kk <= n_pad; kk <<= 1)
+        {
+            if (kk <= 256u)
+            {
+                warp_stages(kk, kk >> 1);
+                continue;
             }
             __syncthreads();
+            for (uint32_t j = kk >> 1; j >= 256u; j >>= 1)
+            {
+                for (uint32_t t = tid; t < (n_pad >> 1); t += kFitThreads)
+                    exchange(((t & ~(j - 1u)) << 1) | (t & (j - 1u)), j, kk);
+                __syncthreads();
+            }
+            warp_stages(kk, 128u);
         }
+        __syncthreads();
+    }
     // ascending sequential float sum (segmentation.cpp:189-197) — order-exact, one thread
     if (tid == 0)
     {
         float zsum = 0.0f;
-        for (uint32_t i = 0; i < c_less; ++i)
+        uint32_t i = 0;
+        for (; i + 8u <= c_less; i += 8u) // loads ahead of the dependent FADD chain
+        {
+            const uint4 a = *reinterpret_cast<const uint4 *>(&sm.buf[i]);
+            const uint4 b = *reinterpret_cast<const uint4 *>(&sm.buf[i + 4u]);
+            zsum = __fadd_rn(zsum, ordered_to_float(a.x));
+            zsum = __fadd_rn(zsum, ordered_to_float(a.y));
+            zsum = __fadd_rn(zsum, ordered_to_float(a.z));
+            zsum = __fadd_rn(zsum, ordered_to_float(a.w));
+            zsum = __fadd_rn(zsum, ordered_to_float(b.x));
+            zsum = __fadd_rn(zsum, ordered_to_float(b.y));
+            zsum = __fadd_rn(zsum, ordered_to_float(b.z));
+            zsum = __fadd_rn(zsum, ordered_to_float(b.w));
+        }
+        for (; i < c_less; ++i)
             zsum = __fadd_rn(zsum, ordered_to_float(sm.buf[i]));
         const float zt = ordered_to_float(kT);
         for (uint32_t i = 0; i < remaining; ++i)
@@ -450,34 +527,49 @@ seg_fit_kernel(const float4 *__restrict__ spts, BatchView bv, SegParams prm, uin
         const bool last = it == prm.iterations;
         double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t cnt = 0u;
-        for (uint32_t i = lo + tid; i < hi; i += kFitThreads)
+        for (uint32_t base = lo; base < hi; base += kFitThreads * kFitUnroll)
         {
-            const float4 p = seg[i];
-            bool g;
-            if (it == 0u)
+            float4 pp[kFitUnroll];
+#pragma unroll
+            for (int h = 0; h < kFitUnroll; ++h)
             {
-                const uint32_t k = float_to_ordered(p.z);
-                g = (!use_kmin || k > kmin) && k <= kzmax;
+                const uint32_t i = base + h * kFitThreads + tid;
+                if (i < hi)
+                    pp[h] = __ldg(&seg[i]);
             }
-            else
-                g = fit_is_ground(p, plane);
-            if (last)
-                fl[i] = g ? 1u : 2u;
-            else if (g)
+#pragma unroll
+            for (int h = 0; h < kFitUnroll; ++h)
             {
-                const double x = static_cast<double>(p.x) - sx;
-                const double y = static_cast<double>(p.y) - sy;
-                const double z = static_cast<double>(p.z) - sz;
-                acc[0] += x;
-                acc[1] += y;
-                acc[2] += z;
-                acc[3] += x * x;
-                acc[4] += x * y;
-                acc[5] += x * z;
-                acc[6] += y * y;
-                acc[7] += y * z;
-                acc[8] += z * z;
-                ++cnt;
+                const uint32_t i = base + h * kFitThreads + tid;
+                if (i >= hi)
+                    break;
+                const float4 p = pp[h];
+                bool g;
+                if (it == 0u)
+                {
+                    const uint32_t k = float_to_ordered(p.z);
+                    g = (!use_kmin || k > kmin) && k <= kzmax;
+                }
+                else
+                    g = fit_is_ground(p, plane);
+                if (last)
+                    fl[i] = g ? 1u : 2u;
+                else if (g)
+                {
+                    const double x = static_cast<double>(p.x) - sx;
+                    const double y = static_cast<double>(p.y) - sy;
+                    const double z = static_cast<double>(p.z) - sz;
+                    acc[0] += x;
+                    acc[1] += y;
+                    acc[2] += z;
+                    acc[3] += x * x;
+                    acc[4] += x * y;
+                    acc[5] += x * z;
+                    acc[6] += y * y;
+                    acc[7] += y * z;
+                    acc[8] += z * z;
+                    ++cnt;
+                }
             }
         }
         if (last)

@@ -57,6 +57,7 @@ void Clusterer::cluster(const pcl::PointCloud<PointT> &cloud_in, std::vector<Clu
 {
     static_assert(sizeof(PointT) % 4 == 0 && sizeof(PointT) >= 12, "point layout");
     labels.assign(cloud_in.size(), UNDEFINED);
+    last_cloud_size_ = static_cast<std::uint32_t>(cloud_in.size());
     if (cloud_in.empty())
     {
         return;
@@ -65,6 +66,34 @@ void Clusterer::cluster(const pcl::PointCloud<PointT> &cloud_in, std::vector<Clu
                                           static_cast<std::uint32_t>(sizeof(PointT)), labels.data());
     if (status != LIDAR_B200_OK)
         raise(context_, status, "Clusterer::cluster");
+}
+
+void Clusterer::split_last_clusters(std::vector<pcl::PointCloud<pcl::PointXYZ>> &clustered_cloud)
+{
+    static_assert(sizeof(pcl::PointXYZ) == 16, "the device writes 16-byte PointXYZ records");
+    clustered_cloud.clear();
+    if (last_cloud_size_ == 0U)
+    {
+        return;
+    }
+    int status = lidar_b200_batch_group_clusters(context_);
+    if (status != LIDAR_B200_OK)
+        raise(context_, status, "Clusterer::split_last_clusters");
+    const std::size_t padded = (static_cast<std::size_t>(last_cloud_size_) + 31U) & ~static_cast<std::size_t>(31U);
+    split_offsets_.assign(padded + 1U, 0U);
+    split_points_.resize(padded * 4U);
+    std::uint32_t number_of_clusters = 0U;
+    status = lidar_b200_batch_fetch_clusters(context_, &number_of_clusters, split_offsets_.data(), split_points_.data(), nullptr);
+    if (status != LIDAR_B200_OK)
+        raise(context_, status, "Clusterer::split_last_clusters");
+    clustered_cloud.resize(number_of_clusters);
+    const auto *records = reinterpret_cast<const pcl::PointXYZ *>(split_points_.data());
+    for (std::uint32_t k = 0U; k < number_of_clusters; ++k)
+    {
+        clustered_cloud[k].points.assign(records + split_offsets_[k], records + split_offsets_[k + 1U]);
+        clustered_cloud[k].width = static_cast<std::uint32_t>(clustered_cloud[k].points.size());
+        clustered_cloud[k].height = 1U;
+    }
 }
 
 template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZ> &cloud_in, std::vector<ClusteringLabel> &labels);

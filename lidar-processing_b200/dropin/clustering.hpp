@@ -49,9 +49,18 @@ class Clusterer final
     template <typename PointT>
     void cluster(const pcl::PointCloud<PointT> &cloud_in, std::vector<ClusteringLabel> &labels);
 
+    // Extension (not in the reference class): the split of the cloud by cluster label that the reference's
+    // caller does on the host right after cluster() (reference src/processor.cpp:180-200), done on the
+    // device for the cloud of the LAST cluster() call. clustered_cloud[k] receives PointXYZ(x, y, z) of
+    // every point with label k in ascending point index; INVALID points are skipped.
+    void split_last_clusters(std::vector<pcl::PointCloud<pcl::PointXYZ>> &clustered_cloud);
+
   private:
     lidar_b200_ctx *context_{nullptr};
     ClusteringConfiguration configuration_{};
+    std::uint32_t last_cloud_size_{0U};
+    std::vector<std::uint32_t> split_offsets_;
+    std::vector<float> split_points_;
 };
 
 extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZ> &cloud_in,

@@ -305,3 +305,26 @@ def reference_frame_paths():
     if not REFERENCE_DATA.is_dir():
         return []
     return sorted(REFERENCE_DATA.glob("*.pcd"))
+
+
+def split_clusters(obstacle_points, labels):
+    """CPU restatement of the per-cluster split in Processor::process (reference src/processor.cpp:180-200):
+    clustered_obstacle_cloud.resize(max_label + 1); for i ascending: UNDEFINED -> runtime_error, INVALID
+    skipped, else clustered_obstacle_cloud[label].emplace_back(x, y, z); empty clouds erased.
+    Returns a list of (points[n_k,3] float32, source indices) per remaining cluster, in label order."""
+    labels = np.asarray(labels)
+    pts = np.asarray(obstacle_points, np.float32)[:, :3]
+    if labels.size == 0:
+        return []  # (the reference's max_element on an empty vector is UB in the caller, SURVEY.md 8b)
+    if np.any(labels == UNDEFINED):
+        raise RuntimeError("Undefined label found (clustering)")
+    clouds = [[] for _ in range(int(labels.max()) + 1)]
+    for i, l in enumerate(labels.tolist()):
+        if l != INVALID:
+            clouds[l].append(i)
+    out = []
+    for idx in clouds:
+        if idx:  # std::remove_if(cloud.empty())
+            ii = np.asarray(idx, np.int64)
+            out.append((pts[ii], ii))
+    return out

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <stdexcept>
@@ -56,6 +57,33 @@ int main(int argc, char **argv)
             if (label == Clusterer::UNDEFINED)
                 throw std::runtime_error("Undefined label found (clustering)"); // processor.cpp:186-189
 
+        // the caller's split by label (processor.cpp:180-200), once on the host as the reference does it and
+        // once through the device-side extension; both must agree point for point
+        std::vector<pcl::PointCloud<pcl::PointXYZ>> host_split, device_split;
+        if (!cluster_labels.empty())
+        {
+            const auto max_label = *std::max_element(cluster_labels.cbegin(), cluster_labels.cend());
+            host_split.resize(max_label + 1);
+            for (std::size_t i = 0; i < obstacle_cloud.size(); ++i)
+                if (cluster_labels[i] != Clusterer::INVALID)
+                    host_split[cluster_labels[i]].emplace_back(obstacle_cloud.points[i].x, obstacle_cloud.points[i].y,
+                                                               obstacle_cloud.points[i].z);
+            host_split.erase(std::remove_if(host_split.begin(), host_split.end(),
+                                            [](const pcl::PointCloud<pcl::PointXYZ> &c) { return c.empty(); }),
+                             host_split.end());
+        }
+        clusterer.split_last_clusters(device_split);
+        if (device_split.size() != host_split.size())
+            return 4;
+        for (std::size_t k = 0; k < host_split.size(); ++k)
+        {
+            if (device_split[k].size() != host_split[k].size())
+                return 5;
+            if (std::memcmp(device_split[k].points.data(), host_split[k].points.data(),
+                            host_split[k].size() * sizeof(pcl::PointXYZ)) != 0)
+                return 6;
+        }
+
         std::vector<std::uint32_t> seg(segmentation_labels.size());
         for (std::size_t i = 0; i < seg.size(); ++i)
             seg[i] = static_cast<std::uint32_t>(segmentation_labels[i]);
@@ -89,9 +117,10 @@ int main(int argc, char **argv)
         clusterer.cluster(empty_in, cl);
         if (!threw || !l.empty() || !cl.empty())
             return 3;
-        std::printf("ok %zu points, %zu ground, %zu obstacle, %d clusters\n", n, ground_points.size(),
+        std::printf("ok %zu points, %zu ground, %zu obstacle, %d clusters, %zu split clouds\n", n, ground_points.size(),
                     obstacle_points.size(),
-                    cluster_labels.empty() ? 0 : 1 + *std::max_element(cluster_labels.begin(), cluster_labels.end()));
+                    cluster_labels.empty() ? 0 : 1 + *std::max_element(cluster_labels.begin(), cluster_labels.end()),
+                    device_split.size());
     }
     catch (const std::exception &e)
     {

@@ -138,3 +138,46 @@ def test_pcd_reader_and_frame_cache_round_trip(tmp_path, golden_frames):
     assert np.array_equal(back.view(np.uint32), pts.view(np.uint32))
     pack([path], tmp_path / "c.xz")
     assert np.array_equal(unpack(tmp_path / "c.xz")[0].view(np.uint32), pts.view(np.uint32))
+
+
+def test_library_pcd_reader(pkg, tmp_path, golden_frames):
+    """lidar_b200_pcd_read (host code of the product, reference src/dataloader.cpp:87-126,139) against the
+    oracle's reader: binary and ascii, field order, extra fields, both output layouts, error reporting."""
+    pts = golden_frames[0][:777]
+    n = pts.shape[0]
+    base = "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\n"
+    tail = f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\n"
+    # 1. the layout of data/*.pcd
+    p1 = tmp_path / "a.pcd"
+    p1.write_bytes((base + "FIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n" + tail + "DATA binary\n").encode()
+                   + pts.tobytes())
+    got = pkg.read_pcd(p1)
+    assert np.array_equal(got.view(np.uint32), O.read_pcd(p1).view(np.uint32))
+    wire = pkg.read_pcd(p1, stride_bytes=32)  # pcl::PointXYZI: x y z 1.0 | intensity 0 0 0
+    assert wire.shape == (n, 8) and np.array_equal(wire[:, :3], pts[:, :3]) and np.all(wire[:, 3] == 1.0)
+    assert np.array_equal(wire[:, 4], pts[:, 3]) and not wire[:, 5:].any()
+    # 2. permuted fields with an extra 2-byte x 3 field in the middle, no intensity
+    rec = np.zeros(n, dtype=[("z", "<f4"), ("ring", "<u2", 3), ("x", "<f4"), ("y", "<f4")])
+    rec["x"], rec["y"], rec["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    p2 = tmp_path / "b.pcd"
+    p2.write_bytes((base + "FIELDS z ring x y\nSIZE 4 2 4 4\nTYPE F U F F\nCOUNT 1 3 1 1\n" + tail + "DATA binary\n").encode()
+                   + rec.tobytes())
+    got = pkg.read_pcd(p2)
+    assert np.array_equal(got[:, :3].view(np.uint32), pts[:, :3].view(np.uint32)) and not got[:, 3].any()
+    # 3. ascii (9 significant digits round-trip float32 exactly)
+    p3 = tmp_path / "c.pcd"
+    rows = "\n".join(" ".join(f"{v:.9g}" for v in r) for r in pts.tolist())
+    p3.write_text(base + "FIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n" + tail + "DATA ascii\n" + rows + "\n")
+    assert np.array_equal(pkg.read_pcd(p3).view(np.uint32), pts.view(np.uint32))
+    # 4. errors are reported, not swallowed
+    p4 = tmp_path / "d.pcd"
+    p4.write_bytes((base + "FIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n" + tail + "DATA binary\n").encode()
+                   + pts.tobytes()[:-100])
+    with pytest.raises(pkg.LidarB200Error, match="shorter"):
+        pkg.read_pcd(p4)
+    p5 = tmp_path / "e.pcd"
+    p5.write_text(base + "FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n" + tail + "DATA binary_compressed\n")
+    with pytest.raises(pkg.LidarB200Error, match="unsupported DATA"):
+        pkg.read_pcd(p5)
+    with pytest.raises(pkg.LidarB200Error, match="cannot open"):
+        pkg.read_pcd(tmp_path / "missing.pcd")

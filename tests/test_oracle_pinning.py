@@ -160,3 +160,22 @@ def test_mix64_fingerprints_match_oracle_on_golden_frames(golden_frames, fingerp
         assert mix64(lab) == row["cluster_labels_mix64"]
     assert mix64(np.array([], np.int32)) == f"{0:016x}"
     assert mix64(np.array([1, 2], np.int32)) != mix64(np.array([2, 1], np.int32))
+
+
+def test_split_clusters_restatement(golden_frames):
+    """processor.cpp:180-200: split by label, ascending index inside a cluster, INVALID skipped, empties erased."""
+    pts = golden_frames[0]
+    obs = pts[O.segment(pts, tie_mode=1)["obstacle_idx"]]
+    labels = O.cluster(obs)
+    clouds = O.split_clusters(obs, labels)
+    assert len(clouds) == int(labels.max()) + 1  # labels are dense: nothing to erase
+    assert sum(c[0].shape[0] for c in clouds) == int((labels != O.INVALID).sum())
+    for k in (0, 1, len(clouds) - 1):
+        idx = np.nonzero(labels == k)[0]
+        assert np.array_equal(clouds[k][1], idx) and np.array_equal(clouds[k][0], obs[idx, :3])
+    sparse = np.array([2, -1, 2, 0, -1], np.int32)  # label 1 is empty -> erased
+    out = O.split_clusters(np.arange(20, dtype=np.float32).reshape(5, 4), sparse)
+    assert [c[1].tolist() for c in out] == [[3], [0, 2]]
+    with pytest.raises(RuntimeError):
+        O.split_clusters(np.zeros((1, 4), np.float32), np.array([O.UNDEFINED], np.int32))
+    assert O.split_clusters(np.zeros((0, 4), np.float32), np.zeros(0, np.int32)) == []
