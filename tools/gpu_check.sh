@@ -27,7 +27,7 @@ launches)
   echo "launches exit: $?"; wc -l gpurun_out/launches.csv ;;
 ncu)
   for k in ${NCU_KERNELS:-replay_cta_kernel}; do
-  timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"^${k}" -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} \
+  timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:"${k}" -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} \
      -f -o gpurun_out/prof_${k} python bench.py --steps 1 --warmup 1 --no-cpu-baseline ${NCU_BENCH_ARGS:---frames 16} > gpurun_out/ncu_full_${k}.log 2>&1
   echo "ncu $k exit: $?"
   done

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Per-job counters of the CTA-per-component replay for the 154-frame batch (GPU box).
+usage: LIDAR_B200_REPLAY_STATS=1 python tools/replay_stats.py"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("LIDAR_B200_REPLAY_STATS", "1")
+import __graft_entry__ as ge  # noqa: E402
+from bench import load_workload  # noqa: E402
+
+pkg = ge.load_package()
+frames, name = load_workload(None)
+ctx = pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames))
+ctx.set_profiling(True)
+ctx.batch_stage(frames)
+for _ in range(3):
+    ctx.batch_run()
+    ctx.sync()
+st = ctx.last_replay_stats()
+print("stage ms", {k: round(v, 3) for k, v in ctx.last_stage_ms().items()})
+kc = st[:, 2].astype(np.float64)
+print(f"jobs {st.shape[0]}  sum kcycles {kc.sum():.0f}  max {kc.max():.0f}  mean {kc.mean():.1f}")
+print(f"sum/444 CTAs = {kc.sum()/444:.0f} kcycles = {kc.sum()*1.024/444/1965:.3f} ms ; longest job = {kc.max()*1.024/1965:.3f} ms")
+order = np.argsort(-kc)
+print("top jobs: [frame members kcycles rounds direct kcycA kcycBC kcycEF]  cycles/round   (kcycles = cycles >> 10)")
+for j in order[:12]:
+    r = st[j]
+    print("  ", r.tolist(), round(1024 * r[2] / max(1, r[3] + r[4])))
+rounds = st[:, 3].astype(np.float64) + st[:, 4]
+print(f"total rounds {rounds.sum():.0f}, mean cycles/round {1024*kc.sum()/rounds.sum():.0f}; phase share A {st[:,5].sum()/kc.sum():.2f} BC {st[:,6].sum()/kc.sum():.2f} EF {st[:,7].sum()/kc.sum():.2f}")
+for lo, hi in ((256, 512), (512, 1024), (1024, 2048), (2048, 4096), (4096, 8192), (8192, 1 << 30)):
+    m = (st[:, 1] >= lo) & (st[:, 1] < hi)
+    if m.any():
+        print(f"members [{lo},{hi}): jobs {int(m.sum())}, kcycles {kc[m].sum():.0f} ({100*kc[m].sum()/kc.sum():.1f} %), cycles/member {1024*kc[m].sum()/st[m,1].sum():.0f}")
