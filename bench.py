@@ -42,7 +42,25 @@ METRIC = "frames/s seg+cluster (154-frame HDL-64E sequence, ~121.7k pts/frame)"
 HBM_FALLBACK_GBS = 6650.0
 
 
-def load_workload(max_frames: int | None = None):
+WORKLOADS = ("kitti154", "synth128", "merged1m", "synth64")
+
+
+def load_workload(which: str = "kitti154"):
+    """kitti154 = BASELINE.json configs[1], the configuration the metric is quoted on (default). The others
+    are the synthetic clouds of the named shapes, reported as extra lines."""
+    from tests.synth import make_frame, make_frame_128, make_merged_1m
+
+    if which == "synth128":
+        frames = [make_frame_128(12345 + i) for i in range(64)]
+        return frames, "synth128: config 3, 64 synthetic 128-beam frames (128 x 2048 rays, seed 12345 + i), one batch"
+    if which == "merged1m":
+        frames = [make_merged_1m(777 + i) for i in range(16)]
+        return frames, "merged1m: config 4, 16 merged 4-sensor clouds of ~1.04 M points with blobs and lattice walls (seed 777 + i)"
+    if which == "synth64":
+        distinct = [make_frame(1000 + i) for i in range(64)]
+        frames = [distinct[i % 64] for i in range(256)]
+        return frames, ("synth64: config 5, synthetic 64-beam frames (seed 1000 + i mod 64) in batches of 256 per GPU; "
+                        "the 4096-frame job is 16 such steps split over the GPUs")
     cache = ROOT / "data_cache" / "frames_mm.xz"
     if cache.exists():
         from tools.pack_reference_frames import unpack
@@ -50,13 +68,9 @@ def load_workload(max_frames: int | None = None):
         frames = unpack(cache)
         name = "kitti154: reference data/*.pcd sequence (154 frames, 98.5k-124.1k pts, lossless cache)"
     else:
-        from tests.synth import make_frame
-
         distinct = [make_frame(1000 + i) for i in range(22)]
         frames = [distinct[i % len(distinct)] for i in range(154)]
         name = "synth64x154: 154 synthetic 64-beam frames (22 distinct scenes cycled), reference data cache absent"
-    if max_frames:
-        frames = frames[:max_frames]
     return frames, name
 
 
@@ -240,9 +254,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=22, help="frames per pipeline chunk (e2e path)")
     ap.add_argument("--depth", type=int, default=6, help="pipeline depth = contexts in rotation (e2e path)")
+    ap.add_argument("--workload", default="kitti154", choices=WORKLOADS,
+                    help="kitti154 = the metric's configuration; the rest are the synthetic shapes of SURVEY 8(d)")
     args = ap.parse_args()
 
-    frames, workload = load_workload(None)
+    frames, workload = load_workload(args.workload)
+    global METRIC
+    if args.workload != "kitti154":
+        METRIC = f"frames/s seg+cluster ({args.workload}, SURVEY 8(d) synthetic shape)"
     if args.frame_offset or args.frames:
         frames = frames[args.frame_offset:][: (args.frames or None)]
     if args.impl == "reference":

@@ -12,7 +12,7 @@ import __graft_entry__ as ge  # noqa: E402
 from bench import load_workload  # noqa: E402
 
 pkg = ge.load_package()
-frames, _ = load_workload(None)
+frames, _ = load_workload()
 for K in (1, 2, 3, 4, 7):
     parts = [frames[i::K] for i in range(K)]
     ctxs = [pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in p), max_frames=len(p)) for p in parts]

@@ -11,7 +11,7 @@ from bench import load_workload  # noqa: E402
 
 first, n, reps = (int(a) for a in sys.argv[1:4])
 pkg = ge.load_package()
-frames, _ = load_workload(None)
+frames, _ = load_workload()
 sel = frames[first:first + n]
 ctx = pkg.Context(device=0, max_points=140_000 * n, max_frames=n)
 ctx.set_profiling(True)

@@ -10,8 +10,10 @@ reference's own sequence on the GPU box where /root/reference does not exist. Ru
     python tools/pack_reference_frames.py
 """
 import lzma
+import os
 import struct
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
@@ -20,50 +22,64 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import oracle as O  # noqa: E402  (PCD reader only)
 
-MAGIC = b"LB2FRM01"
+MAGIC_V1 = b"LB2FRM01"
+MAGIC = b"LB2FRM02"  # v2: one xz stream per frame (packed and unpacked by a thread pool)
+
+
+def _encode(p):
+    pts = O.read_pcd(p)
+    q = np.round(pts[:, :3].astype(np.float64) * 1000.0).astype(np.int32)
+    back = (q.astype(np.float64) / 1000.0).astype(np.float32)
+    assert np.array_equal(back, pts[:, :3]), f"{p}: not mm-exact"
+    qi = np.round(pts[:, 3].astype(np.float64) * 100.0).astype(np.int32)
+    assert np.array_equal((qi / 100.0).astype(np.float32), pts[:, 3]) and qi.min() >= 0 and qi.max() < 256
+    dq = np.diff(q, axis=0, prepend=np.zeros((1, 3), np.int32)).T.copy()
+    return pts.shape[0], lzma.compress(dq.tobytes() + qi.astype(np.uint8).tobytes(), preset=6)
 
 
 def pack(paths, out_path):
-    blobs = []
-    for p in paths:
-        pts = O.read_pcd(p)
-        q = np.round(pts[:, :3].astype(np.float64) * 1000.0).astype(np.int32)
-        back = (q.astype(np.float64) / 1000.0).astype(np.float32)
-        assert np.array_equal(back, pts[:, :3]), f"{p}: not mm-exact"
-        qi = np.round(pts[:, 3].astype(np.float64) * 100.0).astype(np.int32)
-        assert np.array_equal((qi / 100.0).astype(np.float32), pts[:, 3]) and qi.min() >= 0 and qi.max() < 256
-        dq = np.diff(q, axis=0, prepend=np.zeros((1, 3), np.int32)).T.copy()
-        blobs.append((pts.shape[0], dq.tobytes() + qi.astype(np.uint8).tobytes()))
-    raw = b"".join(b for _, b in blobs)
-    comp = lzma.compress(raw, preset=6)
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:  # lzma releases the GIL
+        blobs = list(ex.map(_encode, paths))
     with open(out_path, "wb") as f:
         f.write(MAGIC)
         f.write(struct.pack("<I", len(blobs)))
         f.write(np.array([n for n, _ in blobs], np.uint32).tobytes())
-        f.write(comp)
-    return len(comp)
+        f.write(np.array([len(b) for _, b in blobs], np.uint32).tobytes())
+        for _, b in blobs:
+            f.write(b)
+    return sum(len(b) for _, b in blobs)
+
+
+def _decode_raw(n, raw):
+    dq = np.frombuffer(raw, np.int32, 3 * n, 0).reshape(3, n)
+    qi = np.frombuffer(raw, np.uint8, n, 12 * n)
+    q = np.cumsum(dq, axis=1, dtype=np.int64).T
+    out = np.empty((n, 4), np.float32)
+    out[:, :3] = (q.astype(np.float64) / 1000.0).astype(np.float32)
+    out[:, 3] = (qi.astype(np.float64) / 100.0).astype(np.float32)
+    return out
 
 
 def unpack(path):
-    """Returns a list of (N,4) float32 arrays, bit-identical to the PCD files."""
+    """Returns a list of (N,4) float32 arrays, bit-identical to the PCD files. Reads both container versions:
+    v1 = one xz stream over all frames (tests/golden/frames_0_77_153.xz), v2 = one stream per frame."""
     with open(path, "rb") as f:
-        assert f.read(8) == MAGIC
+        magic = f.read(8)
+        assert magic in (MAGIC, MAGIC_V1), f"{path}: not a frame cache"
         (nf,) = struct.unpack("<I", f.read(4))
-        counts = np.frombuffer(f.read(4 * nf), np.uint32)
-        raw = lzma.decompress(f.read())
-    frames, pos = [], 0
-    for n in counts:
-        n = int(n)
-        dq = np.frombuffer(raw, np.int32, 3 * n, pos).reshape(3, n)
-        pos += 12 * n
-        qi = np.frombuffer(raw, np.uint8, n, pos)
-        pos += n
-        q = np.cumsum(dq, axis=1, dtype=np.int64).T
-        out = np.empty((n, 4), np.float32)
-        out[:, :3] = (q.astype(np.float64) / 1000.0).astype(np.float32)
-        out[:, 3] = (qi.astype(np.float64) / 100.0).astype(np.float32)
-        frames.append(out)
-    return frames
+        counts = [int(n) for n in np.frombuffer(f.read(4 * nf), np.uint32)]
+        if magic == MAGIC:
+            sizes = np.frombuffer(f.read(4 * nf), np.uint32)
+            blobs = [f.read(int(sz)) for sz in sizes]
+        else:
+            raw, blobs, pos = lzma.decompress(f.read()), [], 0
+            for n in counts:
+                blobs.append(raw[pos:pos + 13 * n])
+                pos += 13 * n
+    if magic == MAGIC_V1:
+        return [_decode_raw(n, b) for n, b in zip(counts, blobs)]
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        return list(ex.map(lambda a: _decode_raw(a[0], lzma.decompress(a[1])), zip(counts, blobs)))
 
 
 if __name__ == "__main__":

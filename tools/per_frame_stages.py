@@ -10,7 +10,7 @@ import __graft_entry__ as ge  # noqa: E402
 from bench import load_workload  # noqa: E402
 
 pkg = ge.load_package()
-frames, name = load_workload(None)
+frames, name = load_workload()
 ctx = pkg.Context(device=0, max_points=140_000, max_frames=1)
 ctx.set_profiling(True)
 rows = []

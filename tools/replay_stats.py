@@ -14,7 +14,7 @@ import __graft_entry__ as ge  # noqa: E402
 from bench import load_workload  # noqa: E402
 
 pkg = ge.load_package()
-frames, name = load_workload(None)
+frames, name = load_workload()
 ctx = pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames))
 ctx.set_profiling(True)
 ctx.batch_stage(frames)
