@@ -139,6 +139,30 @@ extern "C"
     int lidar_b200_batch_fetch_clusters(lidar_b200_ctx *ctx, uint32_t *n_clusters_out, uint32_t *cluster_offset_out,
                                         float *cluster_points_out, uint32_t *cluster_point_idx_out);
 
+    /* ---- ordered convex outlines per cluster on the device (the polygonization step that follows the
+     * split in the reference's caller, src/processor.cpp:210-214). Runs on the grouped clusters of
+     * lidar_b200_batch_group_clusters and re-enacts, bit for bit in float32:
+     *   LIDAR_B200_HULL_CONVEX        findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79):
+     *       geom::constructConvexHull with ANDREW_MONOTONE_CHAIN up to 1000 points and CHAN above
+     *       (reference Convex-Hull/convex_hull.hpp:212-281, 366-424), COUNTERCLOCKWISE, open;
+     *   LIDAR_B200_HULL_CONCAVE_SMALL the convex branch of findOrderedConcaveOutlines
+     *       (src/polygon_simplification.cpp:100-118): clusters below 20 points. Clusters from 20 points
+     *       on get 0 vertices here: their Delaunay-based concave hull stays on the host.
+     * _fetch_hulls: blocks; per frame f (O = point_offset[f], K = n_clusters[f]):
+     *   hull_offset_out[O + f + k], k = 0..K : CSR offsets into the frame's vertex list; a cluster with an
+     *       empty hull (fewer than 3 points) is the one the reference drops from its output vector
+     *   hull_xy_out : 2 floats per vertex = geom::Point<float>{x, y}, frame f's vertices start at 2 * O
+     *   hull_point_idx_out : obstacle-cloud index of every vertex (optional, may be NULL)
+     *   n_vertices_out[f] = hull_offset[K]
+     * Array sizes: n_vertices_out [n_frames], hull_offset_out [sum n + n_frames], hull_xy_out [sum n][2],
+     * hull_point_idx_out [sum n]. Errors: LIDAR_B200_ERR_UNSUPPORTED for a cluster above ~1.04 M points,
+     * LIDAR_B200_ERR_INPUT when a hull does not close (the reference loops forever on such input). */
+#define LIDAR_B200_HULL_CONVEX 0u
+#define LIDAR_B200_HULL_CONCAVE_SMALL 1u
+    int lidar_b200_batch_hull_outlines(lidar_b200_ctx *ctx, uint32_t mode);
+    int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *ctx, uint32_t *n_vertices_out, uint32_t *hull_offset_out,
+                                     float *hull_xy_out, uint32_t *hull_point_idx_out);
+
     /* Page-locked host memory for clouds and result arrays — the zero-copy counterpart of the
      * caller-owned cloud_in_ / label vectors of the reference (src/processor.cpp:123-126). Every entry
      * point accepts ordinary (pageable) host pointers and stages them through the library's own pinned

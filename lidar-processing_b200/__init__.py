@@ -128,8 +128,11 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
     "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error",
     "lidar_b200_last_replay_stats", "lidar_b200_batch_group_clusters", "lidar_b200_batch_fetch_clusters",
-    "lidar_b200_pcd_read",
+    "lidar_b200_pcd_read", "lidar_b200_batch_hull_outlines", "lidar_b200_batch_fetch_hulls",
 ]
+
+HULL_CONVEX = 0          # findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79)
+HULL_CONCAVE_SMALL = 1   # convex branch of findOrderedConcaveOutlines (:100-118); >= 20 points stay on the host
 
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
@@ -324,6 +327,30 @@ class Context:
             offsets = goff[o + f:o + f + k + 1]
             nv = int(offsets[k]) if offsets.size else 0
             out.append(dict(offsets=offsets, points=gpts[o:o + nv], point_idx=gidx[o:o + nv], n_clusters=k))
+        return out
+
+    def batch_hulls(self, mode: int = HULL_CONVEX):
+        """Ordered convex outlines per cluster on the device (reference src/polygon_simplification.cpp:31-79 /
+        :100-118) of the last batch_clusters(). Returns, per frame, dict(offsets[K+1], xy[n_vertices,2],
+        point_idx[n_vertices]): outline of cluster k = xy[offsets[k]:offsets[k+1]], counter-clockwise, open."""
+        counts = self._n_points
+        nf = counts.size
+        padded = ((counts.astype(np.int64) + 31) & ~31)
+        total = int(padded.sum())
+        off = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64) if nf else np.zeros(0, np.int64)
+        nv = np.zeros(max(nf, 1), np.uint32)
+        nc = np.zeros(max(nf, 1), np.uint32)
+        hoff = np.zeros(max(total + nf, 1), np.uint32)
+        hxy = np.zeros((max(total, 1), 2), np.float32)
+        hidx = np.zeros(max(total, 1), np.uint32)
+        self._check(lib().lidar_b200_batch_hull_outlines(self._h, C.c_uint32(mode)), "batch_hull_outlines")
+        self._check(lib().lidar_b200_batch_fetch_hulls(self._h, _ptr(nv, C.c_uint32), _ptr(hoff, C.c_uint32),
+                                                       _ptr(hxy, C.c_float), _ptr(hidx, C.c_uint32)), "batch_fetch_hulls")
+        self._check(lib().lidar_b200_batch_fetch_clusters(self._h, _ptr(nc, C.c_uint32), None, None, None), "batch_fetch_clusters")
+        out = []
+        for f in range(nf):
+            o, k, n = int(off[f]), int(nc[f]), int(nv[f])
+            out.append(dict(offsets=hoff[o + f:o + f + k + 1], xy=hxy[o:o + n], point_idx=hidx[o:o + n], n_clusters=k))
         return out
 
     def cluster_and_split(self, points):

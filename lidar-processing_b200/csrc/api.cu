@@ -7,6 +7,7 @@
 #include "cluster.cuh"
 #include "common.cuh"
 #include "group.cuh"
+#include "hull.cuh"
 #include "kd_build.cuh"
 #include "pcd_io.h"
 #include "radix_sort.cuh"
@@ -106,6 +107,9 @@ struct lidar_b200_ctx
     uint32_t clu_max_m{0};
     bool grouped{false};
     DevBuf<uint32_t> d_goff; // CSR offsets of the grouped clusters: frame f at [off[f] + f, off[f] + f + K_f]
+    // outlines of the grouped clusters (hull.cuh): CSR offsets in the layout of d_goff, vertices per frame, error bits
+    DevBuf<uint32_t> d_hoff, d_hnv, d_herr;
+    bool hulled{false};
     std::vector<uint32_t> off, cnt;
 
     // optional per-stage CUDA-event timing (lidar_b200_set_profiling)
@@ -465,6 +469,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     c->clu_counts = counts;
     c->clu_max_m = max_m;
     c->grouped = false;
+    c->hulled = false;
     if (max_m == 0u)
         return 0;
     const BatchView bv{c->m_off(), counts, F};
@@ -706,7 +711,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hnv.p, c->d_herr.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -926,6 +931,7 @@ int lidar_b200_batch_group_clusters(lidar_b200_ctx *c)
         return LIDAR_B200_ERR_CUDA;
     cudaStream_t s = c->stream;
     c->grouped = true;
+    c->hulled = false;
     if (F == 0u)
         return 0;
     LB_CUDA(c, cudaMemsetAsync(c->d_goff.p, 0, (static_cast<size_t>(c->total) + F) * 4, s));
@@ -968,6 +974,85 @@ int lidar_b200_batch_fetch_clusters(lidar_b200_ctx *c, uint32_t *n_clusters_out,
     if (total && cluster_point_idx_out)
         LB_CUDA(c, cudaMemcpyAsync(cluster_point_idx_out, c->d_queue.p, total * 4, cudaMemcpyDeviceToHost, s));
     LB_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    if (mode != LIDAR_B200_HULL_CONVEX && mode != LIDAR_B200_HULL_CONCAVE_SMALL)
+        return fail(c, LIDAR_B200_ERR_INVALID, "hull_outlines: unknown mode");
+    if (!c->grouped)
+        return fail(c, LIDAR_B200_ERR_INVALID, "hull_outlines: call lidar_b200_batch_group_clusters first");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t F = c->n_frames;
+    if (dev_alloc(c, c->d_hoff, static_cast<size_t>(c->cap_pts) + c->cap_frames + 1u) ||
+        dev_alloc(c, c->d_hnv, c->cap_frames) || dev_alloc(c, c->d_herr, 4))
+        return LIDAR_B200_ERR_CUDA;
+    cudaStream_t s = c->stream;
+    c->hulled = true;
+    if (F == 0u)
+        return 0;
+    LB_CUDA(c, cudaMemsetAsync(c->d_hoff.p, 0, (static_cast<size_t>(c->total) + F) * 4, s));
+    LB_CUDA(c, cudaMemsetAsync(c->d_hnv.p, 0, static_cast<size_t>(F) * 4, s));
+    LB_CUDA(c, cudaMemsetAsync(c->d_herr.p, 0, 4, s));
+    if (c->clu_max_m == 0u)
+        return 0;
+    static bool attr_done = false; // opt-in to > 48 KB of dynamic shared memory, once per process
+    const size_t smem = sizeof(HullWarpSmem) * kHullWarps;
+    if (!attr_done)
+    {
+        LB_CUDA(c, cudaFuncSetAttribute(hull_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        LB_CUDA(c, cudaFuncSetAttribute(hull_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_done = true;
+    }
+    const BatchView bv{c->m_off(), c->clu_counts, F};
+    // scratch: the per-point arrays of the clustering stage and of the group sort are free by now
+    const HullView hv{c->d_nodes.p, c->d_goff.p, c->d_queue.p, c->d_key_a.p, c->d_hoff.p, c->d_key_b.p, c->d_val_a.p,
+                      c->d_val_b.p, reinterpret_cast<float2 *>(c->d_pkey.p), c->d_herr.p};
+    hull_warp_kernel<<<dim3(16, F), 32 * kHullWarps, smem, s>>>(bv, c->m_nc(), hv, mode);
+    uint32_t nl = 3u;
+    if (mode == LIDAR_B200_HULL_CONVEX && c->clu_max_m > kHullMonotoneMax)
+    {
+        hull_chan_kernel<<<dim3(8, F), 32 * kHullWarps, smem, s>>>(bv, c->m_nc(), hv);
+        ++nl;
+    }
+    hull_scan_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_hoff.p, c->d_hnv.p);
+    hull_emit_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), hv, reinterpret_cast<float2 *>(c->d_spill.p), c->d_gepos.p);
+    c->launches += nl;
+    LB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *c, uint32_t *n_vertices_out, uint32_t *hull_offset_out, float *hull_xy_out,
+                                 uint32_t *hull_point_idx_out)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    if (!c->hulled)
+        return fail(c, LIDAR_B200_ERR_INVALID, "fetch_hulls: call lidar_b200_batch_hull_outlines first");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t F = c->n_frames;
+    const size_t total = c->total;
+    uint32_t herr = 0u;
+    if (F)
+        LB_CUDA(c, cudaMemcpyAsync(&herr, c->d_herr.p, 4, cudaMemcpyDeviceToHost, s));
+    if (F && n_vertices_out)
+        LB_CUDA(c, cudaMemcpyAsync(n_vertices_out, c->d_hnv.p, static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
+    if (F && hull_offset_out)
+        LB_CUDA(c, cudaMemcpyAsync(hull_offset_out, c->d_hoff.p, (total + F) * 4, cudaMemcpyDeviceToHost, s));
+    if (total && hull_xy_out)
+        LB_CUDA(c, cudaMemcpyAsync(hull_xy_out, c->d_spill.p, total * sizeof(float2), cudaMemcpyDeviceToHost, s));
+    if (total && hull_point_idx_out)
+        LB_CUDA(c, cudaMemcpyAsync(hull_point_idx_out, c->d_gepos.p, total * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    if (herr & kHullErrSubset)
+        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "hull_outlines: a cluster above ~1.04 M points exceeds the CHAN subset buffers");
+    if (herr)
+        return fail(c, LIDAR_B200_ERR_INPUT, "hull_outlines: degenerate input (hull longer than its cluster or a Jarvis march "
+                                             "that does not close; the reference does not terminate on it either)");
     return 0;
 }
 

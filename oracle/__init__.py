@@ -49,9 +49,9 @@ class CluCfg(C.Structure):
 def build(force: bool = False) -> None:
     """Compile liboracle.so, and oracle/_ref when /root/reference is present (else keep prebuilt)."""
     lib = HERE / "liboracle.so"
-    lib_deps = [HERE / "oracle.cpp", HERE / "oracle.h", HERE / "Makefile"]
-    ref = HERE / "_ref" / "libref_cluster.so"
-    ref_deps = lib_deps + [HERE / "ref_wrap.cpp"]
+    lib_deps = [HERE / "oracle.cpp", HERE / "hull_oracle.cpp", HERE / "oracle.h", HERE / "Makefile"]
+    ref = HERE / "_ref" / "libref_hull.so"  # the last target of `make ref`
+    ref_deps = lib_deps + [HERE / "ref_wrap.cpp", HERE / "ref_hull_wrap.cpp"]
     need = force or not lib.exists() or lib.stat().st_mtime < max(s.stat().st_mtime for s in lib_deps)
     have_reference = Path("/root/reference/src/clustering.cpp").exists()
     if have_reference and (force or not ref.exists() or ref.stat().st_mtime < max(s.stat().st_mtime for s in ref_deps)):
@@ -327,4 +327,72 @@ def split_clusters(obstacle_points, labels):
         if idx:  # std::remove_if(cloud.empty())
             ii = np.asarray(idx, np.int64)
             out.append((pts[ii], ii))
+    return out
+
+
+_REF_HULL = None
+
+
+def ref_hull_available() -> bool:
+    return (HERE / "_ref" / "libref_hull.so").exists()
+
+
+def _clusters_csr(clusters):
+    """list of (n_k, >=2) arrays -> (points[n,4] float32, offsets[K+1] uint32)"""
+    offsets = np.zeros(len(clusters) + 1, np.uint32)
+    if clusters:
+        offsets[1:] = np.cumsum([len(c) for c in clusters])
+    pts = np.zeros((max(int(offsets[-1]), 1), 4), np.float32)
+    at = 0
+    for c in clusters:
+        c = np.asarray(c, np.float32)
+        pts[at:at + len(c), :min(c.shape[1], 3)] = c[:, :3] if c.size else 0
+        at += len(c)
+    return pts, offsets
+
+
+def convex_outlines(clusters, mode: int = 0):
+    """Restated findOrderedConvexOutlines (mode 0) / convex branch of findOrderedConcaveOutlines (mode 1),
+    oracle/hull_oracle.cpp. Returns one (xy[h,2] float32, local_idx[h]) per cluster (h = 0: dropped / host)."""
+    pts, offsets = _clusters_csr(clusters)
+    k = len(clusters)
+    sizes = np.zeros(max(k, 1), np.uint32)
+    idx = np.zeros(max(int(offsets[-1]) * 2, 1), np.uint32)
+    f = lib().oracle_convex_outlines
+    f.restype = C.c_longlong
+    n = f(_p(pts, C.c_float), _p(offsets, C.c_uint32), C.c_uint32(k), C.c_uint32(4), C.c_int(mode),
+          _p(sizes, C.c_uint32), _p(idx, C.c_uint32), C.c_longlong(idx.size))
+    assert n >= 0
+    out, at = [], 0
+    for c in range(k):
+        h = int(sizes[c])
+        li = idx[at:at + h].astype(np.int64)
+        out.append((pts[int(offsets[c]) + li][:, :2].copy(), li))
+        at += h
+    return out
+
+
+def ref_outlines(clusters, mode: int = 0):
+    """UNMODIFIED reference findOrderedConvexOutlines (mode 0) / findOrderedConcaveOutlines (mode 1).
+    Returns one xy[h,2] float32 array per cluster (h = 0: the reference dropped the outline; None: it threw)."""
+    global _REF_HULL
+    if _REF_HULL is None:
+        build()
+        _REF_HULL = C.CDLL(str(HERE / "_ref" / "libref_hull.so"))
+        _REF_HULL.ref_outlines.restype = C.c_longlong
+    pts, offsets = _clusters_csr(clusters)
+    k = len(clusters)
+    sizes = np.zeros(max(k, 1), np.uint32)
+    xy = np.zeros((max(int(offsets[-1]) * 2, 1), 2), np.float32)
+    n = _REF_HULL.ref_outlines(_p(pts, C.c_float), _p(offsets, C.c_uint32), C.c_uint32(k), C.c_uint32(4), C.c_int(mode),
+                               _p(sizes, C.c_uint32), _p(xy, C.c_float), C.c_longlong(xy.shape[0]))
+    assert n >= 0
+    out, at = [], 0
+    for c in range(k):
+        h = int(sizes[c])
+        if h == 0xFFFFFFFF:  # the reference threw (delaunator on degenerate input)
+            out.append(None)
+            continue
+        out.append(xy[at:at + h].copy())
+        at += h
     return out

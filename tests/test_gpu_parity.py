@@ -452,3 +452,90 @@ def test_cluster_split_batch_and_edges(pkg, ctx, golden_frames, synth_small):
         assert labels.size == 0 and got["n_clusters"] == 0
     finally:
         c2.close()
+
+
+# ---- ordered convex outlines on the device vs the UNMODIFIED reference outline functions
+
+def _check_outlines(obs, groups, hulls, mode):
+    """groups = batch_clusters() entry, hulls = batch_hulls(mode) entry of the same frame."""
+    k = groups["n_clusters"]
+    assert hulls["n_clusters"] == k
+    go, ho = groups["offsets"].astype(np.int64), hulls["offsets"].astype(np.int64)
+    clusters = [groups["points"][go[c]:go[c + 1], :3] for c in range(k)]
+    want = O.ref_outlines(clusters, mode) if O.ref_hull_available() else None
+    port = O.convex_outlines(clusters, mode)
+    n_device = 0
+    for c in range(k):
+        xy = hulls["xy"][ho[c]:ho[c + 1]]
+        src = hulls["point_idx"][ho[c]:ho[c + 1]]
+        n = len(clusters[c])
+        if mode == 1 and n >= 20:
+            assert xy.shape[0] == 0  # the host's concave hull
+            continue
+        assert np.array_equal(xy, port[c][0]), f"cluster {c} ({n} points) differs from the restated oracle"
+        if want is not None:
+            assert np.array_equal(xy, want[c]), f"cluster {c} ({n} points) differs from the reference"
+        # vertices are points of the cluster: obstacle-cloud index -> same coordinates, and the first such point
+        assert np.array_equal(obs[src][:, :2], xy)
+        assert np.array_equal(src, groups["point_idx"][go[c]:go[c + 1]][port[c][1]])
+        n_device += 1
+    return n_device
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_outlines_golden_frames(ctx, golden_frames, mode):
+    res = ctx.process_batch(golden_frames)
+    groups = ctx.batch_clusters()
+    hulls = ctx.batch_hulls(mode)
+    total = 0
+    for pts, r, g, h in zip(golden_frames, res, groups, hulls):
+        total += _check_outlines(pts[r["obstacle_idx"]], g, h, mode)
+    assert total > (300 if mode == 1 else 1200)
+
+
+@pytest.mark.gpu
+def test_outlines_chan_and_degenerate_clusters(pkg):
+    """Clusters above 1000 points (CHAN: subsets + Jarvis march), duplicates, collinear runs, lattices, -0.0."""
+    from tests.test_oracle_pinning import _hull_stress_clusters
+
+    rng = np.random.default_rng(11)
+    clusters = [c for c in _hull_stress_clusters() if len(c) >= 4]
+    clusters += [np.round(rng.normal(size=(n, 3)) * s, 3).astype(np.float32) for n, s in ((2500, 2.0), (20000, 8.0), (1024, 0.5), (1025, 0.5))]
+    ring = rng.uniform(0, 2 * np.pi, 6000)
+    clusters.append(np.round(np.stack([30 * np.cos(ring), 30 * np.sin(ring), np.zeros_like(ring)], 1), 3).astype(np.float32))
+    # one "obstacle cloud": every cluster far from the others, labels given directly through cluster-only mode is not
+    # possible (labels come from the clusterer), so feed each cluster as its own frame with r large enough to join it
+    c2 = pkg.Context(device=0, max_points=300_000, max_frames=len(clusters))
+    try:
+        c2.clu_configure(pkg.ClusteringConfiguration(distance_squared=1.0e6, min_cluster_size=1))
+        for mode in (0, 1):
+            for c in clusters:
+                obs = np.zeros((len(c), 4), np.float32)
+                obs[:, :3] = c
+                labels, g = c2.cluster_and_split(obs)
+                assert g["n_clusters"] == 1 and np.all(labels == 0)
+                h = c2.batch_hulls(mode)[0]
+                assert _check_outlines(obs, g, h, mode) == (0 if (mode == 1 and len(c) >= 20) else 1)
+    finally:
+        c2.close()
+
+
+@pytest.mark.gpu
+def test_outlines_api_edges(pkg, ctx, synth_small):
+    with pytest.raises(pkg.LidarB200Error):
+        c2 = pkg.Context(device=0, max_points=10_000, max_frames=1)
+        try:
+            c2._n_points = np.array([0], np.uint32)
+            c2.batch_hulls(0)  # no grouped clusters on this context
+        finally:
+            c2.close()
+    tiny = np.array([[0, 0, 0, 0], [0.1, 0, 0, 0], [50, 50, 0, 0]], np.float32)  # no valid cluster at all
+    frames = [synth_small, tiny, np.zeros((0, 4), np.float32)]
+    res = ctx.process_batch(frames)
+    groups = ctx.batch_clusters()
+    for mode in (0, 1):
+        hulls = ctx.batch_hulls(mode)
+        for pts, r, g, h in zip(frames, res, groups, hulls):
+            _check_outlines(pts[r["obstacle_idx"]], g, h, mode)
+        assert hulls[1]["xy"].shape[0] == 0 and hulls[2]["xy"].shape[0] == 0

@@ -179,3 +179,46 @@ def test_split_clusters_restatement(golden_frames):
     with pytest.raises(RuntimeError):
         O.split_clusters(np.zeros((1, 4), np.float32), np.array([O.UNDEFINED], np.int32))
     assert O.split_clusters(np.zeros((0, 4), np.float32), np.zeros(0, np.int32)) == []
+
+
+# ---- outlines: restated convex hulls vs the UNMODIFIED reference outline functions
+
+def _hull_stress_clusters():
+    rng = np.random.default_rng(5)
+    out = []
+    for n in (0, 1, 2, 3, 4, 7, 19, 20, 64, 257, 999, 1000, 1001, 1500, 4097):
+        out.append(np.round(rng.normal(size=(n, 3)) * 3.0, 3).astype(np.float32))
+    # duplicates in (x, y) with different z, collinear runs, an axis-aligned lattice, -0.0 coordinates
+    dup = np.round(rng.normal(size=(40, 3)), 2).astype(np.float32)
+    out.append(np.concatenate([dup, dup[::-1] + np.float32([0, 0, 1])]))
+    line = np.stack([np.arange(30, dtype=np.float32) * 0.25, np.arange(30, dtype=np.float32) * 0.5, np.zeros(30, np.float32)], 1)
+    out.append(line)
+    out.append(line[:, [1, 0, 2]][::-1].copy())
+    gx, gy = np.meshgrid(np.arange(40, dtype=np.float32) * 0.05, np.arange(35, dtype=np.float32) * 0.05)
+    out.append(np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size, np.float32)], 1))       # 1400 points -> CHAN
+    z = np.zeros((8, 3), np.float32)
+    z[:, 0] = [-0.0, 0.0, 1.0, -1.0, -0.0, 0.0, 0.5, -0.5]
+    z[:, 1] = [0.0, -0.0, -0.0, 0.0, 1.0, -1.0, 0.5, -0.5]
+    out.append(z)
+    out.append(np.repeat(np.float32([[1.5, -2.5, 0.0]]), 12, axis=0))                      # one point, 12 times
+    return out
+
+
+@pytest.mark.skipif(not O.ref_hull_available(), reason="oracle/_ref/libref_hull.so not built")
+@pytest.mark.parametrize("mode", [0, 1])
+def test_restated_outlines_match_reference(mode, golden_frames):
+    clusters = _hull_stress_clusters()
+    pts = golden_frames[0]
+    obs = pts[O.segment(pts, tie_mode=1)["obstacle_idx"]]
+    clusters += [c for c, _ in O.split_clusters(obs, O.cluster(obs))]
+    got = O.convex_outlines(clusters, mode)
+    want = O.ref_outlines(clusters, mode)
+    n_checked = 0
+    for c, (xy, li), ref in zip(clusters, got, want):
+        if mode == 1 and len(c) >= 20:
+            assert len(xy) == 0  # concave hull: outside the restatement (and outside the device path)
+            continue
+        assert np.array_equal(xy, ref), f"cluster of {len(c)} points"
+        assert np.array_equal(np.asarray(c, np.float32)[li][:, :2], xy)
+        n_checked += 1
+    assert n_checked > (100 if mode == 1 else 400)
