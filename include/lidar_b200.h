@@ -163,6 +163,30 @@ extern "C"
     int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *ctx, uint32_t *n_vertices_out, uint32_t *hull_offset_out,
                                      float *hull_xy_out, uint32_t *hull_point_idx_out);
 
+    /* ---- output packing on the device: the two conversions the reference's caller runs before publishing
+     * (reference src/processor.cpp:249-272).
+     *
+     * _fetch_colorized: convertClusteredCloudToColorizedCloud (reference src/conversions.cpp:32-60) of the grouped
+     *   clusters, as the 32-byte pcl::PointXYZRGB records that convertPCLToPointCloud2 copies into the message
+     *   (floats x, y, z, 1.0f; colour word b | g << 8 | r << 16 | 255 << 24 at byte 16; 12 padding bytes = 0).
+     *   cluster_rgb: one word r << 16 | g << 8 | b per cluster, the frames' clusters end to end (n_rgb = sum of
+     *   n_clusters) — the caller draws them the way the reference does (std::rand() % 256 three times per cluster,
+     *   conversions.cpp:49-51), so the process-wide rand() sequence stays the caller's. colorized_out: 8 floats per
+     *   record, frame f's records start at 8 * point_offset[f], cluster after cluster in push order
+     *   (count = cluster_offset[K]). Size [sum n][8].
+     * _fetch_marker_points: the points of convertPointXYZTypeToMarkerArray (reference src/conversions.hpp:72-120) for
+     *   the outlines of lidar_b200_batch_hull_outlines: per non-empty outline its vertices as geometry_msgs::Point
+     *   {double x, y, z = 0} plus the first vertex again (loop closure, :108-117). marker_points_out: 3 doubles per
+     *   point, frame f's points start at 3 * 2 * point_offset[f]. marker_offset_out[O + f + k] = non-empty outlines
+     *   before cluster k (k = 0..K): the marker of cluster k owns points [hull_offset[k] + marker_offset[k],
+     *   hull_offset[k+1] + marker_offset[k+1]) and its marker.id is k when the outline vector keeps empty entries,
+     *   marker_offset[k] after the reference's erase of empty outlines. n_markers_out[f] = markers of frame f.
+     *   Sizes: marker_points_out [2 * sum n][3], marker_offset_out [sum n + n_frames], n_markers_out [n_frames]. */
+    int lidar_b200_batch_fetch_colorized(lidar_b200_ctx *ctx, const uint32_t *cluster_rgb, uint64_t n_rgb,
+                                         float *colorized_out);
+    int lidar_b200_batch_fetch_marker_points(lidar_b200_ctx *ctx, uint32_t *n_markers_out, uint32_t *marker_offset_out,
+                                             double *marker_points_out);
+
     /* Page-locked host memory for clouds and result arrays — the zero-copy counterpart of the
      * caller-owned cloud_in_ / label vectors of the reference (src/processor.cpp:123-126). Every entry
      * point accepts ordinary (pageable) host pointers and stages them through the library's own pinned

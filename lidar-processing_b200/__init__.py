@@ -129,6 +129,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error",
     "lidar_b200_last_replay_stats", "lidar_b200_batch_group_clusters", "lidar_b200_batch_fetch_clusters",
     "lidar_b200_pcd_read", "lidar_b200_batch_hull_outlines", "lidar_b200_batch_fetch_hulls",
+    "lidar_b200_batch_fetch_colorized", "lidar_b200_batch_fetch_marker_points",
 ]
 
 HULL_CONVEX = 0          # findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79)
@@ -352,6 +353,44 @@ class Context:
             o, k, n = int(off[f]), int(nc[f]), int(nv[f])
             out.append(dict(offsets=hoff[o + f:o + f + k + 1], xy=hxy[o:o + n], point_idx=hidx[o:o + n], n_clusters=k))
         return out
+
+    def _slots(self):
+        counts = self._n_points
+        padded = ((counts.astype(np.int64) + 31) & ~31)
+        off = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64) if counts.size else np.zeros(0, np.int64)
+        return counts.size, int(padded.sum()), off
+
+    def batch_colorized(self, cluster_rgb, groups):
+        """convertClusteredCloudToColorizedCloud on the device (reference src/conversions.cpp:32-60) for the clusters of
+        the last batch_clusters() (`groups` = its result). cluster_rgb: uint32 r << 16 | g << 8 | b per cluster, frames end
+        to end. Returns, per frame, the (n_valid, 32) uint8 PointXYZRGB records."""
+        nf, total, off = self._slots()
+        rgb = np.ascontiguousarray(cluster_rgb, np.uint32)
+        out = np.zeros((max(total, 1), 8), np.float32)
+        self._check(lib().lidar_b200_batch_fetch_colorized(self._h, _ptr(rgb, C.c_uint32) if rgb.size else None,
+                                                           C.c_uint64(rgb.size), _ptr(out, C.c_float)), "batch_fetch_colorized")
+        res = []
+        for f in range(nf):
+            nv = int(groups[f]["offsets"][-1]) if groups[f]["offsets"].size else 0
+            res.append(out[int(off[f]):int(off[f]) + nv].view(np.uint8).reshape(nv, 32))
+        return res
+
+    def batch_marker_points(self, hulls):
+        """Points of convertPointXYZTypeToMarkerArray (reference src/conversions.hpp:72-120) for the outlines of the last
+        batch_hulls() (`hulls` = its result). Returns, per frame, dict(points[n,3] float64, offsets[K+1]): the marker of
+        cluster k = points[offsets[k]:offsets[k+1]] (empty outline: no marker)."""
+        nf, total, off = self._slots()
+        nm = np.zeros(max(nf, 1), np.uint32)
+        moff = np.zeros(max(total + nf, 1), np.uint32)
+        pts = np.zeros((max(2 * total, 1), 3), np.float64)
+        self._check(lib().lidar_b200_batch_fetch_marker_points(self._h, _ptr(nm, C.c_uint32), _ptr(moff, C.c_uint32),
+                                                               _ptr(pts, C.c_double)), "batch_fetch_marker_points")
+        res = []
+        for f in range(nf):
+            o, k = int(off[f]), hulls[f]["n_clusters"]
+            offsets = hulls[f]["offsets"].astype(np.int64) + moff[o + f:o + f + k + 1].astype(np.int64) if k else np.zeros(1, np.int64)
+            res.append(dict(points=pts[2 * o:2 * o + int(offsets[-1])], offsets=offsets, n_markers=int(nm[f])))
+        return res
 
     def cluster_and_split(self, points):
         """Clusterer::cluster followed by the device-side split (single frame)."""

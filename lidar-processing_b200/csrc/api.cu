@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "group.cuh"
 #include "hull.cuh"
+#include "pack.cuh"
 #include "kd_build.cuh"
 #include "pcd_io.h"
 #include "radix_sort.cuh"
@@ -108,7 +109,9 @@ struct lidar_b200_ctx
     bool grouped{false};
     DevBuf<uint32_t> d_goff; // CSR offsets of the grouped clusters: frame f at [off[f] + f, off[f] + f + K_f]
     // outlines of the grouped clusters (hull.cuh): CSR offsets in the layout of d_goff, vertices per frame, error bits
-    DevBuf<uint32_t> d_hoff, d_hnv, d_herr;
+    DevBuf<uint32_t> d_hoff, d_hne, d_hnv, d_herr, d_rgb;
+    DevBuf<uint4> d_color;   // 32-byte PointXYZRGB records (pack.cuh), allocated on first use
+    DevBuf<double> d_marker; // marker points, allocated on first use
     bool hulled{false};
     std::vector<uint32_t> off, cnt;
 
@@ -711,7 +714,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hnv.p, c->d_herr.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -988,14 +991,15 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
     LB_CUDA(c, cudaSetDevice(c->device));
     const uint32_t F = c->n_frames;
     if (dev_alloc(c, c->d_hoff, static_cast<size_t>(c->cap_pts) + c->cap_frames + 1u) ||
-        dev_alloc(c, c->d_hnv, c->cap_frames) || dev_alloc(c, c->d_herr, 4))
+        dev_alloc(c, c->d_hne, static_cast<size_t>(c->cap_pts) + c->cap_frames + 1u) ||
+        dev_alloc(c, c->d_hnv, 4 * static_cast<size_t>(c->cap_frames) + 2) || dev_alloc(c, c->d_herr, 4))
         return LIDAR_B200_ERR_CUDA;
     cudaStream_t s = c->stream;
     c->hulled = true;
     if (F == 0u)
         return 0;
     LB_CUDA(c, cudaMemsetAsync(c->d_hoff.p, 0, (static_cast<size_t>(c->total) + F) * 4, s));
-    LB_CUDA(c, cudaMemsetAsync(c->d_hnv.p, 0, static_cast<size_t>(F) * 4, s));
+    LB_CUDA(c, cudaMemsetAsync(c->d_hnv.p, 0, (4 * static_cast<size_t>(c->cap_frames) + 2) * 4, s)); // vertices, tasks, prefix, cursor, outlines
     LB_CUDA(c, cudaMemsetAsync(c->d_herr.p, 0, 4, s));
     if (c->clu_max_m == 0u)
         return 0;
@@ -1003,22 +1007,29 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
     const size_t smem = sizeof(HullWarpSmem) * kHullWarps;
     if (!attr_done)
     {
-        LB_CUDA(c, cudaFuncSetAttribute(hull_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        LB_CUDA(c, cudaFuncSetAttribute(hull_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        LB_CUDA(c, cudaFuncSetAttribute(hull_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_done = true;
     }
     const BatchView bv{c->m_off(), c->clu_counts, F};
     // scratch: the per-point arrays of the clustering stage and of the group sort are free by now
     const HullView hv{c->d_nodes.p, c->d_goff.p, c->d_queue.p, c->d_key_a.p, c->d_hoff.p, c->d_key_b.p, c->d_val_a.p,
-                      c->d_val_b.p, reinterpret_cast<float2 *>(c->d_pkey.p), c->d_herr.p};
-    hull_warp_kernel<<<dim3(16, F), 32 * kHullWarps, smem, s>>>(bv, c->m_nc(), hv, mode);
-    uint32_t nl = 3u;
+                      c->d_val_b.p, reinterpret_cast<float2 *>(c->d_pkey.p), reinterpret_cast<unsigned long long *>(c->d_cpts.p),
+                      c->d_slot_of.p, reinterpret_cast<uint32_t *>(c->d_rpts.p), c->d_herr.p};
+    // d_hnv: [vertices per frame | tasks per frame | task prefix (F + 1) | cursor | non-empty outlines per frame]
+    uint32_t *n_tasks = c->d_hnv.p + c->cap_frames, *task_base = c->d_hnv.p + 2 * static_cast<size_t>(c->cap_frames),
+             *cursor = c->d_hnv.p + 3 * static_cast<size_t>(c->cap_frames) + 1;
+    hull_tasks_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), hv, mode, c->d_lepos.p, c->d_state.p, n_tasks);
+    hull_task_base_kernel<<<1, 256, 0, s>>>(n_tasks, F, task_base);
+    hull_sort_kernel<<<c->sm_count * 4u, 32 * kHullWarps, smem, s>>>(bv, hv, c->d_lepos.p, c->d_state.p, task_base, cursor);
+    hull_scan_chain_kernel<<<c->sm_count * 16u, 128, 0, s>>>(bv, hv, c->d_lepos.p, c->d_state.p, task_base);
+    uint32_t nl = 6u;
     if (mode == LIDAR_B200_HULL_CONVEX && c->clu_max_m > kHullMonotoneMax)
     {
-        hull_chan_kernel<<<dim3(8, F), 32 * kHullWarps, smem, s>>>(bv, c->m_nc(), hv);
+        hull_chan_merge_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), hv);
         ++nl;
     }
-    hull_scan_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_hoff.p, c->d_hnv.p);
+    hull_scan_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_hoff.p, c->d_hne.p, c->d_hnv.p,
+                                       c->d_hnv.p + 3 * static_cast<size_t>(c->cap_frames) + 2);
     hull_emit_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), hv, reinterpret_cast<float2 *>(c->d_spill.p), c->d_gepos.p);
     c->launches += nl;
     LB_CUDA(c, cudaGetLastError());
@@ -1035,24 +1046,128 @@ int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *c, uint32_t *n_vertices_out, ui
     LB_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const uint32_t F = c->n_frames;
-    const size_t total = c->total;
+    if (F == 0u)
+        return 0;
+    // counts first: only the used part of every frame slot crosses the bus
+    std::vector<uint32_t> nv(F), nc(F);
     uint32_t herr = 0u;
-    if (F)
-        LB_CUDA(c, cudaMemcpyAsync(&herr, c->d_herr.p, 4, cudaMemcpyDeviceToHost, s));
-    if (F && n_vertices_out)
-        LB_CUDA(c, cudaMemcpyAsync(n_vertices_out, c->d_hnv.p, static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
-    if (F && hull_offset_out)
-        LB_CUDA(c, cudaMemcpyAsync(hull_offset_out, c->d_hoff.p, (total + F) * 4, cudaMemcpyDeviceToHost, s));
-    if (total && hull_xy_out)
-        LB_CUDA(c, cudaMemcpyAsync(hull_xy_out, c->d_spill.p, total * sizeof(float2), cudaMemcpyDeviceToHost, s));
-    if (total && hull_point_idx_out)
-        LB_CUDA(c, cudaMemcpyAsync(hull_point_idx_out, c->d_gepos.p, total * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(nv.data(), c->d_hnv.p, static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(nc.data(), c->m_nc(), static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(&herr, c->d_herr.p, 4, cudaMemcpyDeviceToHost, s));
     LB_CUDA(c, cudaStreamSynchronize(s));
     if (herr & kHullErrSubset)
         return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "hull_outlines: a cluster above ~1.04 M points exceeds the CHAN subset buffers");
     if (herr)
         return fail(c, LIDAR_B200_ERR_INPUT, "hull_outlines: degenerate input (hull longer than its cluster or a Jarvis march "
                                              "that does not close; the reference does not terminate on it either)");
+    const float2 *hxy = reinterpret_cast<const float2 *>(c->d_spill.p);
+    for (uint32_t f = 0; f < F; ++f)
+    {
+        const size_t o = c->off[f];
+        if (n_vertices_out)
+            n_vertices_out[f] = nv[f];
+        if (hull_offset_out)
+            LB_CUDA(c, cudaMemcpyAsync(hull_offset_out + o + f, c->d_hoff.p + o + f, (static_cast<size_t>(nc[f]) + 1u) * 4,
+                                       cudaMemcpyDeviceToHost, s));
+        if (nv[f] && hull_xy_out)
+            LB_CUDA(c, cudaMemcpyAsync(hull_xy_out + 2u * o, hxy + o, static_cast<size_t>(nv[f]) * sizeof(float2),
+                                       cudaMemcpyDeviceToHost, s));
+        if (nv[f] && hull_point_idx_out)
+            LB_CUDA(c, cudaMemcpyAsync(hull_point_idx_out + o, c->d_gepos.p + o, static_cast<size_t>(nv[f]) * 4,
+                                       cudaMemcpyDeviceToHost, s));
+    }
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int lidar_b200_batch_fetch_colorized(lidar_b200_ctx *c, const uint32_t *cluster_rgb, uint64_t n_rgb, float *colorized_out)
+{
+    if (!c || !colorized_out || (!cluster_rgb && n_rgb))
+        return LIDAR_B200_ERR_INVALID;
+    if (!c->grouped)
+        return fail(c, LIDAR_B200_ERR_INVALID, "fetch_colorized: call lidar_b200_batch_group_clusters first");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t F = c->n_frames;
+    if (F == 0u || c->clu_max_m == 0u)
+        return n_rgb ? fail(c, LIDAR_B200_ERR_INVALID, "fetch_colorized: colours given but there is no cluster") : 0;
+    std::vector<uint32_t> nc(F), rgb_off(F + 1u, 0u);
+    LB_CUDA(c, cudaMemcpyAsync(nc.data(), c->m_nc(), static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    for (uint32_t f = 0; f < F; ++f)
+        rgb_off[f + 1u] = rgb_off[f] + nc[f];
+    if (n_rgb != rgb_off[F])
+        return fail(c, LIDAR_B200_ERR_INVALID, "fetch_colorized: n_rgb must be the number of clusters of the batch");
+    if (dev_alloc(c, c->d_rgb, static_cast<size_t>(c->cap_pts) + c->cap_frames + 1u)) // K <= points per frame
+        return LIDAR_B200_ERR_CUDA;
+    if (n_rgb == 0u)
+        return 0;
+    // colour words, then the per-frame prefix behind them
+    LB_CUDA(c, cudaMemcpyAsync(c->d_rgb.p, cluster_rgb, n_rgb * 4, cudaMemcpyHostToDevice, s));
+    LB_CUDA(c, cudaMemcpyAsync(c->d_rgb.p + c->cap_pts, rgb_off.data(), static_cast<size_t>(F) * 4, cudaMemcpyHostToDevice, s));
+    const BatchView bv{c->m_off(), c->clu_counts, F};
+    // 32-byte records per grouped point, allocated on first use
+    if (dev_alloc(c, c->d_color, 2 * static_cast<size_t>(c->cap_pts)))
+        return LIDAR_B200_ERR_CUDA;
+    colorize_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), c->d_nodes.p, c->d_goff.p, c->d_rgb.p, c->d_rgb.p + c->cap_pts,
+                                               c->d_color.p);
+    ++c->launches;
+    LB_CUDA(c, cudaGetLastError());
+    // valid points per frame = offset[K]: one more small read, then only the used part of every slot is copied
+    std::vector<uint32_t> n_valid(F, 0u);
+    for (uint32_t f = 0; f < F; ++f)
+        LB_CUDA(c, cudaMemcpyAsync(&n_valid[f], c->d_goff.p + c->off[f] + f + nc[f], 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    for (uint32_t f = 0; f < F; ++f)
+        if (n_valid[f])
+            LB_CUDA(c, cudaMemcpyAsync(colorized_out + 8u * static_cast<size_t>(c->off[f]), c->d_color.p + 2u * static_cast<size_t>(c->off[f]),
+                                       static_cast<size_t>(n_valid[f]) * 32u, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int lidar_b200_batch_fetch_marker_points(lidar_b200_ctx *c, uint32_t *n_markers_out, uint32_t *marker_offset_out,
+                                         double *marker_points_out)
+{
+    if (!c || !marker_points_out)
+        return LIDAR_B200_ERR_INVALID;
+    if (!c->hulled)
+        return fail(c, LIDAR_B200_ERR_INVALID, "fetch_marker_points: call lidar_b200_batch_hull_outlines first");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t F = c->n_frames;
+    if (F == 0u)
+        return 0;
+    std::vector<uint32_t> nv(F), no(F), nc(F);
+    LB_CUDA(c, cudaMemcpyAsync(nv.data(), c->d_hnv.p, static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(no.data(), c->d_hnv.p + 3 * static_cast<size_t>(c->cap_frames) + 2, static_cast<size_t>(F) * 4,
+                               cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaMemcpyAsync(nc.data(), c->m_nc(), static_cast<size_t>(F) * 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaStreamSynchronize(s));
+    if (c->clu_max_m)
+    {
+        if (dev_alloc(c, c->d_marker, 6 * static_cast<size_t>(c->cap_pts))) // 3 doubles per point, two slots per grouped point
+            return LIDAR_B200_ERR_CUDA;
+        const BatchView bv{c->m_off(), c->clu_counts, F};
+        marker_points_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), c->d_hoff.p, c->d_hne.p,
+                                                        reinterpret_cast<const float2 *>(c->d_spill.p), c->d_marker.p);
+        ++c->launches;
+        LB_CUDA(c, cudaGetLastError());
+    }
+    for (uint32_t f = 0; f < F; ++f)
+    {
+        const size_t o = c->off[f];
+        if (n_markers_out)
+            n_markers_out[f] = no[f];
+        // marker k of the frame owns points [hoff[k] + hne[k], hoff[k+1] + hne[k+1]): the host adds the two CSR arrays
+        if (marker_offset_out)
+            LB_CUDA(c, cudaMemcpyAsync(marker_offset_out + o + f, c->d_hne.p + o + f, (static_cast<size_t>(nc[f]) + 1u) * 4,
+                                       cudaMemcpyDeviceToHost, s));
+        if (nv[f])
+            LB_CUDA(c, cudaMemcpyAsync(marker_points_out + 6u * o, c->d_marker.p + 6u * o,
+                                       (static_cast<size_t>(nv[f]) + no[f]) * 3u * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    LB_CUDA(c, cudaStreamSynchronize(s));
     return 0;
 }
 

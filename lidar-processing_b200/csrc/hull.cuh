@@ -13,15 +13,19 @@
 //     monotone chain below 20 points (:100-118) and the Delaunay-based concave hull from 20 points on —
 //     that part stays on the host (BASELINE north star) and such clusters are reported as "host".
 //
-// Work decomposition: the sort is a warp-wide bitonic network over 64-bit (y, x) keys in shared memory
-// (a subset or a cluster of the warp path has at most 1024 points); the stack scan is an inherently
-// sequential chain and runs on lane 0 out of shared memory; the map-back and the Jarvis fold are
-// warp-parallel re-enactments that evaluate every predicate against the same operands as the
-// sequential loops. Equal (x, y) pairs are value-identical, so the unstable std::sort needs no replay.
+// Work decomposition: every monotone chain (a cluster up to 1000 points, or one CHAN subset) is a task.
+// Sort: persistent warps pull tasks from a batch-wide counter and run a warp-wide bitonic network over
+// 64-bit (y, x) keys with the original index as tie-break in shared memory. Scan: the stack scan is an
+// inherently sequential chain, so it runs one THREAD per task (about 2000 tasks per frame) over the
+// sorted keys; the map-back reads the head of the run of equal points. The Jarvis fold is a
+// warp-parallel re-enactment that evaluates every predicate against the same operands as the sequential
+// loop, on merged points staged in shared memory. Equal (x, y) pairs are value-identical, so the
+// unstable std::sort needs no replay.
 //
 // Envelope: distinct y (and x) values of a cluster are either equal or at least FLT_EPSILON apart
 // (true for |v| >= 1 and for mm-quantised LiDAR returns); otherwise the reference's operator< is not a
-// strict weak order and std::sort's result is unspecified. CHAN subsets must fit a warp's buffers:
+// strict weak order and std::sort's result is unspecified. Inside the envelope the reference's epsilon
+// equality is plain equality. CHAN subsets must fit a warp's buffers:
 // clusters up to ~1.04 M points; larger ones raise the error flag.
 #pragma once
 
@@ -33,15 +37,17 @@ namespace lb
 constexpr uint32_t kHullWarpCap = 1024u;        // points one warp sorts in shared memory
 constexpr uint32_t kHullMonotoneMax = 1000u;    // cluster_points.size() > 1000 -> CHAN (polygon_simplification.cpp:55)
 constexpr uint32_t kHullConcaveMin = 20u;       // cluster.size() < 20 -> monotone chain (polygon_simplification.cpp:100)
-constexpr int kHullWarps = 8;                  // warps per CTA, 12 KB of dynamic shared memory each
+constexpr int kHullWarps = 8;                   // warps per CTA of hull_chain_kernel, 12 KB of dynamic shared memory each
 constexpr uint32_t kHullModeConvex = 0u;        // findOrderedConvexOutlines
 constexpr uint32_t kHullModeConcaveSmall = 1u;  // the convex branch of findOrderedConcaveOutlines
+constexpr uint32_t kHullThreadScanMax = 192u;   // tasks up to this size are scanned one thread per task, larger ones by lane 0 of the sorting warp
 constexpr uint32_t kHullErrOverflow = 1u, kHullErrSubset = 2u, kHullErrJarvis = 4u;
 
 struct __align__(16) HullWarpSmem
 {
     unsigned long long key[kHullWarpCap];  // (ordered y) << 32 | ordered x, sorted ascending
-    uint16_t stack[2u * kHullWarpCap];     // hull_indices(2 * n) of convex_hull.hpp:222
+    uint16_t idx[kHullWarpCap];            // original index of the sorted point (ties in key: ascending)
+    uint16_t stack[2u * kHullWarpCap];     // hull_indices(2 * n) of convex_hull.hpp:222 (tasks scanned by their warp)
 };
 
 struct HullView
@@ -55,6 +61,9 @@ struct HullView
     uint32_t *sub_cnt;    // CHAN: vertices per subset, at cluster start + subset number
     uint32_t *mrg_idx;    // CHAN: merged_indices
     float2 *mrg_xy;       // CHAN: merged_points
+    unsigned long long *skey; // per task, at its own point range: the (y, x) keys in sorted order
+    uint32_t *sidx;       // original index (inside the task's range) of every sorted point
+    uint32_t *stk;        // two words per point: hull_indices(2 * n) of convex_hull.hpp:222
     uint32_t *err;        // error bits
 };
 
@@ -73,8 +82,10 @@ LB_D float2 hull_decode(unsigned long long k)
     return make_float2(ordered_to_float(static_cast<uint32_t>(k)), ordered_to_float(static_cast<uint32_t>(k >> 32)));
 }
 
-// Ascending sort of n <= kHullWarpCap keys by one warp ("flip" bitonic network: slots past n act as +inf).
-LB_D void hull_warp_sort(unsigned long long *a, uint32_t n)
+// Ascending sort of n <= kHullWarpCap (key, original index) pairs by one warp ("flip" bitonic network: slots
+// past n act as +inf). The index is the tie-break, so the first element of a run of equal points is the
+// one with the smallest original index.
+LB_D void hull_warp_sort(unsigned long long *a, uint16_t *ix, uint32_t n)
 {
     const uint32_t lane = lane_id();
     uint32_t n_pad = 2u;
@@ -83,12 +94,13 @@ LB_D void hull_warp_sort(unsigned long long *a, uint32_t n)
     for (uint32_t kk = 2u; kk <= n_pad; kk <<= 1)
         for (uint32_t jj = kk >> 1; jj > 0u; jj >>= 1)
         {
+            const uint32_t lj = 31u - __clz(jj); // jj is a power of two
             for (uint32_t t = lane; t < (n_pad >> 1); t += 32u)
             {
                 uint32_t i0, i1;
                 if (jj == (kk >> 1))
                 {
-                    const uint32_t blk = t / jj, o = t - blk * jj;
+                    const uint32_t blk = t >> lj, o = t & (jj - 1u);
                     i0 = blk * kk + o;
                     i1 = blk * kk + kk - 1u - o;
                 }
@@ -100,10 +112,13 @@ LB_D void hull_warp_sort(unsigned long long *a, uint32_t n)
                 if (i1 < n)
                 {
                     const unsigned long long x = a[i0], y = a[i1];
-                    if (x > y)
+                    const uint16_t xi = ix[i0], yi = ix[i1];
+                    if (x > y || (x == y && xi > yi))
                     {
                         a[i0] = y;
                         a[i1] = x;
+                        ix[i0] = yi;
+                        ix[i1] = xi;
                     }
                 }
             }
@@ -111,146 +126,340 @@ LB_D void hull_warp_sort(unsigned long long *a, uint32_t n)
         }
 }
 
-// constructAndrewMonotoneChainConvexHull(points[0..n), COUNTERCLOCKWISE, OPEN) by one warp, n <= kHullWarpCap.
-// Writes the hull as indices into `pts` (plus `base`) to out[0..h) and returns h (0 when n < 3); at most
-// `out_cap` vertices are kept (more is reported through *err).
-LB_D uint32_t hull_warp_monotone_chain(const float4 *__restrict__ pts, uint32_t n, uint32_t base, HullWarpSmem &ws,
-                                       uint32_t *__restrict__ out, uint32_t out_cap, uint32_t *__restrict__ err)
+// Number of CHAN subsets of a cluster of n points: static_cast<int>(std::ceil(std::sqrt(n))) (convex_hull.hpp:376).
+LB_D uint32_t hull_chan_subsets(uint32_t n)
 {
-    if (n < 3u)
-        return 0u; // convex_hull.hpp:217-220
-    const uint32_t lane = lane_id();
-    for (uint32_t i = lane; i < n; i += 32u)
+    return static_cast<uint32_t>(ceil(sqrt(static_cast<double>(n))));
+}
+
+// Task list of a frame (one CTA per frame): one task per monotone chain to run — a whole cluster, or one CHAN
+// subset of a cluster above 1000 points — so that the warps of hull_chain_kernel pull equally small pieces of
+// work. Tasks of frame f live at task_k / task_s [off[f] ..) (a cluster owns at most as many tasks as points);
+// n_tasks[f] = their number. Clusters that run nothing here (mode 1, from 20 points on) get 0 vertices.
+__global__ void __launch_bounds__(256)
+hull_tasks_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView hv, uint32_t mode,
+                  uint32_t *__restrict__ task_k, uint32_t *__restrict__ task_s, uint32_t *__restrict__ n_tasks)
+{
+    __shared__ uint32_t ws[9];
+    __shared__ uint32_t carry;
+    const uint32_t f = blockIdx.x;
+    const uint32_t off = bv.off[f];
+    const uint32_t K = n_clusters[f];
+    const uint32_t *go = hv.goff + off + f;
+    uint32_t *hc = hv.hcnt + off + f;
+    if (threadIdx.x == 0)
+        carry = 0u;
+    __syncthreads();
+    for (uint32_t k0 = 0; k0 < K; k0 += 256u)
     {
-        const float4 p = __ldg(&pts[i]);
-        ws.key[i] = (static_cast<unsigned long long>(float_to_ordered(p.y)) << 32) | float_to_ordered(p.x);
+        const uint32_t k = k0 + threadIdx.x;
+        uint32_t cnt = 0u;
+        if (k < K)
+        {
+            const uint32_t n = go[k + 1u] - go[k];
+            if (mode == kHullModeConvex)
+            {
+                cnt = n <= kHullMonotoneMax ? 1u : hull_chan_subsets(n);
+                if (n > kHullMonotoneMax && n / cnt + 1u > kHullWarpCap)
+                {
+                    atomicOr(hv.err, kHullErrSubset);
+                    cnt = 0u;
+                }
+            }
+            else
+                cnt = n < kHullConcaveMin ? 1u : 0u;
+            if (cnt == 0u)
+                hc[k] = 0u;
+        }
+        uint32_t total;
+        const uint32_t base = block_exclusive_scan<256>(cnt, ws, &total) + carry;
+        for (uint32_t s = 0; s < cnt; ++s)
+        {
+            task_k[off + base + s] = k;
+            task_s[off + base + s] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            carry += total;
+        __syncthreads();
     }
-    __syncwarp();
-    hull_warp_sort(ws.key, n);
-    uint32_t k = 0u;
-    if (lane == 0u)
+    if (threadIdx.x == 0)
+        n_tasks[f] = carry;
+}
+
+// task_base[f] = tasks of the frames before f, task_base[F] = all tasks (one CTA).
+__global__ void __launch_bounds__(256)
+hull_task_base_kernel(const uint32_t *__restrict__ n_tasks, uint32_t frames, uint32_t *__restrict__ task_base)
+{
+    __shared__ uint32_t ws[9];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0)
+        carry = 0u;
+    __syncthreads();
+    for (uint32_t f0 = 0; f0 < frames; f0 += 256u)
     {
+        const uint32_t f = f0 + threadIdx.x;
+        const uint32_t v = f < frames ? n_tasks[f] : 0u;
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan<256>(v, ws, &total) + carry;
+        if (f < frames)
+            task_base[f] = excl;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        task_base[frames] = carry;
+}
+
+struct HullTask
+{
+    uint32_t f, k, pt0, start, size; // frame, cluster, first grouped point of the cluster (absolute), range inside it
+    bool subset;                     // a CHAN subset (else the whole cluster)
+    uint32_t s;
+};
+
+// batch-wide task number -> task (binary search over the per-frame prefix)
+LB_D HullTask hull_task(uint32_t g, const BatchView &bv, const HullView &hv, const uint32_t *__restrict__ task_base,
+                        const uint32_t *__restrict__ task_k, const uint32_t *__restrict__ task_s)
+{
+    uint32_t lo = 0u, hi = bv.frames - 1u;
+    while (lo < hi) // last frame whose base is <= g
+    {
+        const uint32_t mid = (lo + hi + 1u) >> 1;
+        if (task_base[mid] <= g)
+            lo = mid;
+        else
+            hi = mid - 1u;
+    }
+    HullTask t;
+    t.f = lo;
+    const uint32_t off = bv.off[lo];
+    const uint32_t local = g - task_base[lo];
+    t.k = task_k[off + local];
+    t.s = task_s[off + local];
+    const uint32_t *go = hv.goff + off + lo;
+    const uint32_t c0 = go[t.k];
+    const uint32_t n = go[t.k + 1u] - c0;
+    t.pt0 = off + c0;
+    t.subset = n > kHullMonotoneMax;
+    if (!t.subset)
+    {
+        t.start = 0u;
+        t.size = n;
+    }
+    else
+    {
+        // partitionVector (convex_hull.hpp:337-364): the first n % S subsets hold one point more
+        const uint32_t S = hull_chan_subsets(n);
+        const uint32_t per = n / S, rem = n % S;
+        t.start = t.s * per + min(t.s, rem);
+        t.size = per + (t.s < rem ? 1u : 0u);
+    }
+    return t;
+}
+
+// Persistent warps pull tasks from one batch-wide counter and sort the task's points by Point::operator<
+// (convex_hull.hpp:51-61, 224-226): keys and original indices go to the task's own range of skey / sidx.
+__global__ void __launch_bounds__(32 * kHullWarps)
+hull_sort_kernel(BatchView bv, HullView hv, const uint32_t *__restrict__ task_k, const uint32_t *__restrict__ task_s,
+                 const uint32_t *__restrict__ task_base, uint32_t *__restrict__ cursor)
+{
+    extern __shared__ __align__(16) unsigned char hull_smem[];
+    HullWarpSmem &ws = reinterpret_cast<HullWarpSmem *>(hull_smem)[threadIdx.x >> 5];
+    const uint32_t lane = lane_id();
+    const uint32_t T = task_base[bv.frames];
+    while (true)
+    {
+        uint32_t g = 0u;
+        if (lane == 0u)
+            g = atomicAdd(cursor, 1u);
+        g = __shfl_sync(kFullMask, g, 0);
+        if (g >= T)
+            break;
+        const HullTask t = hull_task(g, bv, hv, task_base, task_k, task_s);
+        if (t.size < 3u)
+            continue; // convex_hull.hpp:217-220: no hull, nothing to sort
+        const float4 *pts = hv.gpts + t.pt0 + t.start;
+        for (uint32_t i = lane; i < t.size; i += 32u)
+        {
+            const float4 p = __ldg(&pts[i]);
+            ws.key[i] = (static_cast<unsigned long long>(float_to_ordered(p.y)) << 32) | float_to_ordered(p.x);
+            ws.idx[i] = static_cast<uint16_t>(i);
+        }
+        __syncwarp();
+        hull_warp_sort(ws.key, ws.idx, t.size);
+        if (t.size <= kHullThreadScanMax)
+        {
+            unsigned long long *sk = hv.skey + t.pt0 + t.start;
+            uint32_t *si = hv.sidx + t.pt0 + t.start;
+            for (uint32_t i = lane; i < t.size; i += 32u)
+            {
+                sk[i] = ws.key[i];
+                si[i] = ws.idx[i];
+            }
+            __syncwarp();
+            continue;
+        }
+        // a long chain: scanned right here by lane 0 out of shared memory (the same loops as hull_scan_chain_kernel)
+        const uint32_t n = t.size;
+        uint32_t k = 0u;
+        if (lane == 0u)
+        {
+            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                const float2 p = hull_decode(ws.key[i]);
+                while (k >= 2u && !(hull_cross(a.x, a.y, b.x, b.y, p.x, p.y) > 0.0f))
+                {
+                    --k;
+                    b = a;
+                    if (k >= 2u)
+                        a = hull_decode(ws.key[ws.stack[k - 2u]]);
+                }
+                ws.stack[k++] = static_cast<uint16_t>(i);
+                a = b;
+                b = p;
+            }
+            const uint32_t floor_k = k + 1u;
+            for (uint32_t i = n - 1u; i-- > 0u;)
+            {
+                const float2 p = hull_decode(ws.key[i]);
+                while (k >= floor_k && !(hull_cross(a.x, a.y, b.x, b.y, p.x, p.y) > 0.0f))
+                {
+                    --k;
+                    b = a;
+                    if (k >= 2u)
+                        a = hull_decode(ws.key[ws.stack[k - 2u]]);
+                }
+                ws.stack[k++] = static_cast<uint16_t>(i);
+                a = b;
+                b = p;
+            }
+        }
+        __syncwarp();
+        k = __shfl_sync(kFullMask, k, 0);
+        uint32_t h = k - 1u;
+        if (h > n)
+        {
+            if (lane == 0u)
+                atomicOr(hv.err, kHullErrOverflow);
+            h = n;
+        }
+        uint32_t *out = (t.subset ? hv.sub_idx : hv.hres) + t.pt0 + t.start;
+        for (uint32_t v = lane; v < h; v += 32u)
+        {
+            uint32_t pos = ws.stack[v];
+            const unsigned long long kv = ws.key[pos];
+            while (pos > 0u && ws.key[pos - 1u] == kv)
+                --pos;
+            out[v] = t.start + ws.idx[pos];
+        }
+        if (lane == 0u)
+        {
+            if (t.subset)
+                hv.sub_cnt[t.pt0 + t.s] = h;
+            else
+                hv.hcnt[bv.off[t.f] + t.f + t.k] = h;
+        }
+        __syncwarp();
+    }
+}
+
+// Thread per task: the lower / upper stack scans of constructAndrewMonotoneChainConvexHull (convex_hull.hpp:
+// 227-251, COUNTERCLOCKWISE, OPEN) over the sorted points, then the map-back to original indices. The scan is
+// a sequential chain per task; the tasks are what runs in parallel.
+__global__ void __launch_bounds__(128)
+hull_scan_chain_kernel(BatchView bv, HullView hv, const uint32_t *__restrict__ task_k, const uint32_t *__restrict__ task_s,
+                       const uint32_t *__restrict__ task_base)
+{
+    const uint32_t T = task_base[bv.frames];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < T; g += gridDim.x * blockDim.x)
+    {
+    const HullTask t = hull_task(g, bv, hv, task_base, task_k, task_s);
+    const uint32_t n = t.size;
+    if (n > kHullThreadScanMax)
+        continue; // scanned by the warp that sorted it
+    uint32_t h = 0u;
+    if (n >= 3u)
+    {
+        const unsigned long long *sk = hv.skey + t.pt0 + t.start;
+        uint32_t *st = hv.stk + 2ull * (t.pt0 + t.start);
+        uint32_t k = 0u;
         float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f); // sorted_points[hull[k-2]], [k-1]
         for (uint32_t i = 0; i < n; ++i) // lower chain, convex_hull.hpp:229-237
         {
-            const float2 p = hull_decode(ws.key[i]);
+            const float2 p = hull_decode(sk[i]);
             while (k >= 2u && !(hull_cross(a.x, a.y, b.x, b.y, p.x, p.y) > 0.0f))
             {
                 --k;
                 b = a;
                 if (k >= 2u)
-                    a = hull_decode(ws.key[ws.stack[k - 2u]]);
+                    a = hull_decode(sk[st[k - 2u]]);
             }
-            ws.stack[k++] = static_cast<uint16_t>(i);
+            st[k++] = i;
             a = b;
             b = p;
         }
-        const uint32_t t = k + 1u;
+        const uint32_t floor_k = k + 1u;
         for (uint32_t i = n - 1u; i-- > 0u;) // upper chain, convex_hull.hpp:240-248
         {
-            const float2 p = hull_decode(ws.key[i]);
-            while (k >= t && !(hull_cross(a.x, a.y, b.x, b.y, p.x, p.y) > 0.0f))
+            const float2 p = hull_decode(sk[i]);
+            while (k >= floor_k && !(hull_cross(a.x, a.y, b.x, b.y, p.x, p.y) > 0.0f))
             {
                 --k;
                 b = a;
                 if (k >= 2u)
-                    a = hull_decode(ws.key[ws.stack[k - 2u]]);
+                    a = hull_decode(sk[st[k - 2u]]);
             }
-            ws.stack[k++] = static_cast<uint16_t>(i);
+            st[k++] = i;
             a = b;
             b = p;
         }
-    }
-    __syncwarp();
-    k = __shfl_sync(kFullMask, k, 0);
-    uint32_t h = k - 1u; // hull_indices.resize(k - 1)
-    if (h > out_cap)
-    {
-        if (lane == 0u)
-            atomicOr(err, kHullErrOverflow);
-        h = out_cap;
-    }
-    // map back: first j with sorted_points[hull] == points[j] (epsilon equality, convex_hull.hpp:63-73, 254-265)
-    const float eps = 1.1920928955078125e-07f;
-    for (uint32_t v = 0; v < h; ++v)
-    {
-        const float2 s = hull_decode(ws.key[ws.stack[v]]);
-        uint32_t found = 0u; // the reference leaves the sorted position when nothing matches (cannot happen)
-        for (uint32_t j0 = 0; j0 < n; j0 += 32u)
+        h = k - 1u; // hull_indices.resize(k - 1)
+        if (h > n)
         {
-            const uint32_t j = j0 + lane;
-            bool eq = false;
-            if (j < n)
-            {
-                const float4 p = __ldg(&pts[j]);
-                eq = fabsf(__fsub_rn(s.x, p.x)) < eps && fabsf(__fsub_rn(s.y, p.y)) < eps;
-            }
-            const uint32_t bm = __ballot_sync(kFullMask, eq);
-            if (bm)
-            {
-                found = j0 + static_cast<uint32_t>(__ffs(bm) - 1);
-                break;
-            }
+            atomicOr(hv.err, kHullErrOverflow);
+            h = n;
         }
-        if (lane == 0u)
-            out[v] = base + found;
-    }
-    __syncwarp();
-    return h;
-}
-
-// Warp per cluster: monotone chain for the clusters the mode assigns to it. Every cluster of the frame gets
-// its hcnt written here (0 for the ones left to hull_chan_kernel / the host) except the CHAN ones in convex mode.
-__global__ void __launch_bounds__(32 * kHullWarps)
-hull_warp_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView hv, uint32_t mode)
-{
-    extern __shared__ __align__(16) unsigned char hull_smem[];
-    HullWarpSmem *sm = reinterpret_cast<HullWarpSmem *>(hull_smem);
-    const uint32_t f = blockIdx.y;
-    const uint32_t off = bv.off[f];
-    const uint32_t K = n_clusters[f];
-    const uint32_t *go = hv.goff + off + f;
-    uint32_t *hc = hv.hcnt + off + f;
-    const uint32_t warp = threadIdx.x >> 5;
-    HullWarpSmem &ws = sm[warp];
-    for (uint32_t k = blockIdx.x * kHullWarps + warp; k < K; k += gridDim.x * kHullWarps)
-    {
-        const uint32_t c0 = go[k];
-        const uint32_t n = go[k + 1u] - c0;
-        bool run;
-        if (mode == kHullModeConvex)
+        // map back: first j with sorted_points[hull] == points[j] (convex_hull.hpp:254-265). Under the envelope of
+        // this file the epsilon equality (convex_hull.hpp:63-73) is plain equality of both coordinates, the points
+        // equal to a hull vertex are one run of the sorted order, and the run starts with the smallest index.
+        const uint32_t *si = hv.sidx + t.pt0 + t.start;
+        uint32_t *out = (t.subset ? hv.sub_idx : hv.hres) + t.pt0 + t.start;
+        for (uint32_t v = 0; v < h; ++v)
         {
-            if (n > kHullMonotoneMax)
-                continue; // hull_chan_kernel writes this cluster's count
-            run = true;
+            uint32_t pos = st[v];
+            const unsigned long long kv = sk[pos];
+            while (pos > 0u && sk[pos - 1u] == kv)
+                --pos;
+            out[v] = t.start + si[pos];
         }
-        else
-            run = n < kHullConcaveMin; // from 20 points on: the host's concave hull, reported with 0 vertices
-        uint32_t h = 0u;
-        if (run)
-            h = hull_warp_monotone_chain(hv.gpts + off + c0, n, 0u, ws, hv.hres + off + c0, n, hv.err);
-        if (lane_id() == 0u)
-            hc[k] = h;
-        __syncwarp();
+    }
+    if (t.subset)
+        hv.sub_cnt[t.pt0 + t.s] = h;
+    else
+        hv.hcnt[bv.off[t.f] + t.f + t.k] = h;
     }
 }
 
-// CTA per cluster above 1000 points (convex mode): constructChanConvexHull.
-__global__ void __launch_bounds__(32 * kHullWarps)
-hull_chan_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView hv)
+// CTA per cluster above 1000 points: the rest of constructChanConvexHull after the per-subset chains. The
+// merged points are staged in shared memory (kHullMergeCap of them; more spill to the global copy).
+constexpr uint32_t kHullMergeCap = 3584u;
+__global__ void __launch_bounds__(256)
+hull_chan_merge_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView hv)
 {
-    extern __shared__ __align__(16) unsigned char hull_smem[];
-    HullWarpSmem *sm = reinterpret_cast<HullWarpSmem *>(hull_smem);
-    __shared__ uint32_t scan_ws[kHullWarps + 1];
+    __shared__ float2 s_xy[kHullMergeCap];
+    __shared__ uint32_t s_idx[kHullMergeCap];
+    __shared__ uint32_t scan_ws[9];
     __shared__ uint32_t s_carry;
-    constexpr int NT = 32 * kHullWarps;
     const uint32_t f = blockIdx.y;
     const uint32_t off = bv.off[f];
     const uint32_t K = n_clusters[f];
     const uint32_t *go = hv.goff + off + f;
     uint32_t *hc = hv.hcnt + off + f;
     const uint32_t tid = threadIdx.x;
-    const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31u;
     for (uint32_t k = blockIdx.x; k < K; k += gridDim.x)
     {
@@ -258,42 +467,26 @@ hull_chan_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView
         const uint32_t n = go[k + 1u] - c0;
         if (n <= kHullMonotoneMax)
             continue; // uniform across the CTA
-        const float4 *pts = hv.gpts + off + c0;
-        // partitionVector (convex_hull.hpp:337-364) with ceil(sqrt(n)) subsets (:376)
-        const uint32_t S = static_cast<uint32_t>(ceil(sqrt(static_cast<double>(n))));
+        const uint32_t S = hull_chan_subsets(n);
         const uint32_t per = n / S, rem = n % S;
         if (per + 1u > kHullWarpCap)
-        {
-            if (tid == 0)
-            {
-                atomicOr(hv.err, kHullErrSubset);
-                hc[k] = 0u;
-            }
-            continue;
-        }
-        uint32_t *sub_idx = hv.sub_idx + off + c0;
-        uint32_t *sub_cnt = hv.sub_cnt + off + c0;
+            continue; // flagged by hull_tasks_kernel
+        const float4 *pts = hv.gpts + off + c0;
+        const uint32_t *sub_idx = hv.sub_idx + off + c0;
+        const uint32_t *sub_cnt = hv.sub_cnt + off + c0;
         uint32_t *mrg_idx = hv.mrg_idx + off + c0;
         float2 *mrg_xy = hv.mrg_xy + off + c0;
-        for (uint32_t s = warp; s < S; s += kHullWarps)
-        {
-            const uint32_t start = s * per + min(s, rem);
-            const uint32_t size = per + (s < rem ? 1u : 0u);
-            const uint32_t h = hull_warp_monotone_chain(pts + start, size, start, sm[warp], sub_idx + start, size, hv.err);
-            if (lane == 0u)
-                sub_cnt[s] = h;
-        }
-        __syncthreads();
         // merged_points / merged_indices: the sub-hulls end to end in subset order (convex_hull.hpp:392-406)
+        __syncthreads();
         if (tid == 0)
             s_carry = 0u;
         __syncthreads();
-        for (uint32_t s0 = 0; s0 < S; s0 += NT)
+        for (uint32_t s0 = 0; s0 < S; s0 += 256u)
         {
             const uint32_t s = s0 + tid;
             const uint32_t cnt = s < S ? sub_cnt[s] : 0u;
             uint32_t tile_total;
-            const uint32_t excl = block_exclusive_scan<NT>(cnt, scan_ws, &tile_total) + s_carry;
+            const uint32_t base = block_exclusive_scan<256>(cnt, scan_ws, &tile_total) + s_carry;
             if (s < S)
             {
                 const uint32_t start = s * per + min(s, rem);
@@ -301,8 +494,16 @@ hull_chan_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView
                 {
                     const uint32_t li = sub_idx[start + v];
                     const float4 p = __ldg(&pts[li]);
-                    mrg_idx[excl + v] = li;
-                    mrg_xy[excl + v] = make_float2(p.x, p.y);
+                    if (base + v < kHullMergeCap)
+                    {
+                        s_idx[base + v] = li;
+                        s_xy[base + v] = make_float2(p.x, p.y);
+                    }
+                    else
+                    {
+                        mrg_idx[base + v] = li;
+                        mrg_xy[base + v] = make_float2(p.x, p.y);
+                    }
                 }
             }
             __syncthreads();
@@ -311,123 +512,133 @@ hull_chan_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView
             __syncthreads();
         }
         const uint32_t m = s_carry;
-        // constructJarvisMarchConvexHull(merged_points) by warp 0 (convex_hull.hpp:283-335). The inner fold
+        if (tid >= 32u)
+            continue; // warp 0 marches; the others wait at the barrier of the next cluster
+        auto mxy = [&](uint32_t i) -> float2 { return i < kHullMergeCap ? s_xy[i] : mrg_xy[i]; };
+        auto midx = [&](uint32_t i) -> uint32_t { return i < kHullMergeCap ? s_idx[i] : mrg_idx[i]; };
+        // constructJarvisMarchConvexHull(merged_points) (convex_hull.hpp:283-335). The inner fold
         // `if orientation(p, i, q) == CCW then q = i` is re-enacted 32 candidates at a time: the lanes test
         // against the current q, the first hit becomes q and only the lanes behind it are tested again.
-        if (warp == 0u)
+        uint32_t h = 0u;
+        if (m >= 3u)
         {
-            uint32_t h = 0u;
-            if (m >= 3u)
+            float bx = 0.f; // first index holding the minimum x (strict '<' scan)
+            uint32_t bi = 0xFFFFFFFFu;
+            for (uint32_t i = lane; i < m; i += 32u)
             {
-                uint32_t leftmost = 0u;
+                const float x = mxy(i).x;
+                if (bi == 0xFFFFFFFFu || x < bx)
                 {
-                    // first index holding the minimum x (strict '<' scan)
-                    float bx = 0.f;
-                    uint32_t bi = 0xFFFFFFFFu;
-                    for (uint32_t i = lane; i < m; i += 32u)
-                    {
-                        const float x = mrg_xy[i].x;
-                        if (bi == 0xFFFFFFFFu || x < bx)
-                        {
-                            bx = x;
-                            bi = i;
-                        }
-                    }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1)
-                    {
-                        const float ox = __shfl_xor_sync(kFullMask, bx, d);
-                        const uint32_t oi = __shfl_xor_sync(kFullMask, bi, d);
-                        if (oi != 0xFFFFFFFFu && (bi == 0xFFFFFFFFu || ox < bx || (ox == bx && oi < bi)))
-                        {
-                            bx = ox;
-                            bi = oi;
-                        }
-                    }
-                    leftmost = bi;
-                }
-                uint32_t *out = hv.hres + off + c0;
-                uint32_t p = leftmost;
-                bool bad = false;
-                do
-                {
-                    if (h >= n || h > m)
-                    {
-                        bad = true; // the reference would not terminate either
-                        break;
-                    }
-                    if (lane == 0u)
-                        out[h] = mrg_idx[p];
-                    ++h;
-                    const float2 pp = mrg_xy[p];
-                    uint32_t q = p + 1u == m ? 0u : p + 1u;
-                    float2 pq = mrg_xy[q];
-                    for (uint32_t i0 = 0; i0 < m; i0 += 32u)
-                    {
-                        const uint32_t i = i0 + lane;
-                        const float2 pi = i < m ? mrg_xy[i] : pp;
-                        uint32_t todo = kFullMask;
-                        while (true)
-                        {
-                            const bool ccw = i < m && hull_cross(pp.x, pp.y, pi.x, pi.y, pq.x, pq.y) > 0.0f;
-                            const uint32_t bm = __ballot_sync(kFullMask, ccw) & todo;
-                            if (bm == 0u)
-                                break;
-                            const int first = __ffs(bm) - 1;
-                            q = i0 + static_cast<uint32_t>(first);
-                            pq.x = __shfl_sync(kFullMask, pi.x, first);
-                            pq.y = __shfl_sync(kFullMask, pi.y, first);
-                            todo = first == 31 ? 0u : (kFullMask << (first + 1));
-                            if (todo == 0u)
-                                break;
-                        }
-                    }
-                    p = q;
-                } while (p != leftmost);
-                if (bad)
-                {
-                    if (lane == 0u)
-                        atomicOr(hv.err, kHullErrJarvis);
-                    h = 0u;
+                    bx = x;
+                    bi = i;
                 }
             }
-            if (lane == 0u)
-                hc[k] = h;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+            {
+                const float ox = __shfl_xor_sync(kFullMask, bx, d);
+                const uint32_t oi = __shfl_xor_sync(kFullMask, bi, d);
+                if (oi != 0xFFFFFFFFu && (bi == 0xFFFFFFFFu || ox < bx || (ox == bx && oi < bi)))
+                {
+                    bx = ox;
+                    bi = oi;
+                }
+            }
+            const uint32_t leftmost = bi;
+            uint32_t *out = hv.hres + off + c0;
+            uint32_t p = leftmost;
+            bool bad = false;
+            do
+            {
+                if (h >= n || h > m)
+                {
+                    bad = true; // the reference would not terminate either
+                    break;
+                }
+                if (lane == 0u)
+                    out[h] = midx(p);
+                ++h;
+                const float2 pp = mxy(p);
+                uint32_t q = p + 1u == m ? 0u : p + 1u;
+                float2 pq = mxy(q);
+                for (uint32_t i0 = 0; i0 < m; i0 += 32u)
+                {
+                    const uint32_t i = i0 + lane;
+                    const float2 pi = i < m ? mxy(i) : pp;
+                    uint32_t todo = kFullMask;
+                    while (true)
+                    {
+                        const bool ccw = i < m && hull_cross(pp.x, pp.y, pi.x, pi.y, pq.x, pq.y) > 0.0f;
+                        const uint32_t bm = __ballot_sync(kFullMask, ccw) & todo;
+                        if (bm == 0u)
+                            break;
+                        const int first = __ffs(bm) - 1;
+                        q = i0 + static_cast<uint32_t>(first);
+                        pq.x = __shfl_sync(kFullMask, pi.x, first);
+                        pq.y = __shfl_sync(kFullMask, pi.y, first);
+                        todo = first == 31 ? 0u : (kFullMask << (first + 1));
+                        if (todo == 0u)
+                            break;
+                    }
+                }
+                p = q;
+            } while (p != leftmost);
+            if (bad)
+            {
+                if (lane == 0u)
+                    atomicOr(hv.err, kHullErrJarvis);
+                h = 0u;
+            }
         }
-        __syncthreads();
+        if (lane == 0u)
+            hc[k] = h;
     }
 }
 
-// hcnt -> exclusive offsets in place, hoff[K] = vertices of the frame (one CTA per frame).
+// hcnt -> exclusive offsets in place, hoff[K] = vertices of the frame; hne[k] = non-empty outlines before
+// cluster k, hne[K] = their number (one CTA per frame).
 __global__ void __launch_bounds__(256)
 hull_scan_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, uint32_t *__restrict__ hcnt,
-                 uint32_t *__restrict__ n_vertices)
+                 uint32_t *__restrict__ hne_all, uint32_t *__restrict__ n_vertices, uint32_t *__restrict__ n_outlines)
 {
     __shared__ uint32_t ws[9];
-    __shared__ uint32_t carry;
+    __shared__ uint32_t carry, carry_ne;
     const uint32_t f = blockIdx.x;
     const uint32_t K = n_clusters[f];
     uint32_t *hc = hcnt + bv.off[f] + f;
+    uint32_t *ne = hne_all + bv.off[f] + f;
     if (threadIdx.x == 0)
+    {
         carry = 0u;
+        carry_ne = 0u;
+    }
     __syncthreads();
     for (uint32_t k0 = 0; k0 < K; k0 += 256u)
     {
         const uint32_t k = k0 + threadIdx.x;
         const uint32_t v = k < K ? hc[k] : 0u;
-        uint32_t total;
+        uint32_t total, total_ne;
         const uint32_t excl = block_exclusive_scan<256>(v, ws, &total) + carry;
+        const uint32_t excl_ne = block_exclusive_scan<256>(v ? 1u : 0u, ws, &total_ne) + carry_ne;
         if (k < K)
+        {
             hc[k] = excl;
+            ne[k] = excl_ne;
+        }
         __syncthreads();
         if (threadIdx.x == 0)
+        {
             carry += total;
+            carry_ne += total_ne;
+        }
         __syncthreads();
     }
     if (threadIdx.x == 0)
     {
         hc[K] = carry;
+        ne[K] = carry_ne;
         n_vertices[f] = carry;
+        n_outlines[f] = carry_ne;
     }
 }
 

@@ -96,6 +96,41 @@ void Clusterer::split_last_clusters(std::vector<pcl::PointCloud<pcl::PointXYZ>> 
     }
 }
 
+void Clusterer::outline_last_clusters(OutlinePolicy policy, std::vector<std::vector<OutlinePoint>> &outlines,
+                                      std::vector<std::uint32_t> &host_clusters)
+{
+    static_assert(sizeof(OutlinePoint) == 8, "the device writes 8-byte (x, y) records");
+    outlines.clear();
+    host_clusters.clear();
+    if (last_cloud_size_ == 0U)
+    {
+        return;
+    }
+    int status = lidar_b200_batch_hull_outlines(context_, static_cast<std::uint32_t>(policy));
+    if (status != LIDAR_B200_OK)
+        raise(context_, status, "Clusterer::outline_last_clusters");
+    const std::size_t padded = (static_cast<std::size_t>(last_cloud_size_) + 31U) & ~static_cast<std::size_t>(31U);
+    outline_offsets_.assign(padded + 1U, 0U);
+    outline_xy_.resize(padded * 2U);
+    std::uint32_t number_of_vertices = 0U;
+    status = lidar_b200_batch_fetch_hulls(context_, &number_of_vertices, outline_offsets_.data(), outline_xy_.data(), nullptr);
+    if (status != LIDAR_B200_OK)
+        raise(context_, status, "Clusterer::outline_last_clusters");
+    // split_offsets_ still holds the CSR of the split these outlines belong to
+    std::uint32_t number_of_clusters = 0U;
+    status = lidar_b200_batch_fetch_clusters(context_, &number_of_clusters, nullptr, nullptr, nullptr);
+    if (status != LIDAR_B200_OK)
+        raise(context_, status, "Clusterer::outline_last_clusters");
+    outlines.resize(number_of_clusters);
+    const auto *records = reinterpret_cast<const OutlinePoint *>(outline_xy_.data());
+    for (std::uint32_t k = 0U; k < number_of_clusters; ++k)
+    {
+        outlines[k].assign(records + outline_offsets_[k], records + outline_offsets_[k + 1U]);
+        if (policy == OutlinePolicy::CONCAVE_SMALL && split_offsets_[k + 1U] - split_offsets_[k] >= 20U)
+            host_clusters.push_back(k); // reference src/polygon_simplification.cpp:100, 119-140
+    }
+}
+
 template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZ> &cloud_in, std::vector<ClusteringLabel> &labels);
 
 template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZI> &cloud_in, std::vector<ClusteringLabel> &labels);

@@ -55,12 +55,35 @@ class Clusterer final
     // every point with label k in ascending point index; INVALID points are skipped.
     void split_last_clusters(std::vector<pcl::PointCloud<pcl::PointXYZ>> &clustered_cloud);
 
+    // Extension: ordered convex outlines (counter-clockwise, open) of the clusters of the LAST
+    // split_last_clusters() call, computed on the device bit-identically to the reference's host functions.
+    // OutlinePoint has the layout of geom::Point<float> (reference Convex-Hull/convex_hull.hpp:42-49).
+    //   CONVEX        = findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79): every cluster.
+    //   CONCAVE_SMALL = the convex branch of findOrderedConcaveOutlines (:100-118): clusters below 20 points;
+    //                   the ids of the larger ones are returned in host_clusters — the caller runs the
+    //                   reference's geometry::ConcaveHull on those (it stays on the host) and stores the result
+    //                   in outlines[id].
+    // outlines[k] belongs to clustered_cloud[k]; an empty outline is one the reference drops from its output.
+    struct OutlinePoint
+    {
+        float x, y;
+    };
+    enum class OutlinePolicy : std::uint32_t
+    {
+        CONVEX = 0U,
+        CONCAVE_SMALL = 1U
+    };
+    void outline_last_clusters(OutlinePolicy policy, std::vector<std::vector<OutlinePoint>> &outlines,
+                               std::vector<std::uint32_t> &host_clusters);
+
   private:
     lidar_b200_ctx *context_{nullptr};
     ClusteringConfiguration configuration_{};
     std::uint32_t last_cloud_size_{0U};
     std::vector<std::uint32_t> split_offsets_;
     std::vector<float> split_points_;
+    std::vector<std::uint32_t> outline_offsets_;
+    std::vector<float> outline_xy_;
 };
 
 extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZ> &cloud_in,

@@ -396,3 +396,44 @@ def ref_outlines(clusters, mode: int = 0):
         out.append(xy[at:at + h].copy())
         at += h
     return out
+
+
+def colorize(clusters, cluster_rgb) -> np.ndarray:
+    """Restated convertClusteredCloudToColorizedCloud (reference src/conversions.cpp:32-60) + the byte layout
+    convertPCLToPointCloud2 copies out (conversions.cpp:139-162): (n, 32) uint8 pcl::PointXYZRGB records, cluster
+    after cluster. cluster_rgb[k] = r << 16 | g << 8 | b (the reference draws r, g, b with std::rand() % 256).
+    Parity unpinned at the PCL boundary: PCL is absent here; layout per pcl/impl/point_types.hpp (PCL_ADD_POINT4D,
+    PCL_ADD_RGB: b, g, r, a bytes, a = 255, 16-byte aligned, 32 bytes)."""
+    n = sum(len(c) for c in clusters)
+    out = np.zeros((n, 32), np.uint8)
+    at = 0
+    for c, word in zip(clusters, cluster_rgb):
+        c = np.asarray(c, np.float32)
+        m = len(c)
+        rec = out[at:at + m]
+        xyz1 = np.ones((m, 4), np.float32)
+        xyz1[:, :3] = c[:, :3]
+        rec[:, :16] = xyz1.view(np.uint8).reshape(m, 16)
+        w = int(word)
+        rec[:, 16] = w & 0xFF          # b
+        rec[:, 17] = (w >> 8) & 0xFF   # g
+        rec[:, 18] = (w >> 16) & 0xFF  # r
+        rec[:, 19] = 255               # a
+        at += m
+    return out
+
+
+def marker_points(outlines):
+    """Restated point list of convertPointXYZTypeToMarkerArray (reference src/conversions.hpp:72-120): per non-empty
+    outline (h, 2) -> (h + 1, 3) float64 {x, y, 0} with the first vertex appended (loop closure); empty -> None."""
+    res = []
+    for o in outlines:
+        o = np.asarray(o, np.float32).reshape(-1, 2)
+        if o.shape[0] == 0:
+            res.append(None)
+            continue
+        p = np.zeros((o.shape[0] + 1, 3), np.float64)
+        p[:-1, :2] = o.astype(np.float64)
+        p[-1] = p[0]
+        res.append(p)
+    return res

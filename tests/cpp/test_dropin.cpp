@@ -84,6 +84,28 @@ int main(int argc, char **argv)
                 return 6;
         }
 
+        // outlines of those clusters on the device, dumped for the comparison with the reference's host functions
+        for (int policy = 0; policy < 2; ++policy)
+        {
+            std::vector<std::vector<Clusterer::OutlinePoint>> outlines;
+            std::vector<std::uint32_t> host_ids;
+            clusterer.outline_last_clusters(static_cast<Clusterer::OutlinePolicy>(policy), outlines, host_ids);
+            if (outlines.size() != device_split.size())
+                return 7;
+            std::vector<std::uint32_t> sizes;
+            std::vector<float> xy;
+            for (const auto &o : outlines)
+            {
+                sizes.push_back(static_cast<std::uint32_t>(o.size()));
+                for (const auto &v : o)
+                    xy.insert(xy.end(), {v.x, v.y});
+            }
+            const std::string tag = std::string(argv[2]) + (policy == 0 ? ".convex" : ".concave_small");
+            dump(tag + ".sizes.u32", sizes);
+            dump(tag + ".xy.f32", xy);
+            dump(tag + ".host_ids.u32", host_ids);
+        }
+
         std::vector<std::uint32_t> seg(segmentation_labels.size());
         for (std::size_t i = 0; i < seg.size(); ++i)
             seg[i] = static_cast<std::uint32_t>(segmentation_labels[i]);

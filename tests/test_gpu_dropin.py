@@ -32,3 +32,21 @@ def test_cpp_dropin_classes(pkg, ctx, golden_frames, tmp_path):
     assert np.array_equal(obstacle.view(np.uint32), pts[oi].view(np.uint32))
     H.check_segmentation(pts, seg, gi, oi)
     H.check_clustering(obstacle, clusters)
+    # outlines of the split clusters (Clusterer::outline_last_clusters) against the reference's host functions
+    parts = [c for c, _ in O.split_clusters(obstacle, clusters)]
+    for mode, tag in ((0, "convex"), (1, "concave_small")):
+        sizes = np.fromfile(f"{prefix}.{tag}.sizes.u32", np.uint32)
+        xy = np.fromfile(f"{prefix}.{tag}.xy.f32", np.float32).reshape(-1, 2)
+        host_ids = np.fromfile(f"{prefix}.{tag}.host_ids.u32", np.uint32)
+        assert sizes.size == len(parts)
+        want = O.ref_outlines(parts, mode) if O.ref_hull_available() else [w for w, _ in O.convex_outlines(parts, mode)]
+        big = [k for k, c in enumerate(parts) if len(c) >= 20]
+        assert np.array_equal(host_ids, np.asarray(big if mode == 1 else [], np.uint32))
+        at = 0
+        for k, c in enumerate(parts):
+            got = xy[at:at + int(sizes[k])]
+            at += int(sizes[k])
+            if mode == 1 and len(c) >= 20:
+                assert got.shape[0] == 0
+            else:
+                assert np.array_equal(got, want[k])

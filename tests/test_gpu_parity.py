@@ -539,3 +539,38 @@ def test_outlines_api_edges(pkg, ctx, synth_small):
         for pts, r, g, h in zip(frames, res, groups, hulls):
             _check_outlines(pts[r["obstacle_idx"]], g, h, mode)
         assert hulls[1]["xy"].shape[0] == 0 and hulls[2]["xy"].shape[0] == 0
+
+
+# ---- output packing on the device
+
+@pytest.mark.gpu
+def test_colorized_cloud_and_marker_points(ctx, golden_frames, synth_small):
+    tiny = np.array([[0, 0, 0, 0], [0.1, 0, 0, 0], [50, 50, 0, 0]], np.float32)  # no valid cluster
+    frames = [golden_frames[2], synth_small, tiny]
+    res = ctx.process_batch(frames)
+    groups = ctx.batch_clusters()
+    rng = np.random.default_rng(3)
+    rgb = [rng.integers(0, 1 << 24, size=g["n_clusters"], dtype=np.uint32) for g in groups]
+    colored = ctx.batch_colorized(np.concatenate(rgb), groups)
+    for g, col, words in zip(groups, colored, rgb):
+        go = g["offsets"].astype(np.int64)
+        clusters = [g["points"][go[c]:go[c + 1], :3] for c in range(g["n_clusters"])]
+        assert np.array_equal(col, O.colorize(clusters, words))
+    assert colored[2].shape[0] == 0
+    with pytest.raises(Exception):
+        ctx.batch_colorized(np.concatenate(rgb)[:-1], groups)  # one colour short
+    for mode in (0, 1):
+        hulls = ctx.batch_hulls(mode)
+        markers = ctx.batch_marker_points(hulls)
+        for h, m in zip(hulls, markers):
+            ho = h["offsets"].astype(np.int64)
+            outlines = [h["xy"][ho[c]:ho[c + 1]] for c in range(h["n_clusters"])]
+            want = O.marker_points(outlines)
+            assert m["n_markers"] == sum(w is not None for w in want)
+            for c, w in enumerate(want):
+                got = m["points"][m["offsets"][c]:m["offsets"][c + 1]]
+                if w is None:
+                    assert got.shape[0] == 0
+                else:
+                    assert np.array_equal(got, w)
+        assert markers[2]["n_markers"] == 0

@@ -222,3 +222,15 @@ def test_restated_outlines_match_reference(mode, golden_frames):
         assert np.array_equal(np.asarray(c, np.float32)[li][:, :2], xy)
         n_checked += 1
     assert n_checked > (100 if mode == 1 else 400)
+
+
+def test_packing_restatements_layout():
+    """Byte layout of the restated pcl::PointXYZRGB records and of the closed marker strips (row 4)."""
+    cl = [np.float32([[1, 2, 3], [4, 5, 6]]), np.float32([[7, 8, 9]])]
+    rec = O.colorize(cl, [0x112233, 0xA0B0C0])
+    assert rec.shape == (3, 32)
+    assert np.array_equal(rec[:, :16].copy().view(np.float32).reshape(3, 4), np.float32([[1, 2, 3, 1], [4, 5, 6, 1], [7, 8, 9, 1]]))
+    assert rec[0, 16:20].tolist() == [0x33, 0x22, 0x11, 255] and rec[2, 16:20].tolist() == [0xC0, 0xB0, 0xA0, 255]
+    assert not rec[:, 20:].any()
+    m = O.marker_points([np.float32([[0, 0], [1, 0], [0, 1]]), np.zeros((0, 2), np.float32)])
+    assert m[1] is None and m[0].shape == (4, 3) and np.array_equal(m[0][-1], m[0][0]) and not m[0][:, 2].any()
