@@ -346,11 +346,16 @@ def main():
     pipe = pkg.FramePipeline(device=local_rank, depth=args.depth, chunk_frames=args.chunk)
     pinned_frames = pkg.pin_frames(frames)
 
+    # warm-up submits: at least two (both result arenas), and enough chunks to have every one of the `depth`
+    # contexts allocate its arenas outside the timed region (a small workload is a single chunk per submit)
+    chunks_per_submit = max(1, -(-nf // args.chunk))
+    n_warm_submits = max(2, min(args.warmup, 3), -(-args.depth // chunks_per_submit))
+
     def e2e_run(src):
         # steps are submitted back to back (results of step s go to arena s % 2 and stay readable while
         # step s+1 runs); the timed region ends when the last step's results are in host memory
-        for w_ in range(max(2, min(args.warmup, 3))):
-            pipe.submit(src, arena=w_ % 2)  # both result arenas exist before the timed region
+        for w_ in range(n_warm_submits):
+            pipe.submit(src, arena=w_ % 2)  # both result arenas and all `depth` contexts exist before the timed region
         pipe.drain()
         barrier()
         t0 = time.perf_counter()
@@ -364,7 +369,7 @@ def main():
 
     pipe_launches0 = pipe.launch_count()
     e2e_s, e2e_out = e2e_run(pinned_frames)
-    pipe_launches = (pipe.launch_count() - pipe_launches0) // (args.steps + max(2, min(args.warmup, 3)))
+    pipe_launches = (pipe.launch_count() - pipe_launches0) // (args.steps + n_warm_submits)
     e2e_fps = world * nf * args.steps / e2e_s
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_same = all(np.array_equal(a["cluster_labels"], b["cluster_labels"]) and np.array_equal(a["seg_labels"], b["seg_labels"])

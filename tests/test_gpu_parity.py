@@ -574,3 +574,62 @@ def test_colorized_cloud_and_marker_points(ctx, golden_frames, synth_small):
                 else:
                     assert np.array_equal(got, w)
         assert markers[2]["n_markers"] == 0
+
+
+@pytest.mark.gpu
+def test_outlines_all_154_reference_frames(pkg):
+    """Outlines of every cluster of all 154 repo frames (one 154-frame batch), device vs the UNMODIFIED reference
+    outline functions run on the same clusters: findOrderedConvexOutlines for every cluster, and the convex branch
+    of findOrderedConcaveOutlines for the clusters below 20 points. Bit-exact vertex lists."""
+    import json
+    from pathlib import Path
+
+    from tools.pack_reference_frames import unpack
+
+    root = Path(__file__).resolve().parent.parent
+    cache = root / "data_cache" / "frames_mm.xz"
+    if not cache.exists():
+        pytest.skip("data_cache/frames_mm.xz not on this box (run tools/pack_reference_frames.py in the build container)")
+    frames = unpack(cache)
+    big = pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames))
+    try:
+        res = big.process_batch(frames)
+        groups = big.batch_clusters()
+        hulls = [big.batch_hulls(0), big.batch_hulls(1)]
+    finally:
+        big.close()
+    checked = [0, 0]
+    vertices = [0, 0]
+    for pts, r, g, h0, h1 in zip(frames, res, groups, hulls[0], hulls[1]):
+        obs = pts[r["obstacle_idx"]]
+        for mode, h in ((0, h0), (1, h1)):
+            checked[mode] += _check_outlines(obs, g, h, mode)
+            vertices[mode] += int(h["xy"].shape[0])
+    summary = {"frames": len(frames), "clusters": int(sum(g["n_clusters"] for g in groups)),
+               "convex_outlines_checked": checked[0], "convex_vertices": vertices[0],
+               "concave_policy_small_outlines_checked": checked[1], "concave_policy_small_vertices": vertices[1],
+               "reference": "oracle/_ref/libref_hull.so" if O.ref_hull_available() else "restated oracle only"}
+    out = root / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "parity_outlines_154.json").write_text(json.dumps(summary))
+    assert checked[0] == summary["clusters"] and checked[1] > 0
+
+
+@pytest.mark.gpu
+def test_outlines_full_size_synthetic(pkg):
+    """SURVEY configs 3 and 4 at full size: a 128-beam frame and a merged ~1 M-point cloud whose lattice walls are
+    single clusters of > 100 000 points with up to 60 duplicates per (x, y) — CHAN with hundreds of subsets."""
+    from tests.synth import make_frame_128, make_merged_1m
+
+    frames = [make_frame_128(12345), make_merged_1m(777)]
+    big = pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames))
+    try:
+        res = big.process_batch(frames)
+        groups = big.batch_clusters()
+        for mode in (0, 1):
+            hulls = big.batch_hulls(mode)
+            for pts, r, g, h in zip(frames, res, groups, hulls):
+                assert _check_outlines(pts[r["obstacle_idx"]], g, h, mode) > 0
+        assert max(int(np.diff(g["offsets"].astype(np.int64)).max()) for g in groups) > 100_000
+    finally:
+        big.close()
