@@ -13,6 +13,7 @@ importlib) under the module name `lidar_processing_b200`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 import weakref
 from pathlib import Path
@@ -27,7 +28,7 @@ CSRC = HERE / "csrc"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # the reference build has no FMA contraction; parity depends on it
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread",
 ]
 
 UNKNOWN, GROUND, OBSTACLE = 0, 1, 2
@@ -539,6 +540,8 @@ class FramePipeline:
             bases.append(base)
             base += int(padded[a:b].sum())
         self.h2d_bytes = int(counts.astype(np.int64).sum()) * 16 + 16 * nf
+        # default fetch mode: the whole slot range of the four result arrays; with LIDAR_B200_FETCH_MODE >= 2 the library
+        # copies exact sizes (4 B per point, 4 B per ground point, 8 B per obstacle point) and results() corrects this
         self.d2h_bytes = (4 if want_ground_idx else 3) * total * 4 + 12 * nf + 4 * len(chunks)
         return dict(frames=frames, counts=counts, chunks=chunks, bases=bases, arena=arena, want_ground_idx=want_ground_idx)
 
@@ -556,6 +559,11 @@ class FramePipeline:
                 ng, no = int(meta[1, f]), int(meta[2, f])
                 out.append(dict(seg_labels=seg[o:o + n], ground_idx=gidx[o:o + ng] if want else None,
                                 obstacle_idx=oidx[o:o + no], cluster_labels=clab[o:o + no], n_clusters=int(meta[3, f])))
+        nf = len(out)
+        if int(os.environ.get("LIDAR_B200_FETCH_MODE", "0")) >= 2:  # exact-size result copies (opt-in, see api.cu)
+            self.d2h_bytes = (4 * int(counts.astype(np.int64).sum())
+                              + (4 * int(meta[1, :nf].astype(np.int64).sum()) if want else 0)
+                              + 8 * int(meta[2, :nf].astype(np.int64).sum()) + 12 * nf + 4 * len(job["chunks"]))
         return out
 
     def process(self, frames, want_ground_idx: bool = True):

@@ -16,6 +16,10 @@
 #include "segment.cuh"
 
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -128,7 +132,14 @@ struct lidar_b200_ctx
         uint32_t *point_offset{nullptr}, *n_ground{nullptr}, *n_obstacle{nullptr}, *n_clusters{nullptr};
         void *out[4]{nullptr, nullptr, nullptr, nullptr}; // seg labels, ground idx, obstacle idx, cluster labels
         bool direct[4]{false, false, false, false};       // destination is page-locked: DMA went straight into it
+        bool payload_enqueued{false};                     // the result arrays are on their way (counts came first)
+        bool with_worker{false}, worker_done{false};      // pipeline: the second phase belongs to the pipe's worker thread
+        int worker_rc{0};
     } fetch;
+    cudaEvent_t ev_counts{nullptr}; // per-frame counts of the batch are in h_meta
+    std::vector<void *> copy_dst, copy_src; // copy list of the second fetch phase
+    std::vector<size_t> copy_size;
+    int fetch_mode{0}; // LIDAR_B200_FETCH_MODE (default 0, see profiles/README.md "result fetch modes"): 0 = one phase, full slots; 1 = two phases, full slots; 2 = exact sizes, plain copies; 3 = exact sizes, one batched call
 
     uint32_t sm_count{148}, replay_ctas_per_sm{12}, replay_big_ctas_per_sm{3};
     uint64_t launches{0};
@@ -326,6 +337,7 @@ uint32_t grid_x(uint32_t n, uint32_t per_block, uint32_t cap)
 }
 
 int finish_fetch(lidar_b200_ctx *c);
+int enqueue_fetch_payload(lidar_b200_ctx *c, bool block);
 
 // lays the frames of a batch out, stages the points into pinned memory and starts the upload
 int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const uint32_t *n_points,
@@ -582,9 +594,89 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
 
 // completes an asynchronous fetch: waits for the stream, un-stages the results that could not be
 // written by DMA directly and reports the per-frame counts
+// Second phase of a fetch: exact-size copies of the result arrays. `block` = wait for the counts (else return
+// without doing anything while the batch is still running).
+int enqueue_fetch_payload(lidar_b200_ctx *c, bool block)
+{
+    lidar_b200_ctx::FetchReq &r = c->fetch;
+    if (!r.pending || r.payload_enqueued)
+        return 0;
+    LB_CUDA(c, cudaSetDevice(c->device));
+    if (block)
+        LB_CUDA(c, cudaEventSynchronize(c->ev_counts));
+    else
+    {
+        const cudaError_t q = cudaEventQuery(c->ev_counts);
+        if (q == cudaErrorNotReady)
+            return 0;
+        if (q != cudaSuccess)
+            return fail(c, LIDAR_B200_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+    }
+    cudaStream_t s = c->stream;
+    const size_t F = c->cap_frames;
+    const uint32_t *hm = c->h_meta.p;
+    const void *dev[4] = {c->d_labels.p, c->d_gidx.p, c->d_oidx.p, c->d_clabels.p};
+    r.payload_enqueued = true; // (also when a copy below fails: the batch is lost either way)
+    // copy list: the segmentation labels of all frames in one piece (the slots are contiguous, at most 31 padding
+    // entries per frame), the three per-frame lists at their exact sizes
+    std::vector<void *> &dsts = c->copy_dst, &srcs = c->copy_src;
+    std::vector<size_t> &sizes = c->copy_size;
+    dsts.clear();
+    srcs.clear();
+    sizes.clear();
+    auto add = [&](int k, size_t first, size_t count) {
+        if (!r.out[k] || count == 0u)
+            return;
+        dsts.push_back((r.direct[k] ? static_cast<uint32_t *>(r.out[k]) : c->h_u32[k].p) + first);
+        srcs.push_back(const_cast<uint32_t *>(static_cast<const uint32_t *>(dev[k])) + first);
+        sizes.push_back(count * 4u);
+    };
+    if (c->n_frames)
+        add(0, c->off[0], static_cast<size_t>(c->off[c->n_frames - 1u]) + c->cnt[c->n_frames - 1u] - c->off[0]);
+    if (c->fetch_mode == 1 && c->n_frames)
+        for (int k = 1; k < 4; ++k)
+            add(k, 0, c->total);
+    for (uint32_t f = 0; f < c->n_frames && c->fetch_mode != 1; ++f)
+    {
+        // (counts of a batch that raised the input-error flag are not trusted beyond the slot)
+        const uint32_t n_ground = hm[4 * F + f] < c->cnt[f] ? hm[4 * F + f] : c->cnt[f];
+        const uint32_t n_obstacle = hm[5 * F + f] < c->cnt[f] ? hm[5 * F + f] : c->cnt[f];
+        add(1, c->off[f], n_ground);
+        add(2, c->off[f], n_obstacle);
+        add(3, c->off[f], n_obstacle);
+    }
+    if (sizes.empty())
+        return 0;
+    // one driver call for the whole list (cudaMemcpyBatchAsync, CUDA >= 12.8); plain copies if it is refused
+    static bool batch_ok = true;
+    if (batch_ok && sizes.size() > 1u && c->fetch_mode == 3)
+    {
+        cudaMemcpyAttributes attr{};
+        attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t attr_idx = 0, fail_idx = 0;
+        const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), sizes.size(), &attr, &attr_idx, 1,
+                                                   &fail_idx, s);
+        if (e == cudaSuccess)
+            return 0;
+        (void)cudaGetLastError();
+        batch_ok = false;
+    }
+    for (size_t i = 0; i < sizes.size(); ++i)
+        LB_CUDA(c, cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
 int finish_fetch(lidar_b200_ctx *c)
 {
     lidar_b200_ctx::FetchReq &r = c->fetch;
+    {
+        const int rc = enqueue_fetch_payload(c, true);
+        if (rc)
+        {
+            r.pending = false;
+            return rc;
+        }
+    }
     r.pending = false;
     LB_CUDA(c, cudaSetDevice(c->device));
     LB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -608,10 +700,16 @@ int finish_fetch(lidar_b200_ctx *c)
         if (r.n_clusters)
             r.n_clusters[f] = hm[6 * F + f];
     }
-    const size_t bytes = static_cast<size_t>(c->total) * 4;
-    for (int k = 0; k < 4; ++k)
-        if (bytes && r.out[k] && !r.direct[k])
-            std::memcpy(r.out[k], c->h_u32[k].p, bytes);
+    for (uint32_t f = 0; f < c->n_frames; ++f)
+    {
+        const size_t o = c->off[f];
+        const uint32_t n_ground = hm[4 * F + f] < c->cnt[f] ? hm[4 * F + f] : c->cnt[f];
+        const uint32_t n_obstacle = hm[5 * F + f] < c->cnt[f] ? hm[5 * F + f] : c->cnt[f];
+        const uint32_t used[4] = {c->cnt[f], n_ground, n_obstacle, n_obstacle};
+        for (int k = 0; k < 4; ++k)
+            if (r.out[k] && !r.direct[k] && used[k])
+                std::memcpy(static_cast<uint32_t *>(r.out[k]) + o, c->h_u32[k].p + o, static_cast<size_t>(used[k]) * 4);
+    }
     return 0;
 }
 
@@ -649,6 +747,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     lidar_b200_ctx *c = new lidar_b200_ctx();
     c->device = device;
     c->want_job_stats = std::getenv("LIDAR_B200_REPLAY_STATS") != nullptr;
+    if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
+        c->fetch_mode = std::atoi(e);
     lidar_b200_seg_cfg sc;
     lidar_b200_clu_cfg cc;
     lidar_b200_seg_cfg_default(&sc);
@@ -661,6 +761,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_kd, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess || // the waiter sleeps
+       
         [&]() {
             for (auto &e : c->ev_stage)
                 if (cudaEventCreate(&e) != cudaSuccess)
@@ -731,6 +833,8 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
         cudaEventDestroy(c->ev_join);
     if (c->ev_kd)
         cudaEventDestroy(c->ev_kd);
+    if (c->ev_counts)
+        cudaEventDestroy(c->ev_counts);
     if (c->stream_big)
         cudaStreamDestroy(c->stream_big);
     if (c->stream)
@@ -820,19 +924,28 @@ int lidar_b200_batch_fetch_async(lidar_b200_ctx *c, uint32_t *point_offset_out, 
     r.out[1] = ground_idx_out;
     r.out[2] = obstacle_idx_out;
     r.out[3] = cluster_labels_out;
-    const void *dev[4] = {c->d_labels.p, c->d_gidx.p, c->d_oidx.p, c->d_clabels.p};
+    // Two phases, so that only the used part of every result slot crosses the bus: the per-frame counts come
+    // first (3 words per frame); the arrays follow with exact sizes once the counts are on the host — enqueued
+    // by enqueue_fetch_payload() as soon as somebody looks (the pipeline polls, _wait blocks).
     if (c->n_frames)
         LB_CUDA(c, cudaMemcpyAsync(c->h_meta.p + 4 * F, c->m_ng(), 3 * F * 4, cudaMemcpyDeviceToHost, s));
     LB_CUDA(c, cudaMemcpyAsync(c->h_err.p, c->d_err.p, 4, cudaMemcpyDeviceToHost, s));
+    LB_CUDA(c, cudaEventRecord(c->ev_counts, s));
     for (int k = 0; k < 4; ++k)
+        r.direct[k] = bytes && r.out[k] && is_pinned(r.out[k]); // page-locked destination: the copy engine writes it directly
+    r.payload_enqueued = false;
+    if (c->fetch_mode == 0)
     {
-        r.direct[k] = false;
-        if (!bytes || !r.out[k])
-            continue;
-        r.direct[k] = is_pinned(r.out[k]); // page-locked destination: the copy engine writes it directly
-        LB_CUDA(c, cudaMemcpyAsync(r.direct[k] ? r.out[k] : static_cast<void *>(c->h_u32[k].p), dev[k], bytes,
-                                   cudaMemcpyDeviceToHost, s));
+        // one phase: the whole slot range of every array, enqueued right behind the kernels
+        const void *dev[4] = {c->d_labels.p, c->d_gidx.p, c->d_oidx.p, c->d_clabels.p};
+        for (int k = 0; k < 4; ++k)
+            if (bytes && r.out[k])
+                LB_CUDA(c, cudaMemcpyAsync(r.direct[k] ? r.out[k] : static_cast<void *>(c->h_u32[k].p), dev[k], bytes,
+                                           cudaMemcpyDeviceToHost, s));
+        r.payload_enqueued = true;
     }
+    r.with_worker = r.worker_done = false;
+    r.worker_rc = 0;
     r.pending = true;
     return 0;
 }
@@ -1324,12 +1437,52 @@ void lidar_b200_host_free(void *ptr)
 
 // ---- frame pipeline: `depth` contexts used round-robin, so that the upload of chunk k+1, the
 // kernels of chunk k and the download of chunk k-1 overlap (three engines, independent streams)
+// The pipeline's second-phase worker: waits for the counts of a submitted chunk and enqueues its exact-size result
+// copies on the chunk's own stream, so the submitting thread never blocks on a chunk that is still running and the
+// copies start the moment the chunk's kernels end.
 struct lidar_b200_pipe
 {
     std::vector<lidar_b200_ctx *> slots;
     uint32_t next{0};
     std::string err;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<lidar_b200_ctx *> work;
+    bool stop{false};
 };
+
+namespace
+{
+void pipe_worker(lidar_b200_pipe *p)
+{
+    std::unique_lock<std::mutex> lk(p->mu);
+    while (true)
+    {
+        p->cv_work.wait(lk, [p] { return p->stop || !p->work.empty(); });
+        if (p->work.empty())
+            return; // stop requested and nothing left
+        lidar_b200_ctx *c = p->work.front();
+        p->work.pop_front();
+        lk.unlock();
+        const int rc = enqueue_fetch_payload(c, true);
+        lk.lock();
+        c->fetch.worker_rc = rc;
+        c->fetch.worker_done = true;
+        p->cv_done.notify_all();
+    }
+}
+
+// the submitting thread: before touching a slot again, let the worker finish its part of the slot's last chunk
+int pipe_wait_worker(lidar_b200_pipe *p, lidar_b200_ctx *c)
+{
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (!c->fetch.pending || !c->fetch.with_worker)
+        return 0;
+    p->cv_done.wait(lk, [c] { return c->fetch.worker_done; });
+    return c->fetch.worker_rc;
+}
+} // namespace
 
 int lidar_b200_pipe_create(int device, uint32_t depth, uint32_t max_points, uint32_t max_frames, lidar_b200_pipe **pipe_out)
 {
@@ -1348,6 +1501,7 @@ int lidar_b200_pipe_create(int device, uint32_t depth, uint32_t max_points, uint
         }
         p->slots.push_back(c);
     }
+    p->worker = std::thread(pipe_worker, p);
     *pipe_out = p;
     return 0;
 }
@@ -1356,6 +1510,15 @@ void lidar_b200_pipe_destroy(lidar_b200_pipe *p)
 {
     if (!p)
         return;
+    if (p->worker.joinable())
+    {
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->stop = true;
+        }
+        p->cv_work.notify_all();
+        p->worker.join(); // drains the queue first
+    }
     for (lidar_b200_ctx *c : p->slots)
         lidar_b200_destroy(c);
     delete p;
@@ -1403,12 +1566,22 @@ int lidar_b200_pipe_submit(lidar_b200_pipe *p, uint32_t n_frames, const void *co
     lidar_b200_ctx *c = p->slots[p->next];
     p->next = (p->next + 1u) % static_cast<uint32_t>(p->slots.size());
     // staging completes the chunk this slot still owes (its results are in caller memory afterwards)
-    int rc = lidar_b200_batch_stage(c, n_frames, points, n_points, stride_bytes);
+    int rc = pipe_wait_worker(p, c);
+    if (!rc)
+        rc = lidar_b200_batch_stage(c, n_frames, points, n_points, stride_bytes);
     if (!rc)
         rc = lidar_b200_batch_run(c);
     if (!rc)
         rc = lidar_b200_batch_fetch_async(c, point_offset_out, seg_labels_out, ground_idx_out, n_ground_out,
                                           obstacle_idx_out, n_obstacle_out, cluster_labels_out, n_clusters_out);
+    if (!rc && !c->fetch.payload_enqueued)
+    {
+        // hand the second phase (exact-size result copies once the counts are on the host) to the worker
+        std::lock_guard<std::mutex> lk(p->mu);
+        c->fetch.with_worker = true;
+        p->work.push_back(c);
+        p->cv_work.notify_one();
+    }
     if (rc)
         p->err = c->err;
     return rc;
@@ -1423,7 +1596,9 @@ int lidar_b200_pipe_drain(lidar_b200_pipe *p)
     for (uint32_t i = 0; i < k; ++i) // oldest chunk first
     {
         lidar_b200_ctx *c = p->slots[(p->next + i) % k];
-        const int rc = lidar_b200_batch_wait(c);
+        int rc = pipe_wait_worker(p, c);
+        const int rc2 = lidar_b200_batch_wait(c);
+        rc = rc ? rc : rc2;
         if (rc && !first)
         {
             first = rc;
