@@ -45,7 +45,7 @@ constexpr uint32_t kHullErrOverflow = 1u, kHullErrSubset = 2u, kHullErrJarvis = 
 
 struct __align__(16) HullWarpSmem
 {
-    unsigned long long key[kHullWarpCap];  // (ordered y) << 32 | ordered x, sorted ascending
+    unsigned long long key[kHullWarpCap];  // (ordered y) << 32 | ordered x, sorted ascending; then the points' float2 bits
     uint16_t idx[kHullWarpCap];            // original index of the sorted point (ties in key: ascending)
     uint16_t stack[2u * kHullWarpCap];     // hull_indices(2 * n) of convex_hull.hpp:222 (tasks scanned by their warp)
 };
@@ -61,7 +61,7 @@ struct HullView
     uint32_t *sub_cnt;    // CHAN: vertices per subset, at cluster start + subset number
     uint32_t *mrg_idx;    // CHAN: merged_indices
     float2 *mrg_xy;       // CHAN: merged_points
-    unsigned long long *skey; // per task, at its own point range: the (y, x) keys in sorted order
+    unsigned long long *skey; // per task, at its own point range: the points in sorted order (float2 bits, x low)
     uint32_t *sidx;       // original index (inside the task's range) of every sorted point
     uint32_t *stk;        // two words per point: hull_indices(2 * n) of convex_hull.hpp:222
     uint32_t *err;        // error bits
@@ -77,9 +77,18 @@ LB_D float hull_cross(float p1x, float p1y, float p2x, float p2y, float p3x, flo
     return __fsub_rn(__fmul_rn(x1, y2), __fmul_rn(x2, y1));
 }
 
-LB_D float2 hull_decode(unsigned long long k)
+// sort key -> the point itself, as the bits of float2{x, y} (x in the low word); a bijection, so runs of equal
+// points stay runs of equal words
+LB_D unsigned long long hull_key_to_point(unsigned long long k)
 {
-    return make_float2(ordered_to_float(static_cast<uint32_t>(k)), ordered_to_float(static_cast<uint32_t>(k >> 32)));
+    const uint32_t xb = __float_as_uint(ordered_to_float(static_cast<uint32_t>(k)));
+    const uint32_t yb = __float_as_uint(ordered_to_float(static_cast<uint32_t>(k >> 32)));
+    return (static_cast<unsigned long long>(yb) << 32) | xb;
+}
+
+LB_D float2 hull_decode(unsigned long long point_bits)
+{
+    return make_float2(__uint_as_float(static_cast<uint32_t>(point_bits)), __uint_as_float(static_cast<uint32_t>(point_bits >> 32)));
 }
 
 // Ascending sort of n <= kHullWarpCap (key, original index) pairs by one warp ("flip" bitonic network: slots
@@ -290,6 +299,9 @@ hull_sort_kernel(BatchView bv, HullView hv, const uint32_t *__restrict__ task_k,
         }
         __syncwarp();
         hull_warp_sort(ws.key, ws.idx, t.size);
+        for (uint32_t i = lane; i < t.size; i += 32u) // the scans read points, not keys
+            ws.key[i] = hull_key_to_point(ws.key[i]);
+        __syncwarp();
         if (t.size <= kHullThreadScanMax)
         {
             unsigned long long *sk = hv.skey + t.pt0 + t.start;
