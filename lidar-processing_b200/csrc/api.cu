@@ -15,6 +15,7 @@
 #include "replay_cta.cuh"
 #include "segment.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <condition_variable>
 #include <deque>
@@ -116,7 +117,7 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_hoff, d_hne, d_hnv, d_herr, d_rgb;
     DevBuf<uint4> d_color;   // 32-byte PointXYZRGB records (pack.cuh), allocated on first use
     DevBuf<double> d_marker; // marker points, allocated on first use
-    bool hulled{false};
+    bool hulled{false}, hull_attr_done{false};
     std::vector<uint32_t> off, cnt;
 
     // optional per-stage CUDA-event timing (lidar_b200_set_profiling)
@@ -648,7 +649,7 @@ int enqueue_fetch_payload(lidar_b200_ctx *c, bool block)
     if (sizes.empty())
         return 0;
     // one driver call for the whole list (cudaMemcpyBatchAsync, CUDA >= 12.8); plain copies if it is refused
-    static bool batch_ok = true;
+    static std::atomic<bool> batch_ok{true}; // (the pipeline's worker thread and the caller's thread both get here)
     if (batch_ok && sizes.size() > 1u && c->fetch_mode == 3)
     {
         cudaMemcpyAttributes attr{};
@@ -1116,12 +1117,11 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
     LB_CUDA(c, cudaMemsetAsync(c->d_herr.p, 0, 4, s));
     if (c->clu_max_m == 0u)
         return 0;
-    static bool attr_done = false; // opt-in to > 48 KB of dynamic shared memory, once per process
     const size_t smem = sizeof(HullWarpSmem) * kHullWarps;
-    if (!attr_done)
+    if (!c->hull_attr_done) // opt-in to > 48 KB of dynamic shared memory (a per-device attribute: once per context)
     {
         LB_CUDA(c, cudaFuncSetAttribute(hull_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_done = true;
+        c->hull_attr_done = true;
     }
     const BatchView bv{c->m_off(), c->clu_counts, F};
     // scratch: the per-point arrays of the clustering stage and of the group sort are free by now

@@ -17,7 +17,11 @@
 //    With these three predicates a candidate of entry k is treated exactly like the reference's
 //    loop body at clustering.cpp:94-109 treats it; the round's pushes enter the FIFO ordered by
 //    (entry, k-d pre-order rank), i.e. in the reference's order. Warp k owns entry k (lookups,
-//    candidate tests, rank sort of its pushes); entries that are not applied cost nothing.
+//    candidate tests, rank sort of its pushes); entries that are not applied cost nothing. A removal of
+//    a candidate that an EARLIER entry of the round also reaches is only written behind the CTA barrier
+//    that ends the candidate tests: the earlier entry touches it first in the reference's order and must
+//    still see it alive, whichever warp runs first (else one count of the cluster size, which the
+//    reference keeps with multiplicity, is lost). Every other state write is order-independent.
 //  * direct rounds — an entry with more candidates than a warp's buffers hold (a dense
 //    neighbourhood, thousands of candidates) is expanded alone by all 256 threads, its pushes are
 //    sorted by a CTA-wide bitonic network in shared memory.
@@ -43,7 +47,8 @@ struct __align__(16) CtaSmem
     uint32_t ring[kRing];
     union
     {
-        unsigned long long pbuf[kCtaW][kEntryCandCap]; // speculative round: pushes of entry k, rank << 31 | pos
+        unsigned long long pbuf[kCtaW][kEntryCandCap]; // speculative round: pushes of entry k, rank << 31 | pos, from the front;
+                                                       // postponed removals, slot << 32 | pos, from the back (a candidate is one or the other)
         unsigned long long dpush[kDirectPushCap];      // direct round: pushes of the single entry
     } u;
     uint8_t owner[kCtaW][kEntryCandCap]; // candidate number -> neighbour cell (0..26)
@@ -343,6 +348,7 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                 {
                     // ---- C: warp k treats the candidates of entry k like the loop body of clustering.cpp:94-109
                     uint32_t my_np = 0u;
+                    uint32_t my_nd = 0u; // removals postponed to the write pass
                     if (mine && warp < n_use)
                     {
                         const uint32_t earlier = applied & ((1u << warp) - 1u);
@@ -375,7 +381,7 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                                     break;
                                 const float4 cand = cand2[h];
                                 const uint32_t sw = __float_as_uint(cand.w);
-                                bool push = false;
+                                bool push = false, defer = false;
                                 if ((sw & kStRemoved) == 0u) // removed points are skipped (clustering.cpp:94-97)
                                 {
                                     // KDTree::dist_sqr(target, node) (kdtree.hpp:145-163), inclusive test (kdtree.hpp:314)
@@ -384,13 +390,15 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                                     {
                                         // what the entries expanded earlier in this round did to the candidate
                                         bool removed_before = false, queued_before = (sw & kStQueued) != 0u;
+                                        bool shared = false; // an earlier entry of the round reaches the candidate too
                                         for (uint32_t em = earlier; em; em &= em - 1u)
                                         {
                                             const float4 po = sm.ent[__ffs(em) - 1];
                                             const float dj = dist_sqr_ref(po.x, po.y, po.z, cand.x, cand.y, cand.z);
                                             removed_before |= dj <= prm.inner_threshold;
-                                            queued_before |= dj <= prm.distance_squared;
+                                            shared |= dj <= prm.distance_squared;
                                         }
+                                        queued_before |= shared;
                                         if (!removed_before)
                                         {
                                             const uint32_t pos = pos2[h];
@@ -398,8 +406,18 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                                             ++touched;          // indices_.push_back (with multiplicity)
                                             if (d2 <= prm.inner_threshold)
                                             {
-                                                atomicOr(&stw[4u * pos], kStRemoved); // clustering.cpp:102-105
-                                                atomicSub(&tlive[slot2[h]], 1u);
+                                                // clustering.cpp:102-105. An EARLIER entry that reaches this candidate
+                                                // must still see it alive (it touches it first in the reference's
+                                                // order), whichever warp gets here first: such a removal waits for
+                                                // the write pass behind the CTA barrier. Later entries may see it at
+                                                // once — the geometry tells them the same thing.
+                                                if (shared)
+                                                    defer = true;
+                                                else
+                                                {
+                                                    atomicOr(&stw[4u * pos], kStRemoved);
+                                                    atomicSub(&tlive[slot2[h]], 1u);
+                                                }
                                             }
                                             else if (!queued_before)
                                             {
@@ -414,12 +432,24 @@ replay_cta_kernel(float4 *__restrict__ rpts_all, BatchView bv, TableView tv, con
                                     sm.u.pbuf[warp][my_np + __popc(bp & lt)] =
                                         (static_cast<unsigned long long>(sw >> 2) << 31) | static_cast<unsigned long long>(pos2[h]);
                                 my_np += __popc(bp);
+                                const uint32_t bd = __ballot_sync(kFullMask, defer);
+                                if (defer)
+                                    sm.u.pbuf[warp][kEntryCandCap - 1u - (my_nd + __popc(bd & lt))] =
+                                        (static_cast<unsigned long long>(slot2[h]) << 32) | static_cast<unsigned long long>(pos2[h]);
+                                my_nd += __popc(bd);
                             }
                         }
                     }
                     if (lane == 0)
                         sm.np[warp] = my_np;
                     __syncthreads();
+                    // ---- D: all state reads of the round are done; the postponed removals are written
+                    for (uint32_t i = lane; i < my_nd; i += 32u)
+                    {
+                        const unsigned long long e = sm.u.pbuf[warp][kEntryCandCap - 1u - i];
+                        atomicOr(&stw[4u * static_cast<uint32_t>(e)], kStRemoved);
+                        atomicSub(&tlive[static_cast<uint32_t>(e >> 32)], 1u);
+                    }
                     // ---- F: the FIFO receives the pushes ordered by (entry, k-d pre-order rank)
                     uint32_t pre = 0u;
 #pragma unroll
