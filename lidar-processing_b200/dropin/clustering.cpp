@@ -3,6 +3,8 @@
 
 #include "lidar_b200.h"
 
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -87,6 +89,7 @@ void Clusterer::split_last_clusters(std::vector<pcl::PointCloud<pcl::PointXYZ>> 
     if (status != LIDAR_B200_OK)
         raise(context_, status, "Clusterer::split_last_clusters");
     clustered_cloud.resize(number_of_clusters);
+    split_clusters_ = number_of_clusters;
     const auto *records = reinterpret_cast<const pcl::PointXYZ *>(split_points_.data());
     for (std::uint32_t k = 0U; k < number_of_clusters; ++k)
     {
@@ -128,6 +131,69 @@ void Clusterer::outline_last_clusters(OutlinePolicy policy, std::vector<std::vec
         outlines[k].assign(records + outline_offsets_[k], records + outline_offsets_[k + 1U]);
         if (policy == OutlinePolicy::CONCAVE_SMALL && split_offsets_[k + 1U] - split_offsets_[k] >= 20U)
             host_clusters.push_back(k); // reference src/polygon_simplification.cpp:100, 119-140
+    }
+}
+
+void Clusterer::colorize_last_clusters(pcl::PointCloud<pcl::PointXYZRGB> &colorized_cloud)
+{
+    static_assert(sizeof(pcl::PointXYZRGB) == 32, "the device writes 32-byte PointXYZRGB records");
+    colorized_cloud.clear();
+    if (last_cloud_size_ == 0U)
+    {
+        return;
+    }
+    cluster_colors_.resize(split_clusters_);
+    for (auto &word : cluster_colors_)
+    {
+        // conversions.cpp:49-51: r, g, b in this order, one draw each
+        const auto r = static_cast<std::uint32_t>(std::rand() % 256);
+        const auto g = static_cast<std::uint32_t>(std::rand() % 256);
+        const auto b = static_cast<std::uint32_t>(std::rand() % 256);
+        word = (r << 16U) | (g << 8U) | b;
+    }
+    const std::size_t padded = (static_cast<std::size_t>(last_cloud_size_) + 31U) & ~static_cast<std::size_t>(31U);
+    colorized_records_.resize(padded * 8U);
+    const int status = lidar_b200_batch_fetch_colorized(context_, cluster_colors_.data(), cluster_colors_.size(),
+                                                        colorized_records_.data());
+    if (status != LIDAR_B200_OK)
+        raise(context_, status, "Clusterer::colorize_last_clusters");
+    const std::size_t number_of_points = split_clusters_ ? split_offsets_[split_clusters_] : 0U;
+    colorized_cloud.points.resize(number_of_points);
+    if (number_of_points != 0U)
+        std::memcpy(static_cast<void *>(colorized_cloud.points.data()), colorized_records_.data(), number_of_points * 32U);
+    colorized_cloud.width = static_cast<std::uint32_t>(number_of_points);
+    colorized_cloud.height = 1U;
+}
+
+void Clusterer::marker_points_of_last_outlines(std::vector<std::vector<MarkerPoint>> &strips,
+                                               std::vector<std::uint32_t> &marker_ids)
+{
+    static_assert(sizeof(MarkerPoint) == 24, "the device writes three doubles per marker point");
+    strips.clear();
+    marker_ids.clear();
+    if (last_cloud_size_ == 0U)
+    {
+        return;
+    }
+    const std::size_t padded = (static_cast<std::size_t>(last_cloud_size_) + 31U) & ~static_cast<std::size_t>(31U);
+    marker_offsets_.assign(padded + 1U, 0U);
+    marker_points_.resize(padded * 6U);
+    std::uint32_t number_of_markers = 0U;
+    const int status = lidar_b200_batch_fetch_marker_points(context_, &number_of_markers, marker_offsets_.data(), marker_points_.data());
+    if (status != LIDAR_B200_OK)
+        raise(context_, status, "Clusterer::marker_points_of_last_outlines");
+    const auto *records = reinterpret_cast<const MarkerPoint *>(marker_points_.data());
+    strips.reserve(number_of_markers);
+    for (std::uint32_t k = 0U; k < split_clusters_; ++k)
+    {
+        // outline k owns marker points [outline_offset[k] + markers_before[k], outline_offset[k+1] + markers_before[k+1])
+        const std::size_t first = static_cast<std::size_t>(outline_offsets_[k]) + marker_offsets_[k];
+        const std::size_t last = static_cast<std::size_t>(outline_offsets_[k + 1U]) + marker_offsets_[k + 1U];
+        if (last > first)
+        {
+            strips.emplace_back(records + first, records + last);
+            marker_ids.push_back(k);
+        }
     }
 }
 

@@ -76,6 +76,22 @@ class Clusterer final
     void outline_last_clusters(OutlinePolicy policy, std::vector<std::vector<OutlinePoint>> &outlines,
                                std::vector<std::uint32_t> &host_clusters);
 
+    // Extension: convertClusteredCloudToColorizedCloud (reference src/conversions.cpp:32-60) for the clusters of the
+    // LAST split_last_clusters() call: one colour per cluster drawn with std::rand() % 256 for r, g, b in this
+    // order (the caller's process-wide sequence continues exactly as in the reference), the 32-byte PointXYZRGB
+    // records are built on the device.
+    void colorize_last_clusters(pcl::PointCloud<pcl::PointXYZRGB> &colorized_cloud);
+
+    // Extension: the point lists of convertPointXYZTypeToMarkerArray (reference src/conversions.hpp:72-120) for the
+    // outlines of the LAST outline_last_clusters() call: per non-empty outline its vertices as {double x, y, 0.0}
+    // (the layout of geometry_msgs::msg::Point) with the first vertex repeated at the end; marker_ids[i] is the
+    // cluster the i-th strip belongs to.
+    struct MarkerPoint
+    {
+        double x, y, z;
+    };
+    void marker_points_of_last_outlines(std::vector<std::vector<MarkerPoint>> &strips, std::vector<std::uint32_t> &marker_ids);
+
   private:
     lidar_b200_ctx *context_{nullptr};
     ClusteringConfiguration configuration_{};
@@ -84,6 +100,10 @@ class Clusterer final
     std::vector<float> split_points_;
     std::vector<std::uint32_t> outline_offsets_;
     std::vector<float> outline_xy_;
+    std::uint32_t split_clusters_{0U};
+    std::vector<std::uint32_t> cluster_colors_, marker_offsets_;
+    std::vector<float> colorized_records_;
+    std::vector<double> marker_points_;
 };
 
 extern template void Clusterer::cluster(const pcl::PointCloud<pcl::PointXYZ> &cloud_in,

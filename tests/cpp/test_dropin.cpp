@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -104,6 +105,54 @@ int main(int argc, char **argv)
             dump(tag + ".sizes.u32", sizes);
             dump(tag + ".xy.f32", xy);
             dump(tag + ".host_ids.u32", host_ids);
+        }
+
+        // colourised cloud: same std::rand() sequence on both sides (conversions.cpp:32-60)
+        {
+            std::srand(1234U);
+            pcl::PointCloud<pcl::PointXYZRGB> want;
+            for (const auto &cluster : host_split)
+            {
+                const auto r = static_cast<std::uint8_t>(std::rand() % 256);
+                const auto g = static_cast<std::uint8_t>(std::rand() % 256);
+                const auto b = static_cast<std::uint8_t>(std::rand() % 256);
+                for (const auto &point : cluster.points)
+                    want.push_back(pcl::PointXYZRGB(point.x, point.y, point.z, r, g, b));
+            }
+            std::srand(1234U);
+            pcl::PointCloud<pcl::PointXYZRGB> got;
+            clusterer.colorize_last_clusters(got);
+            if (got.size() != want.size())
+                return 8;
+            for (std::size_t i = 0; i < want.size(); ++i)
+                if (std::memcmp(&got.points[i], &want.points[i], 20) != 0) // x, y, z, 1.0f, b g r a
+                    return 9;
+        }
+        // marker strips of the convex outlines (conversions.hpp:72-120): closed, z = 0, empty outlines skipped
+        {
+            std::vector<std::vector<Clusterer::OutlinePoint>> outlines;
+            std::vector<std::uint32_t> host_ids, marker_ids;
+            clusterer.outline_last_clusters(Clusterer::OutlinePolicy::CONVEX, outlines, host_ids);
+            std::vector<std::vector<Clusterer::MarkerPoint>> strips;
+            clusterer.marker_points_of_last_outlines(strips, marker_ids);
+            std::size_t at = 0;
+            for (std::size_t k = 0; k < outlines.size(); ++k)
+            {
+                if (outlines[k].empty())
+                    continue;
+                if (at >= strips.size() || marker_ids[at] != k || strips[at].size() != outlines[k].size() + 1U)
+                    return 10;
+                for (std::size_t v = 0; v <= outlines[k].size(); ++v)
+                {
+                    const auto &o = outlines[k][v == outlines[k].size() ? 0 : v];
+                    const auto &m = strips[at][v];
+                    if (m.x != static_cast<double>(o.x) || m.y != static_cast<double>(o.y) || m.z != 0.0)
+                        return 11;
+                }
+                ++at;
+            }
+            if (at != strips.size())
+                return 12;
         }
 
         std::vector<std::uint32_t> seg(segmentation_labels.size());
