@@ -338,6 +338,43 @@ def main():
     dev_ms_total = max_over_ranks(sum(gpu_ms))
     value = world * nf * args.steps / (dev_ms_total / 1e3)
 
+    # ---- SURVEY 8(f) rows 1 and 3 on the same resident batch (reported beside the metric, not part of it):
+    # extra time per step of the device-side per-cluster split and of the ordered convex outlines behind it
+    next_rows = None
+    if rank == 0:
+        try:
+            L = pkg.lib()
+
+            def timed_ms(extra):
+                for _ in range(2):
+                    ctx.batch_run()
+                    extra()
+                ctx.sync()
+                t_ = time.perf_counter()
+                for _ in range(3):
+                    ctx.batch_run()
+                    extra()
+                ctx.sync()
+                return 1e3 * (time.perf_counter() - t_) / 3
+
+            def split():
+                ctx._check(L.lidar_b200_batch_group_clusters(ctx._h), "batch_group_clusters")
+
+            def split_outlines():
+                split()
+                ctx._check(L.lidar_b200_batch_hull_outlines(ctx._h, pkg.HULL_CONVEX), "batch_hull_outlines")
+
+            base_ms = timed_ms(lambda: None)
+            split_ms = timed_ms(split)
+            outl_ms = timed_ms(split_outlines)
+            hulls = ctx.batch_hulls(pkg.HULL_CONVEX)
+            next_rows = {"what": "wall-clock ms per resident step, 3 steps each: seg+cluster alone, + device-side cluster split "
+                                 "(processor.cpp:180-200), + ordered convex outlines of every cluster (polygon_simplification.cpp:31-79)",
+                         "seg_cluster_ms": base_ms, "plus_split_ms": split_ms, "plus_split_outlines_ms": outl_ms,
+                         "outline_vertices_per_step": int(sum(h["xy"].shape[0] for h in hulls))}
+        except Exception as e:  # the metric must not depend on the extra rows
+            next_rows = {"error": str(e)}
+
     # ---- end to end through the host API ------------------------------------------------------
     # Every step: host clouds -> (H2D) -> kernels -> (D2H) -> host result arrays, through the C ABI's
     # frame pipeline (chunks of frames rotating through `depth` contexts). Headline: clouds and result
@@ -446,6 +483,7 @@ def main():
                 "pageable_host_buffers_value": e2e_pageable_fps, "results_equal_resident_run": bool(e2e_same),
                 "gpu_launches_per_step": int(pipe_launches)},
         "gpu_launches": int(launches),
+        "next_rows": next_rows,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
