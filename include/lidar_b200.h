@@ -156,7 +156,9 @@ extern "C"
      *   n_vertices_out[f] = hull_offset[K]
      * Array sizes: n_vertices_out [n_frames], hull_offset_out [sum n + n_frames], hull_xy_out [sum n][2],
      * hull_point_idx_out [sum n]. Errors: LIDAR_B200_ERR_UNSUPPORTED for a cluster above ~1.04 M points,
-     * LIDAR_B200_ERR_INPUT when a hull does not close (the reference loops forever on such input). */
+     * LIDAR_B200_ERR_INPUT when the Jarvis march of a CHAN cluster does not close (duplicate hull vertices in
+     * different subsets; the reference loops forever on such a cluster): the outputs are still complete, that
+     * cluster has 0 vertices and every other outline is valid. */
 #define LIDAR_B200_HULL_CONVEX 0u
 #define LIDAR_B200_HULL_CONCAVE_SMALL 1u
     int lidar_b200_batch_hull_outlines(lidar_b200_ctx *ctx, uint32_t mode);

@@ -133,6 +133,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_batch_fetch_colorized", "lidar_b200_batch_fetch_marker_points",
 ]
 
+ERR_INPUT = 5            # LIDAR_B200_ERR_INPUT (include/lidar_b200.h)
 HULL_CONVEX = 0          # findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79)
 HULL_CONCAVE_SMALL = 1   # convex branch of findOrderedConcaveOutlines (:100-118); >= 20 points stay on the host
 
@@ -331,7 +332,7 @@ class Context:
             out.append(dict(offsets=offsets, points=gpts[o:o + nv], point_idx=gidx[o:o + nv], n_clusters=k))
         return out
 
-    def batch_hulls(self, mode: int = HULL_CONVEX):
+    def batch_hulls(self, mode: int = HULL_CONVEX, tolerate_open_marches: bool = False):
         """Ordered convex outlines per cluster on the device (reference src/polygon_simplification.cpp:31-79 /
         :100-118) of the last batch_clusters(). Returns, per frame, dict(offsets[K+1], xy[n_vertices,2],
         point_idx[n_vertices]): outline of cluster k = xy[offsets[k]:offsets[k+1]], counter-clockwise, open."""
@@ -346,8 +347,11 @@ class Context:
         hxy = np.zeros((max(total, 1), 2), np.float32)
         hidx = np.zeros(max(total, 1), np.uint32)
         self._check(lib().lidar_b200_batch_hull_outlines(self._h, C.c_uint32(mode)), "batch_hull_outlines")
-        self._check(lib().lidar_b200_batch_fetch_hulls(self._h, _ptr(nv, C.c_uint32), _ptr(hoff, C.c_uint32),
-                                                       _ptr(hxy, C.c_float), _ptr(hidx, C.c_uint32)), "batch_fetch_hulls")
+        rc = lib().lidar_b200_batch_fetch_hulls(self._h, _ptr(nv, C.c_uint32), _ptr(hoff, C.c_uint32),
+                                                _ptr(hxy, C.c_float), _ptr(hidx, C.c_uint32))
+        self.last_hull_status = rc
+        if not (tolerate_open_marches and rc == ERR_INPUT):  # ERR_INPUT: outputs complete, the offending clusters are empty
+            self._check(rc, "batch_fetch_hulls")
         self._check(lib().lidar_b200_batch_fetch_clusters(self._h, _ptr(nc, C.c_uint32), None, None, None), "batch_fetch_clusters")
         out = []
         for f in range(nf):

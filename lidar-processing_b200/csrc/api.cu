@@ -1170,9 +1170,6 @@ int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *c, uint32_t *n_vertices_out, ui
     LB_CUDA(c, cudaStreamSynchronize(s));
     if (herr & kHullErrSubset)
         return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "hull_outlines: a cluster above ~1.04 M points exceeds the CHAN subset buffers");
-    if (herr)
-        return fail(c, LIDAR_B200_ERR_INPUT, "hull_outlines: degenerate input (hull longer than its cluster or a Jarvis march "
-                                             "that does not close; the reference does not terminate on it either)");
     const float2 *hxy = reinterpret_cast<const float2 *>(c->d_spill.p);
     for (uint32_t f = 0; f < F; ++f)
     {
@@ -1190,6 +1187,12 @@ int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *c, uint32_t *n_vertices_out, ui
                                        cudaMemcpyDeviceToHost, s));
     }
     LB_CUDA(c, cudaStreamSynchronize(s));
+    // The outputs are complete either way: a cluster whose Jarvis march does not close (duplicate hull vertices in
+    // different CHAN subsets; the reference never returns from such a cluster) or whose hull would outgrow it has
+    // 0 vertices, every other cluster is exact. The status tells the caller that it happened.
+    if (herr)
+        return fail(c, LIDAR_B200_ERR_INPUT, "hull_outlines: a cluster on which the reference's CHAN hull does not terminate "
+                                             "(Jarvis march that never closes) was given 0 vertices; all other outlines are valid");
     return 0;
 }
 

@@ -353,7 +353,8 @@ def _clusters_csr(clusters):
 
 def convex_outlines(clusters, mode: int = 0):
     """Restated findOrderedConvexOutlines (mode 0) / convex branch of findOrderedConcaveOutlines (mode 1),
-    oracle/hull_oracle.cpp. Returns one (xy[h,2] float32, local_idx[h]) per cluster (h = 0: dropped / host)."""
+    oracle/hull_oracle.cpp. Returns one (xy[h,2] float32, local_idx[h]) per cluster (h = 0: dropped / host; None: the
+    reference's Jarvis march would never close on this cluster, i.e. the reference hangs)."""
     pts, offsets = _clusters_csr(clusters)
     k = len(clusters)
     sizes = np.zeros(max(k, 1), np.uint32)
@@ -366,6 +367,9 @@ def convex_outlines(clusters, mode: int = 0):
     out, at = [], 0
     for c in range(k):
         h = int(sizes[c])
+        if h == 0xFFFFFFFF:  # the reference's Jarvis march does not terminate on this cluster
+            out.append(None)
+            continue
         li = idx[at:at + h].astype(np.int64)
         out.append((pts[int(offsets[c]) + li][:, :2].copy(), li))
         at += h

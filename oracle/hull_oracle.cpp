@@ -127,7 +127,10 @@ std::vector<int> chan(const std::vector<P2> &pts)
         at += size;
     }
     std::vector<int> out;
-    for (const int h : jarvis(merged))
+    const std::vector<int> march = jarvis(merged);
+    if (march.size() > merged.size())
+        return {-1}; // the march never came back to its start: the reference does not terminate on this input
+    for (const int h : march)
         out.push_back(merged_idx[h]);
     return out;
 }
@@ -139,7 +142,8 @@ extern "C"
 // clusters as CSR over `points` (stride_floats floats per point, xyz first). mode 0 = findOrderedConvexOutlines
 // (monotone chain up to 1000 points, CHAN above), 1 = the convex branch of findOrderedConcaveOutlines (below 20
 // points; larger clusters get size 0 here — their concave hull is outside this restatement).
-// sizes_out[k] = vertices of cluster k; idx_out = cluster-local indices of the vertices, end to end.
+// sizes_out[k] = vertices of cluster k (0xFFFFFFFF: the reference's Jarvis march would not terminate);
+// idx_out = cluster-local indices of the vertices, end to end.
 long long oracle_convex_outlines(const float *points, const std::uint32_t *offsets, std::uint32_t n_clusters,
                                  std::uint32_t stride_floats, int mode, std::uint32_t *sizes_out,
                                  std::uint32_t *idx_out, long long capacity)
@@ -159,6 +163,11 @@ long long oracle_convex_outlines(const float *points, const std::uint32_t *offse
             hull = pts.size() > 1000 ? chan(pts) : monotone_chain(pts);
         else if (pts.size() < 20)
             hull = monotone_chain(pts);
+        if (hull.size() == 1 && hull[0] < 0)
+        {
+            sizes_out[k] = 0xFFFFFFFFu; // reference would spin forever (Jarvis march that does not close)
+            continue;
+        }
         sizes_out[k] = static_cast<std::uint32_t>(hull.size());
         if (total + static_cast<long long>(hull.size()) > capacity)
             return -1;

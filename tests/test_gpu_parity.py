@@ -633,3 +633,39 @@ def test_outlines_full_size_synthetic(pkg):
         assert max(int(np.diff(g["offsets"].astype(np.int64)).max()) for g in groups) > 100_000
     finally:
         big.close()
+
+
+@pytest.mark.gpu
+def test_outlines_where_the_reference_does_not_terminate(pkg):
+    """Clusters above 1000 points whose hull vertices repeat in different CHAN subsets: the reference's Jarvis march
+    (Convex-Hull/convex_hull.hpp:283-335) never returns to its start and findOrderedConvexOutlines hangs. The restated
+    oracle detects it (None); the device gives such a cluster 0 vertices, reports LIDAR_B200_ERR_INPUT and still
+    delivers every other outline."""
+    rng = np.random.default_rng(20251017)
+    lattice = None
+    for _ in range(64):  # about one draw in two has the property; the restated oracle tells
+        cand = np.zeros((1524, 4), np.float32)
+        cand[:, :2] = rng.integers(-15, 16, size=(1524, 2)) * 0.05 + np.float32([3.0, -7.0])
+        if O.convex_outlines([cand[:, :3]], 0)[0] is None:
+            lattice = cand
+            break
+    assert lattice is not None
+    blob = np.zeros((300, 4), np.float32)
+    blob[:, :3] = np.round(rng.normal(size=(300, 3)) * 0.3, 3) + np.float32([500.0, 0.0, 0.0])
+    c2 = pkg.Context(device=0, max_points=50_000, max_frames=2)
+    try:
+        c2.clu_configure(pkg.ClusteringConfiguration(distance_squared=4.0, min_cluster_size=1))
+        for frame, expect_error in ((lattice, True), (blob, False)):
+            labels, g = c2.cluster_and_split(frame)
+            assert g["n_clusters"] == 1
+            if expect_error:
+                with pytest.raises(pkg.LidarB200Error):
+                    c2.batch_hulls(0)
+            h = c2.batch_hulls(0, tolerate_open_marches=True)[0]
+            assert (c2.last_hull_status == pkg.ERR_INPUT) == expect_error
+            if expect_error:
+                assert h["xy"].shape[0] == 0
+            else:
+                assert _check_outlines(frame, g, h, 0) == 1
+    finally:
+        c2.close()

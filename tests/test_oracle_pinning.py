@@ -234,3 +234,37 @@ def test_packing_restatements_layout():
     assert not rec[:, 20:].any()
     m = O.marker_points([np.float32([[0, 0], [1, 0], [0, 1]]), np.zeros((0, 2), np.float32)])
     assert m[1] is None and m[0].shape == (4, 3) and np.array_equal(m[0][-1], m[0][0]) and not m[0][:, 2].any()
+
+
+@pytest.mark.skipif(not O.ref_hull_available(), reason="oracle/_ref/libref_hull.so not built")
+def test_restated_outlines_match_reference_random_sweep():
+    """Seeded sweep: 400 clusters of 3..1600 points drawn from mm-quantised blobs, rings, lattices and heavy-duplicate
+    sets — restated convex outlines (monotone chain and CHAN) against the unmodified reference, vertex for vertex."""
+    rng = np.random.default_rng(20251017)
+    clusters = []
+    for i in range(400):
+        n = int(rng.integers(3, 1600)) if i % 4 else int(rng.integers(3, 40))
+        kind = i % 5
+        if kind == 0:
+            p = rng.normal(size=(n, 2)) * rng.uniform(0.05, 5.0)
+        elif kind == 1:
+            a = rng.uniform(0, 2 * np.pi, n)
+            p = np.stack([np.cos(a), np.sin(a)], 1) * rng.uniform(0.5, 20.0)
+        elif kind == 2:
+            p = rng.integers(-15, 16, size=(n, 2)) * 0.05                       # lattice: many collinear runs, duplicates
+        elif kind == 3:
+            base = rng.normal(size=(max(3, n // 8), 2))
+            p = base[rng.integers(0, base.shape[0], n)]                          # ~8 copies of every point
+        else:
+            p = np.stack([rng.uniform(-30, 30, n), rng.normal(size=n) * 0.02], 1)  # thin strip
+        p = p + rng.uniform(-40, 40, size=(1, 2))
+        c = np.zeros((n, 3), np.float32)
+        c[:, :2] = np.round(p, 3)
+        clusters.append(c)
+    got = O.convex_outlines(clusters, 0)
+    # clusters on which the reference's Jarvis march never closes (it would hang) are left out of its run
+    ok = [i for i, g in enumerate(got) if g is not None]
+    want = O.ref_outlines([clusters[i] for i in ok], 0)
+    for i, ref in zip(ok, want):
+        assert np.array_equal(got[i][0], ref), f"cluster {i} of {len(clusters[i])} points"
+    assert len(ok) >= 300
