@@ -29,7 +29,7 @@ extern "C"
         LIDAR_B200_ERR_INVALID = 2,     /* bad argument */
         LIDAR_B200_ERR_UNSUPPORTED = 3, /* configuration outside the supported envelope */
         LIDAR_B200_ERR_CAPACITY = 4,    /* batch larger than the reserved arenas and growth failed */
-        LIDAR_B200_ERR_INPUT = 5        /* non-finite / out-of-range coordinates (unspecified in the reference) */
+        LIDAR_B200_ERR_INPUT = 5        /* non-finite / out-of-range coordinates (unspecified in the reference); outlines: a cluster on which the reference does not terminate */
     } lidar_b200_status;
 
     /* replaces lidar_processing::SegmentationConfiguration (reference src/segmentation.hpp:48-56) */

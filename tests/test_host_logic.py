@@ -181,3 +181,21 @@ def test_library_pcd_reader(pkg, tmp_path, golden_frames):
         pkg.read_pcd(p5)
     with pytest.raises(pkg.LidarB200Error, match="cannot open"):
         pkg.read_pcd(tmp_path / "missing.pcd")
+
+
+def test_c_abi_rejects_a_null_context_without_touching_a_device(pkg):
+    """Argument validation of the entry points added for SURVEY 8f rows 1, 3 and 4 (no GPU needed: a NULL context is
+    refused before any CUDA call)."""
+    lib = pkg.lib()
+    header = (ROOT / "include" / "lidar_b200.h").read_text()
+    inv = int(re.search(r"LIDAR_B200_ERR_INVALID\s*=\s*(\d+)", header).group(1))
+    assert re.search(r"LIDAR_B200_ERR_INPUT\s*=\s*%d\b" % pkg.ERR_INPUT, header)
+    buf = (C.c_uint32 * 4)()
+    fbuf = (C.c_float * 8)()
+    dbuf = (C.c_double * 6)()
+    assert lib.lidar_b200_batch_group_clusters(None) == inv
+    assert lib.lidar_b200_batch_fetch_clusters(None, buf, buf, fbuf, buf) == inv
+    assert lib.lidar_b200_batch_hull_outlines(None, C.c_uint32(pkg.HULL_CONVEX)) == inv
+    assert lib.lidar_b200_batch_fetch_hulls(None, buf, buf, fbuf, buf) == inv
+    assert lib.lidar_b200_batch_fetch_colorized(None, buf, C.c_uint64(1), fbuf) == inv
+    assert lib.lidar_b200_batch_fetch_marker_points(None, buf, buf, dbuf) == inv
