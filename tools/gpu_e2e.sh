@@ -1,4 +1,5 @@
 #!/bin/bash
+# GPU box: the whole -m gpu suite, then one default bench line without the CPU baseline (gpurun_out/bench_trim.json).
 set -u
 mkdir -p gpurun_out
 timeout -k 10 1200 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/pytest_gpu.log 2>&1

@@ -1,4 +1,5 @@
 #!/bin/bash
+# GPU box: the outline tests, then tools/outline_timing.py on the bench workload (gpurun_out/outline_timing.json).
 set -u
 mkdir -p gpurun_out
 timeout -k 10 900 python -m pytest tests -m gpu -q --timeout 600 -k "outlines" > gpurun_out/pytest_hull.log 2>&1
