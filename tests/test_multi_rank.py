@@ -77,3 +77,25 @@ def test_shard_frames_properties():
     assert sharding.job_throughput([10, 10], [1.0, 2.0]) == 10.0
     with pytest.raises(ValueError):
         sharding.shard_frames(10, 2, 2)
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches `bench.py --impl reference --gpus N` like the GPU arm (torchrun, N ranks): rank 0 alone runs the
+    reference's CPU path and prints the line, the other ranks exit 0 without work. CPU only."""
+    import json
+    import subprocess
+
+    cache = ROOT / "data_cache" / "frames_mm.xz"
+    if not cache.exists():
+        pytest.skip("data_cache/frames_mm.xz not built (run __graft_entry__.build() with /root/reference present)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = lines[0]
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["gpu_launches"] == 0
