@@ -66,7 +66,7 @@ def load_workload(which: str = "kitti154"):
         from tools.pack_reference_frames import unpack
 
         frames = unpack(cache)
-        name = "kitti154: reference data/*.pcd sequence (154 frames, 98.5k-124.1k pts, lossless cache)"
+        name = "kitti154: reference data/*.pcd sequence (154 frames, 98.5k-124.1k pts, bit-lossless cache)"
     else:
         distinct = [make_frame(1000 + i) for i in range(22)]
         frames = [distinct[i % len(distinct)] for i in range(154)]

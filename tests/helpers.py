@@ -28,16 +28,32 @@ def segment_ids(pts, partitions):
     return seg
 
 
-def check_segmentation(pts, labels, ground_idx, obstacle_idx, seg_cfg=None, labels_in=None, device_planes=None,
-                       surface_gap_m=2 * FLIP_BAND_M):
-    """Returns the number of flipped points after asserting the stated tolerance. A flipped point must
-    lie within FLIP_BAND_M of the decision surface of the oracle's plane. When `device_planes`
-    ([partition][iteration][4]) is given the criterion is instead that the point lies between the
-    oracle's and the device's decision surfaces and that these are at most `surface_gap_m` apart at
-    that point: for partitions of several 100k points the oracle's sequential float32 sums (relative
-    error ~ sqrt(n)·eps) tilt its plane by ~1e-5 rad against the device's double-precision moments,
-    i.e. a few 1e-4 m at a 60 m lever arm (the reference's Eigen GEMM order is a third, unknowable,
-    rounding)."""
+def _margins(pts, planes_last, seg, thr):
+    """signed distance of every point to the decision surface of its partition's last plane (float64)"""
+    out = np.full(pts.shape[0], np.nan)
+    X = pts[:, :3].astype(np.float64)
+    for s_ in range(planes_last.shape[0]):
+        a = planes_last[s_].astype(np.float64)
+        sel = seg == s_
+        if sel.any() and np.all(np.isfinite(a)):
+            out[sel] = X[sel] @ a[:3] - a[3] - float(thr) * np.linalg.norm(a[:3])
+    return out
+
+
+def check_segmentation(pts, labels, ground_idx, obstacle_idx, seg_cfg=None, labels_in=None, strict=False, report=None):
+    """Asserts the north-star tolerance and returns the number of labels that differ from the oracle's.
+
+    Rule (BASELINE.json north_star): at most FLIP_FRACTION of the points may differ, and a differing point must lie
+    within FLIP_BAND_M of the ORACLE's decision surface (the last plane of its partition, evaluated in float64).
+    The oracle itself is float32 with sequential sums (what Eigen's strided colwise().mean() does; its GEMM order is
+    unknowable here), so on large partitions its own plane drifts from the exact one by more than the band (merged
+    1M-point clouds: d off by 3.5e-4 m, tests/golden/f64_model.py). A differing point outside the band is therefore
+    accepted only when `strict` is False AND the oracle provably mis-rounds that very point: the independent float64
+    evaluation of the same rule (segment_f64) disagrees with the oracle there and agrees with the device.
+    `report` (dict) receives flips, max_gap_m (largest distance of a differing point to the oracle's surface),
+    outside_band (how many needed the second clause) and the same two figures against the float64 model."""
+    from tests.golden.f64_model import segment_f64
+
     cfg = seg_cfg or O.default_seg_cfg()
     ref = O.segment(pts, cfg, tie_mode=1, labels_in=labels_in)
     n = pts.shape[0]
@@ -50,24 +66,31 @@ def check_segmentation(pts, labels, ground_idx, obstacle_idx, seg_cfg=None, labe
     for idx in (ground_idx, obstacle_idx):  # both clouds are x-ascending (segment by segment)
         assert np.all(np.diff(pts[idx, 0]) >= 0)
     assert diff.size <= max(0, int(FLIP_FRACTION * n)), f"{diff.size} of {n} labels differ"
+    info = {"flips": int(diff.size), "max_gap_m": 0.0, "outside_band": 0, "flips_vs_f64": None, "max_gap_f64_m": None}
     if diff.size:
         P = cfg.number_of_planar_partitions
         seg = segment_ids(pts, P)
-        for i in diff:
-            a, b, c, d = (float(v) for v in ref["planes"][seg[i], -1])
-            x, y, z = (float(v) for v in pts[i, :3])
-            dist = x * a + y * b + z * c - d
-            thr = cfg.orthogonal_distance_threshold * np.sqrt(a * a + b * b + c * c)
-            gap = abs(dist - thr)
-            if device_planes is not None:
-                a, b, c, d = (float(v) for v in device_planes[seg[i], -1])
-                gap += abs(x * a + y * b + z * c - d - cfg.orthogonal_distance_threshold * np.sqrt(a * a + b * b + c * c))
-                assert gap < surface_gap_m, f"point {i}: decision surfaces {gap:.3g} m apart"
-                continue
-            assert gap < FLIP_BAND_M, f"point {i} flipped {gap:.3g} m from the decision surface"
+        gap = np.abs(_margins(pts, ref["planes"][:, -1], seg, cfg.orthogonal_distance_threshold)[diff])
+        assert np.all(np.isfinite(gap)), "a label differs in a partition without a fitted plane"
+        info["max_gap_m"] = float(gap.max())
+        outside = diff[gap >= FLIP_BAND_M]
+        info["outside_band"] = int(outside.size)
+        m64 = segment_f64(pts, **{name: getattr(cfg, name) for name, _ in cfg._fields_})
+        d64 = np.nonzero(labels != m64["labels"])[0]
+        info["flips_vs_f64"] = int(d64.size)
+        info["max_gap_f64_m"] = float(np.abs(m64["margin"][d64]).max()) if d64.size else 0.0
+        if outside.size:
+            assert not strict, f"{outside.size} labels differ more than {FLIP_BAND_M} m from the oracle's surface (max {gap.max():.3g} m)"
+            assert np.array_equal(labels[outside], m64["labels"][outside]), (
+                f"labels differ from the oracle {gap.max():.3g} m from its surface and the float64 model sides with the oracle")
+        # against the exact evaluation the device must itself be inside the band, always
+        assert d64.size <= max(0, int(FLIP_FRACTION * n))
+        assert info["max_gap_f64_m"] < FLIP_BAND_M, f"device differs from the float64 model {info['max_gap_f64_m']:.3g} m from its surface"
     else:
         assert np.array_equal(ground_idx, ref["ground_idx"])
         assert np.array_equal(obstacle_idx, ref["obstacle_idx"])
+    if report is not None:
+        report.update(info)
     return int(diff.size)
 
 

@@ -11,6 +11,21 @@ from tests.synth import make_frame, make_stress
 
 pytestmark = pytest.mark.gpu
 
+# stated bounds of the plane pin against the float64 model (tests/golden/f64_model.py); the restated float32 oracle
+# itself sits at 6.5e-6 / 4e-5 m on the 154 frames (fingerprints.json: f64_vs_oracle_summary)
+PLANE_NORMAL_BOUND = 2e-6
+PLANE_D_BOUND_M = 1e-5
+
+
+def _record(name, obj):
+    """numbers the docs quote are written where gpurun brings them back"""
+    import json
+    from pathlib import Path
+
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    if out.is_dir():
+        (out / name).write_text(json.dumps(obj))
+
 
 # ------------------------------------------------------------------ segmentation
 def test_segment_golden_frames(ctx, golden_frames):
@@ -341,9 +356,11 @@ def test_config4_merged_multi_lidar_1m(ctx):
     assert pts.shape[0] > 1_000_000
     res = ctx.process_batch([pts])[0]
     planes, _ = ctx.last_planes(1)
-    flips = H.check_segmentation(pts, res["seg_labels"], res["ground_idx"], res["obstacle_idx"], device_planes=planes[0],
-                                 surface_gap_m=1e-3)
+    rep = {}
+    flips = H.check_segmentation(pts, res["seg_labels"], res["ground_idx"], res["obstacle_idx"], report=rep)
     assert flips <= pts.shape[0] // 1000  # north-star: at most 0.1 % (observed: ~60 of 1.04 M; partitions of ~500k points)
+    print("config 4 mask:", rep)
+    _record("parity_config4.json", rep)
     obs = pts[res["obstacle_idx"]]
     k = H.check_clustering(obs, res["cluster_labels"])
     assert k == res["n_clusters"] and k > 1000
@@ -386,11 +403,22 @@ def test_all_154_reference_frames(pkg, fingerprints):
         planes, _ = big.last_planes(len(frames))
     finally:
         big.close()
-    flips_per_frame, exact = [], 0
+    from tests.golden.f64_model import plane_deviation
+
+    flips_per_frame, exact, max_gap, max_gap_f64, outside, plane_dev = [], 0, 0.0, 0.0, 0, (0.0, 0.0)
     for i, (pts, r, row) in enumerate(zip(frames, res, rows)):
         assert r["seg_labels"].shape[0] == row["n"]
-        flips = H.check_segmentation(pts, r["seg_labels"], r["ground_idx"], r["obstacle_idx"], device_planes=planes[i])
+        rep = {}
+        flips = H.check_segmentation(pts, r["seg_labels"], r["ground_idx"], r["obstacle_idx"], report=rep)
         flips_per_frame.append(flips)
+        max_gap, outside = max(max_gap, rep["max_gap_m"]), outside + rep["outside_band"]
+        max_gap_f64 = max(max_gap_f64, rep["max_gap_f64_m"] or 0.0)
+        # the pin at the Eigen boundary: every fitted plane against the committed float64 (numpy eigh) plane
+        for s_ in range(planes.shape[1]):
+            for it in range(planes.shape[2]):
+                dn, dd = plane_deviation(planes[i, s_, it], row["planes_f64"][s_][it])
+                assert planes[i, s_, it, 2] > 0.0, "normal sign convention (SURVEY 8c)"
+                plane_dev = (max(plane_dev[0], dn), max(plane_dev[1], dd))
         obs = pts[r["obstacle_idx"]]
         assert r["n_clusters"] == H.check_clustering(obs, r["cluster_labels"]), f"frame {i}"
         if flips == 0:
@@ -401,7 +429,12 @@ def test_all_154_reference_frames(pkg, fingerprints):
             exact += 1
     summary = {"frames": len(frames), "frames_equal_to_fingerprints": exact, "mask_flips_total": int(sum(flips_per_frame)),
                "mask_flips_max_per_frame": int(max(flips_per_frame)), "points_total": int(sum(f.shape[0] for f in frames)),
-               "cluster_partitions_bit_exact_vs_reference_on_same_obstacle_cloud": len(frames)}
+               "cluster_partitions_bit_exact_vs_reference_on_same_obstacle_cloud": len(frames),
+               "mask_flip_max_gap_to_oracle_surface_m": max_gap, "mask_flips_outside_1e-4_band": outside,
+               "mask_flip_max_gap_to_f64_surface_m": max_gap_f64,
+               "device_plane_max_dev_vs_f64": {"normal": plane_dev[0], "d_m": plane_dev[1]}}
+    # stated bound of the pin: the device's planes (double moments, float32 Jacobi) vs numpy eigh in float64
+    assert plane_dev[0] < PLANE_NORMAL_BOUND and plane_dev[1] < PLANE_D_BOUND_M, plane_dev
     print(summary)
     out = root / "gpurun_out"
     if out.is_dir():
