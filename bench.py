@@ -13,7 +13,12 @@ used and named in config.workload). Metric: frames/s (whole job, all GPUs).
   e2e           same metric through the public host API (host buffers -> pinned staging -> H2D ->
                 kernels -> D2H -> host arrays every step), wall clock around the calls
   roofline      dominant stage's kernel time vs the algorithmic bytes of SURVEY.md §8(d)
-  cpu_baseline  the reference's CPU path on this box's host cores (rank 0, N=1), bounded sample
+  cpu_baseline  the reference's CPU path on this box's host cores (rank 0, N=1), all 154 frames, warmed
+  workloads     (N=1) compact sub-lines for the synthetic shapes of SURVEY 8(d) configs 3, 4, 5:
+                value, e2e, roofline fraction each (also copied into roofline.other_workloads)
+  config5       BASELINE.json configs[4] as specified: a 4096-frame job, rank g of N takes frames
+                [g*4096/N, (g+1)*4096/N) - STRONG scaling, reported beside the weak-scaling metric
+                (also copied into e2e.config5_strong)
   --impl reference   times only that CPU path (restated Segmenter + UNMODIFIED reference Clusterer
                 from oracle/_ref; this is the one place besides tests/smoke that executes oracle/)
 
@@ -201,46 +206,248 @@ class ClockSampler:
                 "samples_inside_timed_regions": len(inside), "source": self.source}
 
 
-def cpu_reference_run(frames, threads: int, n_sample: int):
-    import oracle as O
-
-    sample = [frames[i % len(frames)] for i in range(n_sample)]
-    res = O.ref_pipeline_run(sample, threads)
-    return res, sample
+def config_of(workload, nf, total_pts, padded, world):
+    """the `config` object: identical keys and values in both arms (the driver compares them)"""
+    return {"workload": workload, "frames_per_step_per_gpu": nf, "points_per_step_per_gpu": total_pts,
+            "l2": "inputs larger than L2 (%.0f MB of points per step)" % (padded * 16 / 1e6),
+            "parallelism": f"frame-sharded x{world}, no collective"}
 
 
 def run_reference(args, frames, workload):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, every step = ALL frames of
+    the workload (the same step as the CUDA arm's), long-lived worker threads and Clusterers (nothing constructed inside
+    a timed step)."""
     import oracle as O
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = min(len(frames), max(32, 2 * threads))
     kind = "reference" if O.ref_available() else "port"
-    times = []
-    for it in range(args.warmup + args.steps):
-        res, _ = cpu_reference_run(frames, threads, n_sample)
-        if it >= args.warmup:
-            times.append(res["wall_s"])
-    total = sum(times)
-    fps = n_sample * args.steps / total
-    pts = sum(frames[i % len(frames)].shape[0] for i in range(n_sample))
+    res = O.ref_pipeline_passes(frames, threads, args.warmup + args.steps)
+    total = float(res["pass_wall_s"][args.warmup:].sum())
+    nf = len(frames)
+    fps = nf * args.steps / total
+    pts = int(sum(f.shape[0] for f in frames))
+    padded = int(sum((f.shape[0] + 31) & ~31 for f in frames))
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "real" if workload.startswith("kitti") else "synthetic",
-        "config": {"workload": workload, "sample": f"{n_sample} frames per step"},
+        "config": config_of(workload, nf, pts, padded, args.gpus),
         "mpts_per_s": pts * args.steps / total / 1e6,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": f"{n_sample} frames/step on {threads} std::threads: restated Segmenter "
+                         "sample": f"all {nf} frames per step on {threads} long-lived std::threads: restated Segmenter "
                                    "(Eigen/PCL absent) + unmodified reference Clusterer (oracle/_ref); TBB absent so "
                                    "the reference's par sorts run serially"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class Env:
+    """rank plumbing: barrier + max-over-ranks (NCCL is used for nothing else)"""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        from lidar_processing_b200 import sharding  # the helper the world-size-2 gloo test covers
+
+        return sharding.reduce_max(x, self.dist, device="cuda")
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def pin_to_gpu_numa_node(local_rank: int):
+    """One feeder process per GPU, kept on the host cores next to it: page-locked buffers allocated
+    afterwards come from that node. A no-op when the box does not expose the topology (VMs often report -1)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(Path(f"/sys/bus/pci/devices/{bus.lower()[-12:]}/numa_node").read_text())
+        if node < 0:
+            return "numa node not exposed"
+        cpus = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, ids)
+        return f"node {node} ({len(ids)} cpus)"
+    except Exception as e:  # topology is an optimisation, never a requirement
+        return f"unavailable ({type(e).__name__})"
+
+
+def measure_resident(pkg, env, frames, steps, warmup, sampler):
+    """device-resident throughput: frames staged once, `steps` passes of all kernels, CUDA events on the library's stream"""
+    nf = len(frames)
+    padded = int(sum((f.shape[0] + 31) & ~31 for f in frames))
+    ctx = pkg.Context(device=env.local_rank, max_points=padded, max_frames=nf)
+    ctx.set_profiling(True)
+    ctx.batch_stage(frames)  # inputs resident in HBM before the timed region
+    for _ in range(warmup):
+        ctx.batch_run()
+        ctx.sync()
+    launches0 = ctx.launch_count()
+    env.barrier()
+    gpu_ms, stage_acc = [], {}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.batch_run()
+        ctx.sync()
+        gpu_ms.append(ctx.last_run_ms())
+        for k, v in ctx.last_stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    env.barrier()
+    wall = time.perf_counter() - t0
+    if sampler is not None:
+        sampler.window(t0, t0 + wall)
+    launches = ctx.launch_count() - launches0
+    res = ctx.batch_fetch()
+    dev_ms_total = env.max_over_ranks(sum(gpu_ms))
+    return dict(ctx=ctx, res=res, dev_ms_total=dev_ms_total, launches=launches, wall=wall,
+                stage_ms={k: v / steps for k, v in stage_acc.items()},
+                n_obstacle=int(sum(r["obstacle_idx"].size for r in res)), n_clusters=int(sum(r["n_clusters"] for r in res)))
+
+
+def measure_e2e(pkg, env, pipe, src, steps, warmup, sampler):
+    """end to end through lidar_b200_pipe_*: host clouds -> (H2D) -> kernels -> (D2H) -> host result arrays every step;
+    steps are submitted back to back (results of step s go to arena s % 2 and stay readable while step s+1 runs); the
+    timed region ends when the last step's results are in host memory"""
+    nf = len(src)
+    chunks_per_submit = max(1, -(-nf // pipe.chunk_frames))
+    n_warm = max(2, min(warmup, 3), -(-pipe.depth // chunks_per_submit))
+    for w_ in range(n_warm):
+        pipe.submit(src, arena=w_ % 2)  # both result arenas and all `depth` contexts exist before the timed region
+    pipe.drain()
+    env.barrier()
+    l0 = pipe.launch_count()
+    t0 = time.perf_counter()
+    for s_ in range(steps):
+        job = pipe.submit(src, arena=s_ % 2)
+    pipe.drain()
+    env.barrier()
+    t1 = time.perf_counter()
+    if sampler is not None:
+        sampler.window(t0, t1)
+    return env.max_over_ranks(t1 - t0), pipe.results(job), (pipe.launch_count() - l0) // max(steps, 1)
+
+
+def roofline_of(stage_ms, algo_bytes, step_ms, nf):
+    peak, peak_src = hbm_peak()
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "n/a"
+    dom_ms = stage_ms.get(dom, 0.0)
+    achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(dom)
+        if t:
+            traffic = t["dram_bytes"] / t["frames_in_capture"] * nf
+            traffic_src = (f"{t['kernel']}: {t['dram_bytes']} B DRAM read+write in a {t['frames_in_capture']}-frame ncu capture "
+                           f"({t['capture']}), scaled per frame to this launch's {nf} frames")
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": dom, "kernel_ms_per_step": dom_ms, "peak_source": peak_src,
+            "algorithmic_bytes_per_step": algo_bytes,
+            "whole_path_achieved_GBs": algo_bytes / (step_ms / 1e3) / 1e9 if step_ms > 0 else 0.0,
+            "stage_ms_per_step": stage_ms}
+
+
+def sub_workload(pkg, env, name, args):
+    """compact line for one of the synthetic shapes (N=1 only): value, e2e, roofline fraction"""
+    frames, workload = load_workload(name)
+    steps, warmup = 5, 3
+    r = measure_resident(pkg, env, frames, steps, warmup, None)
+    nf = len(frames)
+    total_pts = int(sum(f.shape[0] for f in frames))
+    step_ms = r["dev_ms_total"] / steps
+    roof = roofline_of(r["stage_ms"], 20 * total_pts + 4 * r["n_obstacle"], step_ms, nf)
+    lat = []
+    for f in frames[: min(nf, 12)]:
+        t1 = time.perf_counter()
+        r["ctx"].process_batch([f])
+        lat.append(1e3 * (time.perf_counter() - t1))
+    r["ctx"].close()
+    max_chunk_pts = max(sum((f.shape[0] + 31) & ~31 for f in frames[a:a + args.chunk]) for a in range(0, nf, args.chunk))
+    pipe = pkg.FramePipeline(device=env.local_rank, depth=args.depth, chunk_frames=args.chunk, max_points_per_chunk=max_chunk_pts)
+    e2e_s, _, _ = measure_e2e(pkg, env, pipe, pkg.pin_frames(frames), steps, warmup, None)
+    pipe.close()
+    return {"workload": workload, "value": nf * steps / (r["dev_ms_total"] / 1e3), "unit": "frames/s",
+            "mpts_per_s": total_pts * steps / (r["dev_ms_total"] / 1e3) / 1e6, "ms_per_step": step_ms,
+            "e2e": nf * steps / e2e_s, "frac": roof["frac"], "kernel": roof["kernel"], "kernel_ms_per_step": roof["kernel_ms_per_step"],
+            "stage_ms_per_step": r["stage_ms"], "latency_ms_p50": statistics.median(lat[2:] or lat), "steps": steps, "warmup": warmup}
+
+
+def config5_strong(pkg, env, args):
+    """BASELINE.json configs[4] / SURVEY 8(d) config 5 as specified: a job of 4096 frames of the 64-beam generator, rank g of
+    N takes frames [g*4096/N, (g+1)*4096/N) (contiguous blocks, sharding.shard_frames) - STRONG scaling: the job is fixed,
+    the time is the slowest rank's. 64 distinct scenes (seed 1000 + i mod 64) are generated on the host and cycled;
+    resident: the rank's frames are processed in batches of 256 staged in HBM beforehand; e2e: the rank's frames go
+    through the frame pipeline from page-locked host clouds into page-locked result arrays."""
+    from lidar_processing_b200 import sharding
+    from tests.synth import make_frame
+
+    job = 4096
+    distinct = [make_frame(1000 + i) for i in range(64)]
+    mine = sharding.shard_frames(job, env.rank, env.world)
+    batch = min(256, len(mine))
+    frames = [distinct[i % 64] for i in mine[:batch]]  # every batch of the rank has the same composition (i mod 64)
+    n_batches = -(-len(mine) // batch)
+    padded = int(sum((f.shape[0] + 31) & ~31 for f in frames))
+    ctx = pkg.Context(device=env.local_rank, max_points=padded, max_frames=batch)
+    ctx.batch_stage(frames)
+    for _ in range(3):
+        ctx.batch_run()
+        ctx.sync()
+    env.barrier()
+    ms = 0.0
+    for _ in range(n_batches):
+        ctx.batch_run()
+        ctx.sync()
+        ms += ctx.last_run_ms()
+    env.barrier()
+    ms = env.max_over_ranks(ms)
+    ctx.close()
+    pinned = pkg.pin_frames(distinct)
+    src = [pinned[i % 64] for i in mine]
+    pipe = pkg.FramePipeline(device=env.local_rank, depth=args.depth, chunk_frames=args.chunk)
+    pipe.submit(src[: max(batch, args.chunk * args.depth)], arena=0)
+    pipe.drain()
+    env.barrier()
+    t0 = time.perf_counter()
+    pipe.submit(src, arena=1)
+    pipe.drain()
+    env.barrier()
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+    pipe.close()
+    pts = int(sum(distinct[i % 64].shape[0] for i in range(job)))
+    return {"what": "4096-frame job of synthetic 64-beam frames (seed 1000 + i mod 64), rank g takes [g*4096/N, (g+1)*4096/N)",
+            "scaling": "strong", "frames": job, "n_gpus": env.world, "frames_per_gpu": len(mine),
+            "value": job / (ms / 1e3), "unit": "frames/s", "job_ms": ms, "mpts_per_s": pts / (ms / 1e3) / 1e6,
+            "e2e": job / e2e_s, "e2e_job_ms": 1e3 * e2e_s}
 
 
 def main():
@@ -252,6 +459,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="use only the first N frames of the workload (debug)")
     ap.add_argument("--frame-offset", type=int, default=0, help="skip the first N frames (debug / profiling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-workload lines, config 5 and the next-row timings")
     ap.add_argument("--chunk", type=int, default=22, help="frames per pipeline chunk (e2e path)")
     ap.add_argument("--depth", type=int, default=6, help="pipeline depth = contexts in rotation (e2e path)")
     ap.add_argument("--workload", default="kitti154", choices=WORKLOADS,
@@ -272,30 +480,11 @@ def main():
 
     import __graft_entry__ as ge
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    env = Env(torch)
+    rank, local_rank, world = env.rank, env.local_rank, env.world
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else "single process, not pinned"
     pkg = ge.load_package()
     from lidar_processing_b200 import sharding
 
@@ -307,41 +496,20 @@ def main():
     nf = len(frames)
     total_pts = int(sum(f.shape[0] for f in frames))
     padded = int(sum((f.shape[0] + 31) & ~31 for f in frames))
-    ctx = pkg.Context(device=local_rank, max_points=padded, max_frames=nf)
-    ctx.set_profiling(True)
 
     # ---- device-resident throughput (`value`) -------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ctx.batch_stage(frames)  # inputs resident in HBM before the timed region
-    for _ in range(args.warmup):
-        ctx.batch_run()
-        ctx.sync()
-    launches0 = ctx.launch_count()
-    barrier()
-    gpu_ms, stage_acc = [], {}
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.batch_run()
-        ctx.sync()
-        gpu_ms.append(ctx.last_run_ms())
-        for k, v in ctx.last_stage_ms().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
-    barrier()
-    wall_resident = time.perf_counter() - t0
-    sampler.window(t0, t0 + wall_resident)
-    launches = ctx.launch_count() - launches0
-    res = ctx.batch_fetch()
-    n_obstacle = int(sum(r["obstacle_idx"].size for r in res))
-    n_clusters = int(sum(r["n_clusters"] for r in res))
+    r = measure_resident(pkg, env, frames, args.steps, args.warmup, sampler)
+    ctx, res, dev_ms_total, launches = r["ctx"], r["res"], r["dev_ms_total"], r["launches"]
+    n_obstacle, n_clusters = r["n_obstacle"], r["n_clusters"]
     parity = check_fingerprints(res, frame_ids, workload) if rank == 0 else None
-    dev_ms_total = max_over_ranks(sum(gpu_ms))
-    value = world * nf * args.steps / (dev_ms_total / 1e3)
+    value = sharding.job_throughput([nf * args.steps] * world, [dev_ms_total / 1e3] * world)  # all frames / slowest rank
 
     # ---- SURVEY 8(f) rows 1 and 3 on the same resident batch (reported beside the metric, not part of it):
     # extra time per step of the device-side per-cluster split and of the ordered convex outlines behind it
     next_rows = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         try:
             L = pkg.lib()
 
@@ -376,46 +544,21 @@ def main():
             next_rows = {"error": str(e)}
 
     # ---- end to end through the host API ------------------------------------------------------
-    # Every step: host clouds -> (H2D) -> kernels -> (D2H) -> host result arrays, through the C ABI's
-    # frame pipeline (chunks of frames rotating through `depth` contexts). Headline: clouds and result
-    # arrays in page-locked host memory (lidar_b200_host_alloc), as a loader feeding the library would
-    # keep them; the pageable variant (library stages through its own pinned buffers) is reported too.
+    # Headline: clouds and result arrays in page-locked host memory (lidar_b200_host_alloc), as a loader feeding the
+    # library would keep them; the pageable variant (library stages through its own pinned buffers) is reported too.
     pipe = pkg.FramePipeline(device=local_rank, depth=args.depth, chunk_frames=args.chunk)
     pinned_frames = pkg.pin_frames(frames)
-
-    # warm-up submits: at least two (both result arenas), and enough chunks to have every one of the `depth`
-    # contexts allocate its arenas outside the timed region (a small workload is a single chunk per submit)
-    chunks_per_submit = max(1, -(-nf // args.chunk))
-    n_warm_submits = max(2, min(args.warmup, 3), -(-args.depth // chunks_per_submit))
-
-    def e2e_run(src):
-        # steps are submitted back to back (results of step s go to arena s % 2 and stay readable while
-        # step s+1 runs); the timed region ends when the last step's results are in host memory
-        for w_ in range(n_warm_submits):
-            pipe.submit(src, arena=w_ % 2)  # both result arenas and all `depth` contexts exist before the timed region
-        pipe.drain()
-        barrier()
-        t0 = time.perf_counter()
-        for s_ in range(args.steps):
-            job = pipe.submit(src, arena=s_ % 2)
-        pipe.drain()
-        barrier()
-        t1 = time.perf_counter()
-        sampler.window(t0, t1)
-        return max_over_ranks(t1 - t0), pipe.results(job)
-
-    pipe_launches0 = pipe.launch_count()
-    e2e_s, e2e_out = e2e_run(pinned_frames)
-    pipe_launches = (pipe.launch_count() - pipe_launches0) // (args.steps + n_warm_submits)
+    e2e_s, e2e_out, pipe_launches = measure_e2e(pkg, env, pipe, pinned_frames, args.steps, args.warmup, sampler)
     e2e_fps = world * nf * args.steps / e2e_s
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_same = all(np.array_equal(a["cluster_labels"], b["cluster_labels"]) and np.array_equal(a["seg_labels"], b["seg_labels"])
                    for a, b in zip(e2e_out, res))
-    e2e_pageable_s, _ = e2e_run(frames)
+    e2e_pageable_s, _, _ = measure_e2e(pkg, env, pipe, frames, args.steps, args.warmup, sampler)
     e2e_pageable_fps = world * nf * args.steps / e2e_pageable_s
     clocks = sampler.stop()
+    pipe.close()
 
-    # ---- p50 per-frame latency, one frame in flight (submit -> labels on host) ------------------
+    # ---- p50 per-frame latency, one frame in flight (submit -> labels on host), rank 0 at every N ----
     lat = []
     if rank == 0:
         for f in frames[: min(nf, 48)]:
@@ -423,32 +566,32 @@ def main():
             ctx.process_batch([f])
             lat.append(1e3 * (time.perf_counter() - t1))
         lat = lat[4:] if len(lat) > 8 else lat
+    latency = {"p50": statistics.median(lat) if lat else None,
+               "p95": sorted(lat)[int(0.95 * (len(lat) - 1))] if lat else None, "frames": len(lat),
+               "what": "one frame in flight, host buffers in, labels on host out"}
+    ctx.close()
 
     # ---- roofline of the dominant stage ------------------------------------------------------
-    peak, peak_src = hbm_peak()
     algo_bytes = 16 * total_pts + 4 * total_pts + 4 * n_obstacle  # B = 16N + 4N + 4M per frame
-    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
-    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "n/a"
-    dom_ms = stage_ms.get(dom, 0.0)
-    achieved = algo_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    traffic, traffic_src = None, None
-    try:
-        t = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(dom)
-        if t:
-            traffic = t["dram_bytes"] / t["frames_in_capture"] * nf
-            traffic_src = (f"{t['kernel']}: {t['dram_bytes']} B DRAM read+write in a {t['frames_in_capture']}-frame ncu capture "
-                           f"({t['capture']}), scaled per frame to this launch's {nf} frames")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": dom, "kernel_ms_per_step": dom_ms, "peak_source": peak_src,
-                "algorithmic_bytes_per_step": algo_bytes,
-                "whole_path_achieved_GBs": algo_bytes / (dev_ms_total / args.steps / 1e3) / 1e9,
-                "stage_ms_per_step": stage_ms}
+    roofline = roofline_of(r["stage_ms"], algo_bytes, dev_ms_total / args.steps, nf)
+
+    # ---- the other configurations under the driver's eye ---------------------------------------
+    c5, subs = None, None
+    if not args.no_extras and args.workload == "kitti154" and not (args.frames or args.frame_offset):
+        try:
+            c5 = config5_strong(pkg, env, args)  # every rank takes part (strong scaling over the N GPUs)
+        except Exception as e:
+            c5 = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1:
+            subs = {}
+            for name in ("synth128", "merged1m", "synth64"):
+                try:
+                    subs[name] = sub_workload(pkg, env, name, args)
+                except Exception as e:
+                    subs[name] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        env.close()
         return
 
     cpu = None
@@ -456,44 +599,48 @@ def main():
         import oracle as O  # CPU baseline leg only
 
         threads = os.cpu_count() or 1
-        n_sample = min(len(frames), max(32, 2 * threads))
-        r1, _ = cpu_reference_run(frames, 1, min(12, n_sample))
-        rN, _ = cpu_reference_run(frames, threads, n_sample)
-        cpu = {"value": n_sample / rN["wall_s"], "unit": "frames/s", "cores": threads,
+        r1 = O.ref_pipeline_passes(frames[:12], 1, 2)           # 1-thread latency, second (warm) pass
+        rN = O.ref_pipeline_passes(frames, threads, 3)          # all frames; pass 0 is the warm-up
+        wallN = float(rN["pass_wall_s"][1:].mean())
+        cpu = {"value": nf / wallN, "unit": "frames/s", "cores": threads,
                "kind": "reference" if O.ref_available() else "port",
-               "sample": f"{n_sample} frames on {threads} std::threads (restated Segmenter + unmodified reference "
-                         f"Clusterer, TBB absent); 1-thread latency p50 {statistics.median(r1['per_frame_ms']):.1f} ms/frame "
-                         f"over {len(r1['per_frame_ms'])} frames",
+               "sample": f"all {nf} frames on {threads} long-lived std::threads, mean of 2 passes after 1 warm-up pass "
+                         f"(restated Segmenter + unmodified reference Clusterer, TBB absent); 1-thread latency p50 "
+                         f"{statistics.median(r1['per_frame_ms']):.1f} ms/frame over {len(r1['per_frame_ms'])} frames",
                "one_thread_ms_per_frame_p50": statistics.median(r1["per_frame_ms"])}
 
+    def compact(d):
+        return None if d is None else {k: ({kk: vv for kk, vv in v.items() if kk in ("value", "e2e", "frac", "ms_per_step", "error")}
+                                           if isinstance(v, dict) else v) for k, v in d.items()}
+
+    roofline["other_workloads"] = compact(subs)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "real" if workload.startswith("kitti") else "synthetic",
-        "config": {"workload": workload, "frames_per_step_per_gpu": nf, "points_per_step_per_gpu": total_pts,
-                   "l2": "inputs larger than L2 (%.0f MB of points per step)" % (padded * 16 / 1e6),
-                   "parallelism": f"frame-sharded x{world}, no collective"},
+        "config": config_of(workload, nf, total_pts, padded, world),
         "mpts_per_s": world * total_pts * args.steps / (dev_ms_total / 1e3) / 1e6,
-        "latency_ms": {"p50": statistics.median(lat) if lat else None,
-                       "p95": sorted(lat)[int(0.95 * (len(lat) - 1))] if lat else None, "frames": len(lat),
-                       "what": "one frame in flight, host buffers in, labels on host out"},
+        "latency_ms": latency,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": f"lidar_b200_pipe_* : {args.chunk}-frame chunks x depth {args.depth}, clouds and results in "
                         "page-locked host memory, H2D + kernels + D2H every step, wall clock",
                 "pageable_host_buffers_value": e2e_pageable_fps, "results_equal_resident_run": bool(e2e_same),
-                "gpu_launches_per_step": int(pipe_launches)},
+                "gpu_launches_per_step": int(pipe_launches), "latency_ms_p50": latency["p50"], "latency_ms_p95": latency["p95"],
+                "host_affinity": numa,
+                "config5_strong": None if c5 is None else {k: c5.get(k) for k in ("value", "e2e", "frames", "n_gpus", "scaling", "error") if k in c5}},
         "gpu_launches": int(launches),
         "next_rows": next_rows,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "parity": parity,
+        "workloads": subs,
+        "config5": c5,
         "results": {"obstacle_points_per_step": n_obstacle, "clusters_per_step": n_clusters,
-                    "wall_s_resident_region": wall_resident},
+                    "wall_s_resident_region": r["wall"]},
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    env.close()
 
 
 if __name__ == "__main__":

@@ -274,6 +274,25 @@ def ref_pipeline_run(frames, nthreads: int = 1):
     return dict(per_frame_ms=ms, wall_s=wall.value, n_obstacle=nobs, n_clusters=ncl)
 
 
+def ref_pipeline_passes(frames, nthreads: int = 1, n_passes: int = 1):
+    """Like ref_pipeline_run over `n_passes` passes of the frame list with long-lived worker threads and Clusterers
+    (nothing is constructed inside a timed pass). Returns dict(pass_wall_s[n_passes], per_frame_ms (last pass), ...)."""
+    frames = [_f32(f) for f in frames]
+    nf = len(frames)
+    strides = {f.shape[1] for f in frames}
+    assert len(strides) == 1
+    ptrs = (C.POINTER(C.c_float) * nf)(*[_p(f, C.c_float) for f in frames])
+    counts = np.array([f.shape[0] for f in frames], np.uint32)
+    ms = np.zeros(nf, np.float64)
+    walls = np.zeros(max(n_passes, 1), np.float64)
+    nobs = np.zeros(nf, np.uint32)
+    ncl = np.zeros(nf, np.uint32)
+    ref().ref_pipeline_passes(ptrs, _p(counts, C.c_uint32), C.c_uint32(nf), C.c_uint32(strides.pop()), C.c_uint32(nthreads),
+                              C.c_uint32(n_passes), _p(walls, C.c_double), _p(ms, C.c_double), _p(nobs, C.c_uint32),
+                              _p(ncl, C.c_uint32))
+    return dict(pass_wall_s=walls[:n_passes], per_frame_ms=ms, n_obstacle=nobs, n_clusters=ncl)
+
+
 # ---- PCD v0.7 "DATA binary" reader (dataloader.cpp:139 uses pcl::io::loadPCDFile) ------------
 
 def read_pcd(path) -> np.ndarray:

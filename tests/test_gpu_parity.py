@@ -347,6 +347,21 @@ def test_config3_synthetic_128_beam_frames(ctx):
         assert H.check_clustering(pts[res["obstacle_idx"]], res["cluster_labels"]) == res["n_clusters"]
 
 
+def test_config5_synthetic_64_beam_frames_full_size(ctx):
+    """configs[4]: the 64-beam generator at full size (64 x 2083 rays, seed 1000 + i, ~130k returns), batched:
+    strict band against the oracle's surface, cluster labels bit-exact against the unmodified reference Clusterer."""
+    frames = [make_frame(1000 + i) for i in (0, 1, 63)]
+    assert all(f.shape[0] > 100_000 for f in frames)
+    out = ctx.process_batch(frames)
+    reps = []
+    for pts, res in zip(frames, out):
+        rep = {}
+        H.check_segmentation(pts, res["seg_labels"], res["ground_idx"], res["obstacle_idx"], strict=True, report=rep)
+        reps.append(rep)
+        assert H.check_clustering(pts[res["obstacle_idx"]], res["cluster_labels"]) == res["n_clusters"]
+    _record("parity_config5.json", reps)
+
+
 def test_config4_merged_multi_lidar_1m(ctx):
     """configs[3]: merged multi-LiDAR ~1M-point cloud with dense blobs and 100 m walls (components of
     >100k points: the union-find and the CTA-per-component replay under stress)."""
