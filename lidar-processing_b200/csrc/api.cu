@@ -13,6 +13,7 @@
 #include "pcd_io.h"
 #include "radix_sort.cuh"
 #include "replay_cta.cuh"
+#include "replay_cta2.cuh"
 #include "segment.cuh"
 
 #include <atomic>
@@ -66,7 +67,8 @@ struct lidar_b200_ctx
     int device{0};
     cudaStream_t stream{nullptr};
     cudaStream_t stream_big{nullptr}; // the CTA-per-component replay runs beside the warp-per-component one
-    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_fork{nullptr}, ev_join{nullptr}, ev_kd{nullptr};
+    cudaStream_t stream_huge{nullptr}; // ... and the 1-CTA-per-SM launch for components beyond the normal state bitmap
+    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_fork{nullptr}, ev_join{nullptr}, ev_join2{nullptr}, ev_kd{nullptr};
     lidar_b200_seg_cfg seg_cfg{};
     lidar_b200_clu_cfg clu_cfg{};
     SegParams seg{};
@@ -83,6 +85,11 @@ struct lidar_b200_ctx
 
     // device arenas (per point)
     DevBuf<float4> d_pts, d_spts, d_obs, d_nodes, d_cpts, d_rpts;
+    DevBuf<float4> d_ipts, d_mpts; // immutable records of the second-generation CTA replay (replay_cta2.cuh)
+    DevBuf<uint32_t> d_rankpos;
+    DevBuf<unsigned long long> d_mkey;
+    int replay_version{2};         // LIDAR_B200_REPLAY_V: 1 = first-generation CTA replay (state in global memory)
+    bool replay2_attr_done{false};
     DevBuf<uint32_t> d_key_a, d_key_b, d_val_a, d_val_b, d_labels, d_gidx, d_oidx, d_slot_of, d_pos_of, d_parent,
         d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label, d_comp_size, d_pslot;
     DevBuf<int32_t> d_clabels;
@@ -241,7 +248,8 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
             rc |= dev_alloc(c, *b, n);
         rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_pkey, n) | dev_alloc(c, c->d_flags, n) |
               dev_alloc(c, c->d_seed_valid, n) | dev_alloc(c, c->d_nbr, 27u * n) | dev_alloc(c, c->d_cinfo, n) |
-              dev_alloc(c, c->d_biglist, kBigBuckets * (n / kCtaComponentMin + 1u));
+              dev_alloc(c, c->d_biglist, kBigListBuckets * (n / kCtaComponentMin + 1u)) | dev_alloc(c, c->d_ipts, n) |
+              dev_alloc(c, c->d_mpts, n) | dev_alloc(c, c->d_rankpos, n) | dev_alloc(c, c->d_mkey, n);
         if (c->want_job_stats)
             rc |= dev_alloc(c, c->d_job_stats, 8u * (n / kCtaComponentMin + 1u));
         if (rc)
@@ -250,7 +258,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
     }
     if (grow_frames)
     {
-        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames) + 8) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)))
+        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames) + 16) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)))
             return LIDAR_B200_ERR_CUDA;
         c->cap_frames = frames;
     }
@@ -547,6 +555,57 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     // started first on a second stream so that the longest BFS chains begin at time zero
     uint32_t *big_count = c->m_cursor() + 3; // kBigBuckets counters
     const uint32_t bucket_capacity = c->cap_pts / kCtaComponentMin + 1u;
+    bool huge_launched = false;
+    if (c->replay_version >= 2)
+    {
+        // second generation (replay_cta2.cuh): component state in shared memory, immutable point records. Components
+        // beyond the normal bitmap go to a 1-CTA-per-SM launch with a large bitmap, beyond that to the first generation.
+        const uint32_t normal_words = kReplay2NormalWords, huge_words = kReplay2HugeWords;
+        const size_t smem_normal = sizeof(Cta2Smem) + 4u * normal_words, smem_huge = sizeof(Cta2Smem) + 4u * huge_words;
+        if (!c->replay2_attr_done)
+        {
+            LB_CUDA(c, cudaFuncSetAttribute(replay_cta2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_normal)));
+            LB_CUDA(c, cudaFuncSetAttribute(replay_cta2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_huge)));
+            c->replay2_attr_done = true;
+        }
+        replay_init2_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_pkey.p, c->d_ipts.p,
+                                               c->d_rankpos.p, c->d_mpts.p, c->d_mkey.p);
+        replay_biglist2_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->clu.cta_min_members, 16u * normal_words,
+                                                  16u * huge_words, c->d_biglist.p, bucket_capacity, big_count,
+                                                  c->m_cursor() + 8, c->m_cursor() + 10);
+        c->launches += 2;
+        LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
+        LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
+        replay_cta2_kernel<3><<<c->sm_count * 3u, kCtaThreads, smem_normal, c->stream_big>>>(
+            c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, c->d_mkey.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx,
+            c->d_comp_size.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p,
+            bucket_capacity, big_count, kBigBuckets, c->m_cursor() + 2, normal_words, c->d_job_stats.p);
+        ++c->launches;
+        if (max_m > 16u * normal_words) // a component can only be that large in a frame that large
+        {
+            LB_CUDA(c, cudaStreamWaitEvent(c->stream_huge, c->ev_fork, 0));
+            replay_cta2_kernel<1><<<c->sm_count, kCtaThreads, smem_huge, c->stream_huge>>>(
+                c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, c->d_mkey.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx,
+                c->d_comp_size.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
+                c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), bucket_capacity, c->m_cursor() + 8, 1u,
+                c->m_cursor() + 7, huge_words, nullptr);
+            ++c->launches;
+            if (max_m > 16u * huge_words)
+            {
+                // first generation for what is left: its list is bucket 5, its counters sit at cursor[10..13] (11..13 stay 0)
+                replay_cta_kernel<3><<<c->sm_count * 3u, kCtaThreads, 0, c->stream_huge>>>(
+                    c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
+                    c->d_pkey.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
+                    c->d_biglist.p + 5u * static_cast<size_t>(bucket_capacity), bucket_capacity, c->m_cursor() + 10,
+                    c->m_cursor() + 9, nullptr);
+                ++c->launches;
+            }
+            LB_CUDA(c, cudaEventRecord(c->ev_join2, c->stream_huge));
+            huge_launched = true;
+        }
+    }
+    else
+    {
     replay_biglist_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->clu.cta_min_members, c->d_biglist.p,
                                              bucket_capacity, big_count);
     LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
@@ -567,6 +626,8 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
             LB_LAUNCH_REPLAY_CTA(2);
 #undef LB_LAUNCH_REPLAY_CTA
     }
+    c->launches += 2;
+    }
     LB_CUDA(c, cudaEventRecord(c->ev_join, c->stream_big));
     const uint32_t claims = (max_m + 31u) / 32u;
     // persistent grid: a fixed number of CTAs per SM walks the flat (frame, claim) work list
@@ -576,6 +637,8 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
                                                       c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
                                                       c->m_cursor(), claims);
     LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join, 0));
+    if (huge_launched)
+        LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join2, 0));
     mark(c, 8);
     {
         const uint32_t tiles = grid_x(max_m, kLabelTile, 0xFFFFu);
@@ -587,7 +650,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
         label_assign_kernel<<<gp, 256, 0, s>>>(bv, c->d_pos_of.p, c->d_seed_of.p, c->d_seed_valid.p, c->d_seed_label.p,
                                                c->d_clabels.p);
     }
-    c->launches += 8;
+    c->launches += 6;
     mark(c, 9);
     LB_CUDA(c, cudaGetLastError());
     return 0;
@@ -750,6 +813,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     c->want_job_stats = std::getenv("LIDAR_B200_REPLAY_STATS") != nullptr;
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
+    if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
+        c->replay_version = std::atoi(e) == 1 ? 1 : 2;
     lidar_b200_seg_cfg sc;
     lidar_b200_clu_cfg cc;
     lidar_b200_seg_cfg_default(&sc);
@@ -758,6 +823,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     apply_clu_cfg(c, cc);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream_big, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_huge, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -805,6 +872,8 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream_big)
         cudaStreamSynchronize(c->stream_big);
+    if (c->stream_huge)
+        cudaStreamSynchronize(c->stream_huge);
     if (c->stream)
         cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_pts.p);
@@ -817,7 +886,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -836,6 +905,10 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
         cudaEventDestroy(c->ev_kd);
     if (c->ev_counts)
         cudaEventDestroy(c->ev_counts);
+    if (c->ev_join2)
+        cudaEventDestroy(c->ev_join2);
+    if (c->stream_huge)
+        cudaStreamDestroy(c->stream_huge);
     if (c->stream_big)
         cudaStreamDestroy(c->stream_big);
     if (c->stream)

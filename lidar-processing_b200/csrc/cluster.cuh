@@ -548,8 +548,9 @@ replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
     const uint32_t off = bv.off[f];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8)
-        cursor[threadIdx.x] = 0u; // warp-path phases 0/1, CTA-path cursor, CTA-path job counts per size bucket
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 16)
+        cursor[threadIdx.x] = 0u; // [0,1] warp-path phases, [2] CTA-path cursor, [3..6] CTA-path job counts per size bucket,
+                                  // [7,8] cursor / count of the huge list, [9,10] of the first-generation list, [11..13] stay 0
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
         const float4 p = cpts[off + i];
