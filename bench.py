@@ -401,6 +401,27 @@ def sub_workload(pkg, env, name, args):
             "stage_ms_per_step": r["stage_ms"], "latency_ms_p50": statistics.median(lat[2:] or lat), "steps": steps, "warmup": warmup}
 
 
+def dropin_timing(frames):
+    """The REAL drop-in call (reference src/processor.cpp:150-178): C++ Segmenter::segment + Clusterer::cluster on pageable
+    pcl::PointCloud<pcl::PointXYZI> (32-byte records), one frame at a time, synchronous - tests/cpp/bench_dropin.cpp."""
+    import tempfile
+
+    import __graft_entry__ as ge
+
+    exe = ge.build_dropin_bench()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "frames.bin"
+        with open(path, "wb") as f:
+            f.write(np.uint32(len(frames)).tobytes())
+            f.write(np.array([fr.shape[0] for fr in frames], np.uint32).tobytes())
+            for fr in frames:
+                f.write(np.ascontiguousarray(fr, np.float32).tobytes())
+        r = subprocess.run([str(exe), str(path), "2"], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def config5_strong(pkg, env, args):
     """BASELINE.json configs[4] / SURVEY 8(d) config 5 as specified: a job of 4096 frames of the 64-beam generator, rank g of
     N takes frames [g*4096/N, (g+1)*4096/N) (contiguous blocks, sharding.shard_frames) - STRONG scaling: the job is fixed,
@@ -597,6 +618,13 @@ def main():
         env.close()
         return
 
+    dropin = None
+    if not args.no_extras and args.workload == "kitti154":
+        try:
+            dropin = dropin_timing(frames)
+        except Exception as e:
+            dropin = {"error": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import oracle as O  # CPU baseline leg only
@@ -630,6 +658,10 @@ def main():
                 "pageable_host_buffers_value": e2e_pageable_fps, "results_equal_resident_run": bool(e2e_same),
                 "gpu_launches_per_step": int(pipe_launches), "latency_ms_p50": latency["p50"], "latency_ms_p95": latency["p95"],
                 "host_affinity": numa,
+                "dropin_value": None if not dropin else dropin.get("frames_per_s"),
+                "dropin_p50_ms": None if not dropin else dropin.get("p50_ms"),
+                "dropin_what": "C++ Segmenter::segment + Clusterer::cluster (dropin/*.hpp) on pageable 32-byte pcl::PointXYZI "
+                               "clouds, one frame at a time, synchronous (tests/cpp/bench_dropin.cpp)",
                 "config5_strong": None if c5 is None else {k: c5.get(k) for k in ("value", "e2e", "frames", "n_gpus", "scaling", "error") if k in c5}},
         "gpu_launches": int(launches),
         "next_rows": next_rows,
@@ -637,6 +669,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "parity": parity,
+        "dropin": dropin,
         "workloads": subs,
         "config5": c5,
         "results": {"obstacle_points_per_step": n_obstacle, "clusters_per_step": n_clusters,

@@ -133,6 +133,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_batch_fetch_colorized", "lidar_b200_batch_fetch_marker_points",
 ]
 
+DEFAULT_FETCH_MODE = 0   # the library's default LIDAR_B200_FETCH_MODE (api.cu)
 ERR_INPUT = 5            # LIDAR_B200_ERR_INPUT (include/lidar_b200.h)
 HULL_CONVEX = 0          # findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79)
 HULL_CONCAVE_SMALL = 1   # convex branch of findOrderedConcaveOutlines (:100-118); >= 20 points stay on the host
@@ -564,7 +565,7 @@ class FramePipeline:
                 out.append(dict(seg_labels=seg[o:o + n], ground_idx=gidx[o:o + ng] if want else None,
                                 obstacle_idx=oidx[o:o + no], cluster_labels=clab[o:o + no], n_clusters=int(meta[3, f])))
         nf = len(out)
-        if int(os.environ.get("LIDAR_B200_FETCH_MODE", "0")) >= 2:  # exact-size result copies (opt-in, see api.cu)
+        if int(os.environ.get("LIDAR_B200_FETCH_MODE", str(DEFAULT_FETCH_MODE))) >= 2:  # exact-size results (see api.cu)
             self.d2h_bytes = (4 * int(counts.astype(np.int64).sum())
                               + (4 * int(meta[1, :nf].astype(np.int64).sum()) if want else 0)
                               + 8 * int(meta[2, :nf].astype(np.int64).sum()) + 12 * nf + 4 * len(job["chunks"]))

@@ -147,7 +147,7 @@ struct lidar_b200_ctx
     cudaEvent_t ev_counts{nullptr}; // per-frame counts of the batch are in h_meta
     std::vector<void *> copy_dst, copy_src; // copy list of the second fetch phase
     std::vector<size_t> copy_size;
-    int fetch_mode{0}; // LIDAR_B200_FETCH_MODE (default 0, see profiles/README.md "result fetch modes"): 0 = one phase, full slots; 1 = two phases, full slots; 2 = exact sizes, plain copies; 3 = exact sizes, one batched call
+    int fetch_mode{0}; // LIDAR_B200_FETCH_MODE (see profiles/README.md "result fetch modes"): 0 = one phase, full slots; 1 = two phases, full slots; 2 = exact sizes, plain copies; 3 = exact sizes, one batched call; 4 = one kernel writes the exact sizes straight into page-locked host memory (emit_results_kernel)
 
     uint32_t sm_count{148}, replay_ctas_per_sm{12}, replay_big_ctas_per_sm{3};
     uint64_t launches{0};
@@ -171,6 +171,20 @@ int fail(lidar_b200_ctx *c, int code, const std::string &msg)
     if (c)
         c->err = msg;
     return code;
+}
+
+// device-visible address of page-locked host memory (mapped under unified addressing), or null
+void *device_view_of_pinned(const void *p)
+{
+    if (!p)
+        return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 // true when `p` is page-locked host memory known to CUDA (lidar_b200_host_alloc, cudaMallocHost,
@@ -1018,6 +1032,28 @@ int lidar_b200_batch_fetch_async(lidar_b200_ctx *c, uint32_t *point_offset_out, 
                                            cudaMemcpyDeviceToHost, s));
         r.payload_enqueued = true;
     }
+    if (c->fetch_mode == 4 && c->n_frames && bytes)
+    {
+        // one launch writes the used part of every result slot straight into page-locked host memory (the caller's
+        // arrays when they are page-locked, else the library's staging buffers)
+        void *dst[4];
+        bool ok = true;
+        for (int k = 0; k < 4; ++k)
+        {
+            dst[k] = r.out[k] ? device_view_of_pinned(r.direct[k] ? r.out[k] : static_cast<void *>(c->h_u32[k].p)) : nullptr;
+            ok = ok && (!r.out[k] || dst[k]);
+        }
+        if (!ok)
+            return fail(c, LIDAR_B200_ERR_CUDA, "fetch: page-locked host memory is not mapped into the device address space");
+        const BatchView bv{c->m_off(), c->m_cnt(), c->n_frames};
+        emit_results_kernel<<<dim3(8, c->n_frames), 256, 0, s>>>(bv, c->m_ng(), c->m_no(), c->d_labels.p, c->d_gidx.p, c->d_oidx.p,
+                                                                 c->d_clabels.p, static_cast<uint32_t *>(dst[0]),
+                                                                 static_cast<uint32_t *>(dst[1]), static_cast<uint32_t *>(dst[2]),
+                                                                 static_cast<int32_t *>(dst[3]));
+        ++c->launches;
+        LB_CUDA(c, cudaGetLastError());
+        r.payload_enqueued = true;
+    }
     r.with_worker = r.worker_done = false;
     r.worker_rc = 0;
     r.pending = true;
@@ -1496,7 +1532,7 @@ int lidar_b200_host_alloc(void **ptr_out, uint64_t bytes)
     if (!ptr_out)
         return LIDAR_B200_ERR_INVALID;
     *ptr_out = nullptr;
-    if (cudaHostAlloc(ptr_out, bytes ? bytes : 1u, cudaHostAllocPortable) != cudaSuccess)
+    if (cudaHostAlloc(ptr_out, bytes ? bytes : 1u, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess)
     {
         (void)cudaGetLastError();
         *ptr_out = nullptr;

@@ -75,4 +75,47 @@ marker_points_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, cons
     }
 }
 
+// Result emission straight into page-locked HOST memory (fetch mode 4): one launch writes, per frame, exactly the used part
+// of the four result arrays - N segmentation labels, n_ground + n_obstacle indices, n_obstacle cluster labels - to the
+// caller's arrays at the frame's slot offset, with coalesced 16-byte stores over PCIe. No padding crosses the bus (the
+// slot-size copies moved 39 % padding), the sizes never travel to the host first (no host round trip between the last
+// kernel and the transfer), and the copy engines stay free for the next chunk's upload. dst pointers are device-visible
+// addresses of mapped pinned memory; a null pointer skips that array.
+__global__ void __launch_bounds__(256)
+emit_results_kernel(BatchView bv, const uint32_t *__restrict__ n_ground, const uint32_t *__restrict__ n_obstacle,
+                    const uint32_t *__restrict__ labels, const uint32_t *__restrict__ gidx, const uint32_t *__restrict__ oidx,
+                    const int32_t *__restrict__ clabels, uint32_t *dst_labels, uint32_t *dst_gidx, uint32_t *dst_oidx,
+                    int32_t *dst_clabels)
+{
+    const uint32_t f = blockIdx.y;
+    const uint32_t off = bv.off[f]; // multiple of 32 elements: 128-byte aligned on both sides when the bases are
+    const uint32_t n = bv.cnt[f];
+    const uint32_t cnt[4] = {n, min(n_ground[f], n), min(n_obstacle[f], n), min(n_obstacle[f], n)};
+    const uint32_t *src[4] = {labels, gidx, oidx, reinterpret_cast<const uint32_t *>(clabels)};
+    uint32_t *dst[4] = {dst_labels, dst_gidx, dst_oidx, reinterpret_cast<uint32_t *>(dst_clabels)};
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        if (!dst[k])
+            continue;
+        const uint32_t *sp = src[k] + off;
+        uint32_t *dp = dst[k] + off;
+        const uint32_t c = cnt[k];
+        if ((reinterpret_cast<uintptr_t>(dp) & 15u) == 0u)
+        {
+            const uint32_t quads = c >> 2;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(sp);
+            uint4 *d4 = reinterpret_cast<uint4 *>(dp);
+            for (uint32_t i = t; i < quads; i += nt)
+                d4[i] = s4[i];
+            for (uint32_t i = (quads << 2) + t; i < c; i += nt)
+                dp[i] = sp[i];
+        }
+        else
+            for (uint32_t i = t; i < c; i += nt)
+                dp[i] = sp[i];
+    }
+}
+
 } // namespace lb

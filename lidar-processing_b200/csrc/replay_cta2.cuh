@@ -27,23 +27,22 @@
 namespace lb
 {
 
+constexpr uint32_t kPoolCap = 4096u; // candidates of one round (= push + postponed-removal slots) kept in shared memory
+
 struct __align__(16) Cta2Smem
 {
-    uint32_t ring[kRing]; // lids of the most recent FIFO entries
-    union
-    {
-        unsigned long long pbuf[kCtaW][kEntryCandCap]; // speculative round: pushes of entry k, rank << 32 | lid, from the front;
-                                                       // postponed removals (lid) from the back
-        unsigned long long dpush[kDirectPushCap];      // direct round: pushes of the single entry
-    } u;
-    uint8_t owner[kCtaW][kEntryCandCap]; // candidate number -> neighbour cell (0..26)
-    float4 ent[kCtaW];                   // entry coordinates (w = bits(lid))
-    unsigned long long ent_key[kCtaW];   // cell key of the entry
-    uint32_t ent_widx[kCtaW];            // window index of the entry
-    uint32_t tk[kCtaW], np[kCtaW];       // candidates / pushes of entry k
-    uint32_t dstart[27], dexcl[27], dincl[27], dslot[27]; // neighbour cells of entry 0 (direct round)
+    uint32_t ring[kRing];               // lids of the most recent FIFO entries
+    unsigned long long pool[kPoolCap];  // entry k owns [seg[k], seg[k+1]): its pushes (rank << 32 | lid) from the front,
+                                        // its postponed removals (lid) from the back (a candidate is one or the other)
+    float4 ent[kCtaW];                  // entry coordinates (w = bits(lid))
+    unsigned long long ent_key[kCtaW];  // cell key of the entry
+    uint32_t ent_widx[kCtaW];           // window index of the entry
+    uint32_t cstart[kCtaW][27], cincl[kCtaW][27], cslot[kCtaW][27]; // the 27 neighbour cells of entry k: first pos,
+                                        // inclusive candidate prefix, hash slot (live counter)
+    uint32_t tk[kCtaW], np[kCtaW], nd[kCtaW]; // candidates / pushes / postponed removals of entry k
+    uint32_t seg[kCtaW + 1u];                 // exclusive prefix of tk[] (every warp writes the same values)
     uint32_t wcnt[8];
-    uint32_t n_push, claim, found;
+    uint32_t claim, found;
 };
 
 // component state bitmap: 2 bits per member (kStRemoved | kStQueued), 16 members per word
@@ -192,6 +191,7 @@ replay_cta2_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restri
 
         const long long job_t0 = clock64();
         uint32_t st_rounds = 0u, st_direct = 0u, st_taken = 0u, st_seeds = 0u, st_cands = 0u;
+        long long tA = 0, tB = 0, tC = 0, tmark = 0;
         uint32_t u = 0u; // next member (lid) to examine as a seed candidate (ascending index, clustering.cpp:70-75)
         while (true)
         {
@@ -232,6 +232,7 @@ replay_cta2_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restri
             while (head < tail) // clustering.cpp:80-111
             {
                 // ---- A: window of the next 256 FIFO entries, the first kCtaW live ones are taken
+                tmark = clock64();
                 const uint32_t e = head + tid;
                 uint32_t elid = 0u;
                 bool alive = false;
@@ -271,6 +272,7 @@ replay_cta2_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restri
                 __syncthreads();
                 ++st_rounds;
                 st_taken += n_take;
+                { const long long t = clock64(); tA += t - tmark; tmark = t; }
 
                 // ---- which entries are really expanded: lane p < 28 tests the pair (j, k), j < k; every warp
                 // derives the same mask. close bits of entry k sit at bit k(k-1)/2 + j.
@@ -295,309 +297,222 @@ replay_cta2_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restri
 
                 // ---- B: warp k looks up the 27 cells of entry k (applied entries only)
                 const bool mine = warp < n_take && ((applied >> warp) & 1u);
-                uint32_t start = 0u, count = 0u, slot = 0u, incl = 0u, excl = 0u, T = 0u;
-                float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mine)
                 {
-                    pj = sm.ent[warp];
-                    if (lane < 27u)
+                    uint32_t T = 0u;
+                    if (mine)
                     {
-                        // neighbour key = own key + (dx, dy, dz) in the packed 21-bit fields (biased, no borrow)
-                        const long long dk = static_cast<long long>(static_cast<int>(lane % 3u) - 1) +
-                                             (static_cast<long long>(static_cast<int>((lane / 3u) % 3u) - 1) << 21) +
-                                             (static_cast<long long>(static_cast<int>(lane / 9u) - 1) << 42);
-                        cell_lookup_alive(tab, tlive, mask, sm.ent_key[warp] + static_cast<unsigned long long>(dk), &start,
-                                          &count, &slot);
-                    }
-                    incl = warp_inclusive_scan(count);
-                    excl = incl - count;
-                    T = __shfl_sync(kFullMask, incl, 31);
-                    st_cands += T;
-                    if (warp == 0u && lane < 27u)
-                    {
-                        sm.dstart[lane] = start;
-                        sm.dexcl[lane] = excl;
-                        sm.dincl[lane] = incl;
-                        sm.dslot[lane] = slot;
-                    }
-                }
-                if (lane == 0)
-                    sm.tk[warp] = T;
-                __syncthreads();
-                // entries from the first dense one on wait for a later round; a dense FIRST entry is expanded alone
-                uint32_t n_use = n_take;
-#pragma unroll
-                for (uint32_t v = kCtaW; v-- > 0u;)
-                    if (v < n_take && sm.tk[v] > kEntryCandCap)
-                        n_use = v;
-                uint32_t np_total = 0u;
-
-                if (n_use != 0u)
-                {
-                    // ---- C: warp k treats the candidates of entry k like the loop body of clustering.cpp:94-109
-                    uint32_t my_np = 0u;
-                    uint32_t my_nd = 0u; // removals postponed to the write pass
-                    if (mine && warp < n_use)
-                    {
-                        const uint32_t earlier = applied & ((1u << warp) - 1u);
-                        uint8_t *own = sm.owner[warp];
-                        for (uint32_t i = 0; i < count; ++i)
-                            own[excl + i] = static_cast<uint8_t>(lane);
-                        __syncwarp();
-                        for (uint32_t base = 0; base < T; base += 32u * kCtaUnroll)
+                        uint32_t start = 0u, count = 0u, slot = 0u;
+                        if (lane < 27u)
                         {
-                            uint32_t pos2[kCtaUnroll], slot2[kCtaUnroll], rank2[kCtaUnroll];
-                            float4 cand2[kCtaUnroll];
-                            bool valid2[kCtaUnroll];
-#pragma unroll
-                            for (int h = 0; h < kCtaUnroll; ++h)
-                            {
-                                const uint32_t q = base + 32u * h + lane;
-                                valid2[h] = q < T;
-                                const uint32_t c = valid2[h] ? own[q] : 0u;
-                                const uint32_t cstart = __shfl_sync(kFullMask, start, c);
-                                const uint32_t cexcl = __shfl_sync(kFullMask, excl, c);
-                                slot2[h] = __shfl_sync(kFullMask, slot, c);
-                                pos2[h] = cstart + (q - cexcl);
-                                cand2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                rank2[h] = 0u;
-                                if (valid2[h])
-                                {
-                                    cand2[h] = __ldg(&ip[pos2[h]]);
-                                    rank2[h] = __ldg(&rkp[pos2[h]]);
-                                }
-                            }
-#pragma unroll
-                            for (int h = 0; h < kCtaUnroll; ++h)
-                            {
-                                if (h > 0 && base + 32u * h >= T)
-                                    break;
-                                const float4 cand = cand2[h];
-                                bool push = false, defer = false;
-                                uint32_t lidc = 0u;
-                                if (valid2[h])
-                                {
-                                    // KDTree::dist_sqr(target, node) (kdtree.hpp:145-163), inclusive test (kdtree.hpp:314)
-                                    const float d2 = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z);
-                                    lidc = __float_as_uint(cand.w) - t_start;
-                                    if (d2 <= prm.distance_squared && lidc < n_mem)
-                                    {
-                                        const uint32_t sw = st_get(st, lidc);
-                                        if ((sw & kStRemoved) == 0u) // removed points are skipped (clustering.cpp:94-97)
-                                        {
-                                            // what the entries expanded earlier in this round did to the candidate
-                                            bool removed_before = false, queued_before = (sw & kStQueued) != 0u;
-                                            bool shared = false; // an earlier entry of the round reaches the candidate too
-                                            for (uint32_t em = earlier; em; em &= em - 1u)
-                                            {
-                                                const float4 po = sm.ent[__ffs(em) - 1];
-                                                const float dj = dist_sqr_ref(po.x, po.y, po.z, cand.x, cand.y, cand.z);
-                                                removed_before |= dj <= prm.inner_threshold;
-                                                shared |= dj <= prm.distance_squared;
-                                            }
-                                            queued_before |= shared;
-                                            if (!removed_before)
-                                            {
-                                                ++touched; // indices_.push_back (with multiplicity)
-                                                if (d2 <= prm.inner_threshold)
-                                                {
-                                                    // clustering.cpp:99,102-105: the point leaves the cloud with this
-                                                    // seed's label. An EARLIER entry that reaches this candidate must still
-                                                    // see it alive (it touches it first in the reference's order), whichever
-                                                    // warp gets here first: the state write of such a removal waits for the
-                                                    // CTA barrier; the label and the live counter are not read in a round.
-                                                    so[pos2[h]] = seed_idx;
-                                                    atomicSub(&tlive[slot2[h]], 1u);
-                                                    if (shared)
-                                                        defer = true;
-                                                    else
-                                                        st_or(st, lidc, kStRemoved);
-                                                }
-                                                else if (!queued_before)
-                                                {
-                                                    st_or(st, lidc, kStQueued); // clustering.cpp:106-109 (first push only)
-                                                    push = true;
-                                                }
-                                            }
-                                        }
-                                    }
-                                }
-                                const uint32_t bp = __ballot_sync(kFullMask, push);
-                                if (push)
-                                    sm.u.pbuf[warp][my_np + __popc(bp & lt)] =
-                                        (static_cast<unsigned long long>(rank2[h]) << 32) | static_cast<unsigned long long>(lidc);
-                                my_np += __popc(bp);
-                                const uint32_t bd = __ballot_sync(kFullMask, defer);
-                                if (defer)
-                                    sm.u.pbuf[warp][kEntryCandCap - 1u - (my_nd + __popc(bd & lt))] = lidc;
-                                my_nd += __popc(bd);
-                            }
+                            // neighbour key = own key + (dx, dy, dz) in the packed 21-bit fields (biased, no borrow)
+                            const long long dk = static_cast<long long>(static_cast<int>(lane % 3u) - 1) +
+                                                 (static_cast<long long>(static_cast<int>((lane / 3u) % 3u) - 1) << 21) +
+                                                 (static_cast<long long>(static_cast<int>(lane / 9u) - 1) << 42);
+                            cell_lookup_alive(tab, tlive, mask, sm.ent_key[warp] + static_cast<unsigned long long>(dk), &start,
+                                              &count, &slot);
                         }
+                        const uint32_t incl = warp_inclusive_scan(count);
+                        T = __shfl_sync(kFullMask, incl, 26);
+                        if (lane < 27u)
+                        {
+                            sm.cstart[warp][lane] = start;
+                            sm.cincl[warp][lane] = incl;
+                            sm.cslot[warp][lane] = slot;
+                        }
+                        st_cands += T;
                     }
                     if (lane == 0)
-                        sm.np[warp] = my_np;
-                    __syncthreads();
-                    // ---- D: all state reads of the round are done; the postponed removals are written
-                    for (uint32_t i = lane; i < my_nd; i += 32u)
-                        st_or(st, static_cast<uint32_t>(sm.u.pbuf[warp][kEntryCandCap - 1u - i]), kStRemoved);
-                    // ---- F: the FIFO receives the pushes ordered by (entry, k-d pre-order rank)
-                    uint32_t pre = 0u;
-#pragma unroll
-                    for (uint32_t v = 0; v < kCtaW; ++v)
                     {
-                        const uint32_t c = sm.np[v];
-                        pre += v < warp ? c : 0u;
-                        np_total += c;
+                        sm.tk[warp] = T;
+                        sm.np[warp] = 0u;
+                        sm.nd[warp] = 0u;
                     }
-                    for (uint32_t e2 = lane; e2 < my_np; e2 += 32u)
-                    {
-                        const unsigned long long key = sm.u.pbuf[warp][e2];
-                        uint32_t dest = 0u;
-                        for (uint32_t x = 0; x < my_np; ++x)
-                            dest += sm.u.pbuf[warp][x] < key ? 1u : 0u;
-                        const uint32_t lid = static_cast<uint32_t>(key);
-                        qu[tail + pre + dest] = lid;
-                        sm.ring[(tail + pre + dest) & (kRing - 1u)] = lid;
-                        prefetch_l1(&mp[lid]);
-                        prefetch_l1(&mk[lid]);
-                    }
-                    head += sm.ent_widx[n_use - 1u] + 1u;
                 }
-                else
+                __syncthreads();
+                { const long long t = clock64(); tB += t - tmark; tmark = t; }
+                // the round expands the longest prefix of the taken entries whose candidates fit the pool together; a
+                // dense FIRST entry that does not fit is expanded alone and spills its pushes to global memory
+                uint32_t n_use = 0u, seg[kCtaW + 1u];
+                seg[0] = 0u;
+#pragma unroll
+                for (uint32_t v = 0; v < kCtaW; ++v)
                 {
-                    // ---- direct round: entry 0 alone, all 256 threads, acting on the loaded state at once
-                    ++st_direct;
-                    if (tid == 0)
-                        sm.n_push = 0u;
-                    __syncthreads();
-                    pj = sm.ent[0];
-                    T = sm.dincl[26];
-                    for (uint32_t base = 0; base < T; base += kCtaThreads * kCtaUnroll)
+                    const uint32_t c = v < n_take ? sm.tk[v] : 0u;
+                    seg[v + 1u] = seg[v] + c;
+                    if (v < n_take && n_use == v && seg[v + 1u] <= kPoolCap)
+                        n_use = v + 1u;
+                }
+                const bool spill_mode = n_use == 0u; // then entry 0 alone: tk[0] > kPoolCap, no earlier entry, nothing postponed
+                if (spill_mode)
+                    n_use = 1u;
+                if (lane == 0)
+                {
+#pragma unroll
+                    for (uint32_t v = 0; v <= kCtaW; ++v)
+                        sm.seg[v] = seg[v];
+                }
+                __syncwarp();
+                const uint32_t t_total = sm.seg[n_use];
+
+                // ---- C: every candidate of the round is treated like the loop body of clustering.cpp:94-109 by ONE thread:
+                // the (entry, candidate) pairs of all expanded entries are dealt over the whole CTA, so a round makes one
+                // trip to the point records however its candidates are spread over the entries
+                for (uint32_t base = 0; base < t_total; base += kCtaThreads * kCtaUnroll)
+                {
+                    uint32_t pos2[kCtaUnroll], slot2[kCtaUnroll], rank2[kCtaUnroll], ent2[kCtaUnroll], seg2[kCtaUnroll];
+                    float4 cand2[kCtaUnroll];
+                    bool valid2[kCtaUnroll];
+#pragma unroll
+                    for (int h = 0; h < kCtaUnroll; ++h)
                     {
-                        uint32_t pos2[kCtaUnroll], ci2[kCtaUnroll], rank2[kCtaUnroll];
-                        float4 cand2[kCtaUnroll];
-                        bool valid2[kCtaUnroll];
-#pragma unroll
-                        for (int h = 0; h < kCtaUnroll; ++h)
+                        const uint32_t g = base + kCtaThreads * h + tid;
+                        valid2[h] = g < t_total;
+                        cand2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        pos2[h] = slot2[h] = rank2[h] = ent2[h] = seg2[h] = 0u;
+                        if (valid2[h])
                         {
-                            const uint32_t q = base + kCtaThreads * h + tid;
-                            cand2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            pos2[h] = 0u;
-                            ci2[h] = 0u;
-                            rank2[h] = 0u;
-                            valid2[h] = q < T;
-                            if (valid2[h])
-                            {
-                                uint32_t lo = 0u, hi = 26u;
+                            uint32_t k = 0u; // entry owning candidate g
 #pragma unroll
-                                for (int it = 0; it < 5; ++it) // first cell whose inclusive prefix exceeds q
-                                {
-                                    const uint32_t mid = (lo + hi) >> 1;
-                                    if (sm.dincl[mid] > q)
-                                        hi = mid;
-                                    else
-                                        lo = mid + 1u;
-                                }
-                                ci2[h] = lo;
-                                pos2[h] = sm.dstart[lo] + (q - sm.dexcl[lo]);
-                                cand2[h] = __ldg(&ip[pos2[h]]);
-                                rank2[h] = __ldg(&rkp[pos2[h]]);
-                            }
-                        }
+                            for (uint32_t v = 1; v < kCtaW; ++v)
+                                k += (v < n_use && g >= sm.seg[v]) ? 1u : 0u;
+                            const uint32_t segk = sm.seg[k];
+                            const uint32_t q = g - segk;
+                            seg2[h] = segk;
+                            const uint32_t *ci = sm.cincl[k];
+                            uint32_t lo = 0u, hi = 26u;
 #pragma unroll
-                        for (int h = 0; h < kCtaUnroll; ++h)
-                        {
-                            if (h > 0 && base + kCtaThreads * h >= T)
-                                break;
-                            const float4 cand = cand2[h];
-                            bool push = false;
-                            uint32_t lidc = 0u;
-                            if (valid2[h])
+                            for (int it = 0; it < 5; ++it) // first cell whose inclusive prefix exceeds q
                             {
-                                const float d2 = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z);
-                                lidc = __float_as_uint(cand.w) - t_start;
-                                if (d2 <= prm.distance_squared && lidc < n_mem)
-                                {
-                                    const uint32_t sw = st_get(st, lidc);
-                                    if ((sw & kStRemoved) == 0u)
-                                    {
-                                        ++touched;
-                                        if (d2 <= prm.inner_threshold)
-                                        {
-                                            so[pos2[h]] = seed_idx;
-                                            st_or(st, lidc, kStRemoved);
-                                            atomicSub(&tlive[sm.dslot[ci2[h]]], 1u);
-                                        }
-                                        else if ((sw & kStQueued) == 0u)
-                                        {
-                                            st_or(st, lidc, kStQueued);
-                                            push = true;
-                                        }
-                                    }
-                                }
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (ci[mid] > q)
+                                    hi = mid;
+                                else
+                                    lo = mid + 1u;
                             }
-                            const uint32_t bp = __ballot_sync(kFullMask, push);
-                            if (bp)
-                            {
-                                uint32_t pb = 0u;
-                                if (lane == 0)
-                                    pb = atomicAdd(&sm.n_push, static_cast<uint32_t>(__popc(bp)));
-                                pb = __shfl_sync(kFullMask, pb, 0);
-                                if (push)
-                                {
-                                    const uint32_t idx = pb + __popc(bp & lt);
-                                    const unsigned long long key =
-                                        (static_cast<unsigned long long>(rank2[h]) << 32) | static_cast<unsigned long long>(lidc);
-                                    if (idx < kDirectPushCap)
-                                        sm.u.dpush[idx] = key;
-                                    else
-                                        spill[tail + idx] = key;
-                                }
-                            }
+                            ent2[h] = k;
+                            pos2[h] = sm.cstart[k][lo] + (q - (lo ? ci[lo - 1u] : 0u));
+                            slot2[h] = sm.cslot[k][lo];
+                            cand2[h] = __ldg(&ip[pos2[h]]);
+                            rank2[h] = __ldg(&rkp[pos2[h]]);
                         }
                     }
-                    __syncthreads();
-                    np_total = sm.n_push;
-                    unsigned long long *pbuf = sm.u.dpush;
-                    if (np_total > kDirectPushCap)
+#pragma unroll
+                    for (int h = 0; h < kCtaUnroll; ++h)
                     {
-                        // rare: sort in global memory (the spill area holds entries kDirectPushCap.. already)
-                        for (uint32_t i = tid; i < kDirectPushCap; i += kCtaThreads)
-                            spill[tail + i] = sm.u.dpush[i];
+                        if (!valid2[h])
+                            continue;
+                        const float4 cand = cand2[h];
+                        const uint32_t k = ent2[h];
+                        const float4 pj = sm.ent[k];
+                        // KDTree::dist_sqr(target, node) (kdtree.hpp:145-163), inclusive test (kdtree.hpp:314)
+                        const float d2 = dist_sqr_ref(pj.x, pj.y, pj.z, cand.x, cand.y, cand.z);
+                        const uint32_t lidc = __float_as_uint(cand.w) - t_start;
+                        if (!(d2 <= prm.distance_squared) || lidc >= n_mem)
+                            continue;
+                        const uint32_t sw = st_get(st, lidc);
+                        if (sw & kStRemoved) // removed points are skipped (clustering.cpp:94-97)
+                            continue;
+                        // what the entries expanded earlier in this round did to the candidate
+                        bool removed_before = false, queued_before = (sw & kStQueued) != 0u;
+                        bool shared = false; // an earlier entry of the round reaches the candidate too
+                        for (uint32_t em = applied & ((1u << k) - 1u); em; em &= em - 1u)
+                        {
+                            const float4 po = sm.ent[__ffs(em) - 1];
+                            const float dj = dist_sqr_ref(po.x, po.y, po.z, cand.x, cand.y, cand.z);
+                            removed_before |= dj <= prm.inner_threshold;
+                            shared |= dj <= prm.distance_squared;
+                        }
+                        queued_before |= shared;
+                        if (removed_before)
+                            continue;
+                        ++touched; // indices_.push_back (with multiplicity)
+                        if (d2 <= prm.inner_threshold)
+                        {
+                            // clustering.cpp:99,102-105: the point leaves the cloud with this seed's label. An EARLIER
+                            // entry that reaches this candidate must still see it alive (it touches it first in the
+                            // reference's order), whichever thread gets here first: the state write of such a removal waits
+                            // for the CTA barrier; the label and the live counter are not read inside a round.
+                            so[pos2[h]] = seed_idx;
+                            atomicSub(&tlive[slot2[h]], 1u);
+                            if (shared)
+                                sm.pool[seg2[h] + sm.tk[k] - 1u - atomicAdd(&sm.nd[k], 1u)] = lidc;
+                            else
+                                st_or(st, lidc, kStRemoved);
+                        }
+                        else if (!queued_before)
+                        {
+                            st_or(st, lidc, kStQueued); // clustering.cpp:106-109 (first push only)
+                            const uint32_t idx = atomicAdd(&sm.np[k], 1u);
+                            const unsigned long long key =
+                                (static_cast<unsigned long long>(rank2[h]) << 32) | static_cast<unsigned long long>(lidc);
+                            if (idx < kPoolCap)
+                                sm.pool[seg2[h] + idx] = key; // (the segment starts at 0 in spill mode)
+                            else
+                                spill[tail + idx] = key;
+                        }
+                    }
+                }
+                __syncthreads();
+                { const long long t = clock64(); tC += t - tmark; tmark = t; }
+                // ---- D: all state reads of the round are done; the postponed removals are written
+                if (warp < n_use)
+                {
+                    const uint32_t seg_end = sm.seg[warp + 1u];
+                    for (uint32_t i = lane; i < sm.nd[warp]; i += 32u)
+                        st_or(st, static_cast<uint32_t>(sm.pool[seg_end - 1u - i]), kStRemoved);
+                }
+                // ---- F: the FIFO receives the pushes ordered by (entry, k-d pre-order rank)
+                uint32_t np_total = 0u, seg_k = 0u;
+                for (uint32_t k = 0; k < n_use; seg_k += sm.tk[k], ++k)
+                {
+                    const uint32_t npk = sm.np[k];
+                    if (npk == 0u)
+                        continue;
+                    unsigned long long *pbuf = sm.pool + seg_k;
+                    if (npk > kPoolCap)
+                    {
+                        // rare (spill mode only): sort in global memory, the spill area holds entries kPoolCap.. already
+                        for (uint32_t i = tid; i < kPoolCap; i += kCtaThreads)
+                            spill[tail + i] = sm.pool[i];
                         pbuf = spill + tail;
                         __syncthreads();
                     }
-                    if (np_total != 0u)
+                    if (npk <= 64u)
                     {
-                        if (np_total <= kCtaThreads)
-                        {
-                            if (tid < np_total)
+                        if (warp == (k & 7u)) // short lists: one warp ranks every key by counting the smaller ones
+                            for (uint32_t e2 = lane; e2 < npk; e2 += 32u)
                             {
-                                const unsigned long long mine_key = pbuf[tid];
+                                const unsigned long long key = pbuf[e2];
                                 uint32_t dest = 0u;
-                                for (uint32_t x = 0; x < np_total; ++x)
-                                    dest += pbuf[x] < mine_key ? 1u : 0u;
-                                const uint32_t lid = static_cast<uint32_t>(mine_key);
-                                qu[tail + dest] = lid;
-                                sm.ring[(tail + dest) & (kRing - 1u)] = lid;
+                                for (uint32_t x = 0; x < npk; ++x)
+                                    dest += pbuf[x] < key ? 1u : 0u;
+                                const uint32_t lid = static_cast<uint32_t>(key);
+                                qu[tail + np_total + dest] = lid;
+                                sm.ring[(tail + np_total + dest) & (kRing - 1u)] = lid;
+                                prefetch_l1(&mp[lid]);
+                                prefetch_l1(&mk[lid]);
+                            }
+                    }
+                    else
+                    {
+                        cta_bitonic_sort(pbuf, npk); // (uniform branch: npk comes from shared memory)
+                        for (uint32_t i = tid; i < npk; i += kCtaThreads)
+                        {
+                            const uint32_t lid = static_cast<uint32_t>(pbuf[i]);
+                            qu[tail + np_total + i] = lid;
+                            if (npk - i <= kRing)
+                                sm.ring[(tail + np_total + i) & (kRing - 1u)] = lid;
+                            if (i < 64u)
+                            {
                                 prefetch_l1(&mp[lid]);
                                 prefetch_l1(&mk[lid]);
                             }
                         }
-                        else
-                        {
-                            cta_bitonic_sort(pbuf, np_total);
-                            for (uint32_t i = tid; i < np_total; i += kCtaThreads)
-                            {
-                                const uint32_t lid = static_cast<uint32_t>(pbuf[i]);
-                                qu[tail + i] = lid;
-                                if (np_total - i <= kRing)
-                                    sm.ring[(tail + i) & (kRing - 1u)] = lid;
-                            }
-                        }
                     }
-                    head += sm.ent_widx[0] + 1u;
+                    np_total += npk;
                 }
+                head += sm.ent_widx[n_use - 1u] + 1u;
+                st_direct += spill_mode ? 1u : 0u;
                 tail += np_total;
                 __syncthreads();
             }
@@ -624,9 +539,9 @@ replay_cta2_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restri
             js[2] = static_cast<uint32_t>((clock64() - job_t0) >> 10);
             js[3] = st_rounds;
             js[4] = st_direct;
-            js[5] = st_taken;
-            js[6] = st_seeds;
-            js[7] = st_cands;
+            js[5] = static_cast<uint32_t>(tA >> 10);
+            js[6] = static_cast<uint32_t>(tB >> 10);
+            js[7] = static_cast<uint32_t>(tC >> 10);
         }
     }
 }

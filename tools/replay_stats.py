@@ -28,14 +28,14 @@ print(f"jobs {st.shape[0]}  sum kcycles {kc.sum():.0f}  max {kc.max():.0f}  mean
 print(f"sum/444 CTAs = {kc.sum()/444:.0f} kcycles = {kc.sum()*1.024/444/1965:.3f} ms ; longest job = {kc.max()*1.024/1965:.3f} ms")
 order = np.argsort(-kc)
 v2 = os.environ.get("LIDAR_B200_REPLAY_V", "2") != "1"
-print("top jobs: [frame members kcycles rounds direct " + ("taken seeds candidates" if v2 else "kcycA kcycBC kcycEF") + "]  cycles/round   (kcycles = cycles >> 10)")
+print("top jobs: [frame members kcycles rounds direct " + ("kcycA kcycB kcycC" if v2 else "kcycA kcycBC kcycEF") + "]  cycles/round   (kcycles = cycles >> 10)")
 for j in order[:12]:
     r = st[j]
     print("  ", r.tolist(), round(1024 * r[2] / max(1, r[3] + r[4])))
-rounds = st[:, 3].astype(np.float64) + st[:, 4]
+rounds = st[:, 3].astype(np.float64) + (0 if v2 else st[:, 4])
 if v2:
-    print(f"total rounds {rounds.sum():.0f}, mean cycles/round {1024*kc.sum()/rounds.sum():.0f}; entries taken per round "
-          f"{st[:,5].sum()/rounds.sum():.2f}, candidates per round {st[:,7].astype(np.float64).sum()/rounds.sum():.1f}")
+    print(f"total rounds {rounds.sum():.0f}, mean cycles/round {1024*kc.sum()/rounds.sum():.0f}; phase share A (window) "
+          f"{st[:,5].sum()/kc.sum():.2f} B (lookup) {st[:,6].sum()/kc.sum():.2f} C (candidates) {st[:,7].sum()/kc.sum():.2f}, rest = write-back")
 else:
     print(f"total rounds {rounds.sum():.0f}, mean cycles/round {1024*kc.sum()/rounds.sum():.0f}; phase share A {st[:,5].sum()/kc.sum():.2f} BC {st[:,6].sum()/kc.sum():.2f} EF {st[:,7].sum()/kc.sum():.2f}")
 for lo, hi in ((256, 512), (512, 1024), (1024, 2048), (2048, 4096), (4096, 8192), (8192, 1 << 30)):
