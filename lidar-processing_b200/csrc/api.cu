@@ -14,6 +14,8 @@
 #include "radix_sort.cuh"
 #include "replay_cta.cuh"
 #include "replay_cta2.cuh"
+#include "replay_cta3.cuh"
+#include "replay_frame.cuh"
 #include "segment.cuh"
 
 #include <atomic>
@@ -88,8 +90,14 @@ struct lidar_b200_ctx
     DevBuf<float4> d_ipts, d_mpts; // immutable records of the second-generation CTA replay (replay_cta2.cuh)
     DevBuf<uint32_t> d_rankpos;
     DevBuf<unsigned long long> d_mkey;
-    int replay_version{2};         // LIDAR_B200_REPLAY_V: 1 = first-generation CTA replay (state in global memory)
-    bool replay2_attr_done{false};
+    int replay_version{4};         // LIDAR_B200_REPLAY_V: 1 = first-generation CTA replay (state in global memory),
+                                   // 2 = second (state bitmap by member), 3 = third (live-candidate bitmaps by cell order),
+                                   // 4 = warp per component, frame bitmaps shared by the CTA (replay_frame.cuh)
+    bool replay2_attr_done{false}, replay3_attr_done{false}, replay4_attr_done{false};
+    uint32_t replay4_ctas_per_sm{3}; // LIDAR_B200_REPLAY4_CTAS_PER_SM
+    DevBuf<uint32_t> d_complist;   // fourth generation: per-frame component lists (first member slot), longest first
+    DevBuf<uint32_t> d_frame_meta; // ... and per-frame counters (kV4MetaStride words each)
+    DevBuf<uint32_t> d_nb27;       // packed neighbour table of the third generation: first pos | count << 20, 27 per cell
     DevBuf<uint32_t> d_key_a, d_key_b, d_val_a, d_val_b, d_labels, d_gidx, d_oidx, d_slot_of, d_pos_of, d_parent,
         d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label, d_comp_size, d_pslot;
     DevBuf<int32_t> d_clabels;
@@ -263,7 +271,8 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
         rc |= dev_alloc(c, c->d_clabels, n) | dev_alloc(c, c->d_spill, n) | dev_alloc(c, c->d_pkey, n) | dev_alloc(c, c->d_flags, n) |
               dev_alloc(c, c->d_seed_valid, n) | dev_alloc(c, c->d_nbr, 27u * n) | dev_alloc(c, c->d_cinfo, n) |
               dev_alloc(c, c->d_biglist, kBigListBuckets * (n / kCtaComponentMin + 1u)) | dev_alloc(c, c->d_ipts, n) |
-              dev_alloc(c, c->d_mpts, n) | dev_alloc(c, c->d_rankpos, n) | dev_alloc(c, c->d_mkey, n);
+              dev_alloc(c, c->d_mpts, n) | dev_alloc(c, c->d_rankpos, n) | dev_alloc(c, c->d_mkey, n) |
+              dev_alloc(c, c->d_nb27, 27u * n) | dev_alloc(c, c->d_complist, n);
         if (c->want_job_stats)
             rc |= dev_alloc(c, c->d_job_stats, 8u * (n / kCtaComponentMin + 1u));
         if (rc)
@@ -272,7 +281,8 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
     }
     if (grow_frames)
     {
-        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames) + 16) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)))
+        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames) + 16) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)) ||
+            dev_alloc(c, c->d_frame_meta, kV4MetaStride * static_cast<size_t>(frames)))
             return LIDAR_B200_ERR_CUDA;
         c->cap_frames = frames;
     }
@@ -539,7 +549,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     {
         const uint32_t *cell_of = c->d_state.p;
         cc_nbr_kernel<<<dim3(grid_x(max_m, 256u, 2048u), F), 256, 0, s>>>(c->d_cpts.p, bv, tv, c->d_cells.p, c->d_slot_of.p,
-                                                                          cell_of, c->d_nbr.p, c->d_cinfo.p);
+                                                                          cell_of, c->d_nbr.p, c->d_cinfo.p, c->d_nb27.p);
         cc_sample_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->clu, cell_of, c->d_nbr.p, c->d_cinfo.p, c->d_parent.p);
         cc_compress_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p);
         cc_cell_parent_kernel<<<gp, 256, 0, s>>>(bv, cell_of, c->d_parent.p, c->d_cinfo.p);
@@ -561,6 +571,49 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_kd, 0)); // k-d order built on the second stream meanwhile
 
     mark(c, 7);
+    if (c->replay_version >= 4 && max_m <= kV4MaxPoints)
+    {
+        // fourth generation (replay_frame.cuh): one warp per component, the CTA's warps share the frame's bitmaps
+        const uint32_t words = (max_m + 31u) >> 5;
+        const size_t smem = sizeof(V4Smem) + 8u * words;
+        if (!c->replay4_attr_done)
+        {
+            const int smem_max = static_cast<int>(sizeof(V4Smem) + 8u * (kV4MaxPoints >> 5));
+            LB_CUDA(c, cudaFuncSetAttribute(replay_frame_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+            LB_CUDA(c, cudaFuncSetAttribute(replay_frame_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+            LB_CUDA(c, cudaFuncSetAttribute(replay_frame_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+            c->replay4_attr_done = true;
+        }
+        LB_CUDA(c, cudaMemsetAsync(c->d_frame_meta.p, 0, static_cast<size_t>(F) * kV4MetaStride * 4, s));
+        replay_init4_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_ipts.p, c->d_seed_of.p,
+                                               c->d_member_pos.p, c->m_cursor());
+        replay_complist_count_kernel<<<gp, 256, 0, s>>>(bv, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
+                                                        c->d_seed_of.p, c->d_seed_valid.p, c->d_frame_meta.p);
+        replay_complist_fill_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->d_frame_meta.p, c->d_complist.p);
+        // how many CTAs may serve one frame at a time: enough tickets to occupy the machine, at most 16 per frame
+        uint32_t per_sm = c->replay4_ctas_per_sm;
+        while (per_sm > 1u && per_sm * smem > 220u * 1024u)
+            --per_sm;
+        const uint32_t slots = c->sm_count * per_sm;
+        const uint32_t per_frame = std::max(1u, std::min(16u, (slots + F - 1u) / F));
+        const uint32_t n_tickets = F * per_frame;
+        const uint32_t grid = std::min(n_tickets, slots);
+#define LB_LAUNCH_REPLAY_FRAME(MINB)                                                                                   \
+    replay_frame_kernel<MINB><<<grid, kV4Warps * 32, smem, s>>>(                                                       \
+        c->d_ipts.p, c->d_state.p /* cell_of */, c->d_nb27.p, c->d_cinfo.p, bv, c->clu, member_root, member_idx,       \
+        c->d_member_pos.p, c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,            \
+        c->d_complist.p, c->d_frame_meta.p, c->m_cursor() + 14, n_tickets, words)
+        if (per_sm >= 4u)
+            LB_LAUNCH_REPLAY_FRAME(4);
+        else if (per_sm == 3u)
+            LB_LAUNCH_REPLAY_FRAME(3);
+        else
+            LB_LAUNCH_REPLAY_FRAME(2);
+#undef LB_LAUNCH_REPLAY_FRAME
+        c->launches += 4;
+    }
+    else
+    {
     replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_slot_of.p,
                                           c->d_rpts.p, c->d_seed_of.p, c->d_member_pos.p, c->d_pslot.p, c->m_cursor(), tv,
                                           c->d_cells.p, c->d_pkey.p);
@@ -570,7 +623,57 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     uint32_t *big_count = c->m_cursor() + 3; // kBigBuckets counters
     const uint32_t bucket_capacity = c->cap_pts / kCtaComponentMin + 1u;
     bool huge_launched = false;
-    if (c->replay_version >= 2)
+    if (c->replay_version >= 3 && max_m < (1u << kV3PosBits))
+    {
+        // third generation (replay_cta3.cuh): live-candidate bitmaps by cell order in shared memory. Frames whose two
+        // bitmaps do not fit beside two other CTAs go to a 1-CTA-per-SM launch, frames beyond that to the first generation.
+        // (227 KB of dynamic shared memory per CTA on sm_100a)
+        const uint32_t normal_pts = 131072u, huge_pts = static_cast<uint32_t>((227u * 1024u - sizeof(Cta3Smem)) / 8u / 32u * 32u) * 32u;
+        const uint32_t normal_words = (std::min(max_m, normal_pts) + 31u) >> 5, huge_words = (std::min(max_m, huge_pts) + 31u) >> 5;
+        const size_t smem_normal = sizeof(Cta3Smem) + 8u * normal_words, smem_huge = sizeof(Cta3Smem) + 8u * huge_words;
+        if (!c->replay3_attr_done)
+        {
+            LB_CUDA(c, cudaFuncSetAttribute(replay_cta3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(sizeof(Cta3Smem) + 8u * (normal_pts >> 5))));
+            LB_CUDA(c, cudaFuncSetAttribute(replay_cta3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(sizeof(Cta3Smem) + 8u * (huge_pts >> 5))));
+            c->replay3_attr_done = true;
+        }
+        replay_init3_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, c->d_ipts.p);
+        replay_biglist3_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->clu.cta_min_members, normal_pts, huge_pts,
+                                                  c->d_biglist.p, bucket_capacity, big_count, c->m_cursor() + 8,
+                                                  c->m_cursor() + 10);
+        c->launches += 2;
+        LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
+        LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
+        replay_cta3_kernel<3><<<c->sm_count * 3u, kCtaThreads, smem_normal, c->stream_big>>>(
+            c->d_ipts.p, c->d_state.p /* cell_of */, c->d_nb27.p, c->d_cinfo.p, bv, c->clu, member_root, member_idx,
+            c->d_member_pos.p, c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p,
+            bucket_capacity, big_count, kBigBuckets, c->m_cursor() + 2, normal_words, c->d_job_stats.p);
+        ++c->launches;
+        if (max_m > normal_pts)
+        {
+            LB_CUDA(c, cudaStreamWaitEvent(c->stream_huge, c->ev_fork, 0));
+            replay_cta3_kernel<1><<<c->sm_count, kCtaThreads, smem_huge, c->stream_huge>>>(
+                c->d_ipts.p, c->d_state.p, c->d_nb27.p, c->d_cinfo.p, bv, c->clu, member_root, member_idx, c->d_member_pos.p,
+                c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
+                c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), bucket_capacity, c->m_cursor() + 8, 1u,
+                c->m_cursor() + 7, huge_words, nullptr);
+            ++c->launches;
+            if (max_m > huge_pts)
+            {
+                replay_cta_kernel<3><<<c->sm_count * 3u, kCtaThreads, 0, c->stream_huge>>>(
+                    c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
+                    c->d_pkey.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
+                    c->d_biglist.p + 5u * static_cast<size_t>(bucket_capacity), bucket_capacity, c->m_cursor() + 10,
+                    c->m_cursor() + 9, nullptr);
+                ++c->launches;
+            }
+            LB_CUDA(c, cudaEventRecord(c->ev_join2, c->stream_huge));
+            huge_launched = true;
+        }
+    }
+    else if (c->replay_version >= 2)
     {
         // second generation (replay_cta2.cuh): component state in shared memory, immutable point records. Components
         // beyond the normal bitmap go to a 1-CTA-per-SM launch with a large bitmap, beyond that to the first generation.
@@ -653,6 +756,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join, 0));
     if (huge_launched)
         LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join2, 0));
+    }
     mark(c, 8);
     {
         const uint32_t tiles = grid_x(max_m, kLabelTile, 0xFFFFu);
@@ -828,7 +932,9 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
     if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
-        c->replay_version = std::atoi(e) == 1 ? 1 : 2;
+        c->replay_version = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? std::atoi(e) : 4;
+    if (const char *e = std::getenv("LIDAR_B200_REPLAY4_CTAS_PER_SM"))
+        c->replay4_ctas_per_sm = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? static_cast<uint32_t>(std::atoi(e)) : 3u;
     lidar_b200_seg_cfg sc;
     lidar_b200_clu_cfg cc;
     lidar_b200_seg_cfg_default(&sc);
@@ -900,7 +1006,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p, c->d_nb27.p, c->d_complist.p, c->d_frame_meta.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);

@@ -325,7 +325,7 @@ constexpr uint32_t kNoCell = 0xFFFFFFFFu;
 __global__ void __launch_bounds__(256)
 cc_nbr_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const uint4 *__restrict__ cells,
               const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ cell_of, uint32_t *__restrict__ nbr,
-              uint2 *__restrict__ cinfo)
+              uint2 *__restrict__ cinfo, uint32_t *__restrict__ nb27 /* packed copy for the replay: first pos | count << 20 */)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
@@ -364,6 +364,8 @@ cc_nbr_kernel(const float4 *__restrict__ cpts, BatchView bv, TableView tv, const
                 uint32_t nstart, ncount;
                 cell_lookup(tab, mask, key, &nstart, &ncount);
                 nbr[(static_cast<size_t>(off) + cid) * 27u + lane] = ncount ? nstart : kNoCell;
+                nb27[(static_cast<size_t>(off) + cid) * 27u + lane] =
+                    ncount ? (nstart | ((ncount < 4095u ? ncount : 4095u) << 20)) : 0u;
             }
             if (lane == 0)
                 cinfo[off + cid] = make_uint2(own.w, kNoCell);

@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "kd_select.h"
 
+#include <cstdlib>
+
 namespace lb
 {
 
@@ -42,21 +44,23 @@ template <int NT> struct KdCoopSmem
     uint32_t K, min_unswapped_ge, min_swapped_le;
 };
 
-template <int NT> LB_D void kd_block_sync()
+// barrier of a group of NT threads: a warp, or NT/32 whole warps meeting at the named barrier `bar_id` (0 = the
+// barrier __syncthreads() uses: right when the group is the whole CTA)
+template <int NT> LB_D void kd_block_sync(uint32_t bar_id)
 {
     if (NT > 32)
-        __syncthreads();
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
     else
         __syncwarp();
 }
 
-// std::nth_element(nodes+first, nodes+nth, nodes+last) by a CTA of NT threads.
+// std::nth_element(nodes+first, nodes+nth, nodes+last) by a group of NT threads (`tid` = thread number inside the
+// group, `bar_id` = the group's named barrier). nodes / gepos / lepos may live in global or in shared memory.
 template <int NT>
 LB_D void kd_coop_nth_element(float4 *nodes, uint32_t first, uint32_t nth, uint32_t last, int axis, uint32_t *gepos,
-                              uint32_t *lepos, KdCoopSmem<NT> &sm)
+                              uint32_t *lepos, KdCoopSmem<NT> &sm, uint32_t tid = threadIdx.x, uint32_t bar_id = 0u)
 {
     constexpr uint32_t NW = NT / 32;
-    const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31u;
     if (first == last || nth == last)
@@ -74,7 +78,7 @@ LB_D void kd_coop_nth_element(float4 *nodes, uint32_t first, uint32_t nth, uint3
             sm.min_unswapped_ge = 0xFFFFFFFFu;
             sm.min_swapped_le = 0xFFFFFFFFu;
         }
-        kd_block_sync<NT>();
+        kd_block_sync<NT>(bar_id);
         const float kp = kd_key(nodes[first], axis);
         const uint32_t rb = first + 1u;
         const uint32_t r = last - rb;
@@ -104,7 +108,7 @@ LB_D void kd_coop_nth_element(float4 *nodes, uint32_t first, uint32_t nth, uint3
             sm.ge_w[warp] = ge_cnt;
             sm.le_w[warp] = le_cnt;
         }
-        kd_block_sync<NT>();
+        kd_block_sync<NT>(bar_id);
         uint32_t ge_before = 0u, le_after = 0u;
         for (uint32_t v = 0; v < NW; ++v)
         {
@@ -162,7 +166,7 @@ LB_D void kd_coop_nth_element(float4 *nodes, uint32_t first, uint32_t nth, uint3
             atomicMin(&sm.min_swapped_le, my_min_swapped_le);
         }
         __threadfence_block();
-        kd_block_sync<NT>();
+        kd_block_sync<NT>(bar_id);
         const uint32_t K = sm.K;
         for (uint32_t k = tid; k < K; k += NT)
             kd_swap(nodes, gepos[rb + k], lepos[rb + k]);
@@ -172,12 +176,12 @@ LB_D void kd_coop_nth_element(float4 *nodes, uint32_t first, uint32_t nth, uint3
         else
             last = cut;
         __threadfence_block();
-        kd_block_sync<NT>();
+        kd_block_sync<NT>(bar_id);
     }
     if (tid == 0)
         kd_introselect_from(nodes, first, nth, last, depth_limit, axis);
     __threadfence_block();
-    kd_block_sync<NT>();
+    kd_block_sync<NT>(bar_id);
 }
 
 // One CTA of NT threads per tree node of depth `depth`. grid = (2^depth, frames).
@@ -244,6 +248,115 @@ kd_subtree_kernel(float4 *__restrict__ nodes, BatchView bv, uint32_t depth)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The bottom of the tree in SHARED memory: one CTA of 256 threads takes the tree node of depth `depth` whose range
+// holds at most kKdFusedMax nodes, loads the range once and re-enacts EVERY remaining level there - the same
+// cooperative introselect rounds, run by 256 / 128 / 64 / 32 threads per node as the nodes halve (named barriers per
+// group), then one warp per node, then one thread per subtree of at most kKdSubtreeMax nodes - and writes the final
+// permutation back. The level-synchronous version paid a launch, a drain and several L2 round trips per level and
+// per introselect round for ranges that fit a fraction of one SM's shared memory.
+constexpr uint32_t kKdFusedMax = 2048u;
+constexpr int kKdFusedThreads = 256;
+
+struct KdFusedSmem
+{
+    float4 nodes[kKdFusedMax];
+    uint32_t gepos[kKdFusedMax];
+    uint32_t lepos[kKdFusedMax];
+    KdCoopSmem<32> grp[kKdFusedThreads / 32]; // per-group scratch (the layout does not depend on NT)
+};
+
+template <int NT>
+LB_D void kd_fused_level(KdFusedSmem &sm, uint32_t len, uint32_t level, int axis, uint32_t n_ranges)
+{
+    constexpr uint32_t kGroups = kKdFusedThreads / NT;
+    const uint32_t g = threadIdx.x / NT, gtid = threadIdx.x % NT;
+    for (uint32_t r = g; r < n_ranges; r += kGroups)
+    {
+        uint32_t b, e;
+        if (!kd_range_at(len, level, r, &b, &e) || e - b < 2u)
+            continue; // (uniform for the whole group)
+        kd_coop_nth_element<NT>(sm.nodes, b, b + (e - b) / 2u, e, axis, sm.gepos, sm.lepos,
+                                reinterpret_cast<KdCoopSmem<NT> &>(sm.grp[g]), gtid, 1u + g);
+    }
+}
+
+__global__ void __launch_bounds__(kKdFusedThreads)
+kd_fused_kernel(float4 *__restrict__ nodes, BatchView bv, uint32_t depth)
+{
+    extern __shared__ __align__(16) unsigned char kd_fused_raw[];
+    KdFusedSmem &sm = *reinterpret_cast<KdFusedSmem *>(kd_fused_raw);
+    const uint32_t f = blockIdx.y;
+    const uint32_t m = bv.cnt[f];
+    const uint32_t off = bv.off[f];
+    uint32_t b0, e0;
+    if (!kd_range_at(m, depth, blockIdx.x, &b0, &e0))
+        return;
+    const uint32_t len = e0 - b0; // <= kKdFusedMax by the host's level schedule
+    if (len > kKdFusedMax)
+        return;
+    float4 *a = nodes + off + b0;
+    for (uint32_t i = threadIdx.x; i < len; i += kKdFusedThreads)
+        sm.nodes[i] = a[i];
+    __syncthreads();
+    uint32_t level = 0u;
+    for (;; ++level)
+    {
+        const uint32_t n_ranges = 1u << level;
+        if (((len + n_ranges - 1u) >> level) <= kKdSubtreeMax)
+            break;
+        const int axis = static_cast<int>((depth + level) % 3u);
+        if (level == 0u)
+            kd_fused_level<256>(sm, len, level, axis, n_ranges);
+        else if (level == 1u)
+            kd_fused_level<128>(sm, len, level, axis, n_ranges);
+        else if (level == 2u)
+            kd_fused_level<64>(sm, len, level, axis, n_ranges);
+        else
+            kd_fused_level<32>(sm, len, level, axis, n_ranges);
+        __syncthreads();
+    }
+    // one thread per remaining subtree (ranges of at most kKdSubtreeMax nodes), sequential transcription in shared memory
+    for (uint32_t path = threadIdx.x; path < (1u << level); path += kKdFusedThreads)
+    {
+        uint32_t b, e;
+        if (!kd_range_at(len, level, path, &b, &e))
+            continue;
+        uint32_t sb[24], se[24], sd[24];
+        int top = 1;
+        sb[0] = b;
+        se[0] = e;
+        sd[0] = depth + level;
+        while (top > 0)
+        {
+            --top;
+            const uint32_t rb = sb[top], re = se[top], rd = sd[top];
+            if (rb >= re)
+                continue;
+            const uint32_t mid = rb + (re - rb) / 2u;
+            if (re - rb > 1u)
+                kd_nth_element(sm.nodes, rb, mid, re, static_cast<int>(rd % 3u));
+            if (mid > rb && top < 23)
+            {
+                sb[top] = rb;
+                se[top] = mid;
+                sd[top] = rd + 1u;
+                ++top;
+            }
+            if (mid + 1u < re && top < 23)
+            {
+                sb[top] = mid + 1u;
+                se[top] = re;
+                sd[top] = rd + 1u;
+                ++top;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < len; i += kKdFusedThreads)
+        a[i] = sm.nodes[i];
+}
+
 // rank_of_point[index] = pre-order rank of the node holding that point
 __global__ void __launch_bounds__(256)
 kd_rank_kernel(const float4 *__restrict__ nodes, BatchView bv, uint32_t *__restrict__ rank_of_point)
@@ -270,7 +383,13 @@ inline int kd_build_launch(cudaStream_t stream, const float4 *pts, BatchView bv,
     ++launches;
     uint32_t depth = 0u;
     // size of the largest range at `depth` is at most ceil(max_m / 2^depth)
-    while (((max_m + (1u << depth) - 1u) >> depth) > kKdSubtreeMax)
+    // The fused bottom levels shorten the dependent chain of ONE frame (fewer launches and drains: the latency path);
+    // in a large batch the level-synchronous kernels fill the machine anyway and the long-lived 56 KB CTAs of the
+    // fused kernel only take SMs away from the union-find running beside them (measured: union_find 3.2 -> 5.9 ms per
+    // 154 frames). LIDAR_B200_KD_FUSED=0/1 forces either.
+    static const int fused_env = std::getenv("LIDAR_B200_KD_FUSED") ? std::atoi(std::getenv("LIDAR_B200_KD_FUSED")) : -1;
+    const bool fused = fused_env < 0 ? bv.frames <= 4u : fused_env != 0;
+    while (((max_m + (1u << depth) - 1u) >> depth) > (fused ? kKdFusedMax : kKdSubtreeMax))
     {
         const uint32_t range = (max_m + (1u << depth) - 1u) >> depth;
         const dim3 grid(1u << depth, bv.frames);
@@ -283,6 +402,18 @@ inline int kd_build_launch(cudaStream_t stream, const float4 *pts, BatchView bv,
         ++launches;
         ++depth;
     }
+    if (fused)
+    {
+        static bool attr_done = false; // (a per-device function attribute; contexts of one process share the device)
+        if (!attr_done)
+        {
+            cudaFuncSetAttribute(kd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(KdFusedSmem)));
+            attr_done = true;
+        }
+        kd_fused_kernel<<<dim3(1u << depth, bv.frames), kKdFusedThreads, sizeof(KdFusedSmem), stream>>>(nodes, bv, depth);
+        ++launches;
+    }
+    else
     {
         const uint32_t paths = 1u << depth;
         kd_subtree_kernel<<<dim3((paths + 127u) / 128u, bv.frames), 128, 0, stream>>>(nodes, bv, depth);

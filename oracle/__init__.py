@@ -50,8 +50,10 @@ def build(force: bool = False) -> None:
     """Compile liboracle.so, and oracle/_ref when /root/reference is present (else keep prebuilt)."""
     lib = HERE / "liboracle.so"
     lib_deps = [HERE / "oracle.cpp", HERE / "hull_oracle.cpp", HERE / "oracle.h", HERE / "Makefile"]
-    ref = HERE / "_ref" / "libref_hull.so"  # the last target of `make ref`
-    ref_deps = lib_deps + [HERE / "ref_wrap.cpp", HERE / "ref_hull_wrap.cpp"]
+    ref = HERE / "_ref" / "libref_node.so"  # the last target of `make ref`
+    ref_deps = lib_deps + [HERE / "ref_wrap.cpp", HERE / "ref_hull_wrap.cpp", HERE / "ref_seg_wrap.cpp",
+                           HERE / "eigen_shim" / "Eigen" / "Dense", HERE / "ref_node_wrap.cpp",
+                           HERE / "ros_shim" / "rclcpp" / "rclcpp.hpp"]
     need = force or not lib.exists() or lib.stat().st_mtime < max(s.stat().st_mtime for s in lib_deps)
     have_reference = Path("/root/reference/src/clustering.cpp").exists()
     if have_reference and (force or not ref.exists() or ref.stat().st_mtime < max(s.stat().st_mtime for s in ref_deps)):
@@ -127,6 +129,103 @@ def segment(points, cfg: SegCfg | None = None, tie_mode: int = 1, labels_in=None
         raise ValueError("oracle_segment: bad configuration")
     return dict(labels=labels, ground_idx=g[: ng.value].copy(), obstacle_idx=o[: no.value].copy(),
                 planes=planes[:P, :it], status=status[:P])
+
+
+_REF_SEG = None
+
+
+def ref_segment_available() -> bool:
+    return (HERE / "_ref" / "libref_segment.so").exists()
+
+
+def ref_seg() -> C.CDLL:
+    """The UNMODIFIED reference Segmenter (src/segmentation.cpp) compiled against the PCL and Eigen stand-ins."""
+    global _REF_SEG
+    if _REF_SEG is None:
+        build()
+        _REF_SEG = C.CDLL(str(HERE / "_ref" / "libref_segment.so"))
+    return _REF_SEG
+
+
+def ref_segment(points, cfg: SegCfg | None = None, labels_in=None):
+    """lidar_processing::Segmenter::segment of the reference itself. Returns dict(labels, ground_idx, obstacle_idx)."""
+    pts = _f32(points)
+    n = pts.shape[0]
+    cfg = cfg or default_seg_cfg()
+    labels = np.zeros(n, np.uint32) if labels_in is None else np.ascontiguousarray(labels_in, np.uint32).copy()
+    g = np.zeros(max(n, 1), np.uint32)
+    o = np.zeros(max(n, 1), np.uint32)
+    ng, no = C.c_uint32(0), C.c_uint32(0)
+    rc = ref_seg().ref_segment(_p(pts, C.c_float), C.c_uint32(n), C.c_uint32(pts.shape[1]), C.byref(cfg),
+                               _p(labels, C.c_uint32), _p(g, C.c_uint32), C.byref(ng), _p(o, C.c_uint32), C.byref(no))
+    if rc != 0:
+        raise ValueError(f"ref_segment: {rc}")
+    return dict(labels=labels, ground_idx=g[: ng.value].copy(), obstacle_idx=o[: no.value].copy())
+
+
+def ref_segment_pair(points_a, points_b, cfg: SegCfg | None = None) -> np.ndarray:
+    """Two frames through one long-lived reference Segmenter and one labels vector (processor.cpp:129-131,150)."""
+    a, b = _f32(points_a), _f32(points_b)
+    assert a.shape[1] == b.shape[1]
+    cfg = cfg or default_seg_cfg()
+    out = np.zeros(max(a.shape[0], b.shape[0], 1), np.uint32)
+    n = ref_seg().ref_segment_pair(_p(a, C.c_float), C.c_uint32(a.shape[0]), _p(b, C.c_float), C.c_uint32(b.shape[0]),
+                                   C.c_uint32(a.shape[1]), C.byref(cfg), _p(out, C.c_uint32))
+    if n < 0:
+        raise ValueError(f"ref_segment_pair: {n}")
+    return out[:n].copy()
+
+
+_REF_NODE = None
+
+
+def ref_node_available() -> bool:
+    return (HERE / "_ref" / "libref_node.so").exists()
+
+
+def ref_node_run(points, rand_seed: int = 1):
+    """One frame through the UNMODIFIED reference node (src/processor.cpp: Processor::process) built against the ROS 2 /
+    PCL / Eigen stand-ins. Returns what it publishes: dict(ground, obstacle (n, 32) uint8 pcl::PointXYZRGBL records or
+    None, clustered (n, 32) uint8 pcl::PointXYZRGB records or None, marker_ids, markers = list of (k, 3) float64)."""
+    global _REF_NODE
+    if _REF_NODE is None:
+        build()
+        _REF_NODE = C.CDLL(str(HERE / "_ref" / "libref_node.so"))
+    pts = _f32(points)
+    rc = _REF_NODE.ref_node_run(_p(pts, C.c_float), C.c_uint32(pts.shape[0]), C.c_uint32(pts.shape[1]), C.c_uint(rand_seed))
+    if rc != 0:
+        raise RuntimeError("the reference node reported an exception")
+    sizes = np.zeros(9, np.uint64)
+    _REF_NODE.ref_node_sizes(_p(sizes, C.c_uint64))
+    ground = np.zeros(int(sizes[0]), np.uint8)
+    obstacle = np.zeros(int(sizes[1]), np.uint8)
+    clustered = np.zeros(int(sizes[2]), np.uint8)
+    msz = np.zeros(max(int(sizes[3]), 1), np.uint32)
+    mid = np.zeros(max(int(sizes[3]), 1), np.int32)
+    mxyz = np.zeros((max(int(sizes[4]), 1), 3), np.float64)
+    _REF_NODE.ref_node_fetch(_p(ground, C.c_uint8), _p(obstacle, C.c_uint8), _p(clustered, C.c_uint8), _p(msz, C.c_uint32),
+                             _p(mid, C.c_int32), _p(mxyz, C.c_double))
+    topics = int(sizes[8])
+    assert all(int(sizes[k]) in (0, 32) for k in (5, 6, 7))  # point_step of every published cloud
+    markers, at = [], 0
+    for k in range(int(sizes[3])):
+        markers.append(mxyz[at:at + int(msz[k])].copy())
+        at += int(msz[k])
+    return dict(ground=ground.reshape(-1, 32) if topics & 1 else None, obstacle=obstacle.reshape(-1, 32) if topics & 2 else None,
+                clustered=clustered.reshape(-1, 32) if topics & 4 else None, marker_ids=mid[: int(sizes[3])].copy(),
+                markers=markers if topics & 8 else None)
+
+
+def libc_rand_colors(n_clusters: int, rand_seed: int = 1) -> np.ndarray:
+    """The colour words r << 16 | g << 8 | b the node draws with std::rand() % 256 after std::srand(rand_seed)
+    (reference src/conversions.cpp:48-50), from the same C library."""
+    libc = C.CDLL(None)
+    libc.srand(C.c_uint(rand_seed))
+    out = np.zeros(n_clusters, np.uint32)
+    for k in range(n_clusters):
+        r, g, b = libc.rand() % 256, libc.rand() % 256, libc.rand() % 256
+        out[k] = (r << 16) | (g << 8) | b
+    return out
 
 
 def jacobi_svd3(a):

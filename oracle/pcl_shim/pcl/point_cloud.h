@@ -49,6 +49,8 @@ template <typename PointT> class PointCloud
         height = 1U;
         return points.back();
     }
+    PointT &at(std::size_t i) { return points.at(i); }
+    const PointT &at(std::size_t i) const { return points.at(i); }
     PointT &operator[](std::size_t i) { return points[i]; }
     const PointT &operator[](std::size_t i) const { return points[i]; }
     iterator begin() noexcept { return points.begin(); }

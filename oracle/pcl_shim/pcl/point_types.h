@@ -35,14 +35,24 @@ struct alignas(16) PointXYZL
     PointXYZL(float x_, float y_, float z_, std::uint32_t l_ = 0U) : x(x_), y(y_), z(z_), label(l_) {}
 };
 
+// b, g, r, a share their 4 bytes with the packed float `rgb` (PCL_ADD_RGB); the reference takes offsetof(..., rgb)
+// (src/conversions.cpp:96-99).
 struct alignas(16) PointXYZRGB
 {
     float x{0.0F}, y{0.0F}, z{0.0F}, _w{1.0F};
-    std::uint8_t b{0}, g{0}, r{0}, a{255};
+    union
+    {
+        struct
+        {
+            std::uint8_t b, g, r, a;
+        };
+        float rgb;
+        std::uint32_t rgba;
+    };
     std::uint32_t _pad[3]{0U, 0U, 0U};
-    PointXYZRGB() = default;
+    PointXYZRGB() : b(0), g(0), r(0), a(255) {}
     PointXYZRGB(float x_, float y_, float z_, std::uint8_t r_ = 0, std::uint8_t g_ = 0, std::uint8_t b_ = 0)
-        : x(x_), y(y_), z(z_), b(b_), g(g_), r(r_)
+        : x(x_), y(y_), z(z_), b(b_), g(g_), r(r_), a(255)
     {
     }
 };
@@ -50,13 +60,21 @@ struct alignas(16) PointXYZRGB
 struct alignas(16) PointXYZRGBL
 {
     float x{0.0F}, y{0.0F}, z{0.0F}, _w{1.0F};
-    std::uint8_t b{0}, g{0}, r{0}, a{255};
+    union
+    {
+        struct
+        {
+            std::uint8_t b, g, r, a;
+        };
+        float rgb;
+        std::uint32_t rgba;
+    };
     std::uint32_t label{0U};
     std::uint32_t _pad[2]{0U, 0U};
-    PointXYZRGBL() = default;
+    PointXYZRGBL() : b(0), g(0), r(0), a(255) {}
     PointXYZRGBL(float x_, float y_, float z_, std::uint8_t r_ = 0, std::uint8_t g_ = 0, std::uint8_t b_ = 0,
                  std::uint32_t l_ = 0U)
-        : x(x_), y(y_), z(z_), b(b_), g(g_), r(r_), label(l_)
+        : x(x_), y(y_), z(z_), b(b_), g(g_), r(r_), a(255), label(l_)
     {
     }
 };

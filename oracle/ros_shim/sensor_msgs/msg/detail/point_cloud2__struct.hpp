@@ -1,0 +1,2 @@
+#pragma once
+#include <sensor_msgs/msg/point_cloud2.hpp>

@@ -11,7 +11,9 @@ Outputs (committed):
         clustering    = UNMODIFIED reference Clusterer (oracle/_ref)  on that obstacle cloud
     and, for every frame, the result of pinning the oracle against the reference build:
         oracle_cluster == ref_cluster, transcribed k-d order == reference k-d order,
-        device-formulation model == ref_cluster.
+        device-formulation model == ref_cluster,
+        oracle_segment(tie_mode 0) == the unmodified reference src/segmentation.cpp compiled against the PCL / Eigen
+        stand-ins (oracle/eigen_shim: pins everything in that file except Eigen's own floating-point order).
     Every frame row also carries
         planes_f64 / n_ground_f64  the planes of the independent float64 model (tests/golden/f64_model.py:
                                    numpy eigh) per partition x iteration - the pin at the Eigen boundary
@@ -80,12 +82,19 @@ def f64_row(pts, seg):
                    max_normal_dev=dn, max_d_dev_m=dd)
 
 
+def segment_equals_reference_source(pts) -> bool:
+    """Restated Segmenter (std::sort tie order, tie_mode 0) == the UNMODIFIED reference src/segmentation.cpp compiled
+    against the PCL / Eigen stand-ins (oracle/_ref/libref_segment.so): labels and the order of both output clouds."""
+    a, b = O.segment(pts, tie_mode=0), O.ref_segment(pts)
+    return all(np.array_equal(a[k], b[k]) for k in ("labels", "ground_idx", "obstacle_idx"))
+
+
 def main():
     paths = O.reference_frame_paths()
     assert len(paths) == 154, "reference data not found"
     pack([paths[0], paths[77], paths[153]], HERE / "frames_0_77_153.xz")
     rows = []
-    pinned = dict(oracle_cluster_eq_ref=0, kd_transcription_eq_ref=0, model_eq_ref=0, frames=0)
+    pinned = dict(oracle_cluster_eq_ref=0, kd_transcription_eq_ref=0, model_eq_ref=0, frames=0, oracle_segment_eq_ref_source=0)
     for i, p in enumerate(paths):
         pts = O.read_pcd(p)
         seg = O.segment(pts, tie_mode=1)
@@ -101,6 +110,7 @@ def main():
         pinned["oracle_cluster_eq_ref"] += int(np.array_equal(ref_lab, ora_lab))
         pinned["kd_transcription_eq_ref"] += int(np.array_equal(ref_order, tx_order))
         pinned["model_eq_ref"] += int(np.array_equal(ref_lab, model_lab))
+        pinned["oracle_segment_eq_ref_source"] += int(segment_equals_reference_source(pts))
         m64, f64_info = f64_row(pts, seg)
         rows.append(dict(
             planes_f64=[[[float(v) for v in m64["planes"][s_, it]] for it in range(m64["planes"].shape[1])]

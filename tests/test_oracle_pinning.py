@@ -344,3 +344,108 @@ def test_tie_order_gap_against_the_reference_as_compiled_here(golden_frames, fin
     row = tie_order_row(pts, seg, O.ref_cluster(pts[seg["obstacle_idx"]]))
     assert row == rows[NAMES[0]]["tie_order"]
     assert row["n_clusters_introsort"] == 569 and row["n_clusters_stable"] == 572 and row["obstacle_positions_differ"] == 17623
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The restated Segmenter against the UNMODIFIED reference src/segmentation.cpp, compiled where it lies against the PCL
+# and Eigen stand-ins (oracle/_ref/libref_segment.so, oracle/eigen_shim/Eigen/Dense). This pins rows S1-S4 of SURVEY
+# §8(a) — sorts, equal-count partitions and the dropped tail, z-cut / LPR mean / seed cut, iteration and failure paths,
+# signed classification, order of the output clouds, stale labels — against the reference's own code. The arithmetic
+# INSIDE the Eigen calls is the stand-in's (= the oracle's) restatement: Eigen's floating-point order stays unpinned.
+needs_ref_seg = pytest.mark.skipif(not O.ref_segment_available(), reason="oracle/_ref/libref_segment.so not built")
+
+
+def _same_segmentation(pts, cfg=None, labels_in=None):
+    a = O.segment(pts, cfg, tie_mode=0, labels_in=labels_in)
+    b = O.ref_segment(pts, cfg, labels_in=labels_in)
+    for k in ("labels", "ground_idx", "obstacle_idx"):
+        assert np.array_equal(a[k], b[k]), k
+    return a
+
+
+@needs_ref_seg
+def test_restated_segmenter_equals_reference_source_on_golden_frames(golden_frames, fingerprints):
+    assert fingerprints["pinned"]["oracle_segment_eq_ref_source"] == 154  # all data frames (tests/golden/make_golden.py)
+    for pts in golden_frames:
+        seg = _same_segmentation(pts)
+        assert seg["ground_idx"].size + seg["obstacle_idx"].size == pts.shape[0] - (pts.shape[0] & 1)  # dropped tail
+
+
+@needs_ref_seg
+def test_restated_segmenter_equals_reference_source_all_154_frames():
+    from pathlib import Path
+
+    cache = Path(__file__).resolve().parent.parent / "data_cache" / "frames_mm.xz"
+    if not cache.exists():
+        pytest.skip("data_cache/frames_mm.xz not built (needs /root/reference/data)")
+    from tools.pack_reference_frames import unpack
+
+    frames = unpack(cache)
+    assert len(frames) == 154
+    for pts in frames[::7]:  # 22 frames here; all 154 are counted in fingerprints.json by the generating script
+        _same_segmentation(pts)
+
+
+@needs_ref_seg
+@pytest.mark.parametrize("kw", [
+    dict(), dict(number_of_planar_partitions=1), dict(number_of_planar_partitions=3),
+    dict(number_of_planar_partitions=7, number_of_iterations=5), dict(number_of_iterations=1),
+    dict(number_of_iterations=0), dict(number_of_lower_point_representatives=100),
+    dict(number_of_lower_point_representatives=1), dict(number_of_lower_point_representatives=20000),
+    dict(sensor_height_m=1.0, initial_seed_threshold=0.2, orthogonal_distance_threshold=0.1),
+    dict(sensor_height_m=3.0, initial_seed_threshold=1.5, orthogonal_distance_threshold=0.6),
+])
+def test_restated_segmenter_equals_reference_source_configurations(kw):
+    cfg = O.default_seg_cfg(**kw)
+    for seed in (3, 4):
+        pts = make_frame(seed, beams=32, azimuth_steps=384)
+        _same_segmentation(pts, cfg)
+        _same_segmentation(pts[: pts.shape[0] - 3], cfg)
+
+
+@needs_ref_seg
+def test_restated_segmenter_equals_reference_source_edge_cases():
+    cfg = O.default_seg_cfg()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 3, 4, 5, 6, 7, 11):  # "<3 points" partitions stay UNKNOWN (segmentation.cpp:226-230)
+        pts = np.zeros((n, 4), np.float32)
+        pts[:, :3] = rng.normal(0, 1, (n, 3)).astype(np.float32) + np.float32([0, 0, -1.7])
+        _same_segmentation(pts, cfg)
+    flat = np.zeros((100, 4), np.float32)  # no point above the seed cut: "Failed ground segmentation", all OBSTACLE
+    flat[:, 0] = np.arange(100)
+    flat[:, 2] = -1.73
+    assert np.all(_same_segmentation(flat, cfg)["labels"] == O.OBSTACLE)
+    deep = flat.copy()  # every point below -1.5 * sensor height: nothing is dropped by the z-min cut
+    deep[:, 2] = -5.0 - 0.001 * np.arange(100, dtype=np.float32)
+    _same_segmentation(deep, cfg)
+    ties = make_frame(9, beams=16, azimuth_steps=256)  # heavy x / z ties: the introsort permutation is in play
+    ties[:, 0] = np.round(ties[:, 0])
+    ties[:, 2] = np.round(ties[:, 2] * 10) / 10
+    _same_segmentation(ties, cfg)
+    signed = make_frame(10, beams=16, azimuth_steps=256)  # -0.0 compares equal to +0.0 in the reference's comparators
+    signed[::5, 0] = -0.0
+    signed[1::5, 0] = 0.0
+    _same_segmentation(signed, cfg)
+    f = make_frame(2, beams=16, azimuth_steps=256)
+    odd = f[: f.shape[0] - 1 + (f.shape[0] & 1)]
+    res = _same_segmentation(odd, cfg, labels_in=np.full(odd.shape[0], 7, np.uint32))
+    assert (res["labels"] == 7).sum() == 1  # the dropped point keeps the caller's stale label (segmentation.cpp:315)
+
+
+@needs_ref_seg
+def test_stale_labels_through_one_long_lived_reference_segmenter():
+    """processor.cpp:129-131,150: one Segmenter and one labels vector for the whole stream. A shorter second frame
+    shrinks the vector; a longer one appends UNKNOWN; the point dropped by the equal-count split keeps the label the
+    same slot had in the previous frame."""
+    a = make_frame(11, beams=16, azimuth_steps=256)
+    b = make_frame(12, beams=16, azimuth_steps=256)
+    a = a[: a.shape[0] - 1 + (a.shape[0] & 1)]  # odd sizes: one dropped point each
+    b = b[: b.shape[0] - 1 + (b.shape[0] & 1)]
+    for first, second in ((a, b), (b, a), (a[:1001], b), (a, b[:1001])):
+        got = O.ref_segment_pair(first, second)
+        prev = O.segment(first, tie_mode=0)["labels"]
+        carry = np.zeros(second.shape[0], np.uint32)  # labels.resize(n, UNKNOWN) on the vector left by the first call
+        k = min(prev.size, carry.size)
+        carry[:k] = prev[:k]
+        want = O.segment(second, tie_mode=0, labels_in=carry)["labels"]
+        assert np.array_equal(got, want)
