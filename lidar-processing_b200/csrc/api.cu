@@ -16,6 +16,7 @@
 #include "replay_cta2.cuh"
 #include "replay_cta3.cuh"
 #include "replay_frame.cuh"
+#include "replay_gen.cuh"
 #include "segment.cuh"
 
 #include <atomic>
@@ -90,10 +91,13 @@ struct lidar_b200_ctx
     DevBuf<float4> d_ipts, d_mpts; // immutable records of the second-generation CTA replay (replay_cta2.cuh)
     DevBuf<uint32_t> d_rankpos;
     DevBuf<unsigned long long> d_mkey;
-    int replay_version{4};         // LIDAR_B200_REPLAY_V: 1 = first-generation CTA replay (state in global memory),
+    int replay_version{5};         // LIDAR_B200_REPLAY_V: 1 = first-generation CTA replay (state in global memory),
                                    // 2 = second (state bitmap by member), 3 = third (live-candidate bitmaps by cell order),
-                                   // 4 = warp per component, frame bitmaps shared by the CTA (replay_frame.cuh)
-    bool replay2_attr_done{false}, replay3_attr_done{false}, replay4_attr_done{false};
+                                   // 4 = warp per component, frame bitmaps shared by the CTA (replay_frame.cuh),
+                                   // 5 = window-synchronous CTA replay (replay_gen.cuh), the default
+    bool replay2_attr_done{false}, replay3_attr_done{false}, replay4_attr_done{false}, replay5_attr_done{false};
+    bool replay5_live{false};      // LIDAR_B200_REPLAY5_LIVE=1: per-cell live counters skip the cells behind the frontier
+    uint32_t replay5_ctas_per_sm{3}; // LIDAR_B200_REPLAY5_CTAS_PER_SM
     uint32_t replay4_ctas_per_sm{3}; // LIDAR_B200_REPLAY4_CTAS_PER_SM
     DevBuf<uint32_t> d_complist;   // fourth generation: per-frame component lists (first member slot), longest first
     DevBuf<uint32_t> d_frame_meta; // ... and per-frame counters (kV4MetaStride words each)
@@ -571,7 +575,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_kd, 0)); // k-d order built on the second stream meanwhile
 
     mark(c, 7);
-    if (c->replay_version >= 4 && max_m <= kV4MaxPoints)
+    if (c->replay_version == 4 && max_m <= kV4MaxPoints)
     {
         // fourth generation (replay_frame.cuh): one warp per component, the CTA's warps share the frame's bitmaps
         const uint32_t words = (max_m + 31u) >> 5;
@@ -623,7 +627,93 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     uint32_t *big_count = c->m_cursor() + 3; // kBigBuckets counters
     const uint32_t bucket_capacity = c->cap_pts / kCtaComponentMin + 1u;
     bool huge_launched = false;
-    if (c->replay_version >= 3 && max_m < (1u << kV3PosBits))
+    if (c->replay_version >= 5 && max_m < (1u << kGenPosBits))
+    {
+        // fifth generation (replay_gen.cuh): window-synchronous replay, three state planes in shared memory. Components
+        // beyond the normal planes go to a 1-CTA-per-SM launch with large planes, beyond that to the first generation.
+        const uint32_t normal_words = 1024u; // 32 768 members
+        const uint32_t huge_words = static_cast<uint32_t>((227u * 1024u - sizeof(GenSmem)) / 12u) & ~31u;
+        const size_t smem_normal = sizeof(GenSmem) + 12u * normal_words, smem_huge = sizeof(GenSmem) + 12u * huge_words;
+        if (!c->replay5_attr_done)
+        {
+#define LB_GEN_ATTR(MINB, LIVE, BYTES)                                                                                \
+    LB_CUDA(c, cudaFuncSetAttribute(replay_gen_kernel<MINB, LIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(BYTES)))
+            LB_GEN_ATTR(2, false, smem_normal);
+            LB_GEN_ATTR(3, false, smem_normal);
+            LB_GEN_ATTR(4, false, smem_normal);
+            LB_GEN_ATTR(1, false, smem_huge);
+            LB_GEN_ATTR(2, true, smem_normal);
+            LB_GEN_ATTR(3, true, smem_normal);
+            LB_GEN_ATTR(4, true, smem_normal);
+            LB_GEN_ATTR(1, true, smem_huge);
+#undef LB_GEN_ATTR
+            c->replay5_attr_done = true;
+        }
+        uint32_t *mcell = reinterpret_cast<uint32_t *>(c->d_mkey.p), *clive = mcell + c->cap_pts;
+        replay_init5_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_state.p /* cell_of */,
+                                               c->d_cinfo.p, c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, mcell, clive);
+        replay_biglist2_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->clu.cta_min_members, 32u * normal_words,
+                                                  32u * huge_words, c->d_biglist.p, bucket_capacity, big_count,
+                                                  c->m_cursor() + 8, c->m_cursor() + 10);
+        c->launches += 2;
+        LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
+        LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
+        const uint32_t per_sm = std::max(2u, std::min(4u, c->replay5_ctas_per_sm));
+#define LB_GEN_ARGS(LIST, COUNT, NB, CURSOR, WORDS, STATS)                                                            \
+    c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, mcell, c->d_nb27.p, c->d_cinfo.p, clive, bv, c->clu, member_root, member_idx, \
+        c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, LIST, bucket_capacity, COUNT, NB,  \
+        CURSOR, WORDS, STATS
+#define LB_GEN_LAUNCH(MINB, LIVE)                                                                                      \
+    replay_gen_kernel<MINB, LIVE><<<c->sm_count * MINB, kCtaThreads, smem_normal, c->stream_big>>>(                    \
+        LB_GEN_ARGS(c->d_biglist.p, big_count, kBigBuckets, c->m_cursor() + 2, normal_words, c->d_job_stats.p))
+        if (c->replay5_live)
+        {
+            if (per_sm == 2u)
+                LB_GEN_LAUNCH(2, true);
+            else if (per_sm == 3u)
+                LB_GEN_LAUNCH(3, true);
+            else
+                LB_GEN_LAUNCH(4, true);
+        }
+        else
+        {
+            if (per_sm == 2u)
+                LB_GEN_LAUNCH(2, false);
+            else if (per_sm == 3u)
+                LB_GEN_LAUNCH(3, false);
+            else
+                LB_GEN_LAUNCH(4, false);
+        }
+#undef LB_GEN_LAUNCH
+        ++c->launches;
+        if (max_m > 32u * normal_words) // a component can only be that large in a frame that large
+        {
+            LB_CUDA(c, cudaStreamWaitEvent(c->stream_huge, c->ev_fork, 0));
+            if (c->replay5_live)
+                replay_gen_kernel<1, true><<<c->sm_count, kCtaThreads, smem_huge, c->stream_huge>>>(
+                    LB_GEN_ARGS(c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), c->m_cursor() + 8, 1u, c->m_cursor() + 7,
+                                huge_words, nullptr));
+            else
+                replay_gen_kernel<1, false><<<c->sm_count, kCtaThreads, smem_huge, c->stream_huge>>>(
+                    LB_GEN_ARGS(c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), c->m_cursor() + 8, 1u, c->m_cursor() + 7,
+                                huge_words, nullptr));
+            ++c->launches;
+            if (max_m > 32u * huge_words)
+            {
+                // first generation for what is left: its list is bucket 5, its counters sit at cursor[10..13] (11..13 stay 0)
+                replay_cta_kernel<3><<<c->sm_count * 3u, kCtaThreads, 0, c->stream_huge>>>(
+                    c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
+                    c->d_pkey.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
+                    c->d_biglist.p + 5u * static_cast<size_t>(bucket_capacity), bucket_capacity, c->m_cursor() + 10,
+                    c->m_cursor() + 9, nullptr);
+                ++c->launches;
+            }
+            LB_CUDA(c, cudaEventRecord(c->ev_join2, c->stream_huge));
+            huge_launched = true;
+        }
+#undef LB_GEN_ARGS
+    }
+    else if (c->replay_version >= 3 && c->replay_version <= 4 && max_m < (1u << kV3PosBits))
     {
         // third generation (replay_cta3.cuh): live-candidate bitmaps by cell order in shared memory. Frames whose two
         // bitmaps do not fit beside two other CTAs go to a 1-CTA-per-SM launch, frames beyond that to the first generation.
@@ -932,7 +1022,11 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
     if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
-        c->replay_version = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? std::atoi(e) : 4;
+        c->replay_version = std::atoi(e) >= 1 && std::atoi(e) <= 5 ? std::atoi(e) : 5;
+    if (const char *e = std::getenv("LIDAR_B200_REPLAY5_LIVE"))
+        c->replay5_live = std::atoi(e) != 0;
+    if (const char *e = std::getenv("LIDAR_B200_REPLAY5_CTAS_PER_SM"))
+        c->replay5_ctas_per_sm = static_cast<uint32_t>(std::max(2, std::min(4, std::atoi(e))));
     if (const char *e = std::getenv("LIDAR_B200_REPLAY4_CTAS_PER_SM"))
         c->replay4_ctas_per_sm = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? static_cast<uint32_t>(std::atoi(e)) : 3u;
     lidar_b200_seg_cfg sc;

@@ -22,6 +22,25 @@ for _ in range(3):
     ctx.batch_run()
     ctx.sync()
 st = ctx.last_replay_stats()
+if os.environ.get("LIDAR_B200_REPLAY_V", "5") == "5":  # window-synchronous replay (replay_gen.cuh)
+    print("stage ms", {k: round(v, 3) for k, v in ctx.last_stage_ms().items()})
+    kc = st[:, 2].astype(np.float64)
+    print(f"jobs {st.shape[0]}  sum kcycles {kc.sum():.0f}  max {kc.max():.0f}  mean {kc.mean():.1f}")
+    print(f"sum/444 CTAs = {kc.sum()/444:.0f} kcycles = {kc.sum()*1.024/444/1965:.3f} ms ; longest job = {kc.max()*1.024/1965:.3f} ms")
+    ph = np.stack([st[:, 6] & 0xFFFF, st[:, 6] >> 16, st[:, 7] & 0xFFFF, st[:, 7] >> 16], 1).astype(np.float64)
+    print("top jobs: [frame members kcycles windows expanded entries] kcyc[load settle candidates sort+commit]  cycles/window")
+    for j in np.argsort(-kc)[:12]:
+        r = st[j]
+        print("  ", r[:6].tolist(), ph[j].astype(int).tolist(), round(1024 * r[2] / max(1, r[3])))
+    wn = st[:, 3].astype(np.float64)
+    print(f"total windows {wn.sum():.0f}, mean cycles/window {1024*kc.sum()/wn.sum():.0f}; entries/window {st[:,5].sum()/wn.sum():.1f} "
+          f"expanded/window {st[:,4].sum()/wn.sum():.2f}; phase share load {ph[:,0].sum()/kc.sum():.2f} settle {ph[:,1].sum()/kc.sum():.2f} "
+          f"candidates {ph[:,2].sum()/kc.sum():.2f} sort+commit {ph[:,3].sum()/kc.sum():.2f}")
+    for lo, hi in ((256, 512), (512, 1024), (1024, 2048), (2048, 4096), (4096, 8192), (8192, 1 << 30)):
+        m = (st[:, 1] >= lo) & (st[:, 1] < hi)
+        if m.any():
+            print(f"members [{lo},{hi}): jobs {int(m.sum())}, kcycles {kc[m].sum():.0f} ({100*kc[m].sum()/kc.sum():.1f} %), cycles/member {1024*kc[m].sum()/st[m,1].sum():.0f}, cycles/window {1024*kc[m].sum()/wn[m].sum():.0f}")
+    sys.exit(0)
 v3 = os.environ.get("LIDAR_B200_REPLAY_V", "3") not in ("1", "2")
 cands = over = None
 if v3:  # third generation packs more into the 8 words (replay_cta3.cuh)
