@@ -570,11 +570,12 @@ def main():
     # ---- end to end through the host API ------------------------------------------------------
     # Headline: clouds and result arrays in page-locked host memory (lidar_b200_host_alloc), as a loader feeding the
     # library would keep them; the pageable variant (library stages through its own pinned buffers) is reported too.
-    pipe = pkg.FramePipeline(device=local_rank, depth=args.depth, chunk_frames=args.chunk)
+    pipe = pkg.FramePipeline(device=local_rank, depth=args.depth, chunk_frames=args.chunk, gpus_sharing_host=world)
     pinned_frames = pkg.pin_frames(frames)
     e2e_s, e2e_out, pipe_launches = measure_e2e(pkg, env, pipe, pinned_frames, args.steps, args.warmup, sampler)
     e2e_fps = world * nf * args.steps / e2e_s
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    fetch_mode = pipe.fetch_mode()
     e2e_same = all(np.array_equal(a["cluster_labels"], b["cluster_labels"]) and np.array_equal(a["seg_labels"], b["seg_labels"])
                    for a, b in zip(e2e_out, res))
     e2e_pageable_s, _, _ = measure_e2e(pkg, env, pipe, frames, args.steps, args.warmup, sampler)
@@ -658,6 +659,10 @@ def main():
                 "pageable_host_buffers_value": e2e_pageable_fps, "results_equal_resident_run": bool(e2e_same),
                 "gpu_launches_per_step": int(pipe_launches), "latency_ms_p50": latency["p50"], "latency_ms_p95": latency["p95"],
                 "host_affinity": numa,
+                "fetch_mode": fetch_mode,
+                "fetch_mode_what": "0 = copy engines, four result arrays at slot size; 4 = one kernel writes the used part "
+                                   "of every slot into the page-locked result arrays (from 3 GPUs sharing the host's DMA "
+                                   "path on: lidar_b200_pipe_set_host_sharing(world size)); LIDAR_B200_FETCH_MODE overrides",
                 "dropin_value": None if not dropin else dropin.get("frames_per_s"),
                 "dropin_p50_ms": None if not dropin else dropin.get("p50_ms"),
                 "dropin_what": "C++ Segmenter::segment + Clusterer::cluster (dropin/*.hpp) on pageable 32-byte pcl::PointXYZI "

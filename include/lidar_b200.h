@@ -226,6 +226,13 @@ extern "C"
                                uint32_t *n_clusters_out);
     int lidar_b200_pipe_drain(lidar_b200_pipe *pipe);
     uint64_t lidar_b200_pipe_launch_count(const lidar_b200_pipe *pipe);
+    /* Tells the pipe how many GPUs of this host run a pipe at the same time (the local world size). They share the host's
+     * DMA path: from 3 GPUs on the pipe fetches results with one kernel that writes the used part of every result slot into
+     * the caller's page-locked arrays (fewer bytes, mode 4) instead of slot-size copies by the copy engines (mode 0, the
+     * default and the faster one at 1-2 GPUs). LIDAR_B200_FETCH_MODE overrides. */
+    int lidar_b200_pipe_set_host_sharing(lidar_b200_pipe *pipe, uint32_t gpus_sharing_host);
+    /* Result fetch mode the pipe is using (0 or 4, see above). */
+    int lidar_b200_pipe_fetch_mode(const lidar_b200_pipe *pipe);
     const char *lidar_b200_pipe_last_error(const lidar_b200_pipe *pipe);
 
     /* diagnostics */

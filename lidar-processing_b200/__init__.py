@@ -127,7 +127,8 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_set_profiling", "lidar_b200_last_stage_ms", "lidar_b200_batch_fetch_async", "lidar_b200_batch_wait",
     "lidar_b200_host_alloc", "lidar_b200_host_free", "lidar_b200_pipe_create", "lidar_b200_pipe_destroy",
     "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
-    "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error",
+    "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error", "lidar_b200_pipe_fetch_mode",
+    "lidar_b200_pipe_set_host_sharing",
     "lidar_b200_last_replay_stats", "lidar_b200_batch_group_clusters", "lidar_b200_batch_fetch_clusters",
     "lidar_b200_pcd_read", "lidar_b200_batch_hull_outlines", "lidar_b200_batch_fetch_hulls",
     "lidar_b200_batch_fetch_colorized", "lidar_b200_batch_fetch_marker_points",
@@ -468,7 +469,10 @@ class FramePipeline:
     Results are written into one page-locked arena owned by the pipeline and returned as views: they
     stay valid until the next process() call."""
 
-    def __init__(self, device: int = 0, depth: int = 3, chunk_frames: int = 22, max_points_per_chunk: int = 0):
+    def __init__(self, device: int = 0, depth: int = 3, chunk_frames: int = 22, max_points_per_chunk: int = 0,
+                 gpus_sharing_host: int = 1):
+        """gpus_sharing_host: how many GPUs of this host run a pipeline at the same time (the local world size); it
+        selects the result fetch mode (lidar_b200_pipe_set_host_sharing)."""
         self._h = C.c_void_p()
         self.depth, self.chunk_frames = depth, chunk_frames
         rc = lib().lidar_b200_pipe_create(C.c_int(device), C.c_uint32(depth),
@@ -477,6 +481,7 @@ class FramePipeline:
         if rc != 0:
             raise LidarB200Error(f"lidar_b200_pipe_create failed (status {rc}): CUDA device {device} unavailable; "
                                  "there is no CPU fallback")
+        self._check(lib().lidar_b200_pipe_set_host_sharing(self._h, C.c_uint32(max(1, gpus_sharing_host))), "pipe_set_host_sharing")
         self._arenas = {}
         self.h2d_bytes = self.d2h_bytes = 0
 
@@ -504,6 +509,10 @@ class FramePipeline:
 
     def launch_count(self) -> int:
         return int(lib().lidar_b200_pipe_launch_count(self._h))
+
+    def fetch_mode(self) -> int:
+        """0 = slot-size copies by the copy engines, 4 = exact sizes written by a kernel (lidar_b200_pipe_fetch_mode)."""
+        return int(lib().lidar_b200_pipe_fetch_mode(self._h))
 
     def submit(self, frames, want_ground_idx: bool = True, arena: int = 0):
         """Enqueues a job (all its chunks) without waiting; returns a handle for results(). Jobs submitted
@@ -565,7 +574,7 @@ class FramePipeline:
                 out.append(dict(seg_labels=seg[o:o + n], ground_idx=gidx[o:o + ng] if want else None,
                                 obstacle_idx=oidx[o:o + no], cluster_labels=clab[o:o + no], n_clusters=int(meta[3, f])))
         nf = len(out)
-        if int(os.environ.get("LIDAR_B200_FETCH_MODE", str(DEFAULT_FETCH_MODE))) >= 2:  # exact-size results (see api.cu)
+        if self.fetch_mode() >= 2:  # exact-size results (see api.cu)
             self.d2h_bytes = (4 * int(counts.astype(np.int64).sum())
                               + (4 * int(meta[1, :nf].astype(np.int64).sum()) if want else 0)
                               + 8 * int(meta[2, :nf].astype(np.int64).sum()) + 12 * nf + 4 * len(job["chunks"]))

@@ -22,6 +22,7 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <chrono>
 #include <deque>
 #include <mutex>
 #include <thread>
@@ -96,6 +97,7 @@ struct lidar_b200_ctx
                                    // 4 = warp per component, frame bitmaps shared by the CTA (replay_frame.cuh),
                                    // 5 = window-synchronous CTA replay (replay_gen.cuh), the default
     bool replay2_attr_done{false}, replay3_attr_done{false}, replay4_attr_done{false}, replay5_attr_done{false};
+    bool frame_sort{true};         // LIDAR_B200_FRAME_SORT=0: the component sort uses the per-tile radix sort kernels for every batch size
     bool replay5_live{false};      // LIDAR_B200_REPLAY5_LIVE=1: per-cell live counters skip the cells behind the frontier
     uint32_t replay5_ctas_per_sm{3}; // LIDAR_B200_REPLAY5_CTAS_PER_SM
     uint32_t replay4_ctas_per_sm{3}; // LIDAR_B200_REPLAY4_CTAS_PER_SM
@@ -483,6 +485,8 @@ int run_segmentation(lidar_b200_ctx *c)
     seg_keys_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, bv, c->d_key_a.p, c->d_val_a.p);
     ++c->launches;
     int rl = 0;
+    // (the frame-resident sort below was tried here too, with the key generation and the gather fused into its first and
+    // last pass: 1.9 ms against 1.35 + 0.15 ms per 154 frames - one CTA per frame leaves the SMs at 16 warps)
     const int passes = radix_sort_pairs(s, c->d_key_a.p, c->d_val_a.p, c->d_key_b.p, c->d_val_b.p, bv, c->max_n, 32u,
                                         RadixSortScratch{c->d_hist.p}, &rl);
     c->launches += rl;
@@ -565,8 +569,16 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
     int rl = 0;
     const uint32_t bits = ceil_log2(max_m < 2u ? 2u : max_m);
-    const int passes = radix_sort_pairs(s, c->d_key_a.p, c->d_val_a.p, c->d_key_b.p, c->d_val_b.p, bv, max_m, bits,
-                                        RadixSortScratch{c->d_hist.p}, &rl);
+    int passes;
+    if (c->frame_sort && F >= kFsMinFrames)
+    {
+        passes = static_cast<int>((bits + 7u) / 8u);
+        LB_CUDA(c, rs_frame_sort_launch(s, c->sm_count, c->d_key_a.p, c->d_val_a.p, c->d_key_b.p, c->d_val_b.p, bv, passes));
+        rl = 1;
+    }
+    else
+        passes = radix_sort_pairs(s, c->d_key_a.p, c->d_val_a.p, c->d_key_b.p, c->d_val_b.p, bv, max_m, bits,
+                                  RadixSortScratch{c->d_hist.p}, &rl);
     c->launches += rl;
     const uint32_t *member_root = (passes & 1) ? c->d_key_b.p : c->d_key_a.p;
     const uint32_t *member_idx = (passes & 1) ? c->d_val_b.p : c->d_val_a.p;
@@ -1023,6 +1035,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
         c->fetch_mode = std::atoi(e);
     if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
         c->replay_version = std::atoi(e) >= 1 && std::atoi(e) <= 5 ? std::atoi(e) : 5;
+    if (const char *e = std::getenv("LIDAR_B200_FRAME_SORT"))
+        c->frame_sort = std::atoi(e) != 0;
     if (const char *e = std::getenv("LIDAR_B200_REPLAY5_LIVE"))
         c->replay5_live = std::atoi(e) != 0;
     if (const char *e = std::getenv("LIDAR_B200_REPLAY5_CTAS_PER_SM"))
@@ -1762,6 +1776,9 @@ struct lidar_b200_pipe
     std::condition_variable cv_work, cv_done;
     std::deque<lidar_b200_ctx *> work;
     bool stop{false};
+    // Result fetch mode of the pipe: LIDAR_B200_FETCH_MODE pins it, else lidar_b200_pipe_set_host_sharing decides.
+    bool mode_pinned{false};
+    int mode{0};
 };
 
 namespace
@@ -1814,8 +1831,29 @@ int lidar_b200_pipe_create(int device, uint32_t depth, uint32_t max_points, uint
         p->slots.push_back(c);
     }
     p->worker = std::thread(pipe_worker, p);
+    p->mode_pinned = std::getenv("LIDAR_B200_FETCH_MODE") != nullptr;
+    p->mode = p->slots.front()->fetch_mode;
     *pipe_out = p;
     return 0;
+}
+
+// How many GPUs of this host run a pipe at the same time (the caller knows: its local world size). The host's DMA path is
+// shared: measured on the 8-GPU box (profiles/README.md, "copy-only ceiling") the copy engines of 8 GPUs move 124 GB/s in
+// total, so beyond 2 GPUs the bytes decide - mode 4 (exact sizes, 39 % fewer D2H bytes, posted writes from one kernel) is
+// +18 % end to end at 4 GPUs and +38 % at 8; at 1-2 GPUs the copy engines are not the limit and the slot-size copies of
+// mode 0, which cost no SM time, are 10 % faster.
+int lidar_b200_pipe_set_host_sharing(lidar_b200_pipe *p, uint32_t gpus_sharing_host)
+{
+    if (!p)
+        return LIDAR_B200_ERR_INVALID;
+    if (!p->mode_pinned)
+        p->mode = gpus_sharing_host >= 3u ? 4 : 0;
+    return 0;
+}
+
+int lidar_b200_pipe_fetch_mode(const lidar_b200_pipe *p)
+{
+    return p ? p->mode : -1;
 }
 
 void lidar_b200_pipe_destroy(lidar_b200_pipe *p)
@@ -1883,6 +1921,12 @@ int lidar_b200_pipe_submit(lidar_b200_pipe *p, uint32_t n_frames, const void *co
         rc = lidar_b200_batch_stage(c, n_frames, points, n_points, stride_bytes);
     if (!rc)
         rc = lidar_b200_batch_run(c);
+    // (mode 4 needs mapped page-locked destinations; a chunk with pageable result arrays is fetched with the copies)
+    c->fetch_mode = p->mode;
+    if (p->mode == 4 && !p->mode_pinned &&
+        !(device_view_of_pinned(seg_labels_out) && device_view_of_pinned(obstacle_idx_out) && device_view_of_pinned(cluster_labels_out) &&
+          (!ground_idx_out || device_view_of_pinned(ground_idx_out))))
+        c->fetch_mode = 0;
     if (!rc)
         rc = lidar_b200_batch_fetch_async(c, point_offset_out, seg_labels_out, ground_idx_out, n_ground_out,
                                           obstacle_idx_out, n_obstacle_out, cluster_labels_out, n_clusters_out);

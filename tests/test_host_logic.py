@@ -199,3 +199,5 @@ def test_c_abi_rejects_a_null_context_without_touching_a_device(pkg):
     assert lib.lidar_b200_batch_fetch_hulls(None, buf, buf, fbuf, buf) == inv
     assert lib.lidar_b200_batch_fetch_colorized(None, buf, C.c_uint64(1), fbuf) == inv
     assert lib.lidar_b200_batch_fetch_marker_points(None, buf, buf, dbuf) == inv
+    assert lib.lidar_b200_pipe_set_host_sharing(None, C.c_uint32(8)) == inv
+    assert lib.lidar_b200_pipe_fetch_mode(None) == -1
