@@ -449,3 +449,78 @@ def test_stale_labels_through_one_long_lived_reference_segmenter():
         carry[:k] = prev[:k]
         want = O.segment(second, tie_mode=0, labels_in=carry)["labels"]
         assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The caller's side of the hot path against the UNMODIFIED reference node: src/processor.cpp (Processor::process) with
+# src/conversions.cpp, compiled where they lie against the ROS 2 / PCL / Eigen stand-ins (oracle/_ref/libref_node.so,
+# oracle/ros_shim, oracle/ref_node_wrap.cpp) and fed one sensor_msgs::PointCloud2 per frame exactly as the dataloader
+# node builds it. This pins SURVEY §8(f) row 1 (per-cluster split, processor.cpp:180-200), row 4 (colourised cloud,
+# conversions.cpp:32-60, 139-162, and the MarkerArray point lists, conversions.hpp:72-120) and the order in which the
+# node chains Segmenter -> Clusterer -> split -> outlines: the restated oracles these rows are tested with on the GPU
+# (oracle.split_clusters / colorize / marker_points) must reproduce the node's published bytes.
+needs_ref_node = pytest.mark.skipif(not O.ref_node_available(), reason="oracle/_ref/libref_node.so not built")
+
+
+def _restated_node(pts, rand_seed=1):
+    seg = O.segment(pts, tie_mode=0)  # the reference as compiled here sorts with std::sort (introsort)
+    obs = pts[seg["obstacle_idx"]]
+    labels = O.cluster(obs)
+    clusters = O.split_clusters(obs, labels)
+    clouds = [c for c, _ in clusters]
+    colors = O.libc_rand_colors(len(clouds), rand_seed)
+    outlines = O.ref_outlines(clouds, mode=1)  # findOrderedConcaveOutlines (processor.cpp:213), pinned separately
+    return seg, obs, labels, clouds, O.colorize(clouds, colors), O.marker_points(outlines)
+
+
+def _check_against_node(pts):
+    node = O.ref_node_run(pts, rand_seed=1)
+    seg, obs, labels, clouds, colorized, markers = _restated_node(pts, 1)
+    ground = pts[seg["ground_idx"]]
+    # ground / obstacle clouds as pcl::PointXYZRGBL records: x y z 1.0f | b g r a | label (processor.cpp:152-163)
+    for name, cloud, bgr, lab in (("ground", ground, (220, 220, 220), 0), ("obstacle", obs, (0, 255, 0), 1)):
+        rec = node[name]
+        if cloud.shape[0] == 0:
+            assert rec is None
+            continue
+        assert rec.shape == (cloud.shape[0], 32)
+        assert np.array_equal(rec[:, :12].copy().view(np.float32).reshape(-1, 3), cloud[:, :3])
+        assert np.all(rec[:, 12:16].copy().view(np.float32) == 1.0)
+        assert np.all(rec[:, 16] == bgr[0]) and np.all(rec[:, 17] == bgr[1]) and np.all(rec[:, 18] == bgr[2])
+        assert np.all(rec[:, 20:24].copy().view(np.uint32) == lab)
+    # row 1 + row 4: the colourised cloud is the split clusters laid end to end, one std::rand() colour per cluster
+    if clouds:
+        assert node["clustered"] is not None and node["clustered"].shape == colorized.shape
+        assert np.array_equal(node["clustered"][:, :20], colorized[:, :20])  # x y z 1.0f b g r a; the rest is padding
+    else:
+        assert node["clustered"] is None
+    # row 4: one closed line strip per non-empty outline
+    want = [m for m in markers if m is not None]
+    got = node["markers"] or []
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    return len(clouds)
+
+
+@needs_ref_node
+def test_reference_node_pins_split_colorized_cloud_and_markers_on_a_golden_frame(golden_frames):
+    assert _check_against_node(golden_frames[0]) == 569  # clusters of frame 0 in the reference's own sort order
+
+
+@needs_ref_node
+@pytest.mark.parametrize("seed", [3, 5, 8])
+def test_reference_node_pins_split_colorized_cloud_and_markers_on_synthetic_frames(seed):
+    pts = make_frame(seed, beams=32, azimuth_steps=512)
+    assert _check_against_node(pts) > 10
+
+
+@needs_ref_node
+def test_reference_node_without_clusters_or_ground():
+    # every point an obstacle far from the others: all clusters below min_cluster_size -> nothing on the clustered topic
+    rng = np.random.default_rng(2)
+    lonely = np.zeros((64, 4), np.float32)
+    lonely[:, 0] = np.arange(64) * 5.0
+    lonely[:, 1] = rng.normal(0, 0.01, 64)
+    lonely[:, 2] = 1.0 + 0.001 * np.arange(64)
+    assert _check_against_node(lonely) == 0
