@@ -14,8 +14,6 @@
 #include "radix_sort.cuh"
 #include "replay_cta.cuh"
 #include "replay_cta2.cuh"
-#include "replay_cta3.cuh"
-#include "replay_frame.cuh"
 #include "replay_gen.cuh"
 #include "segment.cuh"
 
@@ -72,7 +70,8 @@ struct lidar_b200_ctx
     cudaStream_t stream{nullptr};
     cudaStream_t stream_big{nullptr}; // the CTA-per-component replay runs beside the warp-per-component one
     cudaStream_t stream_huge{nullptr}; // ... and the 1-CTA-per-SM launch for components beyond the normal state bitmap
-    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_fork{nullptr}, ev_join{nullptr}, ev_join2{nullptr}, ev_kd{nullptr};
+    cudaStream_t stream_small{nullptr}; // ... and the short jobs of the window-synchronous replay beside the long ones
+    cudaEvent_t ev_start{nullptr}, ev_stop{nullptr}, ev_fork{nullptr}, ev_join{nullptr}, ev_join2{nullptr}, ev_join3{nullptr}, ev_kd{nullptr};
     lidar_b200_seg_cfg seg_cfg{};
     lidar_b200_clu_cfg clu_cfg{};
     SegParams seg{};
@@ -93,17 +92,17 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_rankpos;
     DevBuf<unsigned long long> d_mkey;
     int replay_version{5};         // LIDAR_B200_REPLAY_V: 1 = first-generation CTA replay (state in global memory),
-                                   // 2 = second (state bitmap by member), 3 = third (live-candidate bitmaps by cell order),
-                                   // 4 = warp per component, frame bitmaps shared by the CTA (replay_frame.cuh),
-                                   // 5 = window-synchronous CTA replay (replay_gen.cuh), the default
-    bool replay2_attr_done{false}, replay3_attr_done{false}, replay4_attr_done{false}, replay5_attr_done{false};
+                                   // 2 = second (state bitmap by member), 5 = window-synchronous CTA replay
+                                   // (replay_gen.cuh), the default. (Generations 3 and 4 - live-candidate bitmaps by cell
+                                   // order, a warp per component - measured slower than 2 and are gone, see profiles/README.md.)
+    bool replay2_attr_done{false}, replay5_attr_done{false};
     bool frame_sort{true};         // LIDAR_B200_FRAME_SORT=0: the component sort uses the per-tile radix sort kernels for every batch size
-    bool replay5_live{false};      // LIDAR_B200_REPLAY5_LIVE=1: per-cell live counters skip the cells behind the frontier
+    uint32_t replay5_big_threads{0};   // LIDAR_B200_REPLAY5_BIG_THREADS: 256 / 512 / 1024 threads per CTA for the long jobs;
+                                       // 0 = by batch size: 512 up to 4 frames (the longest window chain is the latency of
+                                       // a frame: p50 2.95 -> 2.53 ms), 256 beyond (a batch is bound by the total work and
+                                       // wide CTAs only take registers from the other frames' jobs)
     uint32_t replay5_ctas_per_sm{3}; // LIDAR_B200_REPLAY5_CTAS_PER_SM
-    uint32_t replay4_ctas_per_sm{3}; // LIDAR_B200_REPLAY4_CTAS_PER_SM
-    DevBuf<uint32_t> d_complist;   // fourth generation: per-frame component lists (first member slot), longest first
-    DevBuf<uint32_t> d_frame_meta; // ... and per-frame counters (kV4MetaStride words each)
-    DevBuf<uint32_t> d_nb27;       // packed neighbour table of the third generation: first pos | count << 20, 27 per cell
+    DevBuf<uint32_t> d_nb27;       // packed neighbour table of the window-synchronous replay: first pos | count << 20, 27 per cell
     DevBuf<uint32_t> d_key_a, d_key_b, d_val_a, d_val_b, d_labels, d_gidx, d_oidx, d_slot_of, d_pos_of, d_parent,
         d_root, d_rank, d_gepos, d_lepos, d_state, d_seed_of, d_member_pos, d_queue, d_seed_label, d_comp_size, d_pslot;
     DevBuf<int32_t> d_clabels;
@@ -278,7 +277,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
               dev_alloc(c, c->d_seed_valid, n) | dev_alloc(c, c->d_nbr, 27u * n) | dev_alloc(c, c->d_cinfo, n) |
               dev_alloc(c, c->d_biglist, kBigListBuckets * (n / kCtaComponentMin + 1u)) | dev_alloc(c, c->d_ipts, n) |
               dev_alloc(c, c->d_mpts, n) | dev_alloc(c, c->d_rankpos, n) | dev_alloc(c, c->d_mkey, n) |
-              dev_alloc(c, c->d_nb27, 27u * n) | dev_alloc(c, c->d_complist, n);
+              dev_alloc(c, c->d_nb27, 27u * n);
         if (c->want_job_stats)
             rc |= dev_alloc(c, c->d_job_stats, 8u * (n / kCtaComponentMin + 1u));
         if (rc)
@@ -287,8 +286,7 @@ int reserve(lidar_b200_ctx *c, uint32_t pts, uint32_t frames)
     }
     if (grow_frames)
     {
-        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames) + 16) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)) ||
-            dev_alloc(c, c->d_frame_meta, kV4MetaStride * static_cast<size_t>(frames)))
+        if (dev_alloc(c, c->d_meta, 8 * static_cast<size_t>(frames) + 16) || pin_alloc(c, c->h_meta, 7 * static_cast<size_t>(frames)))
             return LIDAR_B200_ERR_CUDA;
         c->cap_frames = frames;
     }
@@ -587,48 +585,6 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_kd, 0)); // k-d order built on the second stream meanwhile
 
     mark(c, 7);
-    if (c->replay_version == 4 && max_m <= kV4MaxPoints)
-    {
-        // fourth generation (replay_frame.cuh): one warp per component, the CTA's warps share the frame's bitmaps
-        const uint32_t words = (max_m + 31u) >> 5;
-        const size_t smem = sizeof(V4Smem) + 8u * words;
-        if (!c->replay4_attr_done)
-        {
-            const int smem_max = static_cast<int>(sizeof(V4Smem) + 8u * (kV4MaxPoints >> 5));
-            LB_CUDA(c, cudaFuncSetAttribute(replay_frame_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-            LB_CUDA(c, cudaFuncSetAttribute(replay_frame_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-            LB_CUDA(c, cudaFuncSetAttribute(replay_frame_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-            c->replay4_attr_done = true;
-        }
-        LB_CUDA(c, cudaMemsetAsync(c->d_frame_meta.p, 0, static_cast<size_t>(F) * kV4MetaStride * 4, s));
-        replay_init4_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_ipts.p, c->d_seed_of.p,
-                                               c->d_member_pos.p, c->m_cursor());
-        replay_complist_count_kernel<<<gp, 256, 0, s>>>(bv, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
-                                                        c->d_seed_of.p, c->d_seed_valid.p, c->d_frame_meta.p);
-        replay_complist_fill_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->d_frame_meta.p, c->d_complist.p);
-        // how many CTAs may serve one frame at a time: enough tickets to occupy the machine, at most 16 per frame
-        uint32_t per_sm = c->replay4_ctas_per_sm;
-        while (per_sm > 1u && per_sm * smem > 220u * 1024u)
-            --per_sm;
-        const uint32_t slots = c->sm_count * per_sm;
-        const uint32_t per_frame = std::max(1u, std::min(16u, (slots + F - 1u) / F));
-        const uint32_t n_tickets = F * per_frame;
-        const uint32_t grid = std::min(n_tickets, slots);
-#define LB_LAUNCH_REPLAY_FRAME(MINB)                                                                                   \
-    replay_frame_kernel<MINB><<<grid, kV4Warps * 32, smem, s>>>(                                                       \
-        c->d_ipts.p, c->d_state.p /* cell_of */, c->d_nb27.p, c->d_cinfo.p, bv, c->clu, member_root, member_idx,       \
-        c->d_member_pos.p, c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,            \
-        c->d_complist.p, c->d_frame_meta.p, c->m_cursor() + 14, n_tickets, words)
-        if (per_sm >= 4u)
-            LB_LAUNCH_REPLAY_FRAME(4);
-        else if (per_sm == 3u)
-            LB_LAUNCH_REPLAY_FRAME(3);
-        else
-            LB_LAUNCH_REPLAY_FRAME(2);
-#undef LB_LAUNCH_REPLAY_FRAME
-        c->launches += 4;
-    }
-    else
     {
     replay_init_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_slot_of.p,
                                           c->d_rpts.p, c->d_seed_of.p, c->d_member_pos.p, c->d_pslot.p, c->m_cursor(), tv,
@@ -638,77 +594,81 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     // started first on a second stream so that the longest BFS chains begin at time zero
     uint32_t *big_count = c->m_cursor() + 3; // kBigBuckets counters
     const uint32_t bucket_capacity = c->cap_pts / kCtaComponentMin + 1u;
-    bool huge_launched = false;
+    bool huge_launched = false, small_launched = false;
     if (c->replay_version >= 5 && max_m < (1u << kGenPosBits))
     {
-        // fifth generation (replay_gen.cuh): window-synchronous replay, three state planes in shared memory. Components
-        // beyond the normal planes go to a 1-CTA-per-SM launch with large planes, beyond that to the first generation.
+        // fifth generation (replay_gen.cuh): window-synchronous replay, three state planes in shared memory. The long jobs
+        // (components of 2048 members and more: their window chains bound the launch) get CTAs of `replay5_big_threads`
+        // threads, the short ones share SMs with 256-thread CTAs on a stream of their own. Components beyond the normal
+        // planes go to a 1-CTA-per-SM launch with large planes, beyond that to the first generation.
         const uint32_t normal_words = 1024u; // 32 768 members
         const uint32_t huge_words = static_cast<uint32_t>((227u * 1024u - sizeof(GenSmem)) / 12u) & ~31u;
         const size_t smem_normal = sizeof(GenSmem) + 12u * normal_words, smem_huge = sizeof(GenSmem) + 12u * huge_words;
         if (!c->replay5_attr_done)
         {
-#define LB_GEN_ATTR(MINB, LIVE, BYTES)                                                                                \
-    LB_CUDA(c, cudaFuncSetAttribute(replay_gen_kernel<MINB, LIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(BYTES)))
-            LB_GEN_ATTR(2, false, smem_normal);
-            LB_GEN_ATTR(3, false, smem_normal);
-            LB_GEN_ATTR(4, false, smem_normal);
-            LB_GEN_ATTR(1, false, smem_huge);
-            LB_GEN_ATTR(2, true, smem_normal);
-            LB_GEN_ATTR(3, true, smem_normal);
-            LB_GEN_ATTR(4, true, smem_normal);
-            LB_GEN_ATTR(1, true, smem_huge);
+#define LB_GEN_ATTR(NT, MINB, BYTES)                                                                                  \
+    LB_CUDA(c, cudaFuncSetAttribute(replay_gen_kernel<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(BYTES)))
+            LB_GEN_ATTR(256, 2, smem_normal);
+            LB_GEN_ATTR(256, 3, smem_normal);
+            LB_GEN_ATTR(512, 2, smem_normal);
+            LB_GEN_ATTR(1024, 1, smem_huge);
 #undef LB_GEN_ATTR
             c->replay5_attr_done = true;
         }
-        uint32_t *mcell = reinterpret_cast<uint32_t *>(c->d_mkey.p), *clive = mcell + c->cap_pts;
+        uint32_t *mcell = reinterpret_cast<uint32_t *>(c->d_mkey.p);
         replay_init5_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, member_idx, c->d_pos_of.p, c->d_state.p /* cell_of */,
-                                               c->d_cinfo.p, c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, mcell, clive);
+                                               c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, mcell);
         replay_biglist2_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->clu.cta_min_members, 32u * normal_words,
                                                   32u * huge_words, c->d_biglist.p, bucket_capacity, big_count,
                                                   c->m_cursor() + 8, c->m_cursor() + 10);
         c->launches += 2;
         LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
         LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
-        const uint32_t per_sm = std::max(2u, std::min(4u, c->replay5_ctas_per_sm));
-#define LB_GEN_ARGS(LIST, COUNT, NB, CURSOR, WORDS, STATS)                                                            \
-    c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, mcell, c->d_nb27.p, c->d_cinfo.p, clive, bv, c->clu, member_root, member_idx, \
-        c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, LIST, bucket_capacity, COUNT, NB,  \
-        CURSOR, WORDS, STATS
-#define LB_GEN_LAUNCH(MINB, LIVE)                                                                                      \
-    replay_gen_kernel<MINB, LIVE><<<c->sm_count * MINB, kCtaThreads, smem_normal, c->stream_big>>>(                    \
-        LB_GEN_ARGS(c->d_biglist.p, big_count, kBigBuckets, c->m_cursor() + 2, normal_words, c->d_job_stats.p))
-        if (c->replay5_live)
+#define LB_GEN_ARGS(LIST, COUNT, NB, CURSOR, WORDS, STATS, SKIP)                                                      \
+    c->d_ipts.p, c->d_rankpos.p, c->d_mpts.p, mcell, c->d_nb27.p, c->d_cinfo.p, bv, c->clu, member_root, member_idx,  \
+        c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, LIST, bucket_capacity, COUNT, NB, \
+        CURSOR, WORDS, STATS, SKIP
+        const bool three_per_sm = c->replay5_ctas_per_sm >= 3u;
+        const uint32_t big_threads = c->replay5_big_threads ? c->replay5_big_threads : (F <= 4u ? 512u : 256u);
+        if (big_threads <= 256u)
         {
-            if (per_sm == 2u)
-                LB_GEN_LAUNCH(2, true);
-            else if (per_sm == 3u)
-                LB_GEN_LAUNCH(3, true);
+            // one launch for every job list
+            if (three_per_sm)
+                replay_gen_kernel<256, 3><<<c->sm_count * 3u, 256, smem_normal, c->stream_big>>>(
+                    LB_GEN_ARGS(c->d_biglist.p, big_count, kBigBuckets, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
             else
-                LB_GEN_LAUNCH(4, true);
+                replay_gen_kernel<256, 2><<<c->sm_count * 2u, 256, smem_normal, c->stream_big>>>(
+                    LB_GEN_ARGS(c->d_biglist.p, big_count, kBigBuckets, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
+            ++c->launches;
         }
         else
         {
-            if (per_sm == 2u)
-                LB_GEN_LAUNCH(2, false);
-            else if (per_sm == 3u)
-                LB_GEN_LAUNCH(3, false);
+            // job lists 0-1 (>= 2048 members) first, with wide CTAs; lists 2-3 beside them
+            if (big_threads >= 1024u)
+                replay_gen_kernel<1024, 1><<<c->sm_count, 1024, smem_normal, c->stream_big>>>(
+                    LB_GEN_ARGS(c->d_biglist.p, big_count, 2u, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
             else
-                LB_GEN_LAUNCH(4, false);
+                replay_gen_kernel<512, 2><<<c->sm_count * 2u, 512, smem_normal, c->stream_big>>>(
+                    LB_GEN_ARGS(c->d_biglist.p, big_count, 2u, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
+            LB_CUDA(c, cudaStreamWaitEvent(c->stream_small, c->ev_fork, 0));
+            if (three_per_sm)
+                replay_gen_kernel<256, 3><<<c->sm_count * 3u, 256, smem_normal, c->stream_small>>>(
+                    LB_GEN_ARGS(c->d_biglist.p + 2u * static_cast<size_t>(bucket_capacity), big_count + 2, 2u, c->m_cursor() + 14,
+                                normal_words, c->d_job_stats.p, 2u));
+            else
+                replay_gen_kernel<256, 2><<<c->sm_count * 2u, 256, smem_normal, c->stream_small>>>(
+                    LB_GEN_ARGS(c->d_biglist.p + 2u * static_cast<size_t>(bucket_capacity), big_count + 2, 2u, c->m_cursor() + 14,
+                                normal_words, c->d_job_stats.p, 2u));
+            LB_CUDA(c, cudaEventRecord(c->ev_join3, c->stream_small));
+            small_launched = true;
+            c->launches += 2;
         }
-#undef LB_GEN_LAUNCH
-        ++c->launches;
         if (max_m > 32u * normal_words) // a component can only be that large in a frame that large
         {
             LB_CUDA(c, cudaStreamWaitEvent(c->stream_huge, c->ev_fork, 0));
-            if (c->replay5_live)
-                replay_gen_kernel<1, true><<<c->sm_count, kCtaThreads, smem_huge, c->stream_huge>>>(
-                    LB_GEN_ARGS(c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), c->m_cursor() + 8, 1u, c->m_cursor() + 7,
-                                huge_words, nullptr));
-            else
-                replay_gen_kernel<1, false><<<c->sm_count, kCtaThreads, smem_huge, c->stream_huge>>>(
-                    LB_GEN_ARGS(c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), c->m_cursor() + 8, 1u, c->m_cursor() + 7,
-                                huge_words, nullptr));
+            replay_gen_kernel<1024, 1><<<c->sm_count, 1024, smem_huge, c->stream_huge>>>(
+                LB_GEN_ARGS(c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), c->m_cursor() + 8, 1u, c->m_cursor() + 7,
+                            huge_words, nullptr, 0u));
             ++c->launches;
             if (max_m > 32u * huge_words)
             {
@@ -724,56 +684,6 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
             huge_launched = true;
         }
 #undef LB_GEN_ARGS
-    }
-    else if (c->replay_version >= 3 && c->replay_version <= 4 && max_m < (1u << kV3PosBits))
-    {
-        // third generation (replay_cta3.cuh): live-candidate bitmaps by cell order in shared memory. Frames whose two
-        // bitmaps do not fit beside two other CTAs go to a 1-CTA-per-SM launch, frames beyond that to the first generation.
-        // (227 KB of dynamic shared memory per CTA on sm_100a)
-        const uint32_t normal_pts = 131072u, huge_pts = static_cast<uint32_t>((227u * 1024u - sizeof(Cta3Smem)) / 8u / 32u * 32u) * 32u;
-        const uint32_t normal_words = (std::min(max_m, normal_pts) + 31u) >> 5, huge_words = (std::min(max_m, huge_pts) + 31u) >> 5;
-        const size_t smem_normal = sizeof(Cta3Smem) + 8u * normal_words, smem_huge = sizeof(Cta3Smem) + 8u * huge_words;
-        if (!c->replay3_attr_done)
-        {
-            LB_CUDA(c, cudaFuncSetAttribute(replay_cta3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(sizeof(Cta3Smem) + 8u * (normal_pts >> 5))));
-            LB_CUDA(c, cudaFuncSetAttribute(replay_cta3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(sizeof(Cta3Smem) + 8u * (huge_pts >> 5))));
-            c->replay3_attr_done = true;
-        }
-        replay_init3_kernel<<<gp, 256, 0, s>>>(c->d_cpts.p, bv, c->d_rank.p, c->d_ipts.p);
-        replay_biglist3_kernel<<<gp, 256, 0, s>>>(bv, member_root, c->d_comp_size.p, c->clu.cta_min_members, normal_pts, huge_pts,
-                                                  c->d_biglist.p, bucket_capacity, big_count, c->m_cursor() + 8,
-                                                  c->m_cursor() + 10);
-        c->launches += 2;
-        LB_CUDA(c, cudaEventRecord(c->ev_fork, s));
-        LB_CUDA(c, cudaStreamWaitEvent(c->stream_big, c->ev_fork, 0));
-        replay_cta3_kernel<3><<<c->sm_count * 3u, kCtaThreads, smem_normal, c->stream_big>>>(
-            c->d_ipts.p, c->d_state.p /* cell_of */, c->d_nb27.p, c->d_cinfo.p, bv, c->clu, member_root, member_idx,
-            c->d_member_pos.p, c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p, c->d_biglist.p,
-            bucket_capacity, big_count, kBigBuckets, c->m_cursor() + 2, normal_words, c->d_job_stats.p);
-        ++c->launches;
-        if (max_m > normal_pts)
-        {
-            LB_CUDA(c, cudaStreamWaitEvent(c->stream_huge, c->ev_fork, 0));
-            replay_cta3_kernel<1><<<c->sm_count, kCtaThreads, smem_huge, c->stream_huge>>>(
-                c->d_ipts.p, c->d_state.p, c->d_nb27.p, c->d_cinfo.p, bv, c->clu, member_root, member_idx, c->d_member_pos.p,
-                c->d_comp_size.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
-                c->d_biglist.p + 4u * static_cast<size_t>(bucket_capacity), bucket_capacity, c->m_cursor() + 8, 1u,
-                c->m_cursor() + 7, huge_words, nullptr);
-            ++c->launches;
-            if (max_m > huge_pts)
-            {
-                replay_cta_kernel<3><<<c->sm_count * 3u, kCtaThreads, 0, c->stream_huge>>>(
-                    c->d_rpts.p, bv, tv, c->d_cells.p, c->clu, member_root, member_idx, c->d_member_pos.p, c->d_comp_size.p,
-                    c->d_pkey.p, c->d_tlive.p, c->d_seed_of.p, c->d_queue.p, c->d_spill.p, c->d_seed_valid.p,
-                    c->d_biglist.p + 5u * static_cast<size_t>(bucket_capacity), bucket_capacity, c->m_cursor() + 10,
-                    c->m_cursor() + 9, nullptr);
-                ++c->launches;
-            }
-            LB_CUDA(c, cudaEventRecord(c->ev_join2, c->stream_huge));
-            huge_launched = true;
-        }
     }
     else if (c->replay_version >= 2)
     {
@@ -858,6 +768,8 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join, 0));
     if (huge_launched)
         LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join2, 0));
+    if (small_launched)
+        LB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join3, 0));
     }
     mark(c, 8);
     {
@@ -1034,15 +946,13 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
     if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
-        c->replay_version = std::atoi(e) >= 1 && std::atoi(e) <= 5 ? std::atoi(e) : 5;
+        c->replay_version = (std::atoi(e) == 1 || std::atoi(e) == 2) ? std::atoi(e) : 5;
     if (const char *e = std::getenv("LIDAR_B200_FRAME_SORT"))
         c->frame_sort = std::atoi(e) != 0;
-    if (const char *e = std::getenv("LIDAR_B200_REPLAY5_LIVE"))
-        c->replay5_live = std::atoi(e) != 0;
+    if (const char *e = std::getenv("LIDAR_B200_REPLAY5_BIG_THREADS"))
+        c->replay5_big_threads = static_cast<uint32_t>(std::atoi(e));
     if (const char *e = std::getenv("LIDAR_B200_REPLAY5_CTAS_PER_SM"))
         c->replay5_ctas_per_sm = static_cast<uint32_t>(std::max(2, std::min(4, std::atoi(e))));
-    if (const char *e = std::getenv("LIDAR_B200_REPLAY4_CTAS_PER_SM"))
-        c->replay4_ctas_per_sm = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? static_cast<uint32_t>(std::atoi(e)) : 3u;
     lidar_b200_seg_cfg sc;
     lidar_b200_clu_cfg cc;
     lidar_b200_seg_cfg_default(&sc);
@@ -1052,7 +962,9 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream_big, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream_huge, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_small, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -1102,6 +1014,8 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
         cudaStreamSynchronize(c->stream_big);
     if (c->stream_huge)
         cudaStreamSynchronize(c->stream_huge);
+    if (c->stream_small)
+        cudaStreamSynchronize(c->stream_small);
     if (c->stream)
         cudaStreamSynchronize(c->stream);
     cudaFreeHost(c->h_pts.p);
@@ -1114,7 +1028,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p, c->d_nb27.p, c->d_complist.p, c->d_frame_meta.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p, c->d_nb27.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -1135,6 +1049,10 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
         cudaEventDestroy(c->ev_counts);
     if (c->ev_join2)
         cudaEventDestroy(c->ev_join2);
+    if (c->ev_join3)
+        cudaEventDestroy(c->ev_join3);
+    if (c->stream_small)
+        cudaStreamDestroy(c->stream_small);
     if (c->stream_huge)
         cudaStreamDestroy(c->stream_huge);
     if (c->stream_big)

@@ -552,7 +552,7 @@ replay_init_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t
     const uint32_t off = bv.off[f];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 16)
         cursor[threadIdx.x] = 0u; // [0,1] warp-path phases, [2] CTA-path cursor, [3..6] CTA-path job counts per size bucket,
-                                  // [7,8] cursor / count of the huge list, [9,10] of the first-generation list, [11..13] stay 0
+                                  // [7,8] cursor / count of the huge list, [9,10] of the first-generation list, [11..13] stay 0 (that list is read as four size buckets), [14] cursor of the short-job launch of the window-synchronous replay
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     {
         const float4 p = cpts[off + i];

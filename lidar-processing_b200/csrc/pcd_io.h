@@ -102,9 +102,12 @@ inline std::string pcd_parse_header(FILE *f, PcdHeader *h)
         counts.assign(fields.size(), 1u);
     if (counts.size() != fields.size())
         return "COUNT inconsistent with FIELDS";
-    uint32_t off = 0, col = 0;
+    uint64_t off = 0, col = 0; // 64-bit: SIZE and COUNT come from the file
+    constexpr uint64_t kMaxRecordBytes = 65536u;
     for (size_t i = 0; i < fields.size(); ++i)
     {
+        if (sizes[i] == 0u || sizes[i] > 8u || counts[i] == 0u || counts[i] > kMaxRecordBytes)
+            return "SIZE / COUNT out of range";
         const bool f32 = types[i] == "F" && sizes[i] == 4u && counts[i] == 1u;
         int *o = nullptr, *c = nullptr;
         if (fields[i] == "x")
@@ -122,11 +125,13 @@ inline std::string pcd_parse_header(FILE *f, PcdHeader *h)
             *o = static_cast<int>(off);
             *c = static_cast<int>(col);
         }
-        off += sizes[i] * counts[i];
+        off += static_cast<uint64_t>(sizes[i]) * counts[i];
         col += counts[i];
+        if (off > kMaxRecordBytes)
+            return "point record larger than 64 KB";
     }
-    h->record_bytes = off;
-    h->columns = col;
+    h->record_bytes = static_cast<uint32_t>(off);
+    h->columns = static_cast<uint32_t>(col);
     if (h->off_x < 0 || h->off_y < 0 || h->off_z < 0)
         return "fields x, y, z are required";
     return std::string();

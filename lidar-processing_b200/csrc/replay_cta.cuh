@@ -65,7 +65,7 @@ static_assert(sizeof(CtaSmem) <= 48u * 1024u, "static shared memory");
 // Sorts n 64-bit keys ascending with the whole CTA; works on shared or global memory. Bitonic network
 // in its "flip" form: every compare-exchange moves the smaller key to the lower index, so the slots
 // past n behave like +infinity without ever being touched (no padding, any n).
-LB_D void cta_bitonic_sort(volatile unsigned long long *a, uint32_t n)
+template <int NT = kCtaThreads> LB_D void cta_bitonic_sort(volatile unsigned long long *a, uint32_t n)
 {
     uint32_t n_pad = 2u;
     while (n_pad < n)
@@ -73,7 +73,7 @@ LB_D void cta_bitonic_sort(volatile unsigned long long *a, uint32_t n)
     for (uint32_t kk = 2u; kk <= n_pad; kk <<= 1)
         for (uint32_t jj = kk >> 1; jj > 0u; jj >>= 1)
         {
-            for (uint32_t t = threadIdx.x; t < (n_pad >> 1); t += kCtaThreads)
+            for (uint32_t t = threadIdx.x; t < (n_pad >> 1); t += NT)
             {
                 uint32_t i0, i1;
                 if (jj == (kk >> 1))

@@ -29,7 +29,8 @@
 // the first behind the barrier that ends the window through a list of the words they touched, so every thread of the
 // window reads the state of the window start. Point records are immutable and read through the read-only path
 // (ipts / rankpos by cell order, mpts / mcell by member); the 27 neighbour cells of an entry come from the packed
-// neighbour table (cc_nbr_kernel) in one load per cell. Per-cell live counters skip the cells behind the frontier.
+// neighbour table (cc_nbr_kernel) in one load per cell. (Per-cell live counters that skip the cells behind the frontier
+// were tried: the extra dependent load per lookup costs more than the skipped candidates save, 6.4 against 6.0 ms.)
 #pragma once
 
 #include "replay_cta2.cuh"
@@ -43,9 +44,9 @@ constexpr uint32_t kGenDirty = 2048u; // state words touched by the removals of 
 constexpr uint32_t kGenPosBits = 20u; // nb27 packs first pos | count << 20
 constexpr uint32_t kGenCountCap = 4095u;
 constexpr uint32_t kGenBatch = 32u; // expanded entries whose neighbour cells are looked up together
-constexpr int kGenUnroll = 4;       // candidates per lane in flight: a chunk is 32 * kGenUnroll candidates of one entry
+constexpr int kGenUnroll = 2;       // candidates per lane in flight: a chunk is 32 * kGenUnroll candidates of one entry
 constexpr uint32_t kGenChunk = 32u * kGenUnroll;
-static_assert(kGenW == static_cast<uint32_t>(kCtaThreads), "one window entry per thread");
+static_assert(kGenW == 256u, "the window masks are 8 words");
 
 struct __align__(16) GenSmem
 {
@@ -58,20 +59,19 @@ struct __align__(16) GenSmem
     uint32_t cst[kGenBatch][27], cin[kGenBatch][27]; // neighbour cells of the batch's expanded entries: first pos, inclusive prefix
     float box_lo[8][4], box_hi[8][4];  // bounding box of the alive entries of every 32-entry word of the window
     uint32_t in_mask[8], out_mask[8];  // expanded / not expanded, one bit per window entry
-    uint32_t wcnt[8];
+    uint32_t wcnt[32];
     uint32_t n_push, n_dirty, claim, found;
     uint16_t dirty[kGenDirty];
     uint8_t in_list[kGenW]; // window positions of the expanded entries, ascending
 };
 
 // ipts[pos] = {x, y, z, bits(member slot t)}, rankpos[pos] = k-d pre-order rank, mpts[t] = {x, y, z, bits(pos)},
-// mcell[t] = cell id, clive[cell id] = points of the cell that are still in the cloud. One thread per member slot.
+// mcell[t] = cell id. One thread per member slot.
 __global__ void __launch_bounds__(256)
 replay_init5_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_t *__restrict__ rank_of_point,
                     const uint32_t *__restrict__ member_idx, const uint32_t *__restrict__ pos_of,
-                    const uint32_t *__restrict__ cell_of, const uint2 *__restrict__ cinfo, float4 *__restrict__ ipts,
-                    uint32_t *__restrict__ rankpos, float4 *__restrict__ mpts, uint32_t *__restrict__ mcell,
-                    uint32_t *__restrict__ clive)
+                    const uint32_t *__restrict__ cell_of, float4 *__restrict__ ipts, uint32_t *__restrict__ rankpos,
+                    float4 *__restrict__ mpts, uint32_t *__restrict__ mcell)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t m = bv.cnt[f];
@@ -86,8 +86,6 @@ replay_init5_kernel(const float4 *__restrict__ cpts, BatchView bv, const uint32_
         rankpos[off + pos] = rank_of_point[off + idx];
         mpts[off + t] = make_float4(p.x, p.y, p.z, __uint_as_float(pos));
         mcell[off + t] = cid;
-        if (cid == pos)
-            clive[off + pos] = cinfo[off + pos].x;
     }
 }
 
@@ -213,27 +211,32 @@ LB_D uint32_t gen_scan_chunk(GenSmem &sm, uint32_t p, uint32_t k, uint32_t g0, u
 
 // MINB = CTAs per SM the register allocation is capped for. Dynamic shared memory: GenSmem followed by three planes of
 // `plane_words` words; the job lists only hold components of at most 32 * plane_words members.
-template <int MINB, bool USE_LIVE>
-__global__ void __launch_bounds__(kCtaThreads, MINB)
+// NT = threads per CTA: the first 256 own the window entries; tiles, lookups, candidate chunks and the sort are dealt over
+// all NT / 32 warps, so the long jobs (whose windows are the chain that bounds the launch, and a single frame's latency)
+// run with 1024 threads on an SM of their own while the many short ones share SMs with 256.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restrict__ rankpos_all,
                   const float4 *__restrict__ mpts_all, const uint32_t *__restrict__ mcell_all,
-                  const uint32_t *__restrict__ nb27_all, const uint2 *__restrict__ cinfo_all,
-                  uint32_t *__restrict__ clive_all, BatchView bv, CluParams prm,
+                  const uint32_t *__restrict__ nb27_all, const uint2 *__restrict__ cinfo_all, BatchView bv, CluParams prm,
                   const uint32_t *__restrict__ member_root, const uint32_t *__restrict__ member_idx,
                   const uint32_t *__restrict__ comp_size, uint32_t *__restrict__ seed_of, uint32_t *__restrict__ queue,
                   unsigned long long *__restrict__ push_spill, uint8_t *__restrict__ seed_valid,
                   const uint2 *__restrict__ biglist, uint32_t bucket_capacity, const uint32_t *__restrict__ big_count,
                   uint32_t n_buckets, uint32_t *__restrict__ cursor, uint32_t plane_words,
-                  uint32_t *__restrict__ job_stats /* optional: 8 words per job */)
+                  uint32_t *__restrict__ job_stats /* optional: 8 words per job */,
+                  uint32_t stats_skip_buckets /* job lists in front of `big_count` that belong to another launch */)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GenSmem &sm = *reinterpret_cast<GenSmem *>(smem_raw);
     uint32_t *rem = reinterpret_cast<uint32_t *>(smem_raw + sizeof(GenSmem)); // removed before this window
     uint32_t *rnew = rem + plane_words;                                       // removed by this window
     uint32_t *qd = rnew + plane_words;                                        // queued (ever pushed)
+    constexpr uint32_t kWarps = NT / 32;
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
+    const bool owner = tid < kGenW; // this thread may own a window entry
     const uint32_t lt = lanemask_lt();
     const float near_sq = __fmul_rn(4.01f, prm.distance_squared); // superset of "within twice the radius"
     uint32_t bucket_end[kBigBuckets];
@@ -269,7 +272,6 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
         const uint32_t *mc = mcell_all + off + t_start;
         const uint32_t *nbt = nb27_all + static_cast<size_t>(off) * 27u;
         const uint2 *ci = cinfo_all + off;
-        uint32_t *clive = clive_all + off;
         uint32_t *so = seed_of + off;
         uint32_t *qu = queue + off + t_start; // the component's FIFO (lids)
         unsigned long long *spill = push_spill + off + t_start;
@@ -280,7 +282,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
         if (n_words > plane_words)
             continue; // never listed (the job lists are routed by size); the labels would stay UNDEFINED
 
-        for (uint32_t i = tid; i < n_words; i += kCtaThreads)
+        for (uint32_t i = tid; i < n_words; i += NT)
         {
             rem[i] = 0u;
             rnew[i] = 0u;
@@ -295,13 +297,13 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
 
         const long long job_t0 = clock64();
         uint32_t st_windows = 0u, st_in = 0u, st_entries = 0u, st_steps = 0u;
-        long long t_load = 0, t_mis = 0, t_cand = 0, t_sort = 0;
+        long long t_load = 0, t_mis = 0, t_cand = 0, t_sort = 0, t_tiles = 0, t_settle = 0, t_look = 0, t_commit = 0;
         uint32_t u = 0u; // next member (lid) to examine as a seed candidate (ascending index, clustering.cpp:70-75)
         while (true)
         {
             // ---- next seed: first member at or after u that is not removed
             uint32_t seed_l = 0xFFFFFFFFu;
-            for (uint32_t wbase = u >> 5; wbase < n_words; wbase += kCtaThreads)
+            for (uint32_t wbase = u >> 5; wbase < n_words; wbase += NT)
             {
                 const uint32_t wi = wbase + tid;
                 uint32_t cand = 0xFFFFFFFFu;
@@ -366,7 +368,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                     }
                 }
                 const uint32_t alive_w = __ballot_sync(kFullMask, alive);
-                if (lane == 0)
+                if (lane == 0 && owner)
                 {
                     sm.in_mask[warp] = 0u;
                     sm.out_mask[warp] = ~alive_w;
@@ -446,7 +448,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                             cw &= keep;
                         }
                         sm.conf[we][wp * 32u + lane] = cw;
-                        for (uint32_t adv = 0; adv < 8u; ++adv) // next tile of this warp
+                        for (uint32_t adv = 0; adv < kWarps; ++adv) // next tile of this warp
                             if (++we > wp)
                             {
                                 we = 0u;
@@ -455,37 +457,56 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                     }
                 }
                 __syncthreads();
+                const long long tw2 = clock64();
+                t_tiles += tw2 - tw1;
 
                 // ---- which entries are expanded: the lexicographically-first independent set. A warp settles its own
                 // entries with ballots; warp w is settled once the warps before it are, i.e. after at most w + 1 steps.
                 bool unresolved = alive, is_in = false;
                 {
-                    uint32_t conf[8];
+                    // conflicts with the entries of earlier warps, of the own warp, and the earlier words that matter to this
+                    // warp at all (uniform): a BFS frontier queues neighbours next to each other, most words hold none
+                    uint32_t conf[8], own_conf = 0u, wmask = 0u;
 #pragma unroll
                     for (int w = 0; w < 8; ++w)
-                        conf[w] = (n > 1u && static_cast<uint32_t>(w) <= warp && static_cast<uint32_t>(w) < nw && alive) ? sm.conf[w][tid] : 0u;
+                    {
+                        conf[w] = 0u;
+                        if (owner && n > 1u && static_cast<uint32_t>(w) <= warp && static_cast<uint32_t>(w) < nw) // (uniform per warp)
+                        {
+                            const uint32_t v = alive ? sm.conf[w][tid] : 0u;
+                            if (static_cast<uint32_t>(w) == warp)
+                                own_conf = v;
+                            else
+                            {
+                                conf[w] = v;
+                                wmask |= __any_sync(kFullMask, v != 0u) ? 1u << w : 0u;
+                            }
+                        }
+                    }
                     uint32_t own_in = 0u, own_out = ~alive_w, st_guard = 0u;
                     const volatile uint32_t *vin = sm.in_mask, *vout = sm.out_mask;
                     while (true)
                     {
                         ++st_steps;
+                        // what the earlier warps have settled so far (a snapshot per step is enough: a warp is settled one
+                        // step after the last warp it depends on)
+                        uint32_t any_in_prev = 0u, pend_prev = 0u;
+#pragma unroll
+                        for (int w = 0; w < 8; ++w)
+                            if ((wmask >> w) & 1u)
+                            {
+                                const uint32_t iw = vin[w], ow = vout[w];
+                                any_in_prev |= conf[w] & iw;
+                                pend_prev |= conf[w] & ~(iw | ow);
+                            }
                         uint32_t moved;
                         do
                         {
                             bool new_in = false, new_out = false;
                             if (unresolved)
                             {
-                                uint32_t any_in = 0u, pending = 0u;
-#pragma unroll
-                                for (int w = 0; w < 8; ++w)
-                                {
-                                    if (static_cast<uint32_t>(w) > warp) // (uniform per warp; conf[w] is 0 there)
-                                        continue;
-                                    const uint32_t iw = static_cast<uint32_t>(w) == warp ? own_in : vin[w];
-                                    const uint32_t ow = static_cast<uint32_t>(w) == warp ? own_out : vout[w];
-                                    any_in |= conf[w] & iw;
-                                    pending |= conf[w] & ~(iw | ow);
-                                }
+                                const uint32_t any_in = any_in_prev | (own_conf & own_in);
+                                const uint32_t pending = pend_prev | (own_conf & ~(own_in | own_out));
                                 new_out = any_in != 0u;
                                 new_in = any_in == 0u && pending == 0u;
                             }
@@ -497,7 +518,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                             unresolved = unresolved && !new_in && !new_out;
                             moved = bi | bo;
                         } while (moved);
-                        if (lane == 0)
+                        if (lane == 0 && owner)
                         {
                             sm.in_mask[warp] = own_in;
                             sm.out_mask[warp] = own_out;
@@ -507,6 +528,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                     }
                 }
                 // (the barrier above made every warp's final masks visible)
+                t_settle += clock64() - tw2;
                 uint32_t n_in = 0u;
                 {
                     uint32_t before = 0u;
@@ -555,7 +577,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                 for (uint32_t b0 = 0; b0 < n_in; b0 += kGenBatch)
                 {
                     const uint32_t nb = min(kGenBatch, n_in - b0);
-                    for (uint32_t k = warp; k < nb; k += 8u)
+                    for (uint32_t k = warp; k < nb; k += kWarps)
                     {
                         const uint32_t cid = sm.ent_cell[sm.in_list[b0 + k]];
                         uint32_t cstart = 0u, count = 0u;
@@ -566,8 +588,6 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                             count = v >> kGenPosBits;
                             if (count == kGenCountCap)
                                 count = __ldg(&ci[cstart]).x;
-                            if (USE_LIVE && count && __ldcg(&clive[cstart]) == 0u)
-                                count = 0u;
                         }
                         const uint32_t incl = warp_inclusive_scan(count);
                         if (lane < 27u)
@@ -577,12 +597,14 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                         }
                     }
                     __syncthreads();
+                    const long long tl1 = clock64();
+                    t_look += tl1 - (b0 == 0u ? tc0 : tl1);
                     {
                         // lane k: chunks of entry k of the batch; chunk c belongs to the first entry whose inclusive prefix exceeds c
                         const uint32_t my_chunks = lane < nb ? (sm.cin[lane][26] + kGenChunk - 1u) / kGenChunk : 0u;
                         const uint32_t cincl = warp_inclusive_scan(my_chunks);
                         const uint32_t n_chunks = __shfl_sync(kFullMask, cincl, 31);
-                        for (uint32_t c = warp; c < n_chunks; c += 8u)
+                        for (uint32_t c = warp; c < n_chunks; c += kWarps)
                         {
                             const uint32_t k = static_cast<uint32_t>(__ffs(__ballot_sync(kFullMask, cincl > c)) - 1);
                             const uint32_t first = __shfl_sync(kFullMask, cincl - my_chunks, k);
@@ -601,43 +623,48 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                 {
                     const uint32_t nd = sm.n_dirty;
                     if (nd <= kGenDirty)
-                        for (uint32_t i = tid; i < nd; i += kCtaThreads)
+                        for (uint32_t i = tid; i < nd; i += NT)
                         {
                             const uint32_t wd = sm.dirty[i];
                             const uint32_t bits = rnew[wd];
                             rem[wd] |= bits;
                             rnew[wd] = 0u;
-                            if (USE_LIVE) // the live counters change behind the window too: its lookups saw its start
-                                for (uint32_t bm = bits; bm; bm &= bm - 1u)
-                                    atomicSub(&clive[__ldg(&mc[(wd << 5) + static_cast<uint32_t>(__ffs(bm) - 1)])], 1u);
                         }
                     else
-                        for (uint32_t i = tid; i < n_words; i += kCtaThreads)
+                        for (uint32_t i = tid; i < n_words; i += NT)
                         {
                             const uint32_t bits = rnew[i];
                             if (bits == 0u)
                                 continue;
                             rem[i] |= bits;
                             rnew[i] = 0u;
-                            if (USE_LIVE)
-                                for (uint32_t bm = bits; bm; bm &= bm - 1u)
-                                    atomicSub(&clive[__ldg(&mc[(i << 5) + static_cast<uint32_t>(__ffs(bm) - 1)])], 1u);
                         }
                 }
+                t_commit += clock64() - tc1;
                 // ---- the FIFO receives the pushes ordered by (window position of the pusher, k-d pre-order rank)
                 const uint32_t np = sm.n_push;
                 if (tail + np > n_mem) // cannot happen (a member is pushed once): never write past the component's FIFO
                     break;
                 if (np)
                 {
-                    if (np <= kGenW)
+                    if (np <= static_cast<uint32_t>(NT))
                     {
-                        if (tid < np) // short lists: every key is ranked by counting the smaller ones
+                        // short lists: every key is ranked by counting the smaller ones; up to 16 adjacent lanes share a key
+                        uint32_t parts = 1u;
+                        while (parts < 16u && 2u * parts * np <= static_cast<uint32_t>(NT))
+                            parts <<= 1;
+                        const uint32_t i = tid / parts, part = tid % parts;
+                        const uint32_t len = (np + parts - 1u) / parts;
+                        const uint32_t xb = min(np, part * len), xe = min(np, xb + len);
+                        const unsigned long long key = sm.pool[min(i, np - 1u)];
+                        uint32_t dest = 0u;
+#pragma unroll 8
+                        for (uint32_t x = xb; x < xe; ++x)
+                            dest += sm.pool[x] < key ? 1u : 0u;
+                        for (uint32_t o = 1u; o < parts; o <<= 1) // (uniform) the shares of the adjacent lanes of a key
+                            dest += __shfl_xor_sync(kFullMask, dest, o);
+                        if (i < np && part == 0u)
                         {
-                            const unsigned long long key = sm.pool[tid];
-                            uint32_t dest = 0u;
-                            for (uint32_t x = 0; x < np; ++x)
-                                dest += sm.pool[x] < key ? 1u : 0u;
                             const uint32_t lid = static_cast<uint32_t>(key);
                             qu[tail + dest] = lid;
                             sm.ring[(tail + dest) & (kRing - 1u)] = lid;
@@ -651,13 +678,13 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                         if (np > kGenPool)
                         {
                             // rare: sort in global memory, the spill area holds the keys from kGenPool on already
-                            for (uint32_t i = tid; i < kGenPool; i += kCtaThreads)
+                            for (uint32_t i = tid; i < kGenPool; i += NT)
                                 spill[tail + i] = sm.pool[i];
                             pbuf = spill + tail;
                             __syncthreads();
                         }
-                        cta_bitonic_sort(pbuf, np); // (uniform branch: np comes from shared memory)
-                        for (uint32_t i = tid; i < np; i += kCtaThreads)
+                        cta_bitonic_sort<NT>(pbuf, np); // (uniform branch: np comes from shared memory)
+                        for (uint32_t i = tid; i < np; i += NT)
                         {
                             const uint32_t lid = static_cast<uint32_t>(pbuf[i]);
                             qu[tail + i] = lid;
@@ -690,7 +717,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
             if (tid == 0)
             {
                 uint32_t tsum = 0u;
-                for (uint32_t v = 0; v < 8u; ++v)
+                for (uint32_t v = 0; v < kWarps; ++v)
                     tsum += sm.wcnt[v];
                 seed_valid[off + seed_idx] = (tsum < prm.min_cluster_size || tsum > prm.max_cluster_size) ? 0u : 1u;
             }
@@ -698,13 +725,16 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
         }
         if (job_stats && tid == 0)
         {
-            uint32_t *js = job_stats + 8u * w_job;
+            uint32_t skip = 0u;
+            for (uint32_t b = 1; b <= stats_skip_buckets; ++b)
+                skip += *(big_count - b);
+            uint32_t *js = job_stats + 8u * (skip + w_job);
             js[0] = f;
             js[1] = n_mem;
             js[2] = static_cast<uint32_t>((clock64() - job_t0) >> 10);
-            js[3] = st_windows;
-            js[4] = st_in;
-            js[5] = st_entries;
+            js[3] = st_windows | (st_in << 16);
+            js[4] = (static_cast<uint32_t>(t_tiles >> 10) & 0xFFFFu) | (static_cast<uint32_t>(t_settle >> 10) << 16);
+            js[5] = (static_cast<uint32_t>(t_look >> 10) & 0xFFFFu) | (static_cast<uint32_t>(t_commit >> 10) << 16);
             js[6] = (static_cast<uint32_t>(t_load >> 10) & 0xFFFFu) | (static_cast<uint32_t>(t_mis >> 10) << 16);
             js[7] = (static_cast<uint32_t>(t_cand >> 10) & 0xFFFFu) | (static_cast<uint32_t>(t_sort >> 10) << 16);
         }

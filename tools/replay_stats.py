@@ -22,11 +22,16 @@ for _ in range(3):
     ctx.batch_run()
     ctx.sync()
 st = ctx.last_replay_stats()
-if os.environ.get("LIDAR_B200_REPLAY_V", "5") == "5":  # window-synchronous replay (replay_gen.cuh)
+if os.environ.get("LIDAR_B200_REPLAY_V", "5") not in ("1", "2"):  # window-synchronous replay (replay_gen.cuh)
     print("stage ms", {k: round(v, 3) for k, v in ctx.last_stage_ms().items()})
     kc = st[:, 2].astype(np.float64)
     print(f"jobs {st.shape[0]}  sum kcycles {kc.sum():.0f}  max {kc.max():.0f}  mean {kc.mean():.1f}")
     print(f"sum/444 CTAs = {kc.sum()/444:.0f} kcycles = {kc.sum()*1.024/444/1965:.3f} ms ; longest job = {kc.max()*1.024/1965:.3f} ms")
+    st = st.copy()
+    extra = st[:, 4:6].copy()  # tiles | settle loop, lookups | commit (kcycles, 16 bits each)
+    st[:, 4] = st[:, 3] >> 16  # expanded
+    st[:, 3] &= 0xFFFF         # windows
+    st[:, 5] = 0               # (entries are no longer recorded)
     ph = np.stack([st[:, 6] & 0xFFFF, st[:, 6] >> 16, st[:, 7] & 0xFFFF, st[:, 7] >> 16], 1).astype(np.float64)
     print("top jobs: [frame members kcycles windows expanded entries] kcyc[load settle candidates sort+commit]  cycles/window")
     for j in np.argsort(-kc)[:12]:
@@ -41,25 +46,16 @@ if os.environ.get("LIDAR_B200_REPLAY_V", "5") == "5":  # window-synchronous repl
         if m.any():
             print(f"members [{lo},{hi}): jobs {int(m.sum())}, kcycles {kc[m].sum():.0f} ({100*kc[m].sum()/kc.sum():.1f} %), cycles/member {1024*kc[m].sum()/st[m,1].sum():.0f}, cycles/window {1024*kc[m].sum()/wn[m].sum():.0f}")
     sys.exit(0)
-v3 = os.environ.get("LIDAR_B200_REPLAY_V", "3") not in ("1", "2")
-cands = over = None
-if v3:  # third generation packs more into the 8 words (replay_cta3.cuh)
-    st = st.copy()
-    cands = st[:, 1] >> 20
-    st[:, 1] &= (1 << 20) - 1
-    over = st[:, 4] >> 16
-    st[:, 4] &= 0xFFFF
 print("stage ms", {k: round(v, 3) for k, v in ctx.last_stage_ms().items()})
 kc = st[:, 2].astype(np.float64)
 print(f"jobs {st.shape[0]}  sum kcycles {kc.sum():.0f}  max {kc.max():.0f}  mean {kc.mean():.1f}")
 print(f"sum/444 CTAs = {kc.sum()/444:.0f} kcycles = {kc.sum()*1.024/444/1965:.3f} ms ; longest job = {kc.max()*1.024/1965:.3f} ms")
 order = np.argsort(-kc)
-v2 = os.environ.get("LIDAR_B200_REPLAY_V", "3") != "1"
+v2 = os.environ.get("LIDAR_B200_REPLAY_V") == "2"
 print("top jobs: [frame members kcycles rounds direct " + ("kcycA kcycB kcycC" if v2 else "kcycA kcycBC kcycEF") + "]  cycles/round   (kcycles = cycles >> 10)")
 for j in order[:12]:
     r = st[j]
-    print("  ", r.tolist(), round(1024 * r[2] / max(1, r[3] + (0 if v3 else r[4]))),
-          f"  live candidates/round {int(cands[j])} re-scanned rounds {int(over[j])}" if v3 else "")
+    print("  ", r.tolist(), round(1024 * r[2] / max(1, r[3] + (0 if v2 else r[4]))))
 rounds = st[:, 3].astype(np.float64) + (0 if v2 else st[:, 4])
 if v2:
     print(f"total rounds {rounds.sum():.0f}, mean cycles/round {1024*kc.sum()/rounds.sum():.0f}; phase share A (window) "
