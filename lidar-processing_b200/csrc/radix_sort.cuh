@@ -16,6 +16,8 @@ constexpr int kRsThreads = 256;
 constexpr int kRsItems = 16;
 constexpr int kRsTile = kRsThreads * kRsItems; // 4096 keys per CTA
 constexpr int kRsRadix = 256;
+constexpr int kRsScatterThreads = 512; // the scatter keeps kRsTile / 512 = 8 pairs per thread in registers: <= 40 registers,
+constexpr int kRsScatterItems = kRsTile / kRsScatterThreads; // 48 warps per SM hide the load latency it is bound by
 
 // Per-tile digit histogram. grid = (max_tiles, frames). Tiles past the end of a frame write zeros
 // so the scan below can run over a fixed-size table.
@@ -80,15 +82,15 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ ti
 }
 
 // Stable scatter of one tile. grid = (max_tiles, frames). Warp w owns the contiguous sub-range
-// [tile_base + w*512, +512); inside it, iteration k / lane l maps to element k*32 + l, so
+// [tile_base + w*256, +256); inside it, iteration k / lane l maps to element k*32 + l, so
 // (warp, k, lane) order equals memory order and equal digits keep their relative order.
-__global__ void __launch_bounds__(kRsThreads)
+__global__ void __launch_bounds__(kRsScatterThreads, 3)
 rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, BatchView bv, uint32_t shift,
                   uint32_t max_tiles, const uint32_t *__restrict__ tile_hist)
 {
-    constexpr int kWarps = kRsThreads / 32;
-    constexpr int kPerWarp = kRsTile / kWarps; // 512
+    constexpr int kWarps = kRsScatterThreads / 32;
+    constexpr int kPerWarp = kRsTile / kWarps; // 256
     __shared__ uint32_t warp_cnt[kWarps][kRsRadix];
 
     const uint32_t f = blockIdx.y;
@@ -105,12 +107,12 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
         warp_cnt[warp][d] = 0u;
     __syncwarp();
 
-    uint32_t key[kRsItems];
-    uint32_t val[kRsItems];
-    uint16_t rank[kRsItems];
+    uint32_t key[kRsScatterItems];
+    uint32_t val[kRsScatterItems];
+    uint16_t rank[kRsScatterItems];
     const uint32_t wbase = base + warp * kPerWarp;
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k)
+    for (int k = 0; k < kRsScatterItems; ++k)
     {
         const uint32_t idx = wbase + k * 32 + lane;
         const bool valid = idx < n;
@@ -118,7 +120,7 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
         val[k] = valid ? vals_in[off + idx] : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k)
+    for (int k = 0; k < kRsScatterItems; ++k)
     {
         const uint32_t idx = wbase + k * 32 + lane;
         const bool valid = idx < n;
@@ -137,18 +139,21 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     {
         // thread d turns the per-warp counts of digit d into global destinations
         const uint32_t d = threadIdx.x;
-        uint32_t run = tile_hist[(static_cast<size_t>(f) * kRsRadix + d) * max_tiles + tile];
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w)
+        if (d < kRsRadix)
         {
-            const uint32_t c = warp_cnt[w][d];
-            warp_cnt[w][d] = run;
-            run += c;
+            uint32_t run = tile_hist[(static_cast<size_t>(f) * kRsRadix + d) * max_tiles + tile];
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w)
+            {
+                const uint32_t c = warp_cnt[w][d];
+                warp_cnt[w][d] = run;
+                run += c;
+            }
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k)
+    for (int k = 0; k < kRsScatterItems; ++k)
     {
         const uint32_t idx = wbase + k * 32 + lane;
         if (idx < n)
@@ -397,7 +402,7 @@ inline int radix_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *val
         const uint32_t shift = static_cast<uint32_t>(p) * 8u;
         rs_hist_kernel<<<grid, kRsThreads, 0, stream>>>(kin, bv, shift, max_tiles, scratch.tile_hist);
         rs_scan_kernel<<<bv.frames, 1024, 0, stream>>>(scratch.tile_hist, kRsRadix * max_tiles);
-        rs_scatter_kernel<<<grid, kRsThreads, 0, stream>>>(kin, vin, kout, vout, bv, shift, max_tiles,
+        rs_scatter_kernel<<<grid, kRsScatterThreads, 0, stream>>>(kin, vin, kout, vout, bv, shift, max_tiles,
                                                             scratch.tile_hist);
         if (launches)
             *launches += 3;
