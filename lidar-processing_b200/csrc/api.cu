@@ -959,6 +959,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     lidar_b200_clu_cfg_default(&cc);
     apply_seg_cfg(c, sc);
     apply_clu_cfg(c, cc);
+    // (a high-priority second stream - the 17 k-d levels and the long replay jobs first - was measured: the k-d order is
+    // ready in time then, but the union-find beside it slows down by the same amount; a step is bound by the total work)
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream_big, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream_huge, cudaStreamNonBlocking) != cudaSuccess ||

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ ti
 // Stable scatter of one tile. grid = (max_tiles, frames). Warp w owns the contiguous sub-range
 // [tile_base + w*256, +256); inside it, iteration k / lane l maps to element k*32 + l, so
 // (warp, k, lane) order equals memory order and equal digits keep their relative order.
+// The tile is ordered by digit in shared memory first and leaves in runs of equal digit: a direct scatter touches ~29
+// sectors per 32-lane store (ncu: L2 at 71 % of its sector throughput, DRAM at 16 %), the staged one 4-8.
 __global__ void __launch_bounds__(kRsScatterThreads, 3)
 rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, BatchView bv, uint32_t shift,
@@ -91,7 +93,12 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
 {
     constexpr int kWarps = kRsScatterThreads / 32;
     constexpr int kPerWarp = kRsTile / kWarps; // 256
-    __shared__ uint32_t warp_cnt[kWarps][kRsRadix];
+    __shared__ uint32_t stage_key[kRsTile];
+    __shared__ uint32_t stage_val[kRsTile];
+    __shared__ uint32_t gbase[kRsRadix];      // first destination of the tile's run of every digit (frame-relative)
+    __shared__ uint32_t tile_excl[kRsRadix];  // first staging slot of every digit
+    __shared__ uint16_t warp_cnt[kWarps][kRsRadix]; // per warp: count, then first staging slot relative to tile_excl
+    __shared__ uint32_t ws[kRsRadix / 32];
 
     const uint32_t f = blockIdx.y;
     const uint32_t tile = blockIdx.x;
@@ -103,6 +110,7 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
+    const uint32_t lt = lanemask_lt();
     for (int d = lane; d < kRsRadix; d += 32)
         warp_cnt[warp][d] = 0u;
     __syncwarp();
@@ -130,39 +138,60 @@ rs_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
         if (valid)
             prev = warp_cnt[warp][digit];
         __syncwarp();
-        if (valid && (peers & lanemask_lt()) == 0u)
-            warp_cnt[warp][digit] = prev + static_cast<uint32_t>(__popc(peers));
+        if (valid && (peers & lt) == 0u)
+            warp_cnt[warp][digit] = static_cast<uint16_t>(prev + __popc(peers));
         __syncwarp();
-        rank[k] = static_cast<uint16_t>(prev + static_cast<uint32_t>(__popc(peers & lanemask_lt())));
+        rank[k] = static_cast<uint16_t>(prev + __popc(peers & lt));
     }
     __syncthreads();
     {
-        // thread d turns the per-warp counts of digit d into global destinations
+        // thread d: counts of the warps for digit d -> first slot of (warp, d); the tile's count of d is scanned over the digits
         const uint32_t d = threadIdx.x;
+        uint32_t c = 0u;
         if (d < kRsRadix)
         {
-            uint32_t run = tile_hist[(static_cast<size_t>(f) * kRsRadix + d) * max_tiles + tile];
+            gbase[d] = tile_hist[(static_cast<size_t>(f) * kRsRadix + d) * max_tiles + tile];
 #pragma unroll
             for (int w = 0; w < kWarps; ++w)
             {
-                const uint32_t c = warp_cnt[w][d];
-                warp_cnt[w][d] = run;
-                run += c;
+                const uint32_t x = warp_cnt[w][d];
+                warp_cnt[w][d] = static_cast<uint16_t>(c);
+                c += x;
             }
+        }
+        const uint32_t incl = warp_inclusive_scan(c);
+        if (lane == 31 && warp < kRsRadix / 32)
+            ws[warp] = incl;
+        __syncthreads();
+        if (d < kRsRadix)
+        {
+            uint32_t before = 0u;
+            for (uint32_t v = 0; v < warp; ++v)
+                before += ws[v];
+            tile_excl[d] = before + incl - c;
         }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kRsScatterItems; ++k)
     {
-        const uint32_t idx = wbase + k * 32 + lane;
-        if (idx < n)
+        if (wbase + k * 32 + lane < n)
         {
             const uint32_t digit = (key[k] >> shift) & 0xFFu;
-            const uint32_t dst = off + warp_cnt[warp][digit] + rank[k];
-            keys_out[dst] = key[k];
-            vals_out[dst] = val[k];
+            const uint32_t slot = tile_excl[digit] + warp_cnt[warp][digit] + rank[k];
+            stage_key[slot] = key[k];
+            stage_val[slot] = val[k];
         }
+    }
+    __syncthreads();
+    const uint32_t tn = min(static_cast<uint32_t>(kRsTile), n - base);
+    for (uint32_t j = threadIdx.x; j < tn; j += kRsScatterThreads)
+    {
+        const uint32_t k2 = stage_key[j];
+        const uint32_t digit = (k2 >> shift) & 0xFFu;
+        const uint32_t dst = off + gbase[digit] + (j - tile_excl[digit]);
+        keys_out[dst] = k2;
+        vals_out[dst] = stage_val[j];
     }
 }
 

@@ -58,7 +58,8 @@ struct __align__(16) GenSmem
     uint32_t ring[kRing];              // lids of the most recent FIFO entries
     uint32_t cst[kGenBatch][27], cin[kGenBatch][27]; // neighbour cells of the batch's expanded entries: first pos, inclusive prefix
     float box_lo[8][4], box_hi[8][4];  // bounding box of the alive entries of every 32-entry word of the window
-    uint32_t in_mask[8], out_mask[8];  // expanded / not expanded, one bit per window entry
+    uint32_t in_mask[2][8], out_mask[2][8]; // expanded / not expanded, one bit per window entry; settle step s reads
+                                            // copy s & 1 and writes the other one (no read races a write)
     uint32_t wcnt[32];
     uint32_t n_push, n_dirty, claim, found;
     uint16_t dirty[kGenDirty];
@@ -370,8 +371,8 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                 const uint32_t alive_w = __ballot_sync(kFullMask, alive);
                 if (lane == 0 && owner)
                 {
-                    sm.in_mask[warp] = 0u;
-                    sm.out_mask[warp] = ~alive_w;
+                    sm.in_mask[0][warp] = 0u;
+                    sm.out_mask[0][warp] = ~alive_w;
                 }
                 if (warp * 32u < n && n > 32u) // bounding box of the word's alive entries: far-apart words skip their tile
                 {
@@ -442,7 +443,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                                 const float d2 = dist_sqr_ref(q.x, q.y, q.z, me.x, me.y, me.z);
                                 cw |= (d2 <= prm.inner_threshold ? 1u : 0u) << b;
                             }
-                            uint32_t keep = ~sm.out_mask[we]; // (only dead entries are in out_mask before the settle starts)
+                            uint32_t keep = ~sm.out_mask[0][we]; // (only dead entries are in out_mask before the settle starts)
                             if (we == wp)
                                 keep &= lt;
                             cw &= keep;
@@ -463,6 +464,7 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                 // ---- which entries are expanded: the lexicographically-first independent set. A warp settles its own
                 // entries with ballots; warp w is settled once the warps before it are, i.e. after at most w + 1 steps.
                 bool unresolved = alive, is_in = false;
+                uint32_t fin = 0u; // which copy of the masks the next settle step reads; the final one afterwards
                 {
                     // conflicts with the entries of earlier warps, of the own warp, and the earlier words that matter to this
                     // warp at all (uniform): a BFS frontier queues neighbours next to each other, most words hold none
@@ -484,9 +486,10 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                         }
                     }
                     uint32_t own_in = 0u, own_out = ~alive_w, st_guard = 0u;
-                    const volatile uint32_t *vin = sm.in_mask, *vout = sm.out_mask;
                     while (true)
                     {
+                        const volatile uint32_t *vin = sm.in_mask[fin], *vout = sm.out_mask[fin];
+                        fin ^= 1u;
                         ++st_steps;
                         // what the earlier warps have settled so far (a snapshot per step is enough: a warp is settled one
                         // step after the last warp it depends on)
@@ -520,8 +523,8 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
                         } while (moved);
                         if (lane == 0 && owner)
                         {
-                            sm.in_mask[warp] = own_in;
-                            sm.out_mask[warp] = own_out;
+                            sm.in_mask[fin][warp] = own_in;
+                            sm.out_mask[fin][warp] = own_out;
                         }
                         if (!__syncthreads_or(unresolved ? 1 : 0) || st_guard++ > 16u) // (settled after <= 8 steps by construction)
                             break;
@@ -535,12 +538,12 @@ replay_gen_kernel(const float4 *__restrict__ ipts_all, const uint32_t *__restric
 #pragma unroll
                     for (uint32_t w = 0; w < 8u; ++w)
                     {
-                        const uint32_t c = __popc(sm.in_mask[w]);
+                        const uint32_t c = __popc(sm.in_mask[fin][w]);
                         before += w < warp ? c : 0u;
                         n_in += c;
                     }
                     if (is_in)
-                        sm.in_list[before + __popc(sm.in_mask[warp] & lt)] = static_cast<uint8_t>(tid);
+                        sm.in_list[before + __popc(sm.in_mask[fin][warp] & lt)] = static_cast<uint8_t>(tid);
                 }
                 st_in += n_in;
                 __syncthreads();
