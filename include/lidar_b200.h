@@ -148,6 +148,12 @@ extern "C"
      *   LIDAR_B200_HULL_CONCAVE_SMALL the convex branch of findOrderedConcaveOutlines
      *       (src/polygon_simplification.cpp:100-118): clusters below 20 points. Clusters from 20 points
      *       on get 0 vertices here: their Delaunay-based concave hull stays on the host.
+     *   LIDAR_B200_HULL_CONCAVE       findOrderedConcaveOutlines as a whole (src/polygon_simplification.cpp:81-149):
+     *       that branch below 20 points, and from 20 points on geometry::ConcaveHull with chi = 0.2
+     *       (reference Concave-Hull/concave_hull.hpp:96-193 over Concave-Hull/delaunator.cpp) re-enacted value for
+     *       value in float64 — seed triangle, sweep order (std::sort by distance from its circumcentre), advancing
+     *       hull, edge flips, erosion of the boundary edges by a max-heap of their lengths. These outlines are
+     *       CLOSED like the reference's (the first vertex is repeated at the end).
      * _fetch_hulls: blocks; per frame f (O = point_offset[f], K = n_clusters[f]):
      *   hull_offset_out[O + f + k], k = 0..K : CSR offsets into the frame's vertex list; a cluster with an
      *       empty hull (fewer than 3 points) is the one the reference drops from its output vector
@@ -157,10 +163,17 @@ extern "C"
      * Array sizes: n_vertices_out [n_frames], hull_offset_out [sum n + n_frames], hull_xy_out [sum n][2],
      * hull_point_idx_out [sum n]. Errors: LIDAR_B200_ERR_UNSUPPORTED for a cluster above ~1.04 M points,
      * LIDAR_B200_ERR_INPUT when the Jarvis march of a CHAN cluster does not close (duplicate hull vertices in
-     * different subsets; the reference loops forever on such a cluster): the outputs are still complete, that
-     * cluster has 0 vertices and every other outline is valid. */
+     * different subsets; the reference loops forever on such a cluster) and, in mode CONCAVE, for a cluster of 20 or
+     * more points that are all collinear or all coincident in (x, y) (the reference throws "not triangulation",
+     * delaunator.cpp:299, respectively reads out of bounds): the outputs are still complete, that cluster has 0
+     * vertices and every other outline is valid. LIDAR_B200_ERR_CAPACITY when the closed outlines of a frame need more
+     * than one vertex per staged point of the frame (only possible when nearly every point is an outline vertex): the
+     * outlines that do not fit have 0 vertices. hull_point_idx_out in mode CONCAVE: a point of the cluster with exactly
+     * the vertex's (x, y); where several points coincide, the one with the lowest index unless the cluster's sweep
+     * order had to be replayed (two different points exactly equally far from the seed circumcentre). */
 #define LIDAR_B200_HULL_CONVEX 0u
 #define LIDAR_B200_HULL_CONCAVE_SMALL 1u
+#define LIDAR_B200_HULL_CONCAVE 2u
     int lidar_b200_batch_hull_outlines(lidar_b200_ctx *ctx, uint32_t mode);
     int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *ctx, uint32_t *n_vertices_out, uint32_t *hull_offset_out,
                                      float *hull_xy_out, uint32_t *hull_point_idx_out);

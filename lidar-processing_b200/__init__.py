@@ -138,6 +138,7 @@ DEFAULT_FETCH_MODE = 0   # the library's default LIDAR_B200_FETCH_MODE (api.cu)
 ERR_INPUT = 5            # LIDAR_B200_ERR_INPUT (include/lidar_b200.h)
 HULL_CONVEX = 0          # findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79)
 HULL_CONCAVE_SMALL = 1   # convex branch of findOrderedConcaveOutlines (:100-118); >= 20 points stay on the host
+HULL_CONCAVE = 2         # findOrderedConcaveOutlines as a whole (:81-149): + the Delaunay-based chi-shape from 20 points on, closed
 
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
@@ -335,9 +336,10 @@ class Context:
         return out
 
     def batch_hulls(self, mode: int = HULL_CONVEX, tolerate_open_marches: bool = False):
-        """Ordered convex outlines per cluster on the device (reference src/polygon_simplification.cpp:31-79 /
-        :100-118) of the last batch_clusters(). Returns, per frame, dict(offsets[K+1], xy[n_vertices,2],
-        point_idx[n_vertices]): outline of cluster k = xy[offsets[k]:offsets[k+1]], counter-clockwise, open."""
+        """Ordered outlines per cluster on the device (reference src/polygon_simplification.cpp:31-79 / :81-149) of
+        the last batch_clusters(). Returns, per frame, dict(offsets[K+1], xy[n_vertices,2], point_idx[n_vertices]):
+        outline of cluster k = xy[offsets[k]:offsets[k+1]]; convex outlines are counter-clockwise and open, the concave
+        ones of mode HULL_CONCAVE (clusters from 20 points on) are closed like the reference's."""
         counts = self._n_points
         nf = counts.size
         padded = ((counts.astype(np.int64) + 31) & ~31)

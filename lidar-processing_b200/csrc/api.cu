@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "group.cuh"
 #include "hull.cuh"
+#include "chi_shape.cuh"
 #include "pack.cuh"
 #include "kd_build.cuh"
 #include "pcd_io.h"
@@ -135,6 +136,9 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_goff; // CSR offsets of the grouped clusters: frame f at [off[f] + f, off[f] + f + K_f]
     // outlines of the grouped clusters (hull.cuh): CSR offsets in the layout of d_goff, vertices per frame, error bits
     DevBuf<uint32_t> d_hoff, d_hne, d_hnv, d_herr, d_rgb;
+    DevBuf<unsigned char> d_chi;   // working sets of the concave outlines (chi_shape.cuh), 96 bytes per point slot
+    DevBuf<uint32_t> d_chi_meta;   // [bucket counts 32 | bucket fill 32 | cursor]
+    uint32_t hull_mode{0};
     DevBuf<uint4> d_color;   // 32-byte PointXYZRGB records (pack.cuh), allocated on first use
     DevBuf<double> d_marker; // marker points, allocated on first use
     bool hulled{false}, hull_attr_done{false};
@@ -1030,7 +1034,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p, c->d_nb27.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p, c->d_nb27.p, c->d_chi.p, c->d_chi_meta.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -1341,7 +1345,7 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
 {
     if (!c)
         return LIDAR_B200_ERR_INVALID;
-    if (mode != LIDAR_B200_HULL_CONVEX && mode != LIDAR_B200_HULL_CONCAVE_SMALL)
+    if (mode != LIDAR_B200_HULL_CONVEX && mode != LIDAR_B200_HULL_CONCAVE_SMALL && mode != LIDAR_B200_HULL_CONCAVE)
         return fail(c, LIDAR_B200_ERR_INVALID, "hull_outlines: unknown mode");
     if (!c->grouped)
         return fail(c, LIDAR_B200_ERR_INVALID, "hull_outlines: call lidar_b200_batch_group_clusters first");
@@ -1351,8 +1355,12 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
         dev_alloc(c, c->d_hne, static_cast<size_t>(c->cap_pts) + c->cap_frames + 1u) ||
         dev_alloc(c, c->d_hnv, 4 * static_cast<size_t>(c->cap_frames) + 2) || dev_alloc(c, c->d_herr, 4))
         return LIDAR_B200_ERR_CUDA;
+    if (mode == LIDAR_B200_HULL_CONCAVE && F && c->clu_max_m &&
+        (dev_alloc(c, c->d_chi, static_cast<size_t>(kChiBytesPerPoint) * c->total + 256u) || dev_alloc(c, c->d_chi_meta, 2u * kChiBuckets + 1u)))
+        return LIDAR_B200_ERR_CUDA;
     cudaStream_t s = c->stream;
     c->hulled = true;
+    c->hull_mode = mode;
     if (F == 0u)
         return 0;
     LB_CUDA(c, cudaMemsetAsync(c->d_hoff.p, 0, (static_cast<size_t>(c->total) + F) * 4, s));
@@ -1384,9 +1392,22 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
         hull_chan_merge_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), hv);
         ++nl;
     }
+    if (mode == LIDAR_B200_HULL_CONCAVE)
+    {
+        // the chi-shape of every cluster from 20 points on: one warp per cluster, largest clusters first
+        uint32_t *counts = c->d_chi_meta.p, *fill = counts + kChiBuckets, *chi_cursor = counts + 2u * kChiBuckets;
+        uint32_t *task_f = c->d_parent.p, *task_k = c->d_comp_size.p; // (the union-find arrays are spent)
+        LB_CUDA(c, cudaMemsetAsync(counts, 0, (2u * kChiBuckets + 1u) * 4, s));
+        const ChiView cv{c->d_nodes.p, c->d_goff.p, c->d_key_a.p, c->d_hoff.p, c->d_chi.p, c->d_herr.p};
+        chi_bucket_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_goff.p, counts);
+        chi_place_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_goff.p, counts, fill, task_f, task_k);
+        chi_outline_kernel<<<c->sm_count * 8u, 32 * kChiWarps, 0, s>>>(bv, cv, counts, task_f, task_k, chi_cursor);
+        nl += 3u;
+    }
     hull_scan_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_hoff.p, c->d_hne.p, c->d_hnv.p,
-                                       c->d_hnv.p + 3 * static_cast<size_t>(c->cap_frames) + 2);
-    hull_emit_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), hv, reinterpret_cast<float2 *>(c->d_spill.p), c->d_gepos.p);
+                                       c->d_hnv.p + 3 * static_cast<size_t>(c->cap_frames) + 2, c->m_cnt(), c->d_herr.p);
+    hull_emit_kernel<<<dim3(8, F), 256, 0, s>>>(bv, c->m_nc(), hv, reinterpret_cast<float2 *>(c->d_spill.p), c->d_gepos.p,
+                                                mode == LIDAR_B200_HULL_CONCAVE ? kHullConcaveMin : 0xFFFFFFFFu);
     c->launches += nl;
     LB_CUDA(c, cudaGetLastError());
     return 0;
@@ -1433,6 +1454,15 @@ int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *c, uint32_t *n_vertices_out, ui
     // The outputs are complete either way: a cluster whose Jarvis march does not close (duplicate hull vertices in
     // different CHAN subsets; the reference never returns from such a cluster) or whose hull would outgrow it has
     // 0 vertices, every other cluster is exact. The status tells the caller that it happened.
+    if (herr & (kHullErrCollinear | kHullErrDegenerate))
+        return fail(c, LIDAR_B200_ERR_INPUT, herr & kHullErrCollinear
+                                                 ? "hull_outlines: a cluster of 20 or more points that are all collinear in (x, y) - the reference throws "
+                                                   "\"not triangulation\" (delaunator.cpp:299) - was given 0 vertices; all other outlines are valid"
+                                                 : "hull_outlines: a cluster of 20 or more points that all coincide in (x, y) (the reference reads out of "
+                                                   "bounds) was given 0 vertices; all other outlines are valid");
+    if (herr & kHullErrSlot)
+        return fail(c, LIDAR_B200_ERR_CAPACITY, "hull_outlines: the closed outlines of a frame outgrow its slot (one vertex per staged point); "
+                                                "the outlines that did not fit were given 0 vertices");
     if (herr)
         return fail(c, LIDAR_B200_ERR_INPUT, "hull_outlines: a cluster on which the reference's CHAN hull does not terminate "
                                              "(Jarvis march that never closes) was given 0 vertices; all other outlines are valid");

@@ -1,0 +1,350 @@
+// Concave outlines of the clusters of 20 points and more on the device (the Delaunay-based
+// chi-shape of findOrderedConcaveOutlines, reference src/polygon_simplification.cpp:119-140 ->
+// Concave-Hull/concave_hull.hpp:96-193 -> Concave-Hull/delaunator.cpp), sm_100a.
+//
+// The algorithm of the reference is a chain of dependent pointer updates per cluster (advancing hull, edge flips, a heap
+// of boundary edges); its result depends on the insertion order and on every epsilon-guarded predicate, so the device
+// runs the same chain (chi_shape.h, float64, no FMA contraction) and takes its parallelism from the batch: a 154-frame
+// batch holds ~20 000 such clusters, one warp each. Inside a cluster the warp works together wherever the reference's
+// result does not depend on an order: copying the points, bounding box, the three seed searches (first index among equal
+// minima = lexicographic (value, index) reduction), the distances, the sort by (distance, index) (a bitonic network over
+// 64-bit keys) and the scan for equally distant different points that sends a cluster to the std::sort re-enactment.
+// The sweep, the flips and the erosion run on lane 0 out of the cluster's own working set, which stays in L1/L2.
+//
+// Scheduling: tasks are bucketed by floor(log2 n), largest bucket first, and pulled from one batch-wide counter by
+// persistent warps, so the few clusters of 10 000+ points start at once and the small ones fill in behind them.
+//
+// Working set: 96 bytes per grouped point, cluster k of frame f at arena + 96 * (off[f] + goff[k]) (chi_layout(n).bytes
+// <= 82 n + 46 < 96 n for n >= 20), so no prefix sum and no host round trip is needed to place it.
+#pragma once
+
+#include "chi_shape.h"
+#include "common.cuh"
+#include "hull.cuh"
+
+namespace lb
+{
+
+constexpr uint32_t kChiBytesPerPoint = 96u;
+constexpr int kChiWarps = 4;
+constexpr uint32_t kChiBuckets = 32u;
+constexpr uint32_t kHullErrCollinear = 8u;  // the reference throws "not triangulation" on this cluster
+constexpr uint32_t kHullErrDegenerate = 16u; // every point of the cluster coincides (the reference reads out of bounds) / flip budget
+constexpr uint32_t kHullErrSlot = 32u;       // closed outlines of a frame beyond its slot
+
+struct ChiView
+{
+    const float4 *gpts;   // grouped points (group.cuh), frame-major
+    const uint32_t *goff; // CSR offsets, frame f at [off[f] + f, off[f] + f + K]
+    uint32_t *hres;       // per cluster, at its CSR position: outline vertices as cluster-local indices (open loop)
+    uint32_t *hcnt;       // per cluster (same layout as goff): vertices of the CLOSED outline
+    unsigned char *arena; // 96 bytes per point slot
+    uint32_t *err;
+};
+
+// counts[b] = clusters of the batch with floor(log2 n) == b and n >= 20 (grid = frames)
+__global__ void __launch_bounds__(256)
+chi_bucket_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, const uint32_t *__restrict__ goff,
+                  uint32_t *__restrict__ counts)
+{
+    __shared__ uint32_t s_cnt[kChiBuckets];
+    const uint32_t f = blockIdx.x;
+    const uint32_t K = n_clusters[f];
+    const uint32_t *go = goff + bv.off[f] + f;
+    if (threadIdx.x < kChiBuckets)
+        s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < K; k += 256u)
+    {
+        const uint32_t n = go[k + 1u] - go[k];
+        if (n >= kHullConcaveMin)
+            atomicAdd(&s_cnt[31u - __clz(n)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kChiBuckets && s_cnt[threadIdx.x])
+        atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// task list in descending bucket order (inside a bucket in arrival order: the order of the tasks changes the schedule,
+// not a result)
+__global__ void __launch_bounds__(256)
+chi_place_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, const uint32_t *__restrict__ goff,
+                 const uint32_t *__restrict__ counts, uint32_t *__restrict__ fill, uint32_t *__restrict__ task_f,
+                 uint32_t *__restrict__ task_k)
+{
+    __shared__ uint32_t s_base[kChiBuckets];
+    const uint32_t f = blockIdx.x;
+    const uint32_t K = n_clusters[f];
+    const uint32_t *go = goff + bv.off[f] + f;
+    if (threadIdx.x < kChiBuckets)
+    {
+        uint32_t before = 0u;
+        for (uint32_t b = threadIdx.x + 1u; b < kChiBuckets; ++b)
+            before += counts[b];
+        s_base[threadIdx.x] = before;
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < K; k += 256u)
+    {
+        const uint32_t n = go[k + 1u] - go[k];
+        if (n >= kHullConcaveMin)
+        {
+            const uint32_t b = 31u - __clz(n);
+            const uint32_t at = s_base[b] + atomicAdd(&fill[b], 1u);
+            task_f[at] = f;
+            task_k[at] = k;
+        }
+    }
+}
+
+// lexicographic (value, index) minimum across the warp; every lane ends with the result
+LB_D void chi_warp_argmin(double &v, uint32_t &i)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const double ov = __shfl_xor_sync(kFullMask, v, d);
+        const uint32_t oi = __shfl_xor_sync(kFullMask, i, d);
+        if (ov < v || (ov == v && oi < i))
+        {
+            v = ov;
+            i = oi;
+        }
+    }
+}
+
+LB_D double chi_warp_min(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v = fmin(v, __shfl_xor_sync(kFullMask, v, d));
+    return v;
+}
+
+LB_D double chi_warp_max(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v = fmax(v, __shfl_xor_sync(kFullMask, v, d));
+    return v;
+}
+
+// The seed triangle of chi_seed_sequential with the warp: same values, every lane holds them afterwards.
+LB_D uint32_t chi_seed_warp(ChiWork &w)
+{
+    const uint32_t n = w.n, lane = lane_id();
+    double max_x = -DBL_MAX, max_y = -DBL_MAX, min_x = DBL_MAX, min_y = DBL_MAX;
+    for (uint32_t i = lane; i < n; i += 32u)
+    {
+        const double x = chi_px(w, i), y = chi_py(w, i);
+        min_x = fmin(min_x, x); // (which of -0.0 / +0.0 survives does not reach any result: the box only enters as
+        min_y = fmin(min_y, y); //  differences and sums that are squared or compared)
+        max_x = fmax(max_x, x);
+        max_y = fmax(max_y, y);
+    }
+    min_x = chi_warp_min(min_x);
+    min_y = chi_warp_min(min_y);
+    max_x = chi_warp_max(max_x);
+    max_y = chi_warp_max(max_y);
+    const double width = max_x - min_x;
+    const double height = max_y - min_y;
+    w.span = width * width + height * height;
+    const double bx = (min_x + max_x) / 2.0, by = (min_y + max_y) / 2.0;
+    double best = DBL_MAX;
+    uint32_t i0 = kChiNone, i1 = kChiNone, i2 = kChiNone;
+    for (uint32_t i = lane; i < n; i += 32u)
+    {
+        const double d = chi_dist2(chi_px(w, i), chi_py(w, i), bx, by);
+        if (d < best)
+        {
+            i0 = i;
+            best = d;
+        }
+    }
+    chi_warp_argmin(best, i0);
+    if (i0 == kChiNone)
+        return kChiErrCoincident;
+    const double p0x = chi_px(w, i0), p0y = chi_py(w, i0);
+    best = DBL_MAX;
+    for (uint32_t i = lane; i < n; i += 32u)
+    {
+        const double d = chi_dist2(chi_px(w, i), chi_py(w, i), p0x, p0y);
+        if (i != i0 && d < best && d > 0.0)
+        {
+            i1 = i;
+            best = d;
+        }
+    }
+    chi_warp_argmin(best, i1);
+    if (i1 == kChiNone)
+        return kChiErrCoincident;
+    const double p1x = chi_px(w, i1), p1y = chi_py(w, i1);
+    best = DBL_MAX;
+    for (uint32_t i = lane; i < n; i += 32u)
+    {
+        if (i == i0 || i == i1)
+            continue;
+        const double r = chi_circumradius2(p0x, p0y, p1x, p1y, chi_px(w, i), chi_py(w, i));
+        if (r < best)
+        {
+            i2 = i;
+            best = r;
+        }
+    }
+    chi_warp_argmin(best, i2);
+    if (!(best < DBL_MAX))
+        return kChiErrCollinear;
+    if (chi_ccw(p0x, p0y, p1x, p1y, chi_px(w, i2), chi_py(w, i2)))
+    {
+        const uint32_t t = i1;
+        i1 = i2;
+        i2 = t;
+    }
+    w.i0 = i0;
+    w.i1 = i1;
+    w.i2 = i2;
+    w.s0x = p0x;
+    w.s0y = p0y;
+    w.s1x = chi_px(w, i1);
+    w.s1y = chi_py(w, i1);
+    w.s2x = chi_px(w, i2);
+    w.s2y = chi_py(w, i2);
+    chi_circumcentre(w.s0x, w.s0y, w.s1x, w.s1y, w.s2x, w.s2y, w.cx, w.cy);
+    for (uint32_t i = lane; i < n; i += 32u)
+        w.dist[i] = chi_dist2(chi_px(w, i), chi_py(w, i), w.cx, w.cy);
+    __syncwarp();
+    return kChiOk;
+}
+
+// Ascending sort of n (key, index) pairs in global memory by one warp ("flip" bitonic network, slots past n = +inf);
+// the index breaks ties, so equal keys end in ascending index order.
+LB_D void chi_warp_sort(unsigned long long *a, uint32_t *ix, uint32_t n)
+{
+    const uint32_t lane = lane_id();
+    uint32_t n_pad = 2u;
+    while (n_pad < n)
+        n_pad <<= 1;
+    for (uint32_t kk = 2u; kk <= n_pad; kk <<= 1)
+        for (uint32_t jj = kk >> 1; jj > 0u; jj >>= 1)
+        {
+            const uint32_t lj = 31u - __clz(jj);
+            for (uint32_t t = lane; t < (n_pad >> 1); t += 32u)
+            {
+                uint32_t p0, p1;
+                if (jj == (kk >> 1))
+                {
+                    const uint32_t blk = t >> lj, o = t & (jj - 1u);
+                    p0 = blk * kk + o;
+                    p1 = blk * kk + kk - 1u - o;
+                }
+                else
+                {
+                    p0 = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u));
+                    p1 = p0 | jj;
+                }
+                if (p1 < n)
+                {
+                    const unsigned long long x = a[p0], y = a[p1];
+                    const uint32_t xi = ix[p0], yi = ix[p1];
+                    if (x > y || (x == y && xi > yi))
+                    {
+                        a[p0] = y;
+                        a[p1] = x;
+                        ix[p0] = yi;
+                        ix[p1] = xi;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+}
+
+// One warp per cluster; persistent warps pull (frame, cluster) tasks in the order of chi_place_kernel.
+__global__ void __launch_bounds__(32 * kChiWarps)
+chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ task_f,
+                   const uint32_t *__restrict__ task_k, uint32_t *__restrict__ cursor)
+{
+    const uint32_t lane = lane_id();
+    uint32_t T = lane < kChiBuckets ? counts[lane] : 0u;
+    T = warp_reduce_add(T);
+    while (true)
+    {
+        uint32_t g = 0u;
+        if (lane == 0u)
+            g = atomicAdd(cursor, 1u);
+        g = __shfl_sync(kFullMask, g, 0);
+        if (g >= T)
+            break;
+        const uint32_t f = task_f[g], k = task_k[g];
+        const uint32_t off = bv.off[f];
+        const uint32_t *go = cv.goff + off + f;
+        const uint32_t c0 = go[k];
+        const uint32_t n = go[k + 1u] - c0;
+        unsigned char *block = cv.arena + static_cast<size_t>(kChiBytesPerPoint) * (static_cast<size_t>(off) + c0);
+        const ChiLayout lay = chi_layout(n);
+        ChiWork w;
+        chi_bind(w, block, lay, n);
+        {
+            ChiXY *xy = reinterpret_cast<ChiXY *>(block + lay.xy);
+            const float4 *src = cv.gpts + off + c0;
+            for (uint32_t i = lane; i < n; i += 32u)
+            {
+                const float4 p = __ldg(&src[i]);
+                xy[i].x = p.x;
+                xy[i].y = p.y;
+                w.onb[i] = 0u;
+            }
+        }
+        __syncwarp();
+        uint32_t err = chi_seed_warp(w);
+        if (err == kChiOk)
+        {
+            // order of the sweep: (distance, index); the keys borrow the triangle arrays, which are empty until the sweep
+            unsigned long long *skey = reinterpret_cast<unsigned long long *>(w.tri);
+            uint32_t *sid = w.half;
+            for (uint32_t i = lane; i < n; i += 32u)
+            {
+                skey[i] = static_cast<unsigned long long>(__double_as_longlong(w.dist[i])); // distances are >= +0.0
+                sid[i] = i;
+            }
+            __syncwarp();
+            chi_warp_sort(skey, sid, n);
+            bool mixed = false;
+            for (uint32_t i = lane; i + 1u < n; i += 32u)
+                if (skey[i] == skey[i + 1u])
+                {
+                    const ChiXY a = w.xy[sid[i]], b = w.xy[sid[i + 1u]];
+                    if (!(a.x == b.x && a.y == b.y) && !(chi_on_seed(w, a.x, a.y) && chi_on_seed(w, b.x, b.y)))
+                        mixed = true;
+                }
+            mixed = __any_sync(kFullMask, mixed);
+            if (!mixed)
+                for (uint32_t i = lane; i < n; i += 32u)
+                    w.ids[i] = sid[i];
+            else
+                for (uint32_t i = lane; i < n; i += 32u)
+                    w.ids[i] = i;
+            __syncwarp();
+            uint32_t h = 0u;
+            if (lane == 0u)
+            {
+                if (mixed) // two different points exactly equally far: the reference's std::sort decides their order
+                    chi_introsort_ids(w.ids, w.dist, n);
+                err = chi_triangulate(w);
+                if (err == kChiOk)
+                    h = chi_erode_and_walk(w, cv.hres + off + c0, true);
+            }
+            err = __shfl_sync(kFullMask, err, 0);
+            h = __shfl_sync(kFullMask, h, 0);
+            if (lane == 0u)
+                cv.hcnt[off + f + k] = err == kChiOk ? h : 0u;
+        }
+        else if (lane == 0u)
+            cv.hcnt[off + f + k] = 0u;
+        if (err != kChiOk && lane == 0u)
+            atomicOr(cv.err, err == kChiErrCollinear ? kHullErrCollinear : kHullErrDegenerate);
+        __syncwarp();
+    }
+}
+
+} // namespace lb

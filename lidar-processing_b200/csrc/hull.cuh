@@ -40,6 +40,7 @@ constexpr uint32_t kHullConcaveMin = 20u;       // cluster.size() < 20 -> monoto
 constexpr int kHullWarps = 8;                   // warps per CTA of hull_chain_kernel, 12 KB of dynamic shared memory each
 constexpr uint32_t kHullModeConvex = 0u;        // findOrderedConvexOutlines
 constexpr uint32_t kHullModeConcaveSmall = 1u;  // the convex branch of findOrderedConcaveOutlines
+constexpr uint32_t kHullModeConcave = 2u;       // findOrderedConcaveOutlines: that branch + the chi-shape from 20 points on (chi_shape.cuh)
 constexpr uint32_t kHullThreadScanMax = 192u;   // tasks up to this size are scanned one thread per task, larger ones by lane 0 of the sorting warp
 constexpr uint32_t kHullErrOverflow = 1u, kHullErrSubset = 2u, kHullErrJarvis = 4u;
 
@@ -177,7 +178,7 @@ hull_tasks_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullVie
             }
             else
                 cnt = n < kHullConcaveMin ? 1u : 0u;
-            if (cnt == 0u)
+            if (cnt == 0u && !(mode == kHullModeConcave && n >= kHullConcaveMin)) // (those belong to chi_outline_kernel)
                 hc[k] = 0u;
         }
         uint32_t total;
@@ -611,7 +612,8 @@ hull_chan_merge_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, Hu
 // cluster k, hne[K] = their number (one CTA per frame).
 __global__ void __launch_bounds__(256)
 hull_scan_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, uint32_t *__restrict__ hcnt,
-                 uint32_t *__restrict__ hne_all, uint32_t *__restrict__ n_vertices, uint32_t *__restrict__ n_outlines)
+                 uint32_t *__restrict__ hne_all, uint32_t *__restrict__ n_vertices, uint32_t *__restrict__ n_outlines,
+                 const uint32_t *__restrict__ slot_points, uint32_t *__restrict__ err)
 {
     __shared__ uint32_t ws[9];
     __shared__ uint32_t carry, carry_ne;
@@ -651,13 +653,38 @@ hull_scan_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, uint32_t
         ne[K] = carry_ne;
         n_vertices[f] = carry;
         n_outlines[f] = carry_ne;
+        // A closed outline repeats its first vertex, so the outlines of a frame can outgrow the frame's slot (one
+        // vertex per staged point) when nearly every point is an outline vertex: the outlines that do not fit any more
+        // get 0 vertices and the status says so.
+        const uint32_t cap = (slot_points[f] + 31u) & ~31u;
+        if (carry > cap)
+        {
+            atomicOr(err, 32u /* kHullErrSlot */);
+            uint32_t old_k = hc[0], acc = 0u, acc_ne = 0u;
+            for (uint32_t k = 0; k < K; ++k)
+            {
+                const uint32_t old_next = hc[k + 1u];
+                uint32_t v = old_next - old_k;
+                if (acc + v > cap)
+                    v = 0u;
+                hc[k] = acc;
+                ne[k] = acc_ne;
+                acc += v;
+                acc_ne += v ? 1u : 0u;
+                old_k = old_next;
+            }
+            hc[K] = acc;
+            ne[K] = acc_ne;
+            n_vertices[f] = acc;
+            n_outlines[f] = acc_ne;
+        }
     }
 }
 
 // Outline vertices of the frame end to end: (x, y) = geom::Point<float> records plus the obstacle-cloud index.
 __global__ void __launch_bounds__(256)
 hull_emit_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView hv, float2 *__restrict__ hxy,
-                 uint32_t *__restrict__ hsrc)
+                 uint32_t *__restrict__ hsrc, uint32_t closed_from)
 {
     const uint32_t f = blockIdx.y;
     const uint32_t off = bv.off[f];
@@ -671,9 +698,12 @@ hull_emit_kernel(BatchView bv, const uint32_t *__restrict__ n_clusters, HullView
         const uint32_t c0 = go[k];
         const uint32_t h0 = ho[k];
         const uint32_t h = ho[k + 1u] - h0;
+        // clusters of closed_from points and more carry a closed outline (getHullIndices repeats hull_start,
+        // delaunator.cpp:693-707): hres holds the open loop
+        const bool closed = go[k + 1u] - c0 >= closed_from;
         for (uint32_t v = lane_id(); v < h; v += 32u)
         {
-            const uint32_t li = hv.hres[off + c0 + v];
+            const uint32_t li = hv.hres[off + c0 + ((closed && v + 1u == h) ? 0u : v)];
             const float4 p = __ldg(&hv.gpts[off + c0 + li]);
             hxy[off + h0 + v] = make_float2(p.x, p.y);
             hsrc[off + h0 + v] = hv.gidx[off + c0 + li];

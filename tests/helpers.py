@@ -106,3 +106,51 @@ def check_clustering(obs_pts, labels, clu_cfg=None, use_ref=True):
         assert np.array_equal(labels, O.ref_cluster(obs_pts, cfg)), "differs from the unmodified reference Clusterer"
     assert not np.any(labels == O.UNDEFINED)
     return int(labels.max() + 1) if labels.size else 0
+
+
+# ---- concave outlines: the product's sequential core (csrc/chi_shape.h) compiled for the host -------------------------
+
+_HC = None
+
+
+def host_checks():
+    """tests/host/libhost_checks.so: the host-compilable PRODUCT headers behind a C interface"""
+    global _HC
+    if _HC is None:
+        import ctypes as C
+
+        import __graft_entry__ as ge
+
+        _HC = C.CDLL(str(ge.build_host_checks()))
+        _HC.hc_chi_outlines.restype = C.c_longlong
+    return _HC
+
+
+def chi_outlines_host(clusters, sort_mode: int = 0):
+    """Concave outlines (clusters of 20 points and more) from csrc/chi_shape.h on the CPU. sort_mode 0 = the device's
+    policy, 1 = always the std::sort re-enactment, 2 = always (distance, index). Returns (list of xy[h,2] float32 or
+    None where the reference does not deliver / 0-row arrays below 20 points, list of local index arrays,
+    (clusters that needed the re-enactment, clusters run))."""
+    import ctypes as C
+
+    pts, offsets = O._clusters_csr(clusters)
+    k = len(clusters)
+    sizes = np.zeros(max(k, 1), np.uint32)
+    idx = np.zeros(int(offsets[-1]) + k + 1, np.uint32)
+    stats = np.zeros(2, np.uint32)
+    n = host_checks().hc_chi_outlines(O._p(pts, C.c_float), O._p(offsets, C.c_uint32), C.c_uint32(k), C.c_uint32(4),
+                                      C.c_int(sort_mode), O._p(sizes, C.c_uint32), O._p(idx, C.c_uint32),
+                                      C.c_longlong(idx.size), O._p(stats, C.c_uint32))
+    assert n >= 0
+    out, loc, at = [], [], 0
+    for c in range(k):
+        h = int(sizes[c])
+        if h == 0xFFFFFFFF:
+            out.append(None)
+            loc.append(None)
+            continue
+        li = idx[at:at + h].astype(np.int64)
+        out.append(pts[int(offsets[c]) + li][:, :2].copy())
+        loc.append(li)
+        at += h
+    return out, loc, (int(stats[0]), int(stats[1]))

@@ -1,6 +1,7 @@
-// Host-side checks of the PRODUCT headers that are host-compilable (kd_select.h, jacobi3.h) and a
+// Host-side checks of the PRODUCT headers that are host-compilable (kd_select.h, jacobi3.h, chi_shape.h) and a
 // lane-by-lane model of the cooperative Hoare-partition formulation used by kd_build.cuh.
 // Built by __graft_entry__.build() into tests/host/libhost_checks.so; driven by tests/test_host_logic.py.
+#include "../../lidar-processing_b200/csrc/chi_shape.h"
 #include "../../lidar-processing_b200/csrc/jacobi3.h"
 #include "../../lidar-processing_b200/csrc/kd_select.h"
 
@@ -183,6 +184,139 @@ int hc_range_at(uint32_t m, uint32_t depth, uint32_t path, uint32_t *b, uint32_t
 int hc_jacobi_svd3(const float *a, float *v, float *sv)
 {
     return lb::jacobi_svd3(a, v, sv) ? 1 : 0;
+}
+
+// std::sort of ids by dist (mode 0) against lb::chi_introsort_ids (mode 1), for the tie-order check
+void hc_sort_ids(uint32_t *ids, const double *dist, uint32_t n, int mode)
+{
+    if (mode == 0)
+        std::sort(ids, ids + n, [dist](uint32_t i, uint32_t j) { return dist[i] < dist[j]; });
+    else
+        lb::chi_introsort_ids(ids, dist, n);
+}
+
+// std::push_heap / std::pop_heap on (edge, length) pairs against lb::chi_heap_push / chi_heap_pop: ops[i] >= 0 pushes
+// lens[i] with edge number i, ops[i] < 0 pops; popped_out receives the edge numbers in pop order. Returns their count.
+uint32_t hc_heap_replay(const int *ops, const double *lens, uint32_t n_ops, int mode, uint32_t *popped_out)
+{
+    uint32_t n_pop = 0u;
+    if (mode == 0)
+    {
+        using HP = std::pair<std::size_t, double>;
+        const auto cmp = [](const HP &l, const HP &r) { return l.second < r.second; };
+        std::vector<HP> h;
+        for (uint32_t i = 0; i < n_ops; ++i)
+        {
+            if (ops[i] >= 0)
+            {
+                h.emplace_back(i, lens[i]);
+                std::push_heap(h.begin(), h.end(), cmp);
+            }
+            else if (!h.empty())
+            {
+                std::pop_heap(h.begin(), h.end(), cmp);
+                popped_out[n_pop++] = static_cast<uint32_t>(h.back().first);
+                h.pop_back();
+            }
+        }
+    }
+    else
+    {
+        std::vector<uint32_t> he(n_ops + 1u);
+        std::vector<double> hl(n_ops + 1u);
+        uint32_t size = 0u;
+        for (uint32_t i = 0; i < n_ops; ++i)
+        {
+            if (ops[i] >= 0)
+                lb::chi_heap_push(he.data(), hl.data(), size, i, lens[i]);
+            else if (size)
+            {
+                uint32_t e;
+                double l;
+                lb::chi_heap_pop(he.data(), hl.data(), size, e, l);
+                popped_out[n_pop++] = e;
+            }
+        }
+    }
+    return n_pop;
+}
+
+// Concave outlines of CSR clusters with the product's sequential core (chi_shape.h), the way chi_shape.cuh drives it.
+// sort_mode 0: order by (distance, index), std::sort re-enactment only when two different points are exactly equally
+// far (the device's policy); 1: always the re-enactment; 2: always (distance, index).
+// sizes_out[k]: vertices of the closed outline (0: fewer than 20 points, not this function's business; 0xFFFFFFFF: the
+// reference throws / reads out of bounds). idx_out: cluster-local vertex indices end to end. stats_out[0] = clusters
+// that needed the re-enactment, [1] = clusters run. Returns the number of indices written or -1 (capacity).
+long long hc_chi_outlines(const float *points, const uint32_t *offsets, uint32_t n_clusters, uint32_t stride_floats,
+                          int sort_mode, uint32_t *sizes_out, uint32_t *idx_out, long long capacity, uint32_t *stats_out)
+{
+    long long total = 0;
+    std::vector<unsigned char> block;
+    std::vector<uint32_t> loop;
+    std::vector<std::pair<double, uint32_t>> order;
+    stats_out[0] = stats_out[1] = 0u;
+    for (uint32_t k = 0; k < n_clusters; ++k)
+    {
+        const uint32_t n = offsets[k + 1] - offsets[k];
+        sizes_out[k] = 0u;
+        if (n < 20u)
+            continue;
+        ++stats_out[1];
+        const lb::ChiLayout lay = lb::chi_layout(n);
+        block.assign(lay.bytes, 0xCD);
+        lb::ChiWork w;
+        lb::chi_bind(w, block.data(), lay, n);
+        lb::ChiXY *xy = reinterpret_cast<lb::ChiXY *>(block.data() + lay.xy);
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            const float *p = points + static_cast<size_t>(offsets[k] + i) * stride_floats;
+            xy[i].x = p[0];
+            xy[i].y = p[1];
+        }
+        uint32_t err = lb::chi_seed_sequential(w);
+        if (err == lb::kChiOk)
+        {
+            order.resize(n);
+            for (uint32_t i = 0; i < n; ++i)
+                order[i] = {w.dist[i], i};
+            std::sort(order.begin(), order.end());
+            bool mixed = false;
+            for (uint32_t i = 0; i + 1 < n; ++i)
+                if (order[i].first == order[i + 1].first)
+                {
+                    // equally far and not the same place - unless both lie on seed vertices (all of those are skipped
+                    // whatever their order, and the three seeds are equally far from their circumcentre by construction)
+                    const lb::ChiXY &a = xy[order[i].second], &b = xy[order[i + 1].second];
+                    if (!(a.x == b.x && a.y == b.y) && !(lb::chi_on_seed(w, a.x, a.y) && lb::chi_on_seed(w, b.x, b.y)))
+                        mixed = true;
+                }
+            if (sort_mode == 1 || (sort_mode == 0 && mixed))
+            {
+                for (uint32_t i = 0; i < n; ++i)
+                    w.ids[i] = i;
+                lb::chi_introsort_ids(w.ids, w.dist, n);
+                ++stats_out[0];
+            }
+            else
+                for (uint32_t i = 0; i < n; ++i)
+                    w.ids[i] = order[i].second;
+            err = lb::chi_triangulate(w);
+        }
+        if (err != lb::kChiOk)
+        {
+            sizes_out[k] = 0xFFFFFFFFu;
+            continue;
+        }
+        loop.resize(n);
+        const uint32_t h = lb::chi_erode_and_walk(w, loop.data());
+        if (total + h > capacity)
+            return -1;
+        sizes_out[k] = h;
+        for (uint32_t v = 0; v + 1 < h; ++v)
+            idx_out[total++] = loop[v];
+        idx_out[total++] = loop[0];
+    }
+    return total;
 }
 
 } // extern "C"

@@ -510,8 +510,9 @@ def _check_outlines(obs, groups, hulls, mode):
     assert hulls["n_clusters"] == k
     go, ho = groups["offsets"].astype(np.int64), hulls["offsets"].astype(np.int64)
     clusters = [groups["points"][go[c]:go[c + 1], :3] for c in range(k)]
-    want = O.ref_outlines(clusters, mode) if O.ref_hull_available() else None
-    port = O.convex_outlines(clusters, mode)
+    want = O.ref_outlines(clusters, min(mode, 1)) if O.ref_hull_available() else None
+    port = O.convex_outlines(clusters, min(mode, 1))
+    chi = H.chi_outlines_host(clusters)[0] if mode == 2 else None
     n_device = 0
     for c in range(k):
         xy = hulls["xy"][ho[c]:ho[c + 1]]
@@ -519,6 +520,17 @@ def _check_outlines(obs, groups, hulls, mode):
         n = len(clusters[c])
         if mode == 1 and n >= 20:
             assert xy.shape[0] == 0  # the host's concave hull
+            continue
+        if mode == 2 and n >= 20:
+            # the Delaunay-based chi-shape, closed: device == the product's sequential core on the CPU == the reference
+            if chi[c] is None:
+                assert xy.shape[0] == 0 and (want is None or want[c] is None)  # the reference throws on this cluster
+                continue
+            assert np.array_equal(xy, chi[c]), f"cluster {c} ({n} points) differs from chi_shape.h on the CPU"
+            if want is not None:
+                assert want[c] is not None and np.array_equal(xy, want[c]), f"cluster {c} ({n} points) differs from the reference"
+            assert np.array_equal(obs[src][:, :2], xy) and np.array_equal(xy[0], xy[-1])
+            n_device += 1
             continue
         assert np.array_equal(xy, port[c][0]), f"cluster {c} ({n} points) differs from the restated oracle"
         if want is not None:
@@ -531,7 +543,7 @@ def _check_outlines(obs, groups, hulls, mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_outlines_golden_frames(ctx, golden_frames, mode):
     res = ctx.process_batch(golden_frames)
     groups = ctx.batch_clusters()
@@ -540,6 +552,44 @@ def test_outlines_golden_frames(ctx, golden_frames, mode):
     for pts, r, g, h in zip(golden_frames, res, groups, hulls):
         total += _check_outlines(pts[r["obstacle_idx"]], g, h, mode)
     assert total > (300 if mode == 1 else 1200)
+
+
+@pytest.mark.gpu
+def test_concave_outlines_sweep_and_degenerate_clusters(pkg):
+    """Mode HULL_CONCAVE on clusters fed one at a time: the seeded sweep of tests/test_oracle_pinning.py (lattices whose
+    cocircular points send the cluster through the std::sort re-enactment, heavy duplicates, rings, strips), the stress
+    clusters, and the two cases in which the reference does not deliver: 30 collinear points (it throws "not
+    triangulation") and 25 coincident points (it reads out of bounds) -> 0 vertices, LIDAR_B200_ERR_INPUT, every other
+    outline of the batch intact."""
+    from tests.test_oracle_pinning import _chi_sweep_clusters, _hull_stress_clusters
+
+    clusters = [c for c in _hull_stress_clusters() if len(c) >= 4] + _chi_sweep_clusters(count=120)
+    c2 = pkg.Context(device=0, max_points=8192, max_frames=1)
+    try:
+        c2.clu_configure(pkg.ClusteringConfiguration(distance_squared=1.0e6, min_cluster_size=1))
+        checked = threw = 0
+        for c in clusters:
+            obs = np.zeros((len(c), 4), np.float32)
+            obs[:, :3] = c
+            labels, g = c2.cluster_and_split(obs)
+            assert g["n_clusters"] == 1 and np.all(labels == 0)
+            h = c2.batch_hulls(pkg.HULL_CONCAVE, tolerate_open_marches=True)[0]
+            got = _check_outlines(obs, g, h, 2)
+            if got == 0:  # the reference throws on this cluster: 0 vertices and the status says so
+                assert c2.last_hull_status == pkg.ERR_INPUT and h["xy"].shape[0] == 0
+                threw += 1
+            else:
+                assert c2.last_hull_status == 0
+            checked += got
+        assert checked > 120 and threw >= 2
+        # 25 coincident points: the reference reads out of bounds (never handed to it) -> 0 vertices, ERR_INPUT
+        obs = np.zeros((25, 4), np.float32)
+        obs[:, :3] = np.float32([1.5, -2.5, 0.0])
+        labels, g = c2.cluster_and_split(obs)
+        h = c2.batch_hulls(pkg.HULL_CONCAVE, tolerate_open_marches=True)[0]
+        assert g["n_clusters"] == 1 and h["xy"].shape[0] == 0 and c2.last_hull_status == pkg.ERR_INPUT
+    finally:
+        c2.close()
 
 
 @pytest.mark.gpu
@@ -627,8 +677,9 @@ def test_colorized_cloud_and_marker_points(ctx, golden_frames, synth_small):
 @pytest.mark.gpu
 def test_outlines_all_154_reference_frames(pkg):
     """Outlines of every cluster of all 154 repo frames (one 154-frame batch), device vs the UNMODIFIED reference
-    outline functions run on the same clusters: findOrderedConvexOutlines for every cluster, and the convex branch
-    of findOrderedConcaveOutlines for the clusters below 20 points. Bit-exact vertex lists."""
+    outline functions run on the same clusters: findOrderedConvexOutlines for every cluster, the convex branch of
+    findOrderedConcaveOutlines for the clusters below 20 points, and findOrderedConcaveOutlines as a whole (mode
+    HULL_CONCAVE: the Delaunay-based chi-shape of every cluster from 20 points on). Bit-exact vertex lists."""
     import json
     from pathlib import Path
 
@@ -643,24 +694,26 @@ def test_outlines_all_154_reference_frames(pkg):
     try:
         res = big.process_batch(frames)
         groups = big.batch_clusters()
-        hulls = [big.batch_hulls(0), big.batch_hulls(1)]
+        hulls = [big.batch_hulls(0), big.batch_hulls(1), big.batch_hulls(2)]
     finally:
         big.close()
-    checked = [0, 0]
-    vertices = [0, 0]
-    for pts, r, g, h0, h1 in zip(frames, res, groups, hulls[0], hulls[1]):
+    checked = [0, 0, 0]
+    vertices = [0, 0, 0]
+    for pts, r, g, h0, h1, h2 in zip(frames, res, groups, hulls[0], hulls[1], hulls[2]):
         obs = pts[r["obstacle_idx"]]
-        for mode, h in ((0, h0), (1, h1)):
+        for mode, h in ((0, h0), (1, h1), (2, h2)):
             checked[mode] += _check_outlines(obs, g, h, mode)
             vertices[mode] += int(h["xy"].shape[0])
     summary = {"frames": len(frames), "clusters": int(sum(g["n_clusters"] for g in groups)),
                "convex_outlines_checked": checked[0], "convex_vertices": vertices[0],
                "concave_policy_small_outlines_checked": checked[1], "concave_policy_small_vertices": vertices[1],
+               "concave_policy_outlines_checked": checked[2], "concave_policy_vertices": vertices[2],
+               "concave_chi_shapes_checked": checked[2] - checked[1],
                "reference": "oracle/_ref/libref_hull.so" if O.ref_hull_available() else "restated oracle only"}
     out = root / "gpurun_out"
     out.mkdir(exist_ok=True)
     (out / "parity_outlines_154.json").write_text(json.dumps(summary))
-    assert checked[0] == summary["clusters"] and checked[1] > 0
+    assert checked[0] == summary["clusters"] and checked[1] > 0 and checked[2] == summary["clusters"]
 
 
 @pytest.mark.gpu
@@ -674,8 +727,10 @@ def test_outlines_full_size_synthetic(pkg):
     try:
         res = big.process_batch(frames)
         groups = big.batch_clusters()
-        for mode in (0, 1):
-            hulls = big.batch_hulls(mode)
+        for mode in (0, 1, 2):
+            # (mode 2: the lattice walls of the merged cloud are vertical, i.e. collinear in (x, y) - the reference
+            # throws "not triangulation" on them, the device reports them and delivers every other outline)
+            hulls = big.batch_hulls(mode, tolerate_open_marches=mode == 2)
             for pts, r, g, h in zip(frames, res, groups, hulls):
                 assert _check_outlines(pts[r["obstacle_idx"]], g, h, mode) > 0
         assert max(int(np.diff(g["offsets"].astype(np.int64)).max()) for g in groups) > 100_000

@@ -201,3 +201,49 @@ def test_c_abi_rejects_a_null_context_without_touching_a_device(pkg):
     assert lib.lidar_b200_batch_fetch_marker_points(None, buf, buf, dbuf) == inv
     assert lib.lidar_b200_pipe_set_host_sharing(None, C.c_uint32(8)) == inv
     assert lib.lidar_b200_pipe_fetch_mode(None) == -1
+
+
+# ---- csrc/chi_shape.h: the libstdc++ re-enactments behind the concave outline ------------------------------------------
+def test_introsort_reenactment_matches_std_sort(hc):
+    """lb::chi_introsort_ids against std::sort(ids, by dist) of this container's libstdc++ on tie-heavy keys: with
+    ties the permutation std::sort leaves behind is exactly what the reference's sweep order depends on
+    (Concave-Hull/delaunator.cpp:339-341). Includes the depth-limit (heap sort) path."""
+    rng = np.random.default_rng(3)
+    cases = []
+    for n in list(range(0, 40)) + [100, 257, 1000, 4096, 20000]:
+        for distinct in (1, 2, 3, 7, max(1, n // 4), max(1, n)):
+            cases.append(rng.integers(0, distinct, size=n).astype(np.float64))
+    # median-of-three killers drive introsort into its heap-sort branch
+    for n in (64, 1000, 5000):
+        k = np.zeros(n)
+        half = n // 2
+        for i in range(half):
+            k[i] = (i + 1) if i % 2 == 0 else (half + i + (1 if half % 2 == 0 else 0))
+            k[half + i] = 2 * (i + 1)
+        cases.append(k)
+        cases.append(np.minimum(k, n // 3))
+    cases.append(np.arange(3000, dtype=np.float64)[::-1].copy())
+    cases.append(np.abs(np.arange(-1500, 1500, dtype=np.float64)))
+    for dist in cases:
+        n = dist.size
+        a = np.arange(n, dtype=np.uint32)
+        b = a.copy()
+        hc.hc_sort_ids(a.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p), n, 0)
+        hc.hc_sort_ids(b.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p), n, 1)
+        assert np.array_equal(a, b), f"n = {n}, {np.unique(dist).size} distinct keys"
+
+
+def test_heap_reenactment_matches_std_heap(hc):
+    """lb::chi_heap_push / chi_heap_pop against std::push_heap / std::pop_heap on pairs compared by length only
+    (Concave-Hull/concave_hull.hpp:91-94): with equal lengths the pop order depends on the sift paths."""
+    rng = np.random.default_rng(4)
+    hc.hc_heap_replay.restype = C.c_uint32
+    for trial in range(60):
+        n = int(rng.integers(1, 3000))
+        ops = np.where(rng.random(n) < (0.35 if trial % 2 else 0.5), -1, 1).astype(np.int32)
+        ops[: min(n, 20)] = 1
+        lens = rng.integers(0, max(2, n // (1 + trial % 7)), size=n).astype(np.float64) * 0.05
+        out = [np.zeros(n, np.uint32), np.zeros(n, np.uint32)]
+        cnt = [hc.hc_heap_replay(ops.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), n, m,
+                                 out[m].ctypes.data_as(C.c_void_p)) for m in (0, 1)]
+        assert cnt[0] == cnt[1] and np.array_equal(out[0][:cnt[0]], out[1][:cnt[1]])

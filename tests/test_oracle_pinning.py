@@ -524,3 +524,63 @@ def test_reference_node_without_clusters_or_ground():
     lonely[:, 1] = rng.normal(0, 0.01, 64)
     lonely[:, 2] = 1.0 + 0.001 * np.arange(64)
     assert _check_against_node(lonely) == 0
+
+
+# ------------------------------------------------------------------ round 2: the Delaunay-based concave outline (row 3)
+def _chi_sweep_clusters(seed=20261018, count=240):
+    """mm-quantised blobs, rings, lattices (cocircular points: equal distances between DIFFERENT points, so the
+    std::sort re-enactment is what decides the sweep order), heavy-duplicate sets, thin strips — 20..3000 points."""
+    rng = np.random.default_rng(seed)
+    clusters = []
+    for i in range(count):
+        n = int(rng.integers(20, 3000)) if i % 3 else int(rng.integers(20, 80))
+        kind = i % 6
+        if kind == 0:
+            p = rng.normal(size=(n, 2)) * rng.uniform(0.05, 5.0)
+        elif kind == 1:
+            a = rng.uniform(0, 2 * np.pi, n)
+            p = np.stack([np.cos(a), np.sin(a)], 1) * rng.uniform(0.5, 20.0) + rng.normal(size=(n, 2)) * 0.05
+        elif kind == 2:
+            p = rng.integers(-20, 21, size=(n, 2)) * 0.05                       # lattice with duplicates
+        elif kind == 3:
+            base = rng.normal(size=(max(8, n // 6), 2))
+            p = base[rng.integers(0, base.shape[0], n)]                          # ~6 copies of every point
+        elif kind == 4:
+            p = np.stack([rng.uniform(-30, 30, n), rng.normal(size=n) * 0.02], 1)  # thin strip
+        else:
+            gx, gy = np.meshgrid(np.arange(int(np.sqrt(n)) + 1) * 0.05, np.arange(int(np.sqrt(n)) + 1) * 0.05)
+            p = np.stack([gx.ravel(), gy.ravel()], 1)[:n]                        # full lattice, no duplicates
+        p = p + rng.uniform(-40, 40, size=(1, 2))
+        c = np.zeros((p.shape[0], 3), np.float32)
+        c[:, :2] = np.round(p, 3)
+        clusters.append(c)
+    return clusters
+
+
+@pytest.mark.skipif(not O.ref_hull_available(), reason="oracle/_ref/libref_hull.so not built")
+@pytest.mark.parametrize("sort_mode", [0, 1])
+def test_restated_concave_outlines_match_reference(golden_frames, sort_mode):
+    """csrc/chi_shape.h (the sequential core of the device's concave outlines) on the CPU against the UNMODIFIED reference
+    findOrderedConcaveOutlines: every cluster of 20+ points of the three golden frames, the stress clusters (a collinear
+    run: the reference throws "not triangulation"; a 1400-point lattice) and a seeded sweep. Closed outlines, vertex for
+    vertex. sort_mode 0 is the device's policy, 1 replays std::sort for every cluster."""
+    from tests.helpers import chi_outlines_host
+
+    clusters = [c for c in _hull_stress_clusters() if 20 <= len(c)]
+    for pts in golden_frames:
+        obs = pts[O.segment(pts, tie_mode=1)["obstacle_idx"]]
+        clusters += [c for c, _ in O.split_clusters(obs, O.cluster(obs)) if len(c) >= 20]
+    clusters += _chi_sweep_clusters()
+    got, loc, (replayed, run) = chi_outlines_host(clusters, sort_mode)
+    want = O.ref_outlines(clusters, 1)
+    threw = 0
+    for i, (c, g, li, ref) in enumerate(zip(clusters, got, loc, want)):
+        if ref is None:
+            assert g is None, f"cluster {i} ({len(c)} points): the reference throws"
+            threw += 1
+            continue
+        assert g is not None and np.array_equal(g, ref), f"cluster {i} ({len(c)} points)"
+        assert np.array_equal(g[0], g[-1]) and np.array_equal(np.asarray(c, np.float32)[li][:, :2], g)
+    assert run == len(clusters) > 600 and threw >= 2
+    if sort_mode == 0:
+        assert 0 < replayed < run  # lattices need the std::sort re-enactment, LiDAR clusters almost never do

@@ -55,8 +55,25 @@ def run_group_hull(mode):
 base = timed(run_only)
 grp = timed(run_group)
 out["ms_per_step"] = {"seg+cluster": base, "+split": grp}
-for mode, label in ((0, "+split+convex_outlines"), (1, "+split+concave_small_outlines")):
-    out["ms_per_step"][label] = timed(run_group_hull(mode))
+for mode, label in ((0, "+split+convex_outlines"), (1, "+split+concave_small_outlines"), (2, "+split+concave_outlines")):
+    out["ms_per_step"][label] = timed(run_group_hull(mode), reps=3 if mode == 2 else 5)
+# one frame in flight: the outline step of a single frame (its largest cluster is the tail)
+one = pkg.Context(device=0, max_points=max(f.shape[0] for f in frames) + 64, max_frames=1)
+lat = []
+for f in list(range(0, len(frames), max(1, len(frames) // 12)))[:12]:
+    one.batch_stage([frames[f]])
+    one.batch_run()
+    one._check(L.lidar_b200_batch_group_clusters(one._h), "group")
+    one.sync()
+    per = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        one._check(L.lidar_b200_batch_hull_outlines(one._h, 2), "hull")
+        one.sync()
+        per.append(1e3 * (time.perf_counter() - t0))
+    lat.append(min(per))
+one.close()
+out["concave_outlines_single_frame_ms"] = {"p50": float(np.median(lat)), "max": float(max(lat)), "frames": len(lat)}
 # results once, for the counts and the CPU sample
 res = ctx.batch_fetch()
 groups = ctx.batch_clusters()
@@ -75,6 +92,15 @@ for f in sample:
         O.ref_outlines(cl, 0)
         t_cpu += time.perf_counter() - t0
         n_cl += len(cl)
+t_cc = 0.0
+for f in sample:
+    go = groups[f]["offsets"].astype(np.int64)
+    cl = [groups[f]["points"][go[c]:go[c + 1], :3] for c in range(groups[f]["n_clusters"])]
+    if O.ref_hull_available():
+        t0 = time.perf_counter()
+        O.ref_outlines(cl, 1)
+        t_cc += time.perf_counter() - t0
+out["cpu_reference_concave_outlines_ms_per_frame"] = 1e3 * t_cc / max(len(sample), 1)
 out["cpu_reference_convex_outlines_ms_per_frame"] = 1e3 * t_cpu / max(len(sample), 1)
 out["cpu_sample"] = f"{len(sample)} frames, {n_cl} clusters, 1 thread, findOrderedConvexOutlines via oracle/_ref (includes the ctypes marshalling of the clusters)"
 print(json.dumps(out))
