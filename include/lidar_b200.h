@@ -256,6 +256,11 @@ extern "C"
     int lidar_b200_last_kd_rank(lidar_b200_ctx *ctx, uint32_t frame, uint32_t *rank_out, uint32_t capacity);
     /* component root (smallest member index) of every obstacle point of a frame of the last batch */
     int lidar_b200_last_cc_root(lidar_b200_ctx *ctx, uint32_t frame, uint32_t *root_out, uint32_t capacity);
+    /* per-cluster timings of the concave outlines of the last lidar_b200_batch_hull_outlines(LIDAR_B200_HULL_CONCAVE)
+     * (development aid; needs LIDAR_B200_CHI_STATS=1 in the environment when the context is created). 8 words per
+     * task, largest clusters first, at most 4096 tasks: points, start ns, end ns (%globaltimer), cycles of the seed
+     * search / the sort / the sweep / the erosion, triangles. */
+    int lidar_b200_last_chi_stats(lidar_b200_ctx *ctx, uint64_t *stats_out, uint32_t capacity_tasks, uint32_t *n_tasks_out);
     /* per-component counters of the CTA-per-component replay of the last run (development aid; needs
      * LIDAR_B200_REPLAY_STATS=1 in the environment when the context is created). 8 words per job:
      * frame, members, kilo-cycles, rounds, direct rounds, entries taken, seeds, candidates scanned. */

@@ -129,7 +129,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
     "lidar_b200_pipe_drain", "lidar_b200_pipe_launch_count", "lidar_b200_pipe_last_error", "lidar_b200_pipe_fetch_mode",
     "lidar_b200_pipe_set_host_sharing",
-    "lidar_b200_last_replay_stats", "lidar_b200_batch_group_clusters", "lidar_b200_batch_fetch_clusters",
+    "lidar_b200_last_replay_stats", "lidar_b200_last_chi_stats", "lidar_b200_batch_group_clusters", "lidar_b200_batch_fetch_clusters",
     "lidar_b200_pcd_read", "lidar_b200_batch_hull_outlines", "lidar_b200_batch_fetch_hulls",
     "lidar_b200_batch_fetch_colorized", "lidar_b200_batch_fetch_marker_points",
 ]
@@ -362,6 +362,14 @@ class Context:
             o, k, n = int(off[f]), int(nc[f]), int(nv[f])
             out.append(dict(offsets=hoff[o + f:o + f + k + 1], xy=hxy[o:o + n], point_idx=hidx[o:o + n], n_clusters=k))
         return out
+
+    def last_chi_stats(self, capacity: int = 4096):
+        """Per-cluster timings of the last batch_hulls(HULL_CONCAVE) (needs LIDAR_B200_CHI_STATS=1 at context creation):
+        (tasks, 8) uint64 = points, start ns, end ns, cycles of seed / sort / sweep / erosion, triangles."""
+        st = np.zeros((capacity, 8), np.uint64)
+        n = C.c_uint32(0)
+        self._check(lib().lidar_b200_last_chi_stats(self._h, _ptr(st, C.c_uint64), C.c_uint32(capacity), C.byref(n)), "last_chi_stats")
+        return st[:min(int(n.value), capacity)], int(n.value)
 
     def _slots(self):
         counts = self._n_points

@@ -138,6 +138,8 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_hoff, d_hne, d_hnv, d_herr, d_rgb;
     DevBuf<unsigned char> d_chi;   // working sets of the concave outlines (chi_shape.cuh), 96 bytes per point slot
     DevBuf<uint32_t> d_chi_meta;   // [bucket counts 32 | bucket fill 32 | cursor]
+    DevBuf<unsigned long long> d_chi_stats; // LIDAR_B200_CHI_STATS=1: 8 words per task for the first kChiStatTasks tasks
+    bool chi_stats{false};
     uint32_t hull_mode{0};
     DevBuf<uint4> d_color;   // 32-byte PointXYZRGB records (pack.cuh), allocated on first use
     DevBuf<double> d_marker; // marker points, allocated on first use
@@ -947,6 +949,7 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     lidar_b200_ctx *c = new lidar_b200_ctx();
     c->device = device;
     c->want_job_stats = std::getenv("LIDAR_B200_REPLAY_STATS") != nullptr;
+    c->chi_stats = std::getenv("LIDAR_B200_CHI_STATS") != nullptr;
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
     if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
@@ -1034,7 +1037,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
                    c->d_slot_of.p,  c->d_pos_of.p, c->d_parent.p,    c->d_root.p,   c->d_rank.p,       c->d_gepos.p,
                    c->d_lepos.p,    c->d_state.p,  c->d_seed_of.p,   c->d_member_pos.p, c->d_queue.p,  c->d_seed_label.p, c->d_comp_size.p, c->d_pslot.p, c->d_rpts.p, c->d_tlive.p,
                    c->d_clabels.p,  c->d_spill.p,  c->d_pkey.p,  c->d_flags.p,     c->d_seed_valid.p, c->d_tkeys.p,  c->d_tcount.p,
-                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p, c->d_nb27.p, c->d_chi.p, c->d_chi_meta.p};
+                   c->d_cells.p,    c->d_nbr.p, c->d_cinfo.p, c->d_biglist.p, c->d_job_stats.p, c->d_meta.p,   c->d_err.p,       c->d_planes.p, c->d_status.p,     c->d_hist.p, c->d_goff.p, c->d_hoff.p, c->d_hne.p, c->d_hnv.p, c->d_herr.p, c->d_rgb.p, c->d_color.p, c->d_marker.p, c->d_ipts.p, c->d_mpts.p, c->d_rankpos.p, c->d_mkey.p, c->d_nb27.p, c->d_chi.p, c->d_chi_meta.p, c->d_chi_stats.p};
     for (void *p : dev)
         if (p)
             cudaFree(p);
@@ -1401,7 +1404,14 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
         const ChiView cv{c->d_nodes.p, c->d_goff.p, c->d_key_a.p, c->d_hoff.p, c->d_chi.p, c->d_herr.p};
         chi_bucket_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_goff.p, counts);
         chi_place_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_goff.p, counts, fill, task_f, task_k);
-        chi_outline_kernel<<<c->sm_count * 8u, 32 * kChiWarps, 0, s>>>(bv, cv, counts, task_f, task_k, chi_cursor);
+        if (c->chi_stats)
+        {
+            if (dev_alloc(c, c->d_chi_stats, static_cast<size_t>(kChiStatTasks) * 8u))
+                return LIDAR_B200_ERR_CUDA;
+            LB_CUDA(c, cudaMemsetAsync(c->d_chi_stats.p, 0, static_cast<size_t>(kChiStatTasks) * 64u, s));
+        }
+        chi_outline_kernel<<<c->sm_count * 8u, 32 * kChiWarps, 0, s>>>(bv, cv, counts, task_f, task_k, chi_cursor,
+                                                                        c->chi_stats ? c->d_chi_stats.p : nullptr);
         nl += 3u;
     }
     hull_scan_kernel<<<F, 256, 0, s>>>(bv, c->m_nc(), c->d_hoff.p, c->d_hne.p, c->d_hnv.p,
@@ -1599,6 +1609,27 @@ int lidar_b200_last_cc_root(lidar_b200_ctx *c, uint32_t frame, uint32_t *root_ou
         return fail(c, LIDAR_B200_ERR_CAPACITY, "root_out too small");
     if (m)
         LB_CUDA(c, cudaMemcpy(root_out, c->d_root.p + c->off[frame], static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lidar_b200_last_chi_stats(lidar_b200_ctx *c, uint64_t *stats_out, uint32_t capacity_tasks, uint32_t *n_tasks_out)
+{
+    if (!c || !n_tasks_out)
+        return LIDAR_B200_ERR_INVALID;
+    *n_tasks_out = 0;
+    if (!c->chi_stats || !c->d_chi_stats.p || !c->d_chi_meta.p)
+        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "set LIDAR_B200_CHI_STATS=1 before creating the context and run mode LIDAR_B200_HULL_CONCAVE");
+    LB_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t nb[kChiBuckets];
+    LB_CUDA(c, cudaMemcpy(nb, c->d_chi_meta.p, sizeof(nb), cudaMemcpyDeviceToHost));
+    uint32_t n = 0;
+    for (uint32_t b = 0; b < kChiBuckets; ++b)
+        n += nb[b];
+    *n_tasks_out = n;
+    n = n < capacity_tasks ? n : capacity_tasks;
+    n = n < kChiStatTasks ? n : kChiStatTasks;
+    if (n && stats_out)
+        LB_CUDA(c, cudaMemcpy(stats_out, c->d_chi_stats.p, static_cast<size_t>(n) * 64, cudaMemcpyDeviceToHost));
     return 0;
 }
 

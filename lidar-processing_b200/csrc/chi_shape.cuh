@@ -15,7 +15,8 @@
 // persistent warps, so the few clusters of 10 000+ points start at once and the small ones fill in behind them.
 //
 // Working set: 96 bytes per grouped point, cluster k of frame f at arena + 96 * (off[f] + goff[k]) (chi_layout(n).bytes
-// <= 82 n + 46 < 96 n for n >= 20), so no prefix sum and no host round trip is needed to place it.
+// <= 92 n + 4 sqrt(n) - 112 + 11 * 15 alignment bytes < 96 n for n >= 20), so no prefix sum and no host round trip is
+// needed to place it.
 #pragma once
 
 #include "chi_shape.h"
@@ -28,6 +29,7 @@ namespace lb
 constexpr uint32_t kChiBytesPerPoint = 96u;
 constexpr int kChiWarps = 4;
 constexpr uint32_t kChiBuckets = 32u;
+constexpr uint32_t kChiStatTasks = 4096u;     // tasks with a diagnostics record (the largest ones come first)
 constexpr uint32_t kHullErrCollinear = 8u;  // the reference throws "not triangulation" on this cluster
 constexpr uint32_t kHullErrDegenerate = 16u; // every point of the cluster coincides (the reference reads out of bounds) / flip budget
 constexpr uint32_t kHullErrSlot = 32u;       // closed outlines of a frame beyond its slot
@@ -211,7 +213,11 @@ LB_D uint32_t chi_seed_warp(ChiWork &w)
     w.s2y = chi_py(w, i2);
     chi_circumcentre(w.s0x, w.s0y, w.s1x, w.s1y, w.s2x, w.s2y, w.cx, w.cy);
     for (uint32_t i = lane; i < n; i += 32u)
-        w.dist[i] = chi_dist2(chi_px(w, i), chi_py(w, i), w.cx, w.cy);
+    {
+        const double x = chi_px(w, i), y = chi_py(w, i);
+        w.dist[i] = chi_dist2(x, y, w.cx, w.cy);
+        w.key[i] = static_cast<uint16_t>(chi_hash_key(w, x, y));
+    }
     __syncwarp();
     return kChiOk;
 }
@@ -220,6 +226,7 @@ LB_D uint32_t chi_seed_warp(ChiWork &w)
 // the index breaks ties, so equal keys end in ascending index order.
 LB_D void chi_warp_sort(unsigned long long *a, uint32_t *ix, uint32_t n)
 {
+    constexpr int kU = 4; // pairs per lane in flight: the pairs of a stage are disjoint, so their loads can all go first
     const uint32_t lane = lane_id();
     uint32_t n_pad = 2u;
     while (n_pad < n)
@@ -228,32 +235,45 @@ LB_D void chi_warp_sort(unsigned long long *a, uint32_t *ix, uint32_t n)
         for (uint32_t jj = kk >> 1; jj > 0u; jj >>= 1)
         {
             const uint32_t lj = 31u - __clz(jj);
-            for (uint32_t t = lane; t < (n_pad >> 1); t += 32u)
+            const bool flip = jj == (kk >> 1);
+            for (uint32_t t0 = lane; t0 < (n_pad >> 1); t0 += 32u * kU)
             {
-                uint32_t p0, p1;
-                if (jj == (kk >> 1))
+                uint32_t p0[kU], p1[kU], xi[kU], yi[kU];
+                unsigned long long x[kU], y[kU];
+                bool on[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
                 {
-                    const uint32_t blk = t >> lj, o = t & (jj - 1u);
-                    p0 = blk * kk + o;
-                    p1 = blk * kk + kk - 1u - o;
-                }
-                else
-                {
-                    p0 = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u));
-                    p1 = p0 | jj;
-                }
-                if (p1 < n)
-                {
-                    const unsigned long long x = a[p0], y = a[p1];
-                    const uint32_t xi = ix[p0], yi = ix[p1];
-                    if (x > y || (x == y && xi > yi))
+                    const uint32_t t = t0 + 32u * u;
+                    if (flip)
                     {
-                        a[p0] = y;
-                        a[p1] = x;
-                        ix[p0] = yi;
-                        ix[p1] = xi;
+                        const uint32_t blk = t >> lj, o = t & (jj - 1u);
+                        p0[u] = blk * kk + o;
+                        p1[u] = blk * kk + kk - 1u - o;
+                    }
+                    else
+                    {
+                        p0[u] = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u));
+                        p1[u] = p0[u] | jj;
+                    }
+                    on[u] = t < (n_pad >> 1) && p1[u] < n;
+                    if (on[u])
+                    {
+                        x[u] = a[p0[u]];
+                        y[u] = a[p1[u]];
+                        xi[u] = ix[p0[u]];
+                        yi[u] = ix[p1[u]];
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (on[u] && (x[u] > y[u] || (x[u] == y[u] && xi[u] > yi[u])))
+                    {
+                        a[p0[u]] = y[u];
+                        a[p1[u]] = x[u];
+                        ix[p0[u]] = yi[u];
+                        ix[p1[u]] = xi[u];
+                    }
             }
             __syncwarp();
         }
@@ -262,7 +282,7 @@ LB_D void chi_warp_sort(unsigned long long *a, uint32_t *ix, uint32_t n)
 // One warp per cluster; persistent warps pull (frame, cluster) tasks in the order of chi_place_kernel.
 __global__ void __launch_bounds__(32 * kChiWarps)
 chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ task_f,
-                   const uint32_t *__restrict__ task_k, uint32_t *__restrict__ cursor)
+                   const uint32_t *__restrict__ task_k, uint32_t *__restrict__ cursor, unsigned long long *__restrict__ stats)
 {
     const uint32_t lane = lane_id();
     uint32_t T = lane < kChiBuckets ? counts[lane] : 0u;
@@ -275,6 +295,15 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
         g = __shfl_sync(kFullMask, g, 0);
         if (g >= T)
             break;
+        // diagnostics (LIDAR_B200_CHI_STATS=1): per task {n, start ns, end ns, cycles of seed / sort / sweep / erosion}
+        const bool rec = stats != nullptr && g < kChiStatTasks && lane == 0u;
+        unsigned long long t_start = 0ull;
+        long long c0k = 0, c1k = 0, c2k = 0, c3k = 0, c4k = 0;
+        if (rec)
+        {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+            c0k = clock64();
+        }
         const uint32_t f = task_f[g], k = task_k[g];
         const uint32_t off = bv.off[f];
         const uint32_t *go = cv.goff + off + f;
@@ -290,13 +319,15 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
             for (uint32_t i = lane; i < n; i += 32u)
             {
                 const float4 p = __ldg(&src[i]);
-                xy[i].x = p.x;
-                xy[i].y = p.y;
+                xy[i].x = static_cast<double>(p.x);
+                xy[i].y = static_cast<double>(p.y);
                 w.onb[i] = 0u;
             }
         }
         __syncwarp();
         uint32_t err = chi_seed_warp(w);
+        if (rec)
+            c1k = clock64();
         if (err == kChiOk)
         {
             // order of the sweep: (distance, index); the keys borrow the triangle arrays, which are empty until the sweep
@@ -321,18 +352,40 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
             if (!mixed)
                 for (uint32_t i = lane; i < n; i += 32u)
                     w.ids[i] = sid[i];
-            else
-                for (uint32_t i = lane; i < n; i += 32u)
-                    w.ids[i] = i;
             __syncwarp();
+            if (mixed)
+            {
+                // two different points exactly equally far: the reference's std::sort decides their order. The records
+                // borrow the triangle array (16 n <= 24 n - 60 bytes for n >= 8).
+                ChiKeyed *rec_sort = reinterpret_cast<ChiKeyed *>(w.tri);
+                for (uint32_t i = lane; i < n; i += 32u)
+                {
+                    ChiKeyed r;
+                    r.d = w.dist[i];
+                    r.id = i;
+                    r.pad = 0u;
+                    rec_sort[i] = r;
+                }
+                __syncwarp();
+                if (lane == 0u)
+                    chi_introsort(rec_sort, n);
+                __syncwarp();
+                for (uint32_t i = lane; i < n; i += 32u)
+                    w.ids[i] = rec_sort[i].id;
+                __syncwarp();
+            }
             uint32_t h = 0u;
             if (lane == 0u)
             {
-                if (mixed) // two different points exactly equally far: the reference's std::sort decides their order
-                    chi_introsort_ids(w.ids, w.dist, n);
+                if (rec)
+                    c2k = clock64();
                 err = chi_triangulate(w);
+                if (rec)
+                    c3k = clock64();
                 if (err == kChiOk)
                     h = chi_erode_and_walk(w, cv.hres + off + c0, true);
+                if (rec)
+                    c4k = clock64();
             }
             err = __shfl_sync(kFullMask, err, 0);
             h = __shfl_sync(kFullMask, h, 0);
@@ -343,6 +396,20 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
             cv.hcnt[off + f + k] = 0u;
         if (err != kChiOk && lane == 0u)
             atomicOr(cv.err, err == kChiErrCollinear ? kHullErrCollinear : kHullErrDegenerate);
+        if (rec)
+        {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            unsigned long long *o = stats + static_cast<size_t>(g) * 8u;
+            o[0] = n;
+            o[1] = t_start;
+            o[2] = t_end;
+            o[3] = static_cast<unsigned long long>(c1k - c0k);
+            o[4] = c2k ? static_cast<unsigned long long>(c2k - c1k) : 0ull;
+            o[5] = c3k ? static_cast<unsigned long long>(c3k - c2k) : 0ull;
+            o[6] = c4k ? static_cast<unsigned long long>(c4k - c3k) : 0ull;
+            o[7] = w.n_half / 3u;
+        }
         __syncwarp();
     }
 }

@@ -17,7 +17,7 @@
 //   * the order of the points: the reference sorts indices with std::sort by distance only. Where all distances
 //     differ, or equal distances belong to coinciding points (value-identical, so their order is invisible in the
 //     outline), any sort gives the reference's sequence and the device sorts in parallel by (distance, index). A
-//     cluster in which two DIFFERENT points are exactly equally far away takes chi_introsort_ids, a step-by-step
+//     cluster in which two DIFFERENT points are exactly equally far away takes chi_introsort, a step-by-step
 //     re-enactment of libstdc++ 13's std::sort (introsort loop with depth limit 2 * floor(log2 n), median of three
 //     moved to the front, unguarded Hoare partition, heap sort when the limit is hit, final insertion sort with its
 //     16-element threshold).
@@ -47,15 +47,16 @@ constexpr uint32_t kChiOk = 0u, kChiErrCollinear = 1u, kChiErrCoincident = 2u, k
 constexpr double kChiEps = DBL_EPSILON;
 constexpr double kChiFactor = 0.2; // geometry::ConcaveHull hull(coordinates, 0.2), polygon_simplification.cpp:132
 
-struct ChiXY
+struct alignas(16) ChiXY // the coordinates as the reference's delaunator sees them: static_cast<double>(float)
 {
-    float x, y;
+    double x, y;
 };
 
 // Per-cluster working set. Every array lives in one block of chi_layout(n).bytes bytes.
 struct ChiWork
 {
-    const ChiXY *xy;  // [n] the cluster's points (x, y of the grouped PointXYZ records)
+    const ChiXY *xy;  // [n] the cluster's points (x, y of the grouped PointXYZ records, widened once)
+    uint16_t *key;    // [n] getHashKey of every point (it depends on the point and the seed circumcentre only)
     uint32_t n;
     double *dist;     // [n + 1] squared distance from the seed circumcentre; later: legalisation stack, then heap lengths
     uint32_t *ids;    // [n + 1] point order; later: heap edges
@@ -76,7 +77,7 @@ struct ChiWork
 
 struct ChiLayout
 {
-    size_t dist, ids, tri, half, hprev, hnext, htri, hash, onb, xy, bytes;
+    size_t dist, ids, tri, half, hprev, hnext, htri, hash, onb, xy, key, bytes;
     uint32_t hash_size;
 };
 
@@ -116,7 +117,9 @@ LB_CHI_HD ChiLayout chi_layout(uint32_t n)
     l.onb = at;
     at = chi_align16(at + np);
     l.xy = at;
-    at = chi_align16(at + 8u * np);
+    at = chi_align16(at + 16u * np);
+    l.key = at;
+    at = chi_align16(at + 2u * np);
     l.bytes = at;
     return l;
 }
@@ -134,6 +137,7 @@ LB_CHI_HD void chi_bind(ChiWork &w, unsigned char *block, const ChiLayout &l, ui
     w.hash = reinterpret_cast<uint32_t *>(block + l.hash);
     w.onb = block + l.onb;
     w.xy = reinterpret_cast<const ChiXY *>(block + l.xy);
+    w.key = reinterpret_cast<uint16_t *>(block + l.key);
     w.hash_size = l.hash_size;
     w.n_half = 0u;
     w.overflow = false;
@@ -141,12 +145,33 @@ LB_CHI_HD void chi_bind(ChiWork &w, unsigned char *block, const ChiLayout &l, ui
 
 LB_CHI_HD double chi_px(const ChiWork &w, uint32_t i)
 {
-    return static_cast<double>(w.xy[i].x);
+    return w.xy[i].x;
 }
 
 LB_CHI_HD double chi_py(const ChiWork &w, uint32_t i)
 {
-    return static_cast<double>(w.xy[i].y);
+    return w.xy[i].y;
+}
+
+// both coordinates with one 16-byte load
+LB_CHI_HD void chi_pt(const ChiWork &w, uint32_t i, double &x, double &y)
+{
+#ifdef __CUDA_ARCH__
+    const double2 p = *reinterpret_cast<const double2 *>(&w.xy[i]);
+#else
+    const ChiXY p = w.xy[i];
+#endif
+    x = p.x;
+    y = p.y;
+}
+
+// Point::equal(a, b, span) (delaunator.hpp:56-61): squared distance / span < epsilon. The division only decides when
+// the squared distance is within a factor of four of epsilon * span; beyond that the quotient is >= 4 eps (1 - 2^-52).
+LB_CHI_HD bool chi_near(double d2, double span, double span_4eps)
+{
+    if (d2 > span_4eps)
+        return false;
+    return d2 / span < kChiEps;
 }
 
 // ---- predicates (delaunator.cpp:40-212) -----------------------------------------------------------------------------
@@ -297,15 +322,24 @@ LB_CHI_HD void chi_heap_pop(uint32_t *he, double *hl, uint32_t &size, uint32_t &
 }
 
 // ---- libstdc++ 13 std::sort(ids, by dist[i] < dist[j]) (delaunator.cpp:339-341), step by step ------------------------
+// The elements travel as (distance, id) records, so that a comparison is one load; the sequence of comparisons and moves
+// is the one std::sort performs on the ids.
 
-LB_CHI_HD void chi_ids_adjust_heap(uint32_t *a, const double *d, uint32_t hole, uint32_t len, uint32_t v)
+struct alignas(16) ChiKeyed
+{
+    double d;
+    uint32_t id;
+    uint32_t pad;
+};
+
+LB_CHI_HD void chi_sort_adjust_heap(ChiKeyed *a, uint32_t hole, uint32_t len, ChiKeyed v)
 {
     const uint32_t top = hole;
     uint32_t child = hole;
     while (len >= 2u && child < (len - 1u) / 2u)
     {
         child = 2u * (child + 1u);
-        if (d[a[child]] < d[a[child - 1u]])
+        if (a[child].d < a[child - 1u].d)
             --child;
         a[hole] = a[child];
         hole = child;
@@ -319,7 +353,7 @@ LB_CHI_HD void chi_ids_adjust_heap(uint32_t *a, const double *d, uint32_t hole, 
     while (hole > top)
     {
         const uint32_t parent = (hole - 1u) / 2u;
-        if (!(d[a[parent]] < d[v]))
+        if (!(a[parent].d < v.d))
             break;
         a[hole] = a[parent];
         hole = parent;
@@ -328,31 +362,30 @@ LB_CHI_HD void chi_ids_adjust_heap(uint32_t *a, const double *d, uint32_t hole, 
 }
 
 // std::__partial_sort(first, last, last): make_heap + sort_heap
-LB_CHI_HD void chi_ids_heap_sort(uint32_t *a, const double *d, uint32_t len)
+LB_CHI_HD void chi_sort_heap_sort(ChiKeyed *a, uint32_t len)
 {
     if (len < 2u)
         return;
     for (uint32_t parent = (len - 2u) / 2u;; --parent)
     {
-        chi_ids_adjust_heap(a, d, parent, len, a[parent]);
+        chi_sort_adjust_heap(a, parent, len, a[parent]);
         if (parent == 0u)
             break;
     }
     for (uint32_t last = len; last > 1u;)
     {
         --last;
-        const uint32_t v = a[last];
+        const ChiKeyed v = a[last];
         a[last] = a[0];
-        chi_ids_adjust_heap(a, d, 0u, last, v);
+        chi_sort_adjust_heap(a, 0u, last, v);
     }
 }
 
-LB_CHI_HD void chi_ids_unguarded_insert(uint32_t *a, const double *d, uint32_t last)
+LB_CHI_HD void chi_sort_unguarded_insert(ChiKeyed *a, uint32_t last)
 {
-    const uint32_t v = a[last];
-    const double dv = d[v];
+    const ChiKeyed v = a[last];
     uint32_t next = last - 1u;
-    while (dv < d[a[next]])
+    while (v.d < a[next].d)
     {
         a[last] = a[next];
         last = next;
@@ -361,25 +394,25 @@ LB_CHI_HD void chi_ids_unguarded_insert(uint32_t *a, const double *d, uint32_t l
     a[last] = v;
 }
 
-LB_CHI_HD void chi_ids_insertion_sort(uint32_t *a, const double *d, uint32_t first, uint32_t last)
+LB_CHI_HD void chi_sort_insertion_sort(ChiKeyed *a, uint32_t first, uint32_t last)
 {
     if (first == last)
         return;
     for (uint32_t i = first + 1u; i != last; ++i)
     {
-        if (d[a[i]] < d[a[first]])
+        if (a[i].d < a[first].d)
         {
-            const uint32_t v = a[i];
+            const ChiKeyed v = a[i];
             for (uint32_t j = i; j > first; --j)
                 a[j] = a[j - 1u];
             a[first] = v;
         }
         else
-            chi_ids_unguarded_insert(a, d, i);
+            chi_sort_unguarded_insert(a, i);
     }
 }
 
-LB_CHI_HD void chi_introsort_ids(uint32_t *a, const double *d, uint32_t n)
+LB_CHI_HD void chi_introsort(ChiKeyed *a, uint32_t n)
 {
     if (n == 0u)
         return;
@@ -404,36 +437,36 @@ LB_CHI_HD void chi_introsort_ids(uint32_t *a, const double *d, uint32_t n)
         {
             if (depth == 0u)
             {
-                chi_ids_heap_sort(a + first, d, last - first);
+                chi_sort_heap_sort(a + first, last - first);
                 break;
             }
             --depth;
             // __move_median_to_first(first, first + 1, mid, last - 1)
             const uint32_t ia = first + 1u, ib = first + (last - first) / 2u, ic = last - 1u;
-            const double ka = d[a[ia]], kb = d[a[ib]], kc = d[a[ic]];
+            const double ka = a[ia].d, kb = a[ib].d, kc = a[ic].d;
             uint32_t pick;
             if (ka < kb)
                 pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
             else
                 pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
             {
-                const uint32_t t = a[first];
+                const ChiKeyed t = a[first];
                 a[first] = a[pick];
                 a[pick] = t;
             }
             // __unguarded_partition(first + 1, last, pivot = first)
-            const double kp = d[a[first]];
+            const double kp = a[first].d;
             uint32_t lo = first + 1u, hi = last;
             while (true)
             {
-                while (d[a[lo]] < kp)
+                while (a[lo].d < kp)
                     ++lo;
                 --hi;
-                while (kp < d[a[hi]])
+                while (kp < a[hi].d)
                     --hi;
                 if (!(lo < hi))
                     break;
-                const uint32_t t = a[lo];
+                const ChiKeyed t = a[lo];
                 a[lo] = a[hi];
                 a[hi] = t;
                 ++lo;
@@ -452,12 +485,26 @@ LB_CHI_HD void chi_introsort_ids(uint32_t *a, const double *d, uint32_t n)
     // __final_insertion_sort
     if (n > 16u)
     {
-        chi_ids_insertion_sort(a, d, 0u, 16u);
+        chi_sort_insertion_sort(a, 0u, 16u);
         for (uint32_t i = 16u; i != n; ++i)
-            chi_ids_unguarded_insert(a, d, i);
+            chi_sort_unguarded_insert(a, i);
     }
     else
-        chi_ids_insertion_sort(a, d, 0u, n);
+        chi_sort_insertion_sort(a, 0u, n);
+}
+
+// ids[0..n) <- what std::sort leaves of 0..n-1 under dist[i] < dist[j]; `scratch` holds n ChiKeyed records
+LB_CHI_HD void chi_introsort_ids(uint32_t *ids, const double *dist, uint32_t n, ChiKeyed *scratch)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        scratch[i].d = dist[i];
+        scratch[i].id = i;
+        scratch[i].pad = 0u;
+    }
+    chi_introsort(scratch, n);
+    for (uint32_t i = 0; i < n; ++i)
+        ids[i] = scratch[i].id;
 }
 
 // ---- seed triangle (delaunator.cpp:214-327), sequential form ---------------------------------------------------------
@@ -540,7 +587,10 @@ LB_CHI_HD uint32_t chi_seed_sequential(ChiWork &w)
     w.s2y = chi_py(w, i2);
     chi_circumcentre(w.s0x, w.s0y, w.s1x, w.s1y, w.s2x, w.s2y, w.cx, w.cy);
     for (uint32_t i = 0; i < n; ++i)
+    {
         w.dist[i] = chi_dist2(chi_px(w, i), chi_py(w, i), w.cx, w.cy);
+        w.key[i] = static_cast<uint16_t>(chi_hash_key(w, chi_px(w, i), chi_py(w, i)));
+    }
     return kChiOk;
 }
 
@@ -587,17 +637,23 @@ LB_CHI_HD uint32_t chi_legalize(ChiWork &w, uint32_t a, uint32_t *stack, uint32_
     while (true)
     {
         const uint32_t b = w.half[a];
-        const uint32_t a0 = a - a % 3u;
-        ar = a0 + (a + 2u) % 3u;
+        const uint32_t ra = a % 3u;
+        const uint32_t a0 = a - ra;
+        ar = a0 + (ra == 0u ? 2u : ra - 1u); // a0 + (a + 2) % 3
         bool flipped = false;
         if (b != kChiNone)
         {
-            const uint32_t b0 = b - b % 3u;
-            const uint32_t al = a0 + (a + 1u) % 3u;
-            const uint32_t bl = b0 + (b + 2u) % 3u;
+            const uint32_t rb = b % 3u;
+            const uint32_t b0 = b - rb;
+            const uint32_t al = a0 + (ra == 2u ? 0u : ra + 1u); // a0 + (a + 1) % 3
+            const uint32_t bl = b0 + (rb == 0u ? 2u : rb - 1u); // b0 + (b + 2) % 3
             const uint32_t p0 = w.tri[ar], pr = w.tri[a], pl = w.tri[al], p1 = w.tri[bl];
-            if (chi_in_circle(chi_px(w, p0), chi_py(w, p0), chi_px(w, pr), chi_py(w, pr), chi_px(w, pl), chi_py(w, pl),
-                              chi_px(w, p1), chi_py(w, p1)))
+            double p0x, p0y, prx, pry, plx, ply, p1x, p1y;
+            chi_pt(w, p0, p0x, p0y);
+            chi_pt(w, pr, prx, pry);
+            chi_pt(w, pl, plx, ply);
+            chi_pt(w, p1, p1x, p1y);
+            if (chi_in_circle(p0x, p0y, prx, pry, plx, ply, p1x, p1y))
             {
                 w.tri[a] = p1;
                 w.tri[b] = p0;
@@ -625,7 +681,7 @@ LB_CHI_HD uint32_t chi_legalize(ChiWork &w, uint32_t a, uint32_t *stack, uint32_
                     return ar;
                 }
                 --guard;
-                stack[depth++] = b0 + (b + 1u) % 3u;
+                stack[depth++] = b0 + (rb == 2u ? 0u : rb + 1u); // br = b0 + (b + 1) % 3
                 flipped = true;
             }
         }
@@ -658,16 +714,18 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
     w.htri[i0] = 0u;
     w.htri[i1] = 1u;
     w.htri[i2] = 2u;
-    w.hash[chi_hash_key(w, w.s0x, w.s0y)] = i0;
-    w.hash[chi_hash_key(w, w.s1x, w.s1y)] = i1;
-    w.hash[chi_hash_key(w, w.s2x, w.s2y)] = i2;
+    w.hash[w.key[i0]] = i0;
+    w.hash[w.key[i1]] = i1;
+    w.hash[w.key[i2]] = i2;
     w.n_half = 0u;
     chi_add_triangle(w, i0, i1, i2, kChiNone, kChiNone, kChiNone);
     double xp = 0.0, yp = 0.0;
+    const double span_4eps = 4.0 * kChiEps * w.span;
     for (uint32_t k = 0; k < n; ++k)
     {
         const uint32_t i = w.ids[k];
-        const double x = chi_px(w, i), y = chi_py(w, i);
+        double x, y;
+        chi_pt(w, i, x, y);
         if (k > 0u && chi_same(x, y, xp, yp))
             continue;
         xp = x;
@@ -676,7 +734,7 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
             continue;
         // a hull vertex near the point's direction, from the pseudo-angle hash
         uint32_t start = 0u;
-        const uint32_t key = chi_hash_key(w, x, y);
+        const uint32_t key = w.key[i];
         for (uint32_t j = 0; j < w.hash_size; ++j)
         {
             uint32_t slot = key + j;
@@ -695,9 +753,11 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
             if (++steps > n + 1u)
                 return kChiErrGuard;
             q = w.hnext[e];
-            const double ex = chi_px(w, e), ey = chi_py(w, e), qx = chi_px(w, q), qy = chi_py(w, q);
+            double ex, ey, qx, qy;
+            chi_pt(w, e, ex, ey);
+            chi_pt(w, q, qx, qy);
             // Point::equal(p, hull vertex, span): squared distance / span < epsilon
-            if (chi_dist2(ex, ey, x, y) / w.span < kChiEps || chi_dist2(qx, qy, x, y) / w.span < kChiEps)
+            if (chi_near(chi_dist2(ex, ey, x, y), w.span, span_4eps) || chi_near(chi_dist2(qx, qy, x, y), w.span, span_4eps))
             {
                 e = kChiNone;
                 break;
@@ -720,7 +780,10 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
         while (true)
         {
             q = w.hnext[next];
-            if (w.overflow || !chi_ccw(x, y, chi_px(w, next), chi_py(w, next), chi_px(w, q), chi_py(w, q)))
+            double nx, ny, qx, qy;
+            chi_pt(w, next, nx, ny);
+            chi_pt(w, q, qx, qy);
+            if (w.overflow || !chi_ccw(x, y, nx, ny, qx, qy))
                 break;
             t = chi_add_triangle(w, next, i, q, w.htri[i], kChiNone, w.htri[next]);
             w.htri[i] = chi_legalize(w, t + 2u, stack, stack_cap, guard);
@@ -732,7 +795,10 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
             while (true)
             {
                 q = w.hprev[e];
-                if (w.overflow || !chi_ccw(x, y, chi_px(w, q), chi_py(w, q), chi_px(w, e), chi_py(w, e)))
+                double ex, ey, qx, qy;
+                chi_pt(w, e, ex, ey);
+                chi_pt(w, q, qx, qy);
+                if (w.overflow || !chi_ccw(x, y, qx, qy, ex, ey))
                     break;
                 t = chi_add_triangle(w, q, i, e, kChiNone, w.htri[e], w.htri[q]);
                 chi_legalize(w, t + 2u, stack, stack_cap, guard);
@@ -746,8 +812,8 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
         w.hprev[next] = i;
         w.hnext[e] = i;
         w.hnext[i] = next;
-        w.hash[chi_hash_key(w, x, y)] = i;
-        w.hash[chi_hash_key(w, chi_px(w, e), chi_py(w, e))] = e;
+        w.hash[key] = i;
+        w.hash[w.key[e]] = e;
         if (guard == 0u || w.overflow)
             return kChiErrGuard;
     }

@@ -186,13 +186,41 @@ int hc_jacobi_svd3(const float *a, float *v, float *sv)
     return lb::jacobi_svd3(a, v, sv) ? 1 : 0;
 }
 
+// bytes of the working set of a cluster of n points (the device places it at 96 bytes per point)
+unsigned long long hc_chi_layout_bytes(uint32_t n)
+{
+    return lb::chi_layout(n).bytes;
+}
+
+// distances from the seed circumcentre of one cluster as the sweep sorts them (diagnostics); returns the seed status
+uint32_t hc_chi_dists(const float *points, uint32_t n, uint32_t stride_floats, double *dist_out)
+{
+    const lb::ChiLayout lay = lb::chi_layout(n);
+    std::vector<unsigned char> block(lay.bytes, 0);
+    lb::ChiWork w;
+    lb::chi_bind(w, block.data(), lay, n);
+    lb::ChiXY *xy = reinterpret_cast<lb::ChiXY *>(block.data() + lay.xy);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        xy[i].x = static_cast<double>(points[static_cast<size_t>(i) * stride_floats]);
+        xy[i].y = static_cast<double>(points[static_cast<size_t>(i) * stride_floats + 1]);
+    }
+    const uint32_t err = lb::chi_seed_sequential(w);
+    if (err == lb::kChiOk)
+        std::memcpy(dist_out, w.dist, sizeof(double) * n);
+    return err;
+}
+
 // std::sort of ids by dist (mode 0) against lb::chi_introsort_ids (mode 1), for the tie-order check
 void hc_sort_ids(uint32_t *ids, const double *dist, uint32_t n, int mode)
 {
     if (mode == 0)
         std::sort(ids, ids + n, [dist](uint32_t i, uint32_t j) { return dist[i] < dist[j]; });
     else
-        lb::chi_introsort_ids(ids, dist, n);
+    {
+        std::vector<lb::ChiKeyed> scratch(n + 1u);
+        lb::chi_introsort_ids(ids, dist, n, scratch.data());
+    }
 }
 
 // std::push_heap / std::pop_heap on (edge, length) pairs against lb::chi_heap_push / chi_heap_pop: ops[i] >= 0 pushes
@@ -270,8 +298,8 @@ long long hc_chi_outlines(const float *points, const uint32_t *offsets, uint32_t
         for (uint32_t i = 0; i < n; ++i)
         {
             const float *p = points + static_cast<size_t>(offsets[k] + i) * stride_floats;
-            xy[i].x = p[0];
-            xy[i].y = p[1];
+            xy[i].x = static_cast<double>(p[0]);
+            xy[i].y = static_cast<double>(p[1]);
         }
         uint32_t err = lb::chi_seed_sequential(w);
         if (err == lb::kChiOk)
@@ -292,9 +320,7 @@ long long hc_chi_outlines(const float *points, const uint32_t *offsets, uint32_t
                 }
             if (sort_mode == 1 || (sort_mode == 0 && mixed))
             {
-                for (uint32_t i = 0; i < n; ++i)
-                    w.ids[i] = i;
-                lb::chi_introsort_ids(w.ids, w.dist, n);
+                lb::chi_introsort_ids(w.ids, w.dist, n, reinterpret_cast<lb::ChiKeyed *>(w.tri)); // (the device's scratch too)
                 ++stats_out[0];
             }
             else

@@ -247,3 +247,10 @@ def test_heap_reenactment_matches_std_heap(hc):
         cnt = [hc.hc_heap_replay(ops.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), n, m,
                                  out[m].ctypes.data_as(C.c_void_p)) for m in (0, 1)]
         assert cnt[0] == cnt[1] and np.array_equal(out[0][:cnt[0]], out[1][:cnt[1]])
+
+
+def test_concave_working_set_fits_its_slot(hc):
+    """chi_shape.cuh places the working set of a cluster of n >= 20 points at 96 bytes per point of its CSR range."""
+    hc.hc_chi_layout_bytes.restype = C.c_ulonglong
+    for n in list(range(20, 3000)) + [4095, 4096, 4097, 65535, 65536, 1 << 20, (1 << 24) + 1, (1 << 31) - 1]:
+        assert hc.hc_chi_layout_bytes(C.c_uint32(n)) <= 96 * n, n

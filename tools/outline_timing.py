@@ -74,6 +74,37 @@ for f in list(range(0, len(frames), max(1, len(frames) // 12)))[:12]:
     lat.append(min(per))
 one.close()
 out["concave_outlines_single_frame_ms"] = {"p50": float(np.median(lat)), "max": float(max(lat)), "frames": len(lat)}
+# several batches in flight (one context + stream each): the outline step of a batch ends with a few warps on its largest
+# clusters, which leaves the GPU to the next batches - the steady-state cost per batch is what a pipeline pays
+import threading  # noqa: E402
+
+K = 4
+others = [pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames)) for _ in range(K - 1)]
+for o in others:
+    o.batch_stage(frames)
+ctxs = [ctx] + others
+
+
+def loop(c, reps):
+    for _ in range(reps):
+        c.batch_run()
+        c._check(L.lidar_b200_batch_group_clusters(c._h), "group")
+        c._check(L.lidar_b200_batch_hull_outlines(c._h, 2), "hull")
+        c.sync()
+
+
+for c in ctxs:
+    loop(c, 1)
+reps = 4
+th = [threading.Thread(target=loop, args=(c, reps)) for c in ctxs]
+t0 = time.perf_counter()
+for t in th:
+    t.start()
+for t in th:
+    t.join()
+out["ms_per_step"]["+split+concave_outlines, 4 batches in flight"] = 1e3 * (time.perf_counter() - t0) / (reps * K)
+for o in others:
+    o.close()
 # results once, for the counts and the CPU sample
 res = ctx.batch_fetch()
 groups = ctx.batch_clusters()
