@@ -556,14 +556,24 @@ def main():
                 split()
                 ctx._check(L.lidar_b200_batch_hull_outlines(ctx._h, pkg.HULL_CONVEX), "batch_hull_outlines")
 
+            def split_concave_outlines():
+                split()
+                ctx._check(L.lidar_b200_batch_hull_outlines(ctx._h, pkg.HULL_CONCAVE), "batch_hull_outlines")
+
             base_ms = timed_ms(lambda: None)
             split_ms = timed_ms(split)
             outl_ms = timed_ms(split_outlines)
             hulls = ctx.batch_hulls(pkg.HULL_CONVEX)
+            concave_ms = timed_ms(split_concave_outlines)
+            chulls = ctx.batch_hulls(pkg.HULL_CONCAVE, tolerate_open_marches=True)
             next_rows = {"what": "wall-clock ms per resident step, 3 steps each: seg+cluster alone, + device-side cluster split "
-                                 "(processor.cpp:180-200), + ordered convex outlines of every cluster (polygon_simplification.cpp:31-79)",
+                                 "(processor.cpp:180-200), + ordered convex outlines of every cluster (polygon_simplification.cpp:31-79), "
+                                 "+ the concave policy instead (polygon_simplification.cpp:81-149: Delaunay-based chi-shape from 20 points on, "
+                                 "one batch in flight - its step ends with single warps on the largest clusters)",
                          "seg_cluster_ms": base_ms, "plus_split_ms": split_ms, "plus_split_outlines_ms": outl_ms,
-                         "outline_vertices_per_step": int(sum(h["xy"].shape[0] for h in hulls))}
+                         "outline_vertices_per_step": int(sum(h["xy"].shape[0] for h in hulls)),
+                         "plus_split_concave_outlines_ms": concave_ms,
+                         "concave_outline_vertices_per_step": int(sum(h["xy"].shape[0] for h in chulls))}
         except Exception as e:  # the metric must not depend on the extra rows
             next_rows = {"error": str(e)}
 

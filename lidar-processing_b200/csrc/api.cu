@@ -136,7 +136,7 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_goff; // CSR offsets of the grouped clusters: frame f at [off[f] + f, off[f] + f + K_f]
     // outlines of the grouped clusters (hull.cuh): CSR offsets in the layout of d_goff, vertices per frame, error bits
     DevBuf<uint32_t> d_hoff, d_hne, d_hnv, d_herr, d_rgb;
-    DevBuf<unsigned char> d_chi;   // working sets of the concave outlines (chi_shape.cuh), 96 bytes per point slot
+    DevBuf<unsigned char> d_chi;   // working sets of the concave outlines (chi_shape.cuh), 144 bytes per point slot
     DevBuf<uint32_t> d_chi_meta;   // [bucket counts 32 | bucket fill 32 | cursor]
     DevBuf<unsigned long long> d_chi_stats; // LIDAR_B200_CHI_STATS=1: 8 words per task for the first kChiStatTasks tasks
     bool chi_stats{false};

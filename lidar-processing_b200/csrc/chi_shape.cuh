@@ -14,9 +14,9 @@
 // Scheduling: tasks are bucketed by floor(log2 n), largest bucket first, and pulled from one batch-wide counter by
 // persistent warps, so the few clusters of 10 000+ points start at once and the small ones fill in behind them.
 //
-// Working set: 96 bytes per grouped point, cluster k of frame f at arena + 96 * (off[f] + goff[k]) (chi_layout(n).bytes
-// <= 92 n + 4 sqrt(n) - 112 + 11 * 15 alignment bytes < 96 n for n >= 20), so no prefix sum and no host round trip is
-// needed to place it.
+// Working set: 144 bytes per grouped point, cluster k of frame f at arena + 144 * (off[f] + goff[k]) (chi_layout(n).bytes
+// = 141 n + 4 sqrt(n) - 138 + alignment < 144 n for n >= 20), so no prefix sum and no host round trip is needed to place
+// it. The pseudo-angle hash of a cluster (ceil(sqrt(n)) words) lives in shared memory.
 #pragma once
 
 #include "chi_shape.h"
@@ -26,7 +26,8 @@
 namespace lb
 {
 
-constexpr uint32_t kChiBytesPerPoint = 96u;
+constexpr uint32_t kChiBytesPerPoint = 144u;
+constexpr uint32_t kChiSmemHash = 512u;      // hash words per warp in shared memory (clusters up to 262 144 points)
 constexpr int kChiWarps = 4;
 constexpr uint32_t kChiBuckets = 32u;
 constexpr uint32_t kChiStatTasks = 4096u;     // tasks with a diagnostics record (the largest ones come first)
@@ -40,7 +41,7 @@ struct ChiView
     const uint32_t *goff; // CSR offsets, frame f at [off[f] + f, off[f] + f + K]
     uint32_t *hres;       // per cluster, at its CSR position: outline vertices as cluster-local indices (open loop)
     uint32_t *hcnt;       // per cluster (same layout as goff): vertices of the CLOSED outline
-    unsigned char *arena; // 96 bytes per point slot
+    unsigned char *arena; // 144 bytes per point slot
     uint32_t *err;
 };
 
@@ -216,7 +217,7 @@ LB_D uint32_t chi_seed_warp(ChiWork &w)
     {
         const double x = chi_px(w, i), y = chi_py(w, i);
         w.dist[i] = chi_dist2(x, y, w.cx, w.cy);
-        w.key[i] = static_cast<uint16_t>(chi_hash_key(w, x, y));
+        w.node[i].key = chi_hash_key(w, x, y);
     }
     __syncwarp();
     return kChiOk;
@@ -280,10 +281,11 @@ LB_D void chi_warp_sort(unsigned long long *a, uint32_t *ix, uint32_t n)
 }
 
 // One warp per cluster; persistent warps pull (frame, cluster) tasks in the order of chi_place_kernel.
-__global__ void __launch_bounds__(32 * kChiWarps)
+__global__ void __launch_bounds__(32 * kChiWarps, 4)
 chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ task_f,
                    const uint32_t *__restrict__ task_k, uint32_t *__restrict__ cursor, unsigned long long *__restrict__ stats)
 {
+    __shared__ uint32_t s_hash[kChiWarps][kChiSmemHash];
     const uint32_t lane = lane_id();
     uint32_t T = lane < kChiBuckets ? counts[lane] : 0u;
     T = warp_reduce_add(T);
@@ -313,14 +315,15 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
         const ChiLayout lay = chi_layout(n);
         ChiWork w;
         chi_bind(w, block, lay, n);
+        if (w.hash_size <= kChiSmemHash)
+            w.hash = s_hash[threadIdx.x >> 5];
         {
-            ChiXY *xy = reinterpret_cast<ChiXY *>(block + lay.xy);
             const float4 *src = cv.gpts + off + c0;
             for (uint32_t i = lane; i < n; i += 32u)
             {
                 const float4 p = __ldg(&src[i]);
-                xy[i].x = static_cast<double>(p.x);
-                xy[i].y = static_cast<double>(p.y);
+                w.node[i].x = static_cast<double>(p.x);
+                w.node[i].y = static_cast<double>(p.y);
                 w.onb[i] = 0u;
             }
         }
@@ -330,9 +333,10 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
             c1k = clock64();
         if (err == kChiOk)
         {
-            // order of the sweep: (distance, index); the keys borrow the triangle arrays, which are empty until the sweep
-            unsigned long long *skey = reinterpret_cast<unsigned long long *>(w.tri);
-            uint32_t *sid = w.half;
+            // order of the sweep: (distance, index); the keys borrow the half-edge records, which are empty until the sweep
+            // (8 n + 4 n of 96 n - 240 bytes)
+            unsigned long long *skey = reinterpret_cast<unsigned long long *>(w.edge);
+            uint32_t *sid = reinterpret_cast<uint32_t *>(skey + ((n + 1u) & ~1u));
             for (uint32_t i = lane; i < n; i += 32u)
             {
                 skey[i] = static_cast<unsigned long long>(__double_as_longlong(w.dist[i])); // distances are >= +0.0
@@ -344,7 +348,7 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
             for (uint32_t i = lane; i + 1u < n; i += 32u)
                 if (skey[i] == skey[i + 1u])
                 {
-                    const ChiXY a = w.xy[sid[i]], b = w.xy[sid[i + 1u]];
+                    const ChiNode &a = w.node[sid[i]], &b = w.node[sid[i + 1u]];
                     if (!(a.x == b.x && a.y == b.y) && !(chi_on_seed(w, a.x, a.y) && chi_on_seed(w, b.x, b.y)))
                         mixed = true;
                 }
@@ -356,8 +360,8 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
             if (mixed)
             {
                 // two different points exactly equally far: the reference's std::sort decides their order. The records
-                // borrow the triangle array (16 n <= 24 n - 60 bytes for n >= 8).
-                ChiKeyed *rec_sort = reinterpret_cast<ChiKeyed *>(w.tri);
+                // borrow the half-edge records too (the keys above are spent).
+                ChiKeyed *rec_sort = reinterpret_cast<ChiKeyed *>(w.edge);
                 for (uint32_t i = lane; i < n; i += 32u)
                 {
                     ChiKeyed r;

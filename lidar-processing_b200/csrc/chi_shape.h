@@ -47,27 +47,41 @@ constexpr uint32_t kChiOk = 0u, kChiErrCollinear = 1u, kChiErrCoincident = 2u, k
 constexpr double kChiEps = DBL_EPSILON;
 constexpr double kChiFactor = 0.2; // geometry::ConcaveHull hull(coordinates, 0.2), polygon_simplification.cpp:132
 
-struct alignas(16) ChiXY // the coordinates as the reference's delaunator sees them: static_cast<double>(float)
+// One record per half-edge: its origin vertex (triangles[e]) WITH that vertex's coordinates, and its twin
+// (half_edges[e]). The legalisation reads what it needs about a triangle with three 16-byte loads whose addresses it
+// knows up front, and about the triangle across an edge with a fourth - instead of half_edges[] -> triangles[] ->
+// coords[] one after the other: on a cluster of 20 000 points every one of those is an L2 round trip of ~290 cycles,
+// and the sweep is a chain of them (profiles/r02_micro_l1_read_after_write.txt, r02_chi_outline_task_phases.txt).
+struct alignas(16) ChiEdge
 {
+    uint32_t twin;
+    uint32_t v;
+    float x, y; // the cluster's float coordinates; the arithmetic widens them like the reference (static_cast<double>)
+};
+
+// One record per point: hull_prev / hull_next / hull_tri, its getHashKey and its coordinates (widened once).
+struct alignas(16) ChiNode
+{
+    uint32_t prev, next, tri, key;
     double x, y;
 };
+
+constexpr uint32_t kChiLocalStack = 32u; // legalisation stack entries kept in thread-local memory (deeper ones spill)
 
 // Per-cluster working set. Every array lives in one block of chi_layout(n).bytes bytes.
 struct ChiWork
 {
-    const ChiXY *xy;  // [n] the cluster's points (x, y of the grouped PointXYZ records, widened once)
-    uint16_t *key;    // [n] getHashKey of every point (it depends on the point and the seed circumcentre only)
+    ChiNode *node;    // [n]
     uint32_t n;
-    double *dist;     // [n + 1] squared distance from the seed circumcentre; later: legalisation stack, then heap lengths
+    double *dist;     // [n + 1] squared distance from the seed circumcentre; later: stack spill, then heap lengths
     uint32_t *ids;    // [n + 1] point order; later: heap edges
-    uint32_t *tri;    // [3 * (2n - 5)] triangles
-    uint32_t *half;   // [3 * (2n - 5)] half_edges
-    uint32_t *hprev, *hnext, *htri; // [n] advancing hull
-    uint32_t *hash;   // [hash_size]
+    ChiEdge *edge;    // [3 * (2n - 5)] triangles + half_edges
+    uint32_t *hash;   // [hash_size] (the device keeps it in shared memory when it fits)
     uint8_t *onb;     // [n] boundary_set of concave_hull.hpp:110
     uint32_t hash_size;
     uint32_t n_half;  // triangles.size()
     bool overflow;    // guard: more triangles than a triangulation can have
+    bool tri_moved;   // legalize moved a hull_tri entry (delaunator.cpp:592-606): copies of .tri held in registers are stale
     uint32_t hull_start;
     uint32_t i0, i1, i2;
     double cx, cy;    // m_center
@@ -77,7 +91,7 @@ struct ChiWork
 
 struct ChiLayout
 {
-    size_t dist, ids, tri, half, hprev, hnext, htri, hash, onb, xy, key, bytes;
+    size_t dist, ids, edge, node, hash, onb, bytes;
     uint32_t hash_size;
 };
 
@@ -92,34 +106,25 @@ LB_CHI_HD uint32_t chi_hash_size(uint32_t n)
     return static_cast<uint32_t>(ceil(sqrt(static_cast<double>(n))));
 }
 
+// 141 n + 4 sqrt(n) - 138 bytes plus alignment: below 144 n for every n >= 20 (tests/test_host_logic.py)
 LB_CHI_HD ChiLayout chi_layout(uint32_t n)
 {
     ChiLayout l;
     const size_t np = n, t3 = n >= 3u ? 3u * (2u * np - 5u) : 3u;
     l.hash_size = chi_hash_size(n);
     size_t at = 0;
+    l.edge = at;
+    at = chi_align16(at + sizeof(ChiEdge) * t3);
+    l.node = at;
+    at = chi_align16(at + sizeof(ChiNode) * np);
     l.dist = at;
     at = chi_align16(at + 8u * (np + 1u));
     l.ids = at;
     at = chi_align16(at + 4u * (np + 1u));
-    l.tri = at;
-    at = chi_align16(at + 4u * t3);
-    l.half = at;
-    at = chi_align16(at + 4u * t3);
-    l.hprev = at;
-    at = chi_align16(at + 4u * np);
-    l.hnext = at;
-    at = chi_align16(at + 4u * np);
-    l.htri = at;
-    at = chi_align16(at + 4u * np);
     l.hash = at;
     at = chi_align16(at + 4u * l.hash_size);
     l.onb = at;
     at = chi_align16(at + np);
-    l.xy = at;
-    at = chi_align16(at + 16u * np);
-    l.key = at;
-    at = chi_align16(at + 2u * np);
     l.bytes = at;
     return l;
 }
@@ -127,42 +132,69 @@ LB_CHI_HD ChiLayout chi_layout(uint32_t n)
 LB_CHI_HD void chi_bind(ChiWork &w, unsigned char *block, const ChiLayout &l, uint32_t n)
 {
     w.n = n;
+    w.edge = reinterpret_cast<ChiEdge *>(block + l.edge);
+    w.node = reinterpret_cast<ChiNode *>(block + l.node);
     w.dist = reinterpret_cast<double *>(block + l.dist);
     w.ids = reinterpret_cast<uint32_t *>(block + l.ids);
-    w.tri = reinterpret_cast<uint32_t *>(block + l.tri);
-    w.half = reinterpret_cast<uint32_t *>(block + l.half);
-    w.hprev = reinterpret_cast<uint32_t *>(block + l.hprev);
-    w.hnext = reinterpret_cast<uint32_t *>(block + l.hnext);
-    w.htri = reinterpret_cast<uint32_t *>(block + l.htri);
     w.hash = reinterpret_cast<uint32_t *>(block + l.hash);
     w.onb = block + l.onb;
-    w.xy = reinterpret_cast<const ChiXY *>(block + l.xy);
-    w.key = reinterpret_cast<uint16_t *>(block + l.key);
     w.hash_size = l.hash_size;
     w.n_half = 0u;
     w.overflow = false;
+    w.tri_moved = false;
 }
 
 LB_CHI_HD double chi_px(const ChiWork &w, uint32_t i)
 {
-    return w.xy[i].x;
+    return w.node[i].x;
 }
 
 LB_CHI_HD double chi_py(const ChiWork &w, uint32_t i)
 {
-    return w.xy[i].y;
+    return w.node[i].y;
 }
 
-// both coordinates with one 16-byte load
-LB_CHI_HD void chi_pt(const ChiWork &w, uint32_t i, double &x, double &y)
+// 16-byte record moves as one load / one store
+LB_CHI_HD ChiEdge chi_load_edge(const ChiEdge *p)
 {
 #ifdef __CUDA_ARCH__
-    const double2 p = *reinterpret_cast<const double2 *>(&w.xy[i]);
+    const uint4 r = *reinterpret_cast<const uint4 *>(p);
+    ChiEdge e;
+    e.twin = r.x;
+    e.v = r.y;
+    e.x = __uint_as_float(r.z);
+    e.y = __uint_as_float(r.w);
+    return e;
 #else
-    const ChiXY p = w.xy[i];
+    return *p;
 #endif
-    x = p.x;
-    y = p.y;
+}
+
+LB_CHI_HD void chi_store_edge(ChiEdge *p, const ChiEdge &e)
+{
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<uint4 *>(p) = make_uint4(e.twin, e.v, __float_as_uint(e.x), __float_as_uint(e.y));
+#else
+    *p = e;
+#endif
+}
+
+LB_CHI_HD ChiNode chi_load_node(const ChiNode *p)
+{
+#ifdef __CUDA_ARCH__
+    const uint4 a = *reinterpret_cast<const uint4 *>(p);
+    const double2 b = *reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(p) + 16);
+    ChiNode nd;
+    nd.prev = a.x;
+    nd.next = a.y;
+    nd.tri = a.z;
+    nd.key = a.w;
+    nd.x = b.x;
+    nd.y = b.y;
+    return nd;
+#else
+    return *p;
+#endif
 }
 
 // Point::equal(a, b, span) (delaunator.hpp:56-61): squared distance / span < epsilon. The division only decides when
@@ -509,8 +541,8 @@ LB_CHI_HD void chi_introsort_ids(uint32_t *ids, const double *dist, uint32_t n, 
 
 // ---- seed triangle (delaunator.cpp:214-327), sequential form ---------------------------------------------------------
 
-// Bounding box, seed triangle, circumcentre, distances. Returns kChiOk or the reason why the reference does not
-// deliver. The device computes the same values with a warp (chi_shape.cuh); this is the definition.
+// Bounding box, seed triangle, circumcentre, distances, hash keys. Returns kChiOk or the reason why the reference does
+// not deliver. The device computes the same values with a warp (chi_shape.cuh); this is the definition.
 LB_CHI_HD uint32_t chi_seed_sequential(ChiWork &w)
 {
     const uint32_t n = w.n;
@@ -589,7 +621,7 @@ LB_CHI_HD uint32_t chi_seed_sequential(ChiWork &w)
     for (uint32_t i = 0; i < n; ++i)
     {
         w.dist[i] = chi_dist2(chi_px(w, i), chi_py(w, i), w.cx, w.cy);
-        w.key[i] = static_cast<uint16_t>(chi_hash_key(w, chi_px(w, i), chi_py(w, i)));
+        w.node[i].key = chi_hash_key(w, chi_px(w, i), chi_py(w, i));
     }
     return kChiOk;
 }
@@ -602,94 +634,159 @@ LB_CHI_HD bool chi_on_seed(const ChiWork &w, double x, double y)
 
 // ---- triangulation (delaunator.cpp:343-487, 520-685) ------------------------------------------------------------------
 
-LB_CHI_HD void chi_link(ChiWork &w, uint32_t a, uint32_t b)
+LB_CHI_HD uint32_t chi_next_half_edge(uint32_t e)
 {
-    w.half[a] = b;
-    if (b != kChiNone)
-        w.half[b] = a;
+    return (e % 3u == 2u) ? e - 2u : e + 1u;
 }
 
-LB_CHI_HD uint32_t chi_add_triangle(ChiWork &w, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t a, uint32_t b, uint32_t c)
+// a triangle corner as the sweep hands it around: vertex id and coordinates
+struct ChiCorner
+{
+    uint32_t v;
+    float x, y;
+};
+
+LB_CHI_HD ChiCorner chi_corner(uint32_t v, double x, double y)
+{
+    ChiCorner c;
+    c.v = v;
+    c.x = static_cast<float>(x); // exact: the coordinates are widened floats
+    c.y = static_cast<float>(y);
+    return c;
+}
+
+// Delaunator::addTriangle: three records, three links. Returns the first half-edge; ea/eb/ec receive the records as
+// written (the legalisation that follows starts from them without reading them back).
+LB_CHI_HD uint32_t chi_add_triangle(ChiWork &w, const ChiCorner &p0, const ChiCorner &p1, const ChiCorner &p2, uint32_t a,
+                                    uint32_t b, uint32_t c, ChiEdge &ea, ChiEdge &eb, ChiEdge &ec)
 {
     uint32_t t = w.n_half;
     if (t + 3u > 3u * (2u * w.n - 5u)) // (a triangulation of n points has at most 2n - 5 triangles; only corrupt links get here)
     {
         w.overflow = true;
         t -= 3u;
-        w.n_half = t;
     }
-    w.tri[t] = p0;
-    w.tri[t + 1u] = p1;
-    w.tri[t + 2u] = p2;
     w.n_half = t + 3u;
-    chi_link(w, t, a);
-    chi_link(w, t + 1u, b);
-    chi_link(w, t + 2u, c);
+    ea.twin = a;
+    ea.v = p0.v;
+    ea.x = p0.x;
+    ea.y = p0.y;
+    eb.twin = b;
+    eb.v = p1.v;
+    eb.x = p1.x;
+    eb.y = p1.y;
+    ec.twin = c;
+    ec.v = p2.v;
+    ec.x = p2.x;
+    ec.y = p2.y;
+    chi_store_edge(&w.edge[t], ea);
+    chi_store_edge(&w.edge[t + 1u], eb);
+    chi_store_edge(&w.edge[t + 2u], ec);
+    if (a != kChiNone)
+        w.edge[a].twin = t;
+    if (b != kChiNone)
+        w.edge[b].twin = t + 1u;
+    if (c != kChiNone)
+        w.edge[c].twin = t + 2u;
     return t;
 }
 
-// Delaunator::legalize: flips until the pair of triangles across every touched edge is locally Delaunay. The pending
-// edges wait in `stack` (capacity stack_cap; the reference's vector grows without bound).
-LB_CHI_HD uint32_t chi_legalize(ChiWork &w, uint32_t a, uint32_t *stack, uint32_t stack_cap, uint32_t &guard)
+// Delaunator::legalize: flips until the pair of triangles across every touched edge is locally Delaunay. `have` says
+// that e_a / e_al / e_ar already hold the records of a and of the two other half-edges of its triangle. After a flip
+// the same half-edge is looked at again (delaunator.cpp:520-633) and its triangle's records are known without a load;
+// a half-edge popped from the stack reloads its triangle.
+LB_CHI_HD uint32_t chi_legalize(ChiWork &w, uint32_t a, ChiEdge e_a, ChiEdge e_al, ChiEdge e_ar, bool have, uint32_t *spill,
+                                uint32_t spill_cap, uint32_t &guard)
 {
+    uint32_t local_stack[kChiLocalStack];
     uint32_t depth = 0u;
     uint32_t ar = 0u;
     while (true)
     {
-        const uint32_t b = w.half[a];
         const uint32_t ra = a % 3u;
         const uint32_t a0 = a - ra;
-        ar = a0 + (ra == 0u ? 2u : ra - 1u); // a0 + (a + 2) % 3
+        ar = a0 + (ra == 0u ? 2u : ra - 1u);              // a0 + (a + 2) % 3
+        const uint32_t al = a0 + (ra == 2u ? 0u : ra + 1u); // a0 + (a + 1) % 3
+        if (!have)
+        {
+            e_a = chi_load_edge(&w.edge[a]);
+            e_al = chi_load_edge(&w.edge[al]);
+            e_ar = chi_load_edge(&w.edge[ar]);
+            have = true;
+        }
+        const uint32_t b = e_a.twin;
         bool flipped = false;
         if (b != kChiNone)
         {
             const uint32_t rb = b % 3u;
             const uint32_t b0 = b - rb;
-            const uint32_t al = a0 + (ra == 2u ? 0u : ra + 1u); // a0 + (a + 1) % 3
             const uint32_t bl = b0 + (rb == 0u ? 2u : rb - 1u); // b0 + (b + 2) % 3
-            const uint32_t p0 = w.tri[ar], pr = w.tri[a], pl = w.tri[al], p1 = w.tri[bl];
-            double p0x, p0y, prx, pry, plx, ply, p1x, p1y;
-            chi_pt(w, p0, p0x, p0y);
-            chi_pt(w, pr, prx, pry);
-            chi_pt(w, pl, plx, ply);
-            chi_pt(w, p1, p1x, p1y);
-            if (chi_in_circle(p0x, p0y, prx, pry, plx, ply, p1x, p1y))
+            const ChiEdge e_bl = chi_load_edge(&w.edge[bl]);
+            // p0 = triangles[ar], pr = triangles[a], pl = triangles[al], p1 = triangles[bl]
+            if (chi_in_circle(static_cast<double>(e_ar.x), static_cast<double>(e_ar.y), static_cast<double>(e_a.x),
+                              static_cast<double>(e_a.y), static_cast<double>(e_al.x), static_cast<double>(e_al.y),
+                              static_cast<double>(e_bl.x), static_cast<double>(e_bl.y)))
             {
-                w.tri[a] = p1;
-                w.tri[b] = p0;
-                const uint32_t hbl = w.half[bl];
+                const uint32_t hbl = e_bl.twin;
                 if (hbl == kChiNone)
                 {
                     // the flipped edge was a hull edge: its hull_tri entry follows it (delaunator.cpp:592-606)
                     uint32_t e = w.hull_start, steps = 0u;
                     do
                     {
-                        if (w.htri[e] == bl)
+                        if (w.node[e].tri == bl)
                         {
-                            w.htri[e] = a;
+                            w.node[e].tri = a;
+                            w.tri_moved = true;
                             break;
                         }
-                        e = w.hprev[e];
+                        e = w.node[e].prev;
                     } while (e != w.hull_start && ++steps <= w.n);
                 }
-                chi_link(w, a, hbl);
-                chi_link(w, b, w.half[ar]);
-                chi_link(w, ar, bl);
-                if (depth >= stack_cap || guard == 0u)
+                const uint32_t har = e_ar.twin;
+                // triangles[a] = p1, link(a, hbl)
+                e_a.v = e_bl.v;
+                e_a.x = e_bl.x;
+                e_a.y = e_bl.y;
+                e_a.twin = hbl;
+                chi_store_edge(&w.edge[a], e_a);
+                if (hbl != kChiNone)
+                    w.edge[hbl].twin = a;
+                // triangles[b] = p0, link(b, half_edges[ar])
+                ChiEdge e_b;
+                e_b.v = e_ar.v;
+                e_b.x = e_ar.x;
+                e_b.y = e_ar.y;
+                e_b.twin = har;
+                chi_store_edge(&w.edge[b], e_b);
+                if (har != kChiNone)
+                    w.edge[har].twin = b;
+                // link(ar, bl)
+                e_ar.twin = bl;
+                w.edge[ar].twin = bl;
+                w.edge[bl].twin = ar;
+                if (guard == 0u || (depth >= kChiLocalStack && depth - kChiLocalStack >= spill_cap))
                 {
                     guard = 0u;
                     return ar;
                 }
                 --guard;
-                stack[depth++] = b0 + (rb == 2u ? 0u : rb + 1u); // br = b0 + (b + 1) % 3
-                flipped = true;
+                const uint32_t br = b0 + (rb == 2u ? 0u : rb + 1u); // b0 + (b + 1) % 3
+                if (depth < kChiLocalStack)
+                    local_stack[depth] = br;
+                else
+                    spill[depth - kChiLocalStack] = br;
+                ++depth;
+                flipped = true; // e_a, e_al, e_ar describe the triangle of `a` after the flip
             }
         }
         if (!flipped)
         {
             if (depth == 0u)
                 break;
-            a = stack[--depth];
+            --depth;
+            a = depth < kChiLocalStack ? local_stack[depth] : spill[depth - kChiLocalStack];
+            have = false;
         }
     }
     return ar;
@@ -699,8 +796,8 @@ LB_CHI_HD uint32_t chi_legalize(ChiWork &w, uint32_t a, uint32_t *stack, uint32_
 LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
 {
     const uint32_t n = w.n;
-    uint32_t *stack = reinterpret_cast<uint32_t *>(w.dist); // the distances are spent once the order stands
-    const uint32_t stack_cap = 2u * n;
+    uint32_t *spill = reinterpret_cast<uint32_t *>(w.dist); // the distances are spent once the order stands
+    const uint32_t spill_cap = 2u * n;
     uint32_t guard = 0xFFFFFFF0u; // (flips are finite for the reference as well; a budget keeps a corrupt input from hanging the GPU)
     if (static_cast<unsigned long long>(n) * 64ull < guard)
         guard = n * 64u;
@@ -708,24 +805,35 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
         w.hash[h] = kChiNone;
     const uint32_t i0 = w.i0, i1 = w.i1, i2 = w.i2;
     w.hull_start = i0;
-    w.hnext[i0] = w.hprev[i2] = i1;
-    w.hnext[i1] = w.hprev[i0] = i2;
-    w.hnext[i2] = w.hprev[i1] = i0;
-    w.htri[i0] = 0u;
-    w.htri[i1] = 1u;
-    w.htri[i2] = 2u;
-    w.hash[w.key[i0]] = i0;
-    w.hash[w.key[i1]] = i1;
-    w.hash[w.key[i2]] = i2;
+    w.node[i0].next = w.node[i2].prev = i1;
+    w.node[i1].next = w.node[i0].prev = i2;
+    w.node[i2].next = w.node[i1].prev = i0;
+    w.node[i0].tri = 0u;
+    w.node[i1].tri = 1u;
+    w.node[i2].tri = 2u;
+    w.hash[w.node[i0].key] = i0;
+    w.hash[w.node[i1].key] = i1;
+    w.hash[w.node[i2].key] = i2;
     w.n_half = 0u;
-    chi_add_triangle(w, i0, i1, i2, kChiNone, kChiNone, kChiNone);
+    ChiEdge ea, eb, ec;
+    chi_add_triangle(w, chi_corner(i0, w.s0x, w.s0y), chi_corner(i1, w.s1x, w.s1y), chi_corner(i2, w.s2x, w.s2y), kChiNone,
+                     kChiNone, kChiNone, ea, eb, ec);
     double xp = 0.0, yp = 0.0;
     const double span_4eps = 4.0 * kChiEps * w.span;
+    // the next point's record is fetched while the current one is being inserted (its coordinates and key never change;
+    // prev / next / tri of a point that is not on the hull yet are not read)
+    ChiNode nd_next = chi_load_node(&w.node[w.ids[0]]);
+    uint32_t i_next = w.ids[0];
     for (uint32_t k = 0; k < n; ++k)
     {
-        const uint32_t i = w.ids[k];
-        double x, y;
-        chi_pt(w, i, x, y);
+        const uint32_t i = i_next;
+        const ChiNode nd_i = nd_next;
+        if (k + 1u < n)
+        {
+            i_next = w.ids[k + 1u];
+            nd_next = chi_load_node(&w.node[i_next]);
+        }
+        const double x = nd_i.x, y = nd_i.y;
         if (k > 0u && chi_same(x, y, xp, yp))
             continue;
         xp = x;
@@ -734,37 +842,44 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
             continue;
         // a hull vertex near the point's direction, from the pseudo-angle hash
         uint32_t start = 0u;
-        const uint32_t key = w.key[i];
-        for (uint32_t j = 0; j < w.hash_size; ++j)
+        const uint32_t key = nd_i.key;
+        ChiNode nd_s;
+        bool found = false;
+        for (uint32_t j = 0; j < w.hash_size && !found; ++j)
         {
             uint32_t slot = key + j;
             if (slot >= w.hash_size)
                 slot %= w.hash_size;
             start = w.hash[slot];
-            if (start != kChiNone && start != w.hnext[start])
-                break;
+            if (start != kChiNone)
+            {
+                nd_s = chi_load_node(&w.node[start]);
+                found = start != nd_s.next; // (a vertex that left the hull points at itself)
+            }
         }
-        if (start == kChiNone)
+        if (!found)
             return kChiErrGuard; // (not reachable: the hull's last two insertions are always in the hash)
-        start = w.hprev[start];
+        start = nd_s.prev;
         uint32_t e = start, q, steps = 0u;
+        ChiNode nd_e = chi_load_node(&w.node[e]);
+        ChiNode nd_q;
         while (true)
         {
             if (++steps > n + 1u)
                 return kChiErrGuard;
-            q = w.hnext[e];
-            double ex, ey, qx, qy;
-            chi_pt(w, e, ex, ey);
-            chi_pt(w, q, qx, qy);
+            q = nd_e.next;
+            nd_q = chi_load_node(&w.node[q]);
             // Point::equal(p, hull vertex, span): squared distance / span < epsilon
-            if (chi_near(chi_dist2(ex, ey, x, y), w.span, span_4eps) || chi_near(chi_dist2(qx, qy, x, y), w.span, span_4eps))
+            if (chi_near(chi_dist2(nd_e.x, nd_e.y, x, y), w.span, span_4eps) ||
+                chi_near(chi_dist2(nd_q.x, nd_q.y, x, y), w.span, span_4eps))
             {
                 e = kChiNone;
                 break;
             }
-            if (chi_ccw(x, y, ex, ey, qx, qy))
+            if (chi_ccw(x, y, nd_e.x, nd_e.y, nd_q.x, nd_q.y))
                 break;
             e = q;
+            nd_e = nd_q;
             if (e == start)
             {
                 e = kChiNone;
@@ -773,47 +888,63 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
         }
         if (e == kChiNone)
             continue;
-        uint32_t t = chi_add_triangle(w, e, i, w.hnext[e], kChiNone, kChiNone, w.htri[e]);
-        w.htri[i] = chi_legalize(w, t + 2u, stack, stack_cap, guard);
-        w.htri[e] = t;
-        uint32_t next = w.hnext[e];
+        const ChiCorner c_i = chi_corner(i, x, y);
+        // add the first triangle from the point: (e, i, hull_next[e]) against hull_tri[e]
+        w.tri_moved = false;
+        uint32_t t = chi_add_triangle(w, chi_corner(e, nd_e.x, nd_e.y), c_i, chi_corner(q, nd_q.x, nd_q.y), kChiNone, kChiNone,
+                                      nd_e.tri, ea, eb, ec);
+        uint32_t tri_i = chi_legalize(w, t + 2u, ec, ea, eb, true, spill, spill_cap, guard); // hull_tri[i]
+        uint32_t tri_e = t;                                                                   // hull_tri[e] = t
+        w.node[e].tri = t;
+        // walk forward through the hull, adding more triangles and flipping
+        uint32_t next = q;
+        ChiNode nd_n = nd_q;
         while (true)
         {
-            q = w.hnext[next];
-            double nx, ny, qx, qy;
-            chi_pt(w, next, nx, ny);
-            chi_pt(w, q, qx, qy);
-            if (w.overflow || !chi_ccw(x, y, nx, ny, qx, qy))
+            q = nd_n.next;
+            nd_q = chi_load_node(&w.node[q]);
+            if (w.overflow || !chi_ccw(x, y, nd_n.x, nd_n.y, nd_q.x, nd_q.y))
                 break;
-            t = chi_add_triangle(w, next, i, q, w.htri[i], kChiNone, w.htri[next]);
-            w.htri[i] = chi_legalize(w, t + 2u, stack, stack_cap, guard);
-            w.hnext[next] = next;
+            const uint32_t tri_n = w.tri_moved ? w.node[next].tri : nd_n.tri;
+            t = chi_add_triangle(w, chi_corner(next, nd_n.x, nd_n.y), c_i, chi_corner(q, nd_q.x, nd_q.y), tri_i, kChiNone, tri_n,
+                                 ea, eb, ec);
+            tri_i = chi_legalize(w, t + 2u, ec, ea, eb, true, spill, spill_cap, guard);
+            w.node[next].next = next; // mark as removed
             next = q;
+            nd_n = nd_q;
         }
+        // walk backward from the other side, adding more triangles and flipping
         if (e == start)
         {
             while (true)
             {
-                q = w.hprev[e];
-                double ex, ey, qx, qy;
-                chi_pt(w, e, ex, ey);
-                chi_pt(w, q, qx, qy);
-                if (w.overflow || !chi_ccw(x, y, qx, qy, ex, ey))
+                q = nd_e.prev;
+                nd_q = chi_load_node(&w.node[q]);
+                if (w.overflow || !chi_ccw(x, y, nd_q.x, nd_q.y, nd_e.x, nd_e.y))
                     break;
-                t = chi_add_triangle(w, q, i, e, kChiNone, w.htri[e], w.htri[q]);
-                chi_legalize(w, t + 2u, stack, stack_cap, guard);
-                w.htri[q] = t;
-                w.hnext[e] = e;
+                const uint32_t tri_q = w.tri_moved ? w.node[q].tri : nd_q.tri;
+                if (w.tri_moved)
+                    tri_e = w.node[e].tri;
+                t = chi_add_triangle(w, chi_corner(q, nd_q.x, nd_q.y), c_i, chi_corner(e, nd_e.x, nd_e.y), kChiNone, tri_e, tri_q,
+                                     ea, eb, ec);
+                chi_legalize(w, t + 2u, ec, ea, eb, true, spill, spill_cap, guard);
+                w.node[q].tri = t;
+                tri_e = t; // (e becomes q below)
+                w.node[e].next = e; // mark as removed
                 e = q;
+                nd_e = nd_q;
             }
         }
-        w.hprev[i] = e;
+        // update the hull indices
+        // (hull_tri[i] lived in a register so far: i is not on the hull before this point, no flip can have moved it)
+        w.node[i].prev = e;
+        w.node[i].next = next;
+        w.node[i].tri = tri_i;
         w.hull_start = e;
-        w.hprev[next] = i;
-        w.hnext[e] = i;
-        w.hnext[i] = next;
+        w.node[next].prev = i;
+        w.node[e].next = i;
         w.hash[key] = i;
-        w.hash[w.key[e]] = e;
+        w.hash[nd_e.key] = e;
         if (guard == 0u || w.overflow)
             return kChiErrGuard;
     }
@@ -822,18 +953,17 @@ LB_CHI_HD uint32_t chi_triangulate(ChiWork &w)
 
 // ---- erosion of the boundary (concave_hull.hpp:96-193) -----------------------------------------------------------------
 
-LB_CHI_HD uint32_t chi_next_half_edge(uint32_t e)
+// Delaunator::edgeLength (delaunator.cpp:709-720); std::pow(v, 2.0) is v * v in the reference binary
+LB_CHI_HD double chi_edge_length(const ChiEdge &a, const ChiEdge &b)
 {
-    return (e % 3u == 2u) ? e - 2u : e + 1u;
+    const double dx = static_cast<double>(a.x) - static_cast<double>(b.x);
+    const double dy = static_cast<double>(a.y) - static_cast<double>(b.y);
+    return sqrt(dx * dx + dy * dy);
 }
 
-// Delaunator::edgeLength (delaunator.cpp:709-720); std::pow(v, 2.0) is v * v in the reference binary
 LB_CHI_HD double chi_edge_length(const ChiWork &w, uint32_t e)
 {
-    const uint32_t a = w.tri[e], b = w.tri[chi_next_half_edge(e)];
-    const double dx = chi_px(w, a) - chi_px(w, b);
-    const double dy = chi_py(w, a) - chi_py(w, b);
-    return sqrt(dx * dx + dy * dy);
+    return chi_edge_length(chi_load_edge(&w.edge[e]), chi_load_edge(&w.edge[chi_next_half_edge(e)]));
 }
 
 // Erodes the hull in place (hull_next / hull_prev) and returns the number of vertices of the closed outline, i.e.
@@ -855,14 +985,14 @@ LB_CHI_HD uint32_t chi_erode_and_walk(ChiWork &w, uint32_t *out, bool onb_cleare
     while (true)
     {
         w.onb[v] = 1u;
-        const uint32_t e = w.htri[v];
+        const uint32_t e = w.node[v].tri;
         const double len = chi_edge_length(w, e);
         chi_heap_push(he, hl, size, e, len);
         min_len = (min_len < len) ? min_len : len; // std::min(len, min_len)
         max_len = (len < max_len) ? max_len : len; // std::max(len, max_len)
         if (closing)
             break;
-        v = w.hnext[v];
+        v = w.node[v].next;
         if (v == w.hull_start)
             closing = true;
     }
@@ -875,23 +1005,25 @@ LB_CHI_HD uint32_t chi_erode_and_walk(ChiWork &w, uint32_t *out, bool onb_cleare
         if (len <= length_param)
             break;
         const uint32_t e_n = chi_next_half_edge(e);
-        const uint32_t c = w.tri[chi_next_half_edge(e_n)]; // getInteriorPoint
+        const uint32_t e_p = chi_next_half_edge(e_n);
+        const ChiEdge r_e = chi_load_edge(&w.edge[e]), r_n = chi_load_edge(&w.edge[e_n]), r_p = chi_load_edge(&w.edge[e_p]);
+        const uint32_t c = r_p.v; // getInteriorPoint
         if (w.onb[c])
             continue;
-        const uint32_t e_b = w.half[e_n];
-        const uint32_t e_a = w.half[chi_next_half_edge(e_n)];
+        const uint32_t e_b = r_n.twin;
+        const uint32_t e_a = r_p.twin;
         if (e_a == kChiNone || e_b == kChiNone || size + 2u > n + 1u)
             break; // (not reachable: an interior vertex has no hull edge, and every erosion adds one vertex)
         const double len_a = chi_edge_length(w, e_a);
         const double len_b = chi_edge_length(w, e_b);
         chi_heap_push(he, hl, size, e_a, len_a);
         chi_heap_push(he, hl, size, e_b, len_b);
-        const uint32_t a = w.tri[e];
-        const uint32_t b = w.tri[e_n];
-        w.hnext[c] = b;
-        w.hprev[c] = a;
-        w.hnext[a] = c;
-        w.hprev[b] = c;
+        const uint32_t a = r_e.v;
+        const uint32_t b = r_n.v;
+        w.node[c].next = b;
+        w.node[c].prev = a;
+        w.node[a].next = c;
+        w.node[b].prev = c;
         w.onb[c] = 1u;
     }
     uint32_t h = 0u;
@@ -901,7 +1033,7 @@ LB_CHI_HD uint32_t chi_erode_and_walk(ChiWork &w, uint32_t *out, bool onb_cleare
         if (h < n)
             out[h] = v;
         ++h;
-        v = w.hnext[v];
+        v = w.node[v].next;
     } while (v != w.hull_start && h <= n);
     return h + 1u;
 }

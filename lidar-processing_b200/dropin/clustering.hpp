@@ -55,7 +55,7 @@ class Clusterer final
     // every point with label k in ascending point index; INVALID points are skipped.
     void split_last_clusters(std::vector<pcl::PointCloud<pcl::PointXYZ>> &clustered_cloud);
 
-    // Extension: ordered convex outlines (counter-clockwise, open) of the clusters of the LAST
+    // Extension: ordered outlines (convex: counter-clockwise, open) of the clusters of the LAST
     // split_last_clusters() call, computed on the device bit-identically to the reference's host functions.
     // OutlinePoint has the layout of geom::Point<float> (reference Convex-Hull/convex_hull.hpp:42-49).
     //   CONVEX        = findOrderedConvexOutlines (reference src/polygon_simplification.cpp:31-79): every cluster.
@@ -63,6 +63,11 @@ class Clusterer final
     //                   the ids of the larger ones are returned in host_clusters — the caller runs the
     //                   reference's geometry::ConcaveHull on those (it stays on the host) and stores the result
     //                   in outlines[id].
+    //   CONCAVE       = findOrderedConcaveOutlines as a whole (:81-149): that branch below 20 points and, from 20
+    //                   points on, geometry::ConcaveHull with chi = 0.2 (Concave-Hull/concave_hull.hpp:96-193 over
+    //                   delaunator.cpp) re-enacted on the device value for value; those outlines are closed (first
+    //                   vertex repeated) like the reference's. host_clusters stays empty. A cluster on which the
+    //                   reference throws "not triangulation" (20+ points collinear in x, y) makes this call throw too.
     // outlines[k] belongs to clustered_cloud[k]; an empty outline is one the reference drops from its output.
     struct OutlinePoint
     {
@@ -71,7 +76,8 @@ class Clusterer final
     enum class OutlinePolicy : std::uint32_t
     {
         CONVEX = 0U,
-        CONCAVE_SMALL = 1U
+        CONCAVE_SMALL = 1U,
+        CONCAVE = 2U
     };
     void outline_last_clusters(OutlinePolicy policy, std::vector<std::vector<OutlinePoint>> &outlines,
                                std::vector<std::uint32_t> &host_clusters);

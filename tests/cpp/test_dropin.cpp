@@ -86,7 +86,7 @@ int main(int argc, char **argv)
         }
 
         // outlines of those clusters on the device, dumped for the comparison with the reference's host functions
-        for (int policy = 0; policy < 2; ++policy)
+        for (int policy = 0; policy < 3; ++policy)
         {
             std::vector<std::vector<Clusterer::OutlinePoint>> outlines;
             std::vector<std::uint32_t> host_ids;
@@ -101,7 +101,7 @@ int main(int argc, char **argv)
                 for (const auto &v : o)
                     xy.insert(xy.end(), {v.x, v.y});
             }
-            const std::string tag = std::string(argv[2]) + (policy == 0 ? ".convex" : ".concave_small");
+            const std::string tag = std::string(argv[2]) + (policy == 0 ? ".convex" : (policy == 1 ? ".concave_small" : ".concave"));
             dump(tag + ".sizes.u32", sizes);
             dump(tag + ".xy.f32", xy);
             dump(tag + ".host_ids.u32", host_ids);

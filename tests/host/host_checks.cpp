@@ -199,11 +199,10 @@ uint32_t hc_chi_dists(const float *points, uint32_t n, uint32_t stride_floats, d
     std::vector<unsigned char> block(lay.bytes, 0);
     lb::ChiWork w;
     lb::chi_bind(w, block.data(), lay, n);
-    lb::ChiXY *xy = reinterpret_cast<lb::ChiXY *>(block.data() + lay.xy);
     for (uint32_t i = 0; i < n; ++i)
     {
-        xy[i].x = static_cast<double>(points[static_cast<size_t>(i) * stride_floats]);
-        xy[i].y = static_cast<double>(points[static_cast<size_t>(i) * stride_floats + 1]);
+        w.node[i].x = static_cast<double>(points[static_cast<size_t>(i) * stride_floats]);
+        w.node[i].y = static_cast<double>(points[static_cast<size_t>(i) * stride_floats + 1]);
     }
     const uint32_t err = lb::chi_seed_sequential(w);
     if (err == lb::kChiOk)
@@ -294,12 +293,11 @@ long long hc_chi_outlines(const float *points, const uint32_t *offsets, uint32_t
         block.assign(lay.bytes, 0xCD);
         lb::ChiWork w;
         lb::chi_bind(w, block.data(), lay, n);
-        lb::ChiXY *xy = reinterpret_cast<lb::ChiXY *>(block.data() + lay.xy);
         for (uint32_t i = 0; i < n; ++i)
         {
             const float *p = points + static_cast<size_t>(offsets[k] + i) * stride_floats;
-            xy[i].x = static_cast<double>(p[0]);
-            xy[i].y = static_cast<double>(p[1]);
+            w.node[i].x = static_cast<double>(p[0]);
+            w.node[i].y = static_cast<double>(p[1]);
         }
         uint32_t err = lb::chi_seed_sequential(w);
         if (err == lb::kChiOk)
@@ -314,13 +312,13 @@ long long hc_chi_outlines(const float *points, const uint32_t *offsets, uint32_t
                 {
                     // equally far and not the same place - unless both lie on seed vertices (all of those are skipped
                     // whatever their order, and the three seeds are equally far from their circumcentre by construction)
-                    const lb::ChiXY &a = xy[order[i].second], &b = xy[order[i + 1].second];
+                    const lb::ChiNode &a = w.node[order[i].second], &b = w.node[order[i + 1].second];
                     if (!(a.x == b.x && a.y == b.y) && !(lb::chi_on_seed(w, a.x, a.y) && lb::chi_on_seed(w, b.x, b.y)))
                         mixed = true;
                 }
             if (sort_mode == 1 || (sort_mode == 0 && mixed))
             {
-                lb::chi_introsort_ids(w.ids, w.dist, n, reinterpret_cast<lb::ChiKeyed *>(w.tri)); // (the device's scratch too)
+                lb::chi_introsort_ids(w.ids, w.dist, n, reinterpret_cast<lb::ChiKeyed *>(w.edge)); // (the device's scratch too)
                 ++stats_out[0];
             }
             else

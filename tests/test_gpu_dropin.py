@@ -34,12 +34,19 @@ def test_cpp_dropin_classes(pkg, ctx, golden_frames, tmp_path):
     H.check_clustering(obstacle, clusters)
     # outlines of the split clusters (Clusterer::outline_last_clusters) against the reference's host functions
     parts = [c for c, _ in O.split_clusters(obstacle, clusters)]
-    for mode, tag in ((0, "convex"), (1, "concave_small")):
+    for mode, tag in ((0, "convex"), (1, "concave_small"), (2, "concave")):
         sizes = np.fromfile(f"{prefix}.{tag}.sizes.u32", np.uint32)
         xy = np.fromfile(f"{prefix}.{tag}.xy.f32", np.float32).reshape(-1, 2)
         host_ids = np.fromfile(f"{prefix}.{tag}.host_ids.u32", np.uint32)
         assert sizes.size == len(parts)
-        want = O.ref_outlines(parts, mode) if O.ref_hull_available() else [w for w, _ in O.convex_outlines(parts, mode)]
+        if mode == 2:  # findOrderedConcaveOutlines as a whole: the unmodified reference, else the host-compiled core
+            want = O.ref_outlines(parts, 1) if O.ref_hull_available() else None
+            if want is None:
+                small = [w for w, _ in O.convex_outlines(parts, 1)]
+                chi = H.chi_outlines_host(parts)[0]
+                want = [chi[k] if len(c) >= 20 else small[k] for k, c in enumerate(parts)]
+        else:
+            want = O.ref_outlines(parts, mode) if O.ref_hull_available() else [w for w, _ in O.convex_outlines(parts, mode)]
         big = [k for k, c in enumerate(parts) if len(c) >= 20]
         assert np.array_equal(host_ids, np.asarray(big if mode == 1 else [], np.uint32))
         at = 0
