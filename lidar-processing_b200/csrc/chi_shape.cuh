@@ -27,6 +27,7 @@ namespace lb
 {
 
 constexpr uint32_t kChiBytesPerPoint = 144u;
+constexpr uint32_t kChiSortSmem = 1024u;     // records of the CTA's staging buffer for the std::sort re-enactment (16 KB)
 constexpr uint32_t kChiSmemHash = 512u;      // hash words per warp in shared memory (clusters up to 262 144 points)
 constexpr int kChiWarps = 4;
 constexpr uint32_t kChiBuckets = 32u;
@@ -280,12 +281,234 @@ LB_D void chi_warp_sort(unsigned long long *a, uint32_t *ix, uint32_t n)
         }
 }
 
+// One step of std::__introsort_loop (chi_sort_partition_step) over a part of more than kChiSortSmem records, by one warp:
+// lane 0 runs the two scans and the swaps of the unguarded Hoare partition out of two windows of the staging buffer, one
+// moving up from the left end and one moving down from the right end; the warp writes a finished window back and loads
+// the next one. When the windows would meet, both go back to global memory and lane 0 finishes the step there (at most
+// kChiSortSmem records). Same comparisons, same swaps, same cut.
+LB_D uint32_t chi_partition_step_warp(ChiKeyed *a, uint32_t first, uint32_t last, ChiKeyed *buf)
+{
+    constexpr uint32_t W = kChiSortSmem / 2u;
+    const uint32_t lane = lane_id();
+    ChiKeyed *wl = buf, *wh = buf + W;
+    double kp = 0.0;
+    if (lane == 0u)
+    {
+        // __move_median_to_first(first, first + 1, mid, last - 1)
+        const uint32_t ia = first + 1u, ib = first + (last - first) / 2u, ic = last - 1u;
+        const double ka = a[ia].d, kb = a[ib].d, kc = a[ic].d;
+        uint32_t pick;
+        if (ka < kb)
+            pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
+        else
+            pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
+        const ChiKeyed t = a[first];
+        a[first] = a[pick];
+        a[pick] = t;
+        kp = a[first].d;
+    }
+    __syncwarp();
+    uint32_t lo = first + 1u, hi = last;           // lane 0's copies count
+    uint32_t lo_base = first + 1u, hi_base = last - W; // last - first > 2 W, so the windows start disjoint
+    bool windowed = true;
+    for (uint32_t i = lane; i < W; i += 32u)
+    {
+        wl[i] = a[lo_base + i];
+        wh[i] = a[hi_base + i];
+    }
+    __syncwarp();
+    uint32_t phase = 0u, cut = 0u;
+    while (true)
+    {
+        uint32_t req = 0u; // 0: done, 1: the left window is used up, 2: the right one
+        if (lane == 0u)
+        {
+            while (true)
+            {
+                if (phase == 0u) // while (comp(first, pivot)) ++first;
+                {
+                    if (windowed && lo >= lo_base + W)
+                    {
+                        req = 1u;
+                        break;
+                    }
+                    const double v = windowed ? wl[lo - lo_base].d : a[lo].d;
+                    if (v < kp)
+                    {
+                        ++lo;
+                        continue;
+                    }
+                    phase = 1u;
+                }
+                if (phase == 1u) // --last;
+                {
+                    --hi;
+                    phase = 2u;
+                }
+                if (phase == 2u) // while (comp(pivot, last)) --last;
+                {
+                    if (windowed && hi < hi_base)
+                    {
+                        req = 2u;
+                        break;
+                    }
+                    const double v = windowed ? wh[hi - hi_base].d : a[hi].d;
+                    if (kp < v)
+                    {
+                        --hi;
+                        continue;
+                    }
+                    phase = 3u;
+                }
+                if (!(lo < hi)) // return first;
+                {
+                    cut = lo;
+                    req = 0u;
+                    break;
+                }
+                ChiKeyed *pl = windowed ? &wl[lo - lo_base] : &a[lo];
+                ChiKeyed *ph = windowed ? &wh[hi - hi_base] : &a[hi];
+                const ChiKeyed t = *pl;
+                *pl = *ph;
+                *ph = t;
+                ++lo;
+                phase = 0u;
+            }
+        }
+        __syncwarp();
+        req = __shfl_sync(kFullMask, req, 0);
+        if (req == 0u)
+            break;
+        // (lo_base, hi_base and windowed change the same way in every lane)
+        if (req == 1u)
+        {
+            for (uint32_t i = lane; i < W; i += 32u)
+                a[lo_base + i] = wl[i];
+            lo_base += W;
+            if (lo_base + W > hi_base)
+            {
+                for (uint32_t i = lane; i < W; i += 32u)
+                    a[hi_base + i] = wh[i];
+                windowed = false;
+            }
+            else
+                for (uint32_t i = lane; i < W; i += 32u)
+                    wl[i] = a[lo_base + i];
+        }
+        else
+        {
+            for (uint32_t i = lane; i < W; i += 32u)
+                a[hi_base + i] = wh[i];
+            if (hi_base < lo_base + 2u * W) // the next window down would reach into the left one
+            {
+                for (uint32_t i = lane; i < W; i += 32u)
+                    a[lo_base + i] = wl[i];
+                windowed = false;
+            }
+            else
+            {
+                hi_base -= W;
+                for (uint32_t i = lane; i < W; i += 32u)
+                    wh[i] = a[hi_base + i];
+            }
+        }
+        __syncwarp();
+    }
+    if (windowed)
+        for (uint32_t i = lane; i < W; i += 32u)
+        {
+            a[lo_base + i] = wl[i];
+            a[hi_base + i] = wh[i];
+        }
+    __syncwarp();
+    return __shfl_sync(kFullMask, cut, 0);
+}
+
+// std::__introsort_loop over n records in global memory by one warp: the partition steps of the large parts run through
+// chi_partition_step_warp, every part of at most kChiSortSmem records is copied into the CTA's staging buffer by the
+// whole warp, finished there by lane 0 (33-cycle loads instead of L2 round trips) and copied back. Same comparisons and
+// moves as chi_introsort_loop. The buffer is shared by the warps of the CTA through `lock` (clusters that need it are rare).
+LB_D void chi_introsort_loop_warp(ChiKeyed *a, uint32_t n, ChiKeyed *buf, int *lock)
+{
+    const uint32_t lane = lane_id();
+    if (lane == 0u)
+        while (atomicCAS(lock, 0, 1) != 0)
+            __nanosleep(200);
+    __syncwarp();
+    uint32_t st_first[64], st_last[64], st_depth[64];
+    uint32_t sp = 1u;
+    st_first[0] = 0u;
+    st_last[0] = n;
+    st_depth[0] = chi_sort_depth_limit(n);
+    while (true)
+    {
+        uint32_t first = 0u, last = 0u, depth = 0u;
+        if (lane == 0u && sp > 0u)
+        {
+            --sp;
+            first = st_first[sp];
+            last = st_last[sp];
+            depth = st_depth[sp];
+        }
+        first = __shfl_sync(kFullMask, first, 0);
+        last = __shfl_sync(kFullMask, last, 0);
+        depth = __shfl_sync(kFullMask, depth, 0);
+        if (last == 0u) // (a part on the stack has last > first >= 0)
+            break;
+        while (last - first > 16u)
+        {
+            const uint32_t m = last - first;
+            if (m <= kChiSortSmem)
+            {
+                for (uint32_t i = lane; i < m; i += 32u)
+                    buf[i] = a[first + i];
+                __syncwarp();
+                if (lane == 0u)
+                    chi_introsort_loop(buf, 0u, m, depth);
+                __syncwarp();
+                for (uint32_t i = lane; i < m; i += 32u)
+                    a[first + i] = buf[i];
+                __syncwarp();
+                break;
+            }
+            if (depth == 0u)
+            {
+                if (lane == 0u)
+                    chi_sort_heap_sort(a + first, m);
+                __syncwarp();
+                break;
+            }
+            --depth;
+            const uint32_t cut = chi_partition_step_warp(a, first, last, buf);
+            if (lane == 0u && sp < 64u)
+            {
+                st_first[sp] = cut;
+                st_last[sp] = last;
+                st_depth[sp] = depth;
+                ++sp;
+            }
+            last = cut;
+        }
+    }
+    __syncwarp();
+    if (lane == 0u)
+    {
+        __threadfence_block();
+        atomicExch(lock, 0);
+    }
+}
+
 // One warp per cluster; persistent warps pull (frame, cluster) tasks in the order of chi_place_kernel.
 __global__ void __launch_bounds__(32 * kChiWarps, 4)
 chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ task_f,
                    const uint32_t *__restrict__ task_k, uint32_t *__restrict__ cursor, unsigned long long *__restrict__ stats)
 {
     __shared__ uint32_t s_hash[kChiWarps][kChiSmemHash];
+    __shared__ ChiKeyed s_sort[kChiSortSmem];
+    __shared__ int s_sort_lock;
+    if (threadIdx.x == 0)
+        s_sort_lock = 0;
+    __syncthreads();
     const uint32_t lane = lane_id();
     uint32_t T = lane < kChiBuckets ? counts[lane] : 0u;
     T = warp_reduce_add(T);
@@ -371,11 +594,21 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
                     rec_sort[i] = r;
                 }
                 __syncwarp();
-                if (lane == 0u)
-                    chi_introsort(rec_sort, n);
-                __syncwarp();
+                chi_introsort_loop_warp(rec_sort, n, s_sort, &s_sort_lock);
+
+                // __final_insertion_sort = a stable sort by key of what the loop left behind: (key, position) through
+                // the same network as above (keys behind the records: 16 n + 8 n + 4 n of 96 n - 240 bytes)
+                unsigned long long *fkey = reinterpret_cast<unsigned long long *>(rec_sort + n);
+                uint32_t *fpos = reinterpret_cast<uint32_t *>(fkey + ((n + 1u) & ~1u));
                 for (uint32_t i = lane; i < n; i += 32u)
-                    w.ids[i] = rec_sort[i].id;
+                {
+                    fkey[i] = static_cast<unsigned long long>(__double_as_longlong(rec_sort[i].d));
+                    fpos[i] = i;
+                }
+                __syncwarp();
+                chi_warp_sort(fkey, fpos, n);
+                for (uint32_t i = lane; i < n; i += 32u)
+                    w.ids[i] = rec_sort[fpos[i]].id;
                 __syncwarp();
             }
             uint32_t h = 0u;

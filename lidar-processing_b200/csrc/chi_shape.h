@@ -444,21 +444,50 @@ LB_CHI_HD void chi_sort_insertion_sort(ChiKeyed *a, uint32_t first, uint32_t las
     }
 }
 
-LB_CHI_HD void chi_introsort(ChiKeyed *a, uint32_t n)
+// __move_median_to_first(first, first + 1, mid, last - 1) + __unguarded_partition(first + 1, last, pivot = first):
+// one step of std::__introsort_loop over [first, last), last - first > 16. Returns the cut.
+LB_CHI_HD uint32_t chi_sort_partition_step(ChiKeyed *a, uint32_t first, uint32_t last)
 {
-    if (n == 0u)
-        return;
-    // std::__introsort_loop with its recursion on the right part turned into a stack (the parts are disjoint, so the
-    // order in which they are finished does not show)
+    const uint32_t ia = first + 1u, ib = first + (last - first) / 2u, ic = last - 1u;
+    const double ka = a[ia].d, kb = a[ib].d, kc = a[ic].d;
+    uint32_t pick;
+    if (ka < kb)
+        pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
+    else
+        pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
+    {
+        const ChiKeyed t = a[first];
+        a[first] = a[pick];
+        a[pick] = t;
+    }
+    const double kp = a[first].d;
+    uint32_t lo = first + 1u, hi = last;
+    while (true)
+    {
+        while (a[lo].d < kp)
+            ++lo;
+        --hi;
+        while (kp < a[hi].d)
+            --hi;
+        if (!(lo < hi))
+            break;
+        const ChiKeyed t = a[lo];
+        a[lo] = a[hi];
+        a[hi] = t;
+        ++lo;
+    }
+    return lo;
+}
+
+// std::__introsort_loop(first, last, depth) with its recursion on the right part turned into a stack (the parts are
+// disjoint, so the order in which they are finished does not show). Leaves runs of at most 16 elements unsorted.
+LB_CHI_HD void chi_introsort_loop(ChiKeyed *a, uint32_t first0, uint32_t last0, uint32_t depth0)
+{
     uint32_t st_first[64], st_last[64], st_depth[64];
-    uint32_t sp = 0u;
-    uint32_t lg = 0u;
-    for (uint32_t v = n; v > 1u; v >>= 1)
-        ++lg;
-    st_first[0] = 0u;
-    st_last[0] = n;
-    st_depth[0] = 2u * lg;
-    sp = 1u;
+    uint32_t sp = 1u;
+    st_first[0] = first0;
+    st_last[0] = last0;
+    st_depth[0] = depth0;
     while (sp > 0u)
     {
         --sp;
@@ -473,48 +502,36 @@ LB_CHI_HD void chi_introsort(ChiKeyed *a, uint32_t n)
                 break;
             }
             --depth;
-            // __move_median_to_first(first, first + 1, mid, last - 1)
-            const uint32_t ia = first + 1u, ib = first + (last - first) / 2u, ic = last - 1u;
-            const double ka = a[ia].d, kb = a[ib].d, kc = a[ic].d;
-            uint32_t pick;
-            if (ka < kb)
-                pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
-            else
-                pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
-            {
-                const ChiKeyed t = a[first];
-                a[first] = a[pick];
-                a[pick] = t;
-            }
-            // __unguarded_partition(first + 1, last, pivot = first)
-            const double kp = a[first].d;
-            uint32_t lo = first + 1u, hi = last;
-            while (true)
-            {
-                while (a[lo].d < kp)
-                    ++lo;
-                --hi;
-                while (kp < a[hi].d)
-                    --hi;
-                if (!(lo < hi))
-                    break;
-                const ChiKeyed t = a[lo];
-                a[lo] = a[hi];
-                a[hi] = t;
-                ++lo;
-            }
-            // right part [lo, last) later, left part [first, lo) now
+            const uint32_t cut = chi_sort_partition_step(a, first, last);
+            // right part [cut, last) later, left part [first, cut) now
             if (sp < 64u)
             {
-                st_first[sp] = lo;
+                st_first[sp] = cut;
                 st_last[sp] = last;
                 st_depth[sp] = depth;
                 ++sp;
             }
-            last = lo;
+            last = cut;
         }
     }
-    // __final_insertion_sort
+}
+
+LB_CHI_HD uint32_t chi_sort_depth_limit(uint32_t n)
+{
+    uint32_t lg = 0u;
+    for (uint32_t v = n; v > 1u; v >>= 1)
+        ++lg;
+    return 2u * lg;
+}
+
+// std::sort: introsort loop, then __final_insertion_sort. The latter is a stable insertion sort of what the loop left
+// behind (its guarded and unguarded halves differ in bounds checks only), i.e. the result is that arrangement stably
+// sorted by key - which is how the device finishes (chi_shape.cuh), with a parallel sort by (key, position).
+LB_CHI_HD void chi_introsort(ChiKeyed *a, uint32_t n)
+{
+    if (n == 0u)
+        return;
+    chi_introsort_loop(a, 0u, n, chi_sort_depth_limit(n));
     if (n > 16u)
     {
         chi_sort_insertion_sort(a, 0u, 16u);

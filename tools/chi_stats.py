@@ -36,17 +36,18 @@ def report(ctx, label):
                   f"cycle share seed/sort/sweep/erosion {np.round(cyc / cyc.sum(), 2).tolist()}, last end {(st[sel, 2].max() - t0) / 1e6:.1f} ms")
 
 
-ctx = pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames))
-ctx.batch_stage(frames)
-for rep in range(2):
-    ctx.batch_run()
-    ctx._check(L.lidar_b200_batch_group_clusters(ctx._h), "group")
-    ctx._check(L.lidar_b200_batch_hull_outlines(ctx._h, 2), "hull")
-    ctx.sync()
-report(ctx, "154-frame batch")
-ctx.close()
+if not os.environ.get("CHI_SKIP_BATCH"):
+    ctx = pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames))
+    ctx.batch_stage(frames)
+    for rep in range(2):
+        ctx.batch_run()
+        ctx._check(L.lidar_b200_batch_group_clusters(ctx._h), "group")
+        ctx._check(L.lidar_b200_batch_hull_outlines(ctx._h, 2), "hull")
+        ctx.sync()
+    report(ctx, "154-frame batch")
+    ctx.close()
 one = pkg.Context(device=0, max_points=max(f.shape[0] for f in frames) + 64, max_frames=1)
-for f in (120, 0):
+for f in [int(x) for x in os.environ.get("CHI_FRAMES", "120,0").split(",")]:
     one.batch_stage([frames[f]])
     for rep in range(2):
         one.batch_run()
