@@ -27,7 +27,7 @@ namespace lb
 {
 
 constexpr uint32_t kChiBytesPerPoint = 144u;
-constexpr uint32_t kChiSortSmem = 1024u;     // records of the CTA's staging buffer for the std::sort re-enactment (16 KB)
+constexpr uint32_t kChiSortSmem = 2048u;     // records of the CTA's staging buffer for the std::sort re-enactment (16 KB)
 constexpr uint32_t kChiSmemHash = 512u;      // hash words per warp in shared memory (clusters up to 262 144 points)
 constexpr int kChiWarps = 4;
 constexpr uint32_t kChiBuckets = 32u;
@@ -291,12 +291,12 @@ LB_D uint32_t chi_partition_step_warp(ChiKeyed *a, uint32_t first, uint32_t last
     constexpr uint32_t W = kChiSortSmem / 2u;
     const uint32_t lane = lane_id();
     ChiKeyed *wl = buf, *wh = buf + W;
-    double kp = 0.0;
+    uint32_t kp = 0u;
     if (lane == 0u)
     {
         // __move_median_to_first(first, first + 1, mid, last - 1)
         const uint32_t ia = first + 1u, ib = first + (last - first) / 2u, ic = last - 1u;
-        const double ka = a[ia].d, kb = a[ib].d, kc = a[ic].d;
+        const uint32_t ka = a[ia].d, kb = a[ib].d, kc = a[ic].d;
         uint32_t pick;
         if (ka < kb)
             pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
@@ -332,7 +332,7 @@ LB_D uint32_t chi_partition_step_warp(ChiKeyed *a, uint32_t first, uint32_t last
                         req = 1u;
                         break;
                     }
-                    const double v = windowed ? wl[lo - lo_base].d : a[lo].d;
+                    const uint32_t v = windowed ? wl[lo - lo_base].d : a[lo].d;
                     if (v < kp)
                     {
                         ++lo;
@@ -352,7 +352,7 @@ LB_D uint32_t chi_partition_step_warp(ChiKeyed *a, uint32_t first, uint32_t last
                         req = 2u;
                         break;
                     }
-                    const double v = windowed ? wh[hi - hi_base].d : a[hi].d;
+                    const uint32_t v = windowed ? wh[hi - hi_base].d : a[hi].d;
                     if (kp < v)
                     {
                         --hi;
@@ -582,27 +582,35 @@ chi_outline_kernel(BatchView bv, ChiView cv, const uint32_t *__restrict__ counts
             __syncwarp();
             if (mixed)
             {
-                // two different points exactly equally far: the reference's std::sort decides their order. The records
-                // borrow the half-edge records too (the keys above are spent).
-                ChiKeyed *rec_sort = reinterpret_cast<ChiKeyed *>(w.edge);
-                for (uint32_t i = lane; i < n; i += 32u)
+                // two different points exactly equally far: the reference's std::sort decides their order. Records
+                // {rank of the distance among the distinct distances, id} in the ORIGINAL order of the points, built from
+                // the sorted keys; they borrow the half-edge records behind the keys (8 n + 4 n | 8 n | 8 n + 4 n of 96 n - 240 bytes)
+                const uint32_t n2 = (n + 1u) & ~1u;
+                ChiKeyed *rec_sort = reinterpret_cast<ChiKeyed *>(skey + 2u * n2);
+                uint32_t carry = 0u;
+                for (uint32_t base = 0; base < n; base += 32u)
                 {
-                    ChiKeyed r;
-                    r.d = w.dist[i];
-                    r.id = i;
-                    r.pad = 0u;
-                    rec_sort[i] = r;
+                    const uint32_t i = base + lane;
+                    const bool fresh = i < n && i > 0u && skey[i] != skey[i - 1u];
+                    const uint32_t m = __ballot_sync(kFullMask, fresh);
+                    if (i < n)
+                    {
+                        ChiKeyed r;
+                        r.d = carry + __popc(m & (0xFFFFFFFFu >> (31u - lane)));
+                        r.id = sid[i];
+                        rec_sort[r.id] = r;
+                    }
+                    carry += __popc(m);
                 }
                 __syncwarp();
                 chi_introsort_loop_warp(rec_sort, n, s_sort, &s_sort_lock);
-
-                // __final_insertion_sort = a stable sort by key of what the loop left behind: (key, position) through
-                // the same network as above (keys behind the records: 16 n + 8 n + 4 n of 96 n - 240 bytes)
-                unsigned long long *fkey = reinterpret_cast<unsigned long long *>(rec_sort + n);
-                uint32_t *fpos = reinterpret_cast<uint32_t *>(fkey + ((n + 1u) & ~1u));
+                // __final_insertion_sort = a stable sort by key of what the loop left behind: (rank, position) as one
+                // 64-bit key through the same network as above
+                unsigned long long *fkey = reinterpret_cast<unsigned long long *>(rec_sort + n2);
+                uint32_t *fpos = reinterpret_cast<uint32_t *>(fkey + n2);
                 for (uint32_t i = lane; i < n; i += 32u)
                 {
-                    fkey[i] = static_cast<unsigned long long>(__double_as_longlong(rec_sort[i].d));
+                    fkey[i] = (static_cast<unsigned long long>(rec_sort[i].d) << 32) | i;
                     fpos[i] = i;
                 }
                 __syncwarp();

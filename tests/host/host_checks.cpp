@@ -121,6 +121,23 @@ void model_coop_nth_element(float4 *a, uint32_t first, uint32_t nth, uint32_t la
 }
 } // namespace
 
+// rec[i] = {rank of dist[i] among the distinct distances, i}: what the device builds from its sorted keys
+void rank_records(const double *dist, uint32_t n, lb::ChiKeyed *rec)
+{
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i)
+        order[i] = i;
+    std::sort(order.begin(), order.end(), [dist](uint32_t x, uint32_t y) { return dist[x] < dist[y] || (dist[x] == dist[y] && x < y); });
+    uint32_t rank = 0u;
+    for (uint32_t j = 0; j < n; ++j)
+    {
+        if (j > 0u && dist[order[j]] != dist[order[j - 1u]])
+            ++rank;
+        rec[order[j]].d = rank;
+        rec[order[j]].id = order[j];
+    }
+}
+
 extern "C"
 {
 
@@ -217,8 +234,11 @@ void hc_sort_ids(uint32_t *ids, const double *dist, uint32_t n, int mode)
         std::sort(ids, ids + n, [dist](uint32_t i, uint32_t j) { return dist[i] < dist[j]; });
     else
     {
-        std::vector<lb::ChiKeyed> scratch(n + 1u);
-        lb::chi_introsort_ids(ids, dist, n, scratch.data());
+        std::vector<lb::ChiKeyed> rec(n + 1u);
+        rank_records(dist, n, rec.data());
+        lb::chi_introsort(rec.data(), n);
+        for (uint32_t i = 0; i < n; ++i)
+            ids[i] = rec[i].id;
     }
 }
 
@@ -318,7 +338,11 @@ long long hc_chi_outlines(const float *points, const uint32_t *offsets, uint32_t
                 }
             if (sort_mode == 1 || (sort_mode == 0 && mixed))
             {
-                lb::chi_introsort_ids(w.ids, w.dist, n, reinterpret_cast<lb::ChiKeyed *>(w.edge)); // (the device's scratch too)
+                lb::ChiKeyed *rec = reinterpret_cast<lb::ChiKeyed *>(w.edge); // (the device's scratch too)
+                rank_records(w.dist, n, rec);
+                lb::chi_introsort(rec, n);
+                for (uint32_t i = 0; i < n; ++i)
+                    w.ids[i] = rec[i].id;
                 ++stats_out[0];
             }
             else
