@@ -166,7 +166,10 @@ extern "C"
      * different subsets; the reference loops forever on such a cluster) and, in mode CONCAVE, for a cluster of 20 or
      * more points that are all collinear or all coincident in (x, y) (the reference throws "not triangulation",
      * delaunator.cpp:299, respectively reads out of bounds): the outputs are still complete, that cluster has 0
-     * vertices and every other outline is valid. LIDAR_B200_ERR_CAPACITY when the closed outlines of a frame need more
+     * vertices and every other outline is valid; also when two different x or y values of a convex chain are less than
+     * FLT_EPSILON apart (possible only for unquantised coordinates below 1 m): the reference's comparators are not a
+     * strict weak order there, its own outline is unspecified, the one delivered uses exact comparisons.
+     * LIDAR_B200_ERR_CAPACITY when the closed outlines of a frame need more
      * than one vertex per staged point of the frame (only possible when nearly every point is an outline vertex): the
      * outlines that do not fit have 0 vertices. hull_point_idx_out in mode CONCAVE: a point of the cluster with exactly
      * the vertex's (x, y); where several points coincide, the one with the lowest index unless the cluster's sweep

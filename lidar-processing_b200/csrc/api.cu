@@ -1470,6 +1470,10 @@ int lidar_b200_batch_fetch_hulls(lidar_b200_ctx *c, uint32_t *n_vertices_out, ui
                                                    "\"not triangulation\" (delaunator.cpp:299) - was given 0 vertices; all other outlines are valid"
                                                  : "hull_outlines: a cluster of 20 or more points that all coincide in (x, y) (the reference reads out of "
                                                    "bounds) was given 0 vertices; all other outlines are valid");
+    if (herr & kHullErrEnvelope)
+        return fail(c, LIDAR_B200_ERR_INPUT, "hull_outlines: a cluster has two different x or y values less than FLT_EPSILON apart; the reference's "
+                                             "comparators are not a strict weak order there (convex_hull.hpp:51-73) and its outline is unspecified - "
+                                             "the outlines delivered use exact comparisons");
     if (herr & kHullErrSlot)
         return fail(c, LIDAR_B200_ERR_CAPACITY, "hull_outlines: the closed outlines of a frame outgrow its slot (one vertex per staged point); "
                                                 "the outlines that did not fit were given 0 vertices");

@@ -25,7 +25,7 @@
 // Envelope: distinct y (and x) values of a cluster are either equal or at least FLT_EPSILON apart
 // (true for |v| >= 1 and for mm-quantised LiDAR returns); otherwise the reference's operator< is not a
 // strict weak order and std::sort's result is unspecified. Inside the envelope the reference's epsilon
-// equality is plain equality. CHAN subsets must fit a warp's buffers:
+// equality is plain equality. A chain outside the envelope raises kHullErrEnvelope (status LIDAR_B200_ERR_INPUT). CHAN subsets must fit a warp's buffers:
 // clusters up to ~1.04 M points; larger ones raise the error flag.
 #pragma once
 
@@ -43,6 +43,7 @@ constexpr uint32_t kHullModeConcaveSmall = 1u;  // the convex branch of findOrde
 constexpr uint32_t kHullModeConcave = 2u;       // findOrderedConcaveOutlines: that branch + the chi-shape from 20 points on (chi_shape.cuh)
 constexpr uint32_t kHullThreadScanMax = 192u;   // tasks up to this size are scanned one thread per task, larger ones by lane 0 of the sorting warp
 constexpr uint32_t kHullErrOverflow = 1u, kHullErrSubset = 2u, kHullErrJarvis = 4u;
+constexpr uint32_t kHullErrEnvelope = 64u; // two coordinates of a chain differ by less than FLT_EPSILON (see the envelope above)
 
 struct __align__(16) HullWarpSmem
 {
@@ -303,6 +304,22 @@ hull_sort_kernel(BatchView bv, HullView hv, const uint32_t *__restrict__ task_k,
         for (uint32_t i = lane; i < t.size; i += 32u) // the scans read points, not keys
             ws.key[i] = hull_key_to_point(ws.key[i]);
         __syncwarp();
+        {
+            // the envelope, checked where it can be violated: neighbours of the sorted chain whose y values differ by
+            // less than FLT_EPSILON without being equal (the reference's operator< then looks at x although y differs,
+            // convex_hull.hpp:51-61), or whose y values are equal and x values that close (its operator== then merges two
+            // different points, :63-73). The outline delivered is the one of exact comparisons; the status says that the
+            // reference's own answer is unspecified here.
+            bool outside = false;
+            for (uint32_t i = lane; i + 1u < t.size; i += 32u)
+            {
+                const float2 p = hull_decode(ws.key[i]), q = hull_decode(ws.key[i + 1u]);
+                const float dy = q.y - p.y, dx = q.x - p.x;
+                outside |= (dy > 0.0f && dy < 1.1920929e-07f) || (dy == 0.0f && dx > 0.0f && dx < 1.1920929e-07f);
+            }
+            if (__any_sync(kFullMask, outside) && lane == 0u)
+                atomicOr(hv.err, kHullErrEnvelope);
+        }
         if (t.size <= kHullThreadScanMax)
         {
             unsigned long long *sk = hv.skey + t.pt0 + t.start;

@@ -639,6 +639,28 @@ def test_outlines_api_edges(pkg, ctx, synth_small):
         assert hulls[1]["xy"].shape[0] == 0 and hulls[2]["xy"].shape[0] == 0
 
 
+@pytest.mark.gpu
+def test_outlines_outside_the_epsilon_envelope_are_reported(pkg):
+    """Unquantised coordinates below 1 m can differ by less than FLT_EPSILON: the reference's Point::operator< is not a
+    strict weak order there (convex_hull.hpp:51-61). The device delivers the exact-comparison outline and says so."""
+    c2 = pkg.Context(device=0, max_points=4096, max_frames=1)
+    try:
+        c2.clu_configure(pkg.ClusteringConfiguration(distance_squared=1.0e6, min_cluster_size=1))
+        rng = np.random.default_rng(3)
+        obs = np.zeros((12, 4), np.float32)
+        obs[:, :2] = rng.uniform(-0.5, 0.5, size=(12, 2)).astype(np.float32)
+        obs[5, 1] = np.nextafter(obs[4, 1], np.float32(1.0))  # two y values one ulp (~3e-8) apart
+        labels, g = c2.cluster_and_split(obs)
+        h = c2.batch_hulls(pkg.HULL_CONVEX, tolerate_open_marches=True)[0]
+        assert c2.last_hull_status == pkg.ERR_INPUT and h["xy"].shape[0] >= 3
+        obs[5, 1] = obs[4, 1] + np.float32(0.01)
+        labels, g = c2.cluster_and_split(obs)
+        h = c2.batch_hulls(pkg.HULL_CONVEX)[0]
+        assert c2.last_hull_status == 0
+    finally:
+        c2.close()
+
+
 # ---- output packing on the device (SURVEY 8f row 4)
 
 @pytest.mark.gpu
