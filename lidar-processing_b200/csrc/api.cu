@@ -320,8 +320,8 @@ int apply_seg_cfg(lidar_b200_ctx *c, const lidar_b200_seg_cfg &cfg)
         return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "number_of_planar_partitions must be in [1, 4096]");
     if (cfg.number_of_iterations == 0u || cfg.number_of_iterations > 64u)
         return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "number_of_iterations must be in [1, 64]");
-    if (cfg.number_of_lower_point_representatives == 0u || cfg.number_of_lower_point_representatives > kMaxLpr)
-        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "number_of_lower_point_representatives must be in [1, 8192]");
+    if (cfg.number_of_lower_point_representatives == 0u)
+        return fail(c, LIDAR_B200_ERR_UNSUPPORTED, "number_of_lower_point_representatives must be at least 1");
     if (!std::isfinite(cfg.sensor_height_m) || !std::isfinite(cfg.orthogonal_distance_threshold) ||
         !std::isfinite(cfg.initial_seed_threshold))
         return fail(c, LIDAR_B200_ERR_INVALID, "non-finite segmentation configuration");
@@ -500,7 +500,8 @@ int run_segmentation(lidar_b200_ctx *c)
     seg_gather_kernel<<<gp, 256, 0, s>>>(c->d_pts.p, sorted_idx, bv, c->d_spts.p, zkeys);
     ++c->launches;
     seg_fit_kernel<<<dim3(c->seg.partitions, F), kFitThreads, sizeof(FitSmem), s>>>(c->d_spts.p, zkeys, bv, c->seg, c->d_flags.p,
-                                                                                    c->d_planes.p, c->d_status.p);
+                                                                                    c->d_planes.p, c->d_status.p,
+                                                                                    c->d_key_b.p /* spare since the x sort */);
     ++c->launches;
     mark(c, 2);
     {

@@ -24,7 +24,7 @@ constexpr uint32_t kSegObstacle = 2u;
 
 constexpr int kFitThreads = 1024;
 constexpr int kFitUnroll = 4; // independent loads in flight per thread in every pass of seg_fit
-constexpr uint32_t kMaxLpr = 8192u; // number_of_lower_point_representatives supported by the in-smem sort
+constexpr uint32_t kMaxLpr = 8192u; // lower point representatives sorted in shared memory; more of them go through global memory
 
 struct SegParams
 {
@@ -216,7 +216,7 @@ LB_D bool fit_is_ground(const float4 &p, const PlaneF &pl)
 __global__ void __launch_bounds__(kFitThreads, 1)
 seg_fit_kernel(const float4 *__restrict__ spts, const uint32_t *__restrict__ zkeys, BatchView bv, SegParams prm,
                uint8_t *__restrict__ flags,
-               float *__restrict__ planes_out, int32_t *__restrict__ status_out)
+               float *__restrict__ planes_out, int32_t *__restrict__ status_out, uint32_t *__restrict__ lpr_spill)
 {
     extern __shared__ __align__(16) unsigned char fit_smem_raw[];
     FitSmem &sm = *reinterpret_cast<FitSmem *>(fit_smem_raw);
@@ -397,8 +397,96 @@ seg_fit_kernel(const float4 *__restrict__ spts, const uint32_t *__restrict__ zke
     fit_find_bin(sm, 256u, remaining, &b3, &before3);
     remaining -= before3; // copies of the threshold value T that belong to the lowest n_lpr (>= 1)
     const uint32_t kT = (prefix24 << 8) | b3;
-    const uint32_t c_less = n_lpr - remaining; // included keys strictly below T  (<= lpr - 1 < kMaxLpr)
+    const uint32_t c_less = n_lpr - remaining; // included keys strictly below T  (<= lpr - 1)
 
+    if (c_less > kMaxLpr)
+    {
+        // More lower point representatives than the shared-memory sort holds (dense sensors, merged clouds): the keys
+        // below T go to the partition's own range of a spare per-point array, are sorted there by the CTA ("flip"
+        // bitonic network, slots past c_less act as +inf) and summed from there. Same values in the same order.
+        uint32_t *g = lpr_spill + off + lo;
+        if (tid == 0)
+            sm.u[5] = 0u;
+        __syncthreads();
+        for (uint32_t base = lo; base < hi; base += kFitThreads * kFitUnroll)
+        {
+#pragma unroll
+            for (int h = 0; h < kFitUnroll; ++h)
+            {
+                const uint32_t i = base + h * kFitThreads + tid;
+                const uint32_t k = i < hi ? __ldg(&zk[i]) : 0u;
+                const bool take = i < hi && (!use_kmin || k > kmin) && k < kT;
+                const uint32_t ballot = __ballot_sync(kFullMask, take);
+                if (ballot == 0u)
+                    continue;
+                uint32_t wbase = 0u;
+                if (lane_id() == 0)
+                    wbase = atomicAdd(&sm.u[5], static_cast<uint32_t>(__popc(ballot)));
+                wbase = __shfl_sync(kFullMask, wbase, 0);
+                if (take)
+                    g[wbase + __popc(ballot & lanemask_lt())] = k;
+            }
+        }
+        __syncthreads();
+        uint32_t n_pad2 = 2u;
+        while (n_pad2 < c_less)
+            n_pad2 <<= 1;
+        for (uint32_t kk = 2u; kk <= n_pad2; kk <<= 1)
+            for (uint32_t jj = kk >> 1; jj > 0u; jj >>= 1)
+            {
+                const uint32_t lj = 31u - __clz(jj);
+                for (uint32_t t = tid; t < (n_pad2 >> 1); t += kFitThreads)
+                {
+                    uint32_t i0, i1;
+                    if (jj == (kk >> 1))
+                    {
+                        const uint32_t blk = t >> lj, o = t & (jj - 1u);
+                        i0 = blk * kk + o;
+                        i1 = blk * kk + kk - 1u - o;
+                    }
+                    else
+                    {
+                        i0 = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u));
+                        i1 = i0 | jj;
+                    }
+                    if (i1 < c_less)
+                    {
+                        const uint32_t a = g[i0], b = g[i1];
+                        if (a > b)
+                        {
+                            g[i0] = b;
+                            g[i1] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        if (tid == 0)
+        {
+            float zsum = 0.0f;
+            uint32_t i = 0;
+            for (; i + 8u <= c_less; i += 8u) // loads ahead of the dependent FADD chain
+            {
+                uint32_t v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    v[q] = g[i + q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    zsum = __fadd_rn(zsum, ordered_to_float(v[q]));
+            }
+            for (; i < c_less; ++i)
+                zsum = __fadd_rn(zsum, ordered_to_float(g[i]));
+            const float zt = ordered_to_float(kT);
+            for (uint32_t r = 0; r < remaining; ++r)
+                zsum = __fadd_rn(zsum, zt);
+            const float zmean = __fdiv_rn(zsum, static_cast<float>(n_lpr));
+            sm.fl[0] = __fadd_rn(zmean, prm.initial_seed_threshold);
+        }
+        __syncthreads();
+    }
+    else
+    {
     // gather the keys below T, sort them ascending (bitonic in smem)
     uint32_t n_pad = 256u; // at least one warp chunk
     while (n_pad < c_less)
@@ -510,6 +598,7 @@ seg_fit_kernel(const float4 *__restrict__ spts, const uint32_t *__restrict__ zke
         sm.fl[0] = __fadd_rn(zmean, prm.initial_seed_threshold);
     }
     __syncthreads();
+    }
     const float zmax = sm.fl[0];
     const uint32_t kzmax = float_to_ordered(zmax);
     // seeds = sorted prefix before the first z > z_max; none found -> zero seeds (segmentation.cpp:199-216)

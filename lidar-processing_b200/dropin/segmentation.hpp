@@ -44,7 +44,7 @@ class Segmenter final
     Segmenter &operator=(const Segmenter &) = delete;
 
     // Throws std::invalid_argument for configurations outside the CUDA path's envelope
-    // (0 partitions / 0 iterations / representatives outside [1, 8192]); see DESIGN.md.
+    // (0 partitions / 0 iterations / 0 representatives); see DESIGN.md.
     void update_configuration(const SegmentationConfiguration &configuration);
 
     void reserve_memory(std::uint32_t number_of_points = 200'000U);

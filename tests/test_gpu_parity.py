@@ -54,7 +54,8 @@ def test_segment_point_stride_16_equals_32(ctx, golden_frames):
         assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("partitions,iterations,lpr", [(1, 3, 5000), (3, 2, 1000), (5, 1, 64), (2, 4, 8192), (7, 3, 1)])
+@pytest.mark.parametrize("partitions,iterations,lpr", [(1, 3, 5000), (3, 2, 1000), (5, 1, 64), (2, 4, 8192), (7, 3, 1),
+                                                       (1, 3, 12000), (2, 2, 1000000)])
 def test_segment_configurations(pkg, ctx, synth_small, partitions, iterations, lpr):
     cfg = pkg.SegmentationConfiguration(number_of_planar_partitions=partitions, number_of_iterations=iterations,
                                         number_of_lower_point_representatives=lpr)
@@ -63,6 +64,20 @@ def test_segment_configurations(pkg, ctx, synth_small, partitions, iterations, l
         for pts in (synth_small, synth_small[:10007], synth_small[:10]):
             labels, gi, oi = ctx.segment(pts)
             H.check_segmentation(pts, labels, gi, oi, H.to_oracle_seg_cfg(cfg))
+    finally:
+        ctx.seg_configure(pkg.SegmentationConfiguration())
+
+
+@pytest.mark.parametrize("lpr", [20000, 61699, 200000])
+def test_segment_many_lower_point_representatives(pkg, ctx, golden_frames, lpr):
+    """More representatives than the shared-memory sort holds (reference src/segmentation.cpp:189-197 has no limit):
+    the lowest-z values are sorted through global memory and summed in the same ascending float order."""
+    cfg = pkg.SegmentationConfiguration(number_of_lower_point_representatives=lpr)
+    ctx.seg_configure(cfg)
+    try:
+        pts = golden_frames[0]
+        labels, gi, oi = ctx.segment(pts)
+        H.check_segmentation(pts, labels, gi, oi, H.to_oracle_seg_cfg(cfg))
     finally:
         ctx.seg_configure(pkg.SegmentationConfiguration())
 
@@ -118,7 +133,7 @@ def test_segment_stale_label_quirk(ctx, synth_small):
 
 def test_unsupported_configuration_fails_loudly(pkg, ctx):
     for bad in (dict(number_of_planar_partitions=0), dict(number_of_iterations=0),
-                dict(number_of_lower_point_representatives=0), dict(number_of_lower_point_representatives=100000)):
+                dict(number_of_lower_point_representatives=0)):
         with pytest.raises(pkg.LidarB200Error):
             ctx.seg_configure(pkg.SegmentationConfiguration(**bad))
     with pytest.raises(pkg.LidarB200Error):
