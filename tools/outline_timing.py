@@ -78,8 +78,8 @@ out["concave_outlines_single_frame_ms"] = {"p50": float(np.median(lat)), "max": 
 # clusters, which leaves the GPU to the next batches - the steady-state cost per batch is what a pipeline pays
 import threading  # noqa: E402
 
-K = 4
-others = [pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames)) for _ in range(K - 1)]
+KMAX = 8
+others = [pkg.Context(device=0, max_points=sum((f.shape[0] + 31) & ~31 for f in frames), max_frames=len(frames)) for _ in range(KMAX - 1)]
 for o in others:
     o.batch_stage(frames)
 ctxs = [ctx] + others
@@ -96,13 +96,14 @@ def loop(c, reps):
 for c in ctxs:
     loop(c, 1)
 reps = 4
-th = [threading.Thread(target=loop, args=(c, reps)) for c in ctxs]
-t0 = time.perf_counter()
-for t in th:
-    t.start()
-for t in th:
-    t.join()
-out["ms_per_step"]["+split+concave_outlines, 4 batches in flight"] = 1e3 * (time.perf_counter() - t0) / (reps * K)
+for K in (4, 8):
+    th = [threading.Thread(target=loop, args=(c, reps)) for c in ctxs[:K]]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    out["ms_per_step"][f"+split+concave_outlines, {K} batches in flight"] = 1e3 * (time.perf_counter() - t0) / (reps * K)
 for o in others:
     o.close()
 # results once, for the counts and the CPU sample
