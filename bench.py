@@ -391,7 +391,7 @@ def sub_workload(pkg, env, name, args):
         r["ctx"].process_batch([f])
         lat.append(1e3 * (time.perf_counter() - t1))
     r["ctx"].close()
-    max_chunk_pts = max(sum((f.shape[0] + 31) & ~31 for f in frames[a:a + args.chunk]) for a in range(0, nf, args.chunk))
+    max_chunk_pts = max(sum((f.shape[0] + 31) & ~31 for f in frames[a:a + args.chunk]) for a in range(0, nf, args.chunk))  # (an upper bound: the pipe cuts equal chunks of at most args.chunk frames)
     pipe = pkg.FramePipeline(device=env.local_rank, depth=args.depth, chunk_frames=args.chunk, max_points_per_chunk=max_chunk_pts)
     e2e_s, _, _ = measure_e2e(pkg, env, pipe, pkg.pin_frames(frames), steps, warmup, None)
     pipe.close()
@@ -484,8 +484,11 @@ def main():
     ap.add_argument("--frame-offset", type=int, default=0, help="skip the first N frames (debug / profiling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-workload lines, config 5 and the next-row timings")
-    ap.add_argument("--chunk", type=int, default=22, help="frames per pipeline chunk (e2e path)")
-    ap.add_argument("--depth", type=int, default=6, help="pipeline depth = contexts in rotation (e2e path)")
+    # (77 x 4 since the window-synchronous replay: larger batches amortise its per-launch tail; 22 x 6 before. Measured
+    # at 1 GPU, 154-frame job: 22x6 9 641, 31x5 10 114, 39x4 10 188, 77x3 10 166-10 526, 77x4 10 675, 154x2 10 275 frames/s,
+    # profiles/r02_e2e_chunk_depth_sweep.txt)
+    ap.add_argument("--chunk", type=int, default=77, help="frames per pipeline chunk (e2e path)")
+    ap.add_argument("--depth", type=int, default=4, help="pipeline depth = contexts in rotation (e2e path)")
     ap.add_argument("--workload", default="kitti154", choices=WORKLOADS,
                     help="kitti154 = the metric's configuration; the rest are the synthetic shapes of SURVEY 8(d)")
     args = ap.parse_args()

@@ -537,7 +537,16 @@ class FramePipeline:
         stride = strides.pop()
         counts = np.array([f.shape[0] for f in frames], np.uint32)
         padded = (counts.astype(np.int64) + 31) & ~31
-        chunks = [(a, min(a + self.chunk_frames, nf)) for a in range(0, nf, self.chunk_frames)]
+        # chunks of equal size, at most chunk_frames frames each (a 154-frame job with chunk_frames = 51 is cut into
+        # 39 + 39 + 38 + 38, not 51 + 51 + 51 + 1: a short last chunk leaves the pipeline's contexts idle)
+        n_chunks = max(1, -(-nf // self.chunk_frames))
+        size, extra = divmod(nf, n_chunks)
+        chunks, a = [], 0
+        for k in range(n_chunks):
+            b = a + size + (1 if k < extra else 0)
+            if b > a:
+                chunks.append((a, b))
+            a = b
         total = int(padded.sum())
         ar = self._arenas.get(arena)
         if ar is None or ar[0].size < max(total, 1) or ar[4].shape[1] < max(nf, 1):
