@@ -166,6 +166,7 @@ struct lidar_b200_ctx
     cudaEvent_t ev_counts{nullptr}; // per-frame counts of the batch are in h_meta
     std::vector<void *> copy_dst, copy_src; // copy list of the second fetch phase
     std::vector<size_t> copy_size;
+    uint32_t stage_threads{4}; // LIDAR_B200_STAGE_THREADS: host threads that stage a batch of pageable clouds (1 = the caller's only)
     int fetch_mode{0}; // LIDAR_B200_FETCH_MODE (see profiles/README.md "result fetch modes"): 0 = one phase, full slots; 1 = two phases, full slots; 2 = exact sizes, plain copies; 3 = exact sizes, one batched call; 4 = one kernel writes the exact sizes straight into page-locked host memory (emit_results_kernel)
 
     uint32_t sm_count{148}, replay_ctas_per_sm{12}, replay_big_ctas_per_sm{3};
@@ -443,33 +444,79 @@ int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const
     if (n_frames)
         LB_CUDA(c, cudaMemcpyAsync(c->d_meta.p, hm, 4 * F * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     // one upload per frame, issued as soon as the frame is staged: the DMA of frame f overlaps the
-    // staging pass of frame f+1. Page-locked 16-byte records need no staging pass at all.
+    // staging pass of the frames behind it. Page-locked 16-byte records need no staging pass at all.
+    // (asked on this thread: the staging threads below make no CUDA call)
+    std::vector<uint8_t> direct(n_frames, 0u);
+    for (uint32_t f = 0; f < n_frames; ++f)
+        direct[f] = (c->cnt[f] == 0u || (stride_bytes == 16u && is_pinned(points[f]))) ? 1u : 0u;
+    auto stage_frame = [&](uint32_t f) -> const void * {
+        const uint32_t n = c->cnt[f];
+        const uint8_t *src = static_cast<const uint8_t *>(points[f]);
+        if (direct[f])
+            return src;
+        float4 *dst = c->h_pts.p + c->off[f];
+        if (stride_bytes == 16u)
+            std::memcpy(dst, src, static_cast<size_t>(n) * 16u);
+        else if (stride_bytes >= 16u)
+            for (uint32_t i = 0; i < n; ++i)
+                std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 16u);
+        else
+            for (uint32_t i = 0; i < n; ++i)
+            {
+                std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 12u);
+                dst[i].w = 1.0f;
+            }
+        return dst;
+    };
+    // A batch of pageable clouds is staged by a few threads (frames handed out through a counter, uploads still issued
+    // in frame order by this thread): one thread copies ~15 GB/s, which capped the pipeline at ~4 000 frames/s.
+    uint32_t n_workers = 0u;
+    if (n_frames >= 4u && total >= (1u << 20) && !direct[0])
+    {
+        n_workers = c->stage_threads;
+        if (n_workers > n_frames / 2u)
+            n_workers = n_frames / 2u;
+    }
+    if (n_workers <= 1u)
+    {
+        for (uint32_t f = 0; f < n_frames; ++f)
+        {
+            if (c->cnt[f] == 0u)
+                continue;
+            const void *from = stage_frame(f);
+            LB_CUDA(c, cudaMemcpyAsync(c->d_pts.p + c->off[f], from, static_cast<size_t>(c->cnt[f]) * sizeof(float4),
+                                       cudaMemcpyHostToDevice, c->stream));
+        }
+        return 0;
+    }
+    std::vector<const void *> from(n_frames, nullptr);
+    std::vector<std::atomic<uint32_t>> done(n_frames);
+    for (auto &d : done)
+        d.store(0u, std::memory_order_relaxed);
+    std::atomic<uint32_t> next{0u};
+    std::vector<std::thread> workers;
+    workers.reserve(n_workers);
+    for (uint32_t t = 0; t < n_workers; ++t)
+        workers.emplace_back([&]() {
+            for (uint32_t f = next.fetch_add(1u); f < n_frames; f = next.fetch_add(1u))
+            {
+                from[f] = stage_frame(f);
+                done[f].store(1u, std::memory_order_release);
+            }
+        });
+    cudaError_t first_error = cudaSuccess;
     for (uint32_t f = 0; f < n_frames; ++f)
     {
-        const uint32_t n = c->cnt[f];
-        if (n == 0u)
+        while (done[f].load(std::memory_order_acquire) == 0u)
+            std::this_thread::yield();
+        if (c->cnt[f] == 0u || first_error != cudaSuccess)
             continue;
-        const uint8_t *src = static_cast<const uint8_t *>(points[f]);
-        const void *from = src;
-        if (!(stride_bytes == 16u && is_pinned(src)))
-        {
-            float4 *dst = c->h_pts.p + c->off[f];
-            if (stride_bytes == 16u)
-                std::memcpy(dst, src, static_cast<size_t>(n) * 16u);
-            else if (stride_bytes >= 16u)
-                for (uint32_t i = 0; i < n; ++i)
-                    std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 16u);
-            else
-                for (uint32_t i = 0; i < n; ++i)
-                {
-                    std::memcpy(&dst[i], src + static_cast<size_t>(i) * stride_bytes, 12u);
-                    dst[i].w = 1.0f;
-                }
-            from = dst;
-        }
-        LB_CUDA(c, cudaMemcpyAsync(c->d_pts.p + c->off[f], from, static_cast<size_t>(n) * sizeof(float4),
-                                   cudaMemcpyHostToDevice, c->stream));
+        first_error = cudaMemcpyAsync(c->d_pts.p + c->off[f], from[f], static_cast<size_t>(c->cnt[f]) * sizeof(float4),
+                                      cudaMemcpyHostToDevice, c->stream);
     }
+    for (auto &w : workers)
+        w.join();
+    LB_CUDA(c, first_error);
     return 0;
 }
 
@@ -953,6 +1000,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     c->chi_stats = std::getenv("LIDAR_B200_CHI_STATS") != nullptr;
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
+    if (const char *e = std::getenv("LIDAR_B200_STAGE_THREADS"))
+        c->stage_threads = static_cast<uint32_t>(std::atoi(e) > 0 ? std::atoi(e) : 1);
     if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
         c->replay_version = (std::atoi(e) == 1 || std::atoi(e) == 2) ? std::atoi(e) : 5;
     if (const char *e = std::getenv("LIDAR_B200_FRAME_SORT"))
