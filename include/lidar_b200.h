@@ -273,6 +273,12 @@ extern "C"
     uint64_t lidar_b200_launch_count(const lidar_b200_ctx *ctx);
     /* elapsed GPU milliseconds between the start and the end of the last lidar_b200_batch_run (CUDA events) */
     int lidar_b200_last_run_ms(lidar_b200_ctx *ctx, float *ms_out);
+    /* device time of a region of calls on this context (benchmarks): _region_begin records a CUDA event on the
+     * context's stream, _region_end_ms records a second one behind everything enqueued since, waits for it and returns
+     * the elapsed milliseconds. Lets a caller enqueue several lidar_b200_batch_run back to back (no host round trip
+     * between them) and still time them on the device. */
+    int lidar_b200_region_begin(lidar_b200_ctx *ctx);
+    int lidar_b200_region_end_ms(lidar_b200_ctx *ctx, float *ms_out);
     /* per-stage GPU times of the last run, measured with CUDA events on the context's stream when
      * profiling is enabled. 9 stages: x-sort | gather+fit | compact | voxel grid | union-find |
      * component sort | k-d order | replay | label compaction. */

@@ -123,7 +123,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_reserve", "lidar_b200_seg_configure", "lidar_b200_clu_configure", "lidar_b200_segment",
     "lidar_b200_cluster", "lidar_b200_batch_stage", "lidar_b200_batch_run", "lidar_b200_batch_fetch",
     "lidar_b200_sync", "lidar_b200_last_planes", "lidar_b200_last_kd_rank", "lidar_b200_last_cc_root",
-    "lidar_b200_launch_count", "lidar_b200_last_run_ms", "lidar_b200_last_error", "lidar_b200_version",
+    "lidar_b200_launch_count", "lidar_b200_last_run_ms", "lidar_b200_region_begin", "lidar_b200_region_end_ms", "lidar_b200_last_error", "lidar_b200_version",
     "lidar_b200_set_profiling", "lidar_b200_last_stage_ms", "lidar_b200_batch_fetch_async", "lidar_b200_batch_wait",
     "lidar_b200_host_alloc", "lidar_b200_host_free", "lidar_b200_pipe_create", "lidar_b200_pipe_destroy",
     "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
@@ -466,6 +466,16 @@ class Context:
         self._check(lib().lidar_b200_last_replay_stats(self._h, _ptr(out, C.c_uint32), C.c_uint32(capacity), C.byref(n)),
                     "last_replay_stats")
         return out[: min(n.value, capacity)]
+
+    def region_begin(self):
+        """CUDA event on the context's stream: start of a device-timed region (see region_end_ms)."""
+        self._check(lib().lidar_b200_region_begin(self._h), "region_begin")
+
+    def region_end_ms(self) -> float:
+        """Device milliseconds since region_begin() once everything enqueued in between has finished."""
+        ms = C.c_float(0)
+        self._check(lib().lidar_b200_region_end_ms(self._h, C.byref(ms)), "region_end_ms")
+        return float(ms.value)
 
     def last_run_ms(self) -> float:
         ms = C.c_float(0)

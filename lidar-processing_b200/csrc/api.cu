@@ -163,6 +163,7 @@ struct lidar_b200_ctx
         bool with_worker{false}, worker_done{false};      // pipeline: the second phase belongs to the pipe's worker thread
         int worker_rc{0};
     } fetch;
+    cudaEvent_t ev_region_a{nullptr}, ev_region_b{nullptr}; // lidar_b200_region_begin / _end_ms
     cudaEvent_t ev_counts{nullptr}; // per-frame counts of the batch are in h_meta
     std::vector<void *> copy_dst, copy_src; // copy list of the second fetch phase
     std::vector<size_t> copy_size;
@@ -1094,6 +1095,10 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     for (auto &e : c->ev_stage)
         if (e)
             cudaEventDestroy(e);
+    if (c->ev_region_a)
+        cudaEventDestroy(c->ev_region_a);
+    if (c->ev_region_b)
+        cudaEventDestroy(c->ev_region_b);
     if (c->ev_start)
         cudaEventDestroy(c->ev_start);
     if (c->ev_stop)
@@ -1724,6 +1729,34 @@ int lidar_b200_last_run_ms(lidar_b200_ctx *c, float *ms_out)
         ms = c->last_run_ms;
     }
     *ms_out = ms;
+    return 0;
+}
+
+int lidar_b200_region_begin(lidar_b200_ctx *c)
+{
+    if (!c)
+        return LIDAR_B200_ERR_INVALID;
+    LB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->ev_region_a)
+    {
+        LB_CUDA(c, cudaEventCreate(&c->ev_region_a));
+        LB_CUDA(c, cudaEventCreate(&c->ev_region_b));
+    }
+    LB_CUDA(c, cudaEventRecord(c->ev_region_a, c->stream));
+    return 0;
+}
+
+int lidar_b200_region_end_ms(lidar_b200_ctx *c, float *ms_out)
+{
+    if (!c || !ms_out)
+        return LIDAR_B200_ERR_INVALID;
+    if (!c->ev_region_a)
+        return fail(c, LIDAR_B200_ERR_INVALID, "region_end_ms: call lidar_b200_region_begin first");
+    LB_CUDA(c, cudaSetDevice(c->device));
+    // every batch_run joins its side streams back into the main stream, so an event on it closes the region
+    LB_CUDA(c, cudaEventRecord(c->ev_region_b, c->stream));
+    LB_CUDA(c, cudaEventSynchronize(c->ev_region_b));
+    LB_CUDA(c, cudaEventElapsedTime(ms_out, c->ev_region_a, c->ev_region_b));
     return 0;
 }
 
