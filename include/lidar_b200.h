@@ -271,6 +271,10 @@ extern "C"
                                      uint32_t *n_jobs_out);
     /* number of kernels launched by this context so far */
     uint64_t lidar_b200_launch_count(const lidar_b200_ctx *ctx);
+    /* single-frame lidar_b200_batch_run calls that went to the device as ONE CUDA-graph launch (the frame's kernels are
+     * captured per launch geometry - the point count rounded up to 4096 - after a first launch-by-launch run; they are
+     * still counted kernel by kernel in lidar_b200_launch_count). LIDAR_B200_GRAPH=0 in the environment turns it off. */
+    uint64_t lidar_b200_graph_launch_count(const lidar_b200_ctx *ctx);
     /* elapsed GPU milliseconds between the start and the end of the last lidar_b200_batch_run (CUDA events) */
     int lidar_b200_last_run_ms(lidar_b200_ctx *ctx, float *ms_out);
     /* device time of a region of calls on this context (benchmarks): _region_begin records a CUDA event on the

@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         L.lidar_b200_last_error.restype = C.c_char_p
         L.lidar_b200_version.restype = C.c_char_p
         L.lidar_b200_launch_count.restype = C.c_uint64
+        L.lidar_b200_graph_launch_count.restype = C.c_uint64
         L.lidar_b200_pipe_launch_count.restype = C.c_uint64
         L.lidar_b200_pipe_last_error.restype = C.c_char_p
         L.lidar_b200_host_free.restype = None
@@ -123,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "lidar_b200_reserve", "lidar_b200_seg_configure", "lidar_b200_clu_configure", "lidar_b200_segment",
     "lidar_b200_cluster", "lidar_b200_batch_stage", "lidar_b200_batch_run", "lidar_b200_batch_fetch",
     "lidar_b200_sync", "lidar_b200_last_planes", "lidar_b200_last_kd_rank", "lidar_b200_last_cc_root",
-    "lidar_b200_launch_count", "lidar_b200_last_run_ms", "lidar_b200_region_begin", "lidar_b200_region_end_ms", "lidar_b200_last_error", "lidar_b200_version",
+    "lidar_b200_launch_count", "lidar_b200_graph_launch_count", "lidar_b200_last_run_ms", "lidar_b200_region_begin", "lidar_b200_region_end_ms", "lidar_b200_last_error", "lidar_b200_version",
     "lidar_b200_set_profiling", "lidar_b200_last_stage_ms", "lidar_b200_batch_fetch_async", "lidar_b200_batch_wait",
     "lidar_b200_host_alloc", "lidar_b200_host_free", "lidar_b200_pipe_create", "lidar_b200_pipe_destroy",
     "lidar_b200_pipe_seg_configure", "lidar_b200_pipe_clu_configure", "lidar_b200_pipe_submit",
@@ -458,6 +459,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().lidar_b200_launch_count(self._h))
+
+    def graph_launch_count(self) -> int:
+        """single-frame batch_run calls replayed as one CUDA-graph launch"""
+        return int(lib().lidar_b200_graph_launch_count(self._h))
 
     def last_replay_stats(self, capacity: int = 65536) -> np.ndarray:
         """(jobs, 8) uint32: frame, members, kilo-cycles, rounds, direct rounds, entries taken, seeds, candidates."""

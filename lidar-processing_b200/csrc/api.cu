@@ -36,6 +36,8 @@ using namespace lb;
 
 namespace
 {
+constexpr uint32_t kGraphBucket = 4096u; // launch geometry of a single frame in flight, in points (see lidar_b200_batch_run)
+
 template <typename T> struct DevBuf
 {
     T *p{nullptr};
@@ -167,6 +169,22 @@ struct lidar_b200_ctx
     cudaEvent_t ev_counts{nullptr}; // per-frame counts of the batch are in h_meta
     std::vector<void *> copy_dst, copy_src; // copy list of the second fetch phase
     std::vector<size_t> copy_size;
+    // One frame in flight: the ~58 launches of a frame (four streams, fork / join events) are captured into a CUDA graph
+    // per launch geometry and replayed, so that the kernels of a 2 ms frame do not wait for the host to enqueue them.
+    // The launch geometry of a single frame is rounded up to kGraphBucket points for that (kernels bound their loops by
+    // the device-side counts). LIDAR_B200_GRAPH=0 turns it off.
+    struct GraphEntry
+    {
+        uint32_t max_n{0};
+        bool warm{false}, bad{false};
+        cudaGraphExec_t exec{nullptr};
+        uint64_t launches{0};
+    };
+    std::vector<GraphEntry> graphs;
+    uint64_t epoch{0}, graphs_epoch{0}; // epoch: bumped by every (re)allocation and configuration change
+    bool use_graph{true};
+    uint32_t geom_total{0}; // c->total, or the single frame's bucketed size: sizes of the memsets / copies inside the run path
+    uint64_t graph_launches{0};
     uint32_t stage_threads{4}; // LIDAR_B200_STAGE_THREADS: host threads that stage a batch of pageable clouds (1 = the caller's only)
     int fetch_mode{0}; // LIDAR_B200_FETCH_MODE (see profiles/README.md "result fetch modes"): 0 = one phase, full slots; 1 = two phases, full slots; 2 = exact sizes, plain copies; 3 = exact sizes, one batched call; 4 = one kernel writes the exact sizes straight into page-locked host memory (emit_results_kernel)
 
@@ -241,6 +259,7 @@ template <typename T> int dev_alloc(lidar_b200_ctx *c, DevBuf<T> &b, size_t n)
     b.n = 0;
     LB_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&b.p), n * sizeof(T)));
     b.n = n;
+    ++c->epoch; // device pointers changed: captured graphs are stale
     return 0;
 }
 
@@ -414,9 +433,19 @@ int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const
     }
     if (total > 0x7FFFFFFFull)
         return fail(c, LIDAR_B200_ERR_CAPACITY, "batch exceeds 2^31 points");
-    if (total > c->cap_pts || n_frames > c->cap_frames)
+    uint64_t geom_total = total;
+    if (n_frames == 1u && c->use_graph && max_n)
     {
-        const int rc = reserve(c, total > c->cap_pts ? static_cast<uint32_t>(total) : c->cap_pts,
+        // one frame in flight: launch geometry in steps of kGraphBucket points, so that the captured graph of a frame
+        // serves the next frames too (grids, tile counts and the sizes of the path's memsets / copies follow max_n and
+        // geom_total; the kernels themselves stop at the frame's own count, which lives in device memory). The slot
+        // layout the callers see (c->total, offsets) stays exact.
+        max_n = (max_n + kGraphBucket - 1u) / kGraphBucket * kGraphBucket;
+        geom_total = max_n;
+    }
+    if (geom_total > c->cap_pts || n_frames > c->cap_frames)
+    {
+        const int rc = reserve(c, geom_total > c->cap_pts ? static_cast<uint32_t>(geom_total) : c->cap_pts,
                                n_frames > c->cap_frames ? n_frames : c->cap_frames);
         if (rc)
             return rc;
@@ -425,6 +454,7 @@ int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const
     LB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_frames = n_frames;
     c->total = static_cast<uint32_t>(total);
+    c->geom_total = static_cast<uint32_t>(geom_total);
     c->max_n = max_n;
     uint32_t *hm = c->h_meta.p;
     const size_t F = c->cap_frames;
@@ -527,7 +557,7 @@ int run_segmentation(lidar_b200_ctx *c)
     if (F == 0u)
         return 0;
     cudaStream_t s = c->stream;
-    LB_CUDA(c, cudaMemsetAsync(c->d_labels.p, 0, static_cast<size_t>(c->total ? c->total : 1) * 4, s));
+    LB_CUDA(c, cudaMemsetAsync(c->d_labels.p, 0, static_cast<size_t>(c->geom_total ? c->geom_total : 1) * 4, s));
     LB_CUDA(c, cudaMemsetAsync(c->m_ng(), 0, 2 * static_cast<size_t>(c->cap_frames) * 4, s)); // n_ground, n_obstacle
     if (c->max_n == 0u)
         return 0;
@@ -619,7 +649,7 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
     cc_flatten_kernel<<<gp, 256, 0, s>>>(bv, c->d_parent.p, c->d_pos_of.p, c->d_key_a.p, c->d_val_a.p, c->d_comp_size.p);
     c->launches += 12;
     mark(c, 5);
-    LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->total) * 4, cudaMemcpyDeviceToDevice, s));
+    LB_CUDA(c, cudaMemcpyAsync(c->d_root.p, c->d_key_a.p, static_cast<size_t>(c->geom_total) * 4, cudaMemcpyDeviceToDevice, s));
     int rl = 0;
     const uint32_t bits = ceil_log2(max_m < 2u ? 2u : max_m);
     int passes;
@@ -966,6 +996,23 @@ int finish_fetch(lidar_b200_ctx *c)
 
 } // namespace
 
+namespace
+{
+void drop_graphs(lidar_b200_ctx *c)
+{
+    for (auto &g : c->graphs)
+        if (g.exec)
+            cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+
+int run_frames(lidar_b200_ctx *c)
+{
+    const int rc = run_segmentation(c);
+    return rc ? rc : run_clustering(c, c->d_obs.p, c->m_no(), c->max_n);
+}
+} // namespace
+
 extern "C"
 {
 
@@ -1001,6 +1048,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     c->chi_stats = std::getenv("LIDAR_B200_CHI_STATS") != nullptr;
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
+    if (const char *e = std::getenv("LIDAR_B200_GRAPH"))
+        c->use_graph = std::atoi(e) != 0;
     if (const char *e = std::getenv("LIDAR_B200_STAGE_THREADS"))
         c->stage_threads = static_cast<uint32_t>(std::atoi(e) > 0 ? std::atoi(e) : 1);
     if (const char *e = std::getenv("LIDAR_B200_REPLAY_V"))
@@ -1095,6 +1144,7 @@ void lidar_b200_destroy(lidar_b200_ctx *c)
     for (auto &e : c->ev_stage)
         if (e)
             cudaEventDestroy(e);
+    drop_graphs(c);
     if (c->ev_region_a)
         cudaEventDestroy(c->ev_region_a);
     if (c->ev_region_b)
@@ -1140,6 +1190,7 @@ int lidar_b200_seg_configure(lidar_b200_ctx *c, const lidar_b200_seg_cfg *cfg)
     const int rc = apply_seg_cfg(c, *cfg);
     if (rc)
         return rc;
+    ++c->epoch; // kernel parameters changed: captured graphs are stale
     return reserve(c, c->cap_pts, c->cap_frames); // plane/status buffers depend on the configuration
 }
 
@@ -1147,6 +1198,7 @@ int lidar_b200_clu_configure(lidar_b200_ctx *c, const lidar_b200_clu_cfg *cfg)
 {
     if (!c || !cfg)
         return LIDAR_B200_ERR_INVALID;
+    ++c->epoch; // kernel parameters change: captured graphs are stale
     return apply_clu_cfg(c, *cfg);
 }
 
@@ -1165,10 +1217,85 @@ int lidar_b200_batch_run(lidar_b200_ctx *c)
         return LIDAR_B200_ERR_INVALID;
     LB_CUDA(c, cudaSetDevice(c->device));
     LB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
-    int rc = run_segmentation(c);
-    if (rc)
-        return rc;
-    rc = run_clustering(c, c->d_obs.p, c->m_no(), c->max_n);
+    const bool graphable = c->use_graph && c->n_frames == 1u && c->max_n != 0u && !c->profiling && !c->want_job_stats;
+    int rc = 0;
+    if (!graphable)
+        rc = run_frames(c);
+    else
+    {
+        if (c->graphs_epoch != c->epoch) // buffers moved or the configuration changed since the graphs were captured
+        {
+            drop_graphs(c);
+            c->graphs_epoch = c->epoch;
+        }
+        lidar_b200_ctx::GraphEntry *g = nullptr;
+        for (auto &e : c->graphs)
+            if (e.max_n == c->max_n)
+                g = &e;
+        if (!g)
+        {
+            c->graphs.emplace_back();
+            g = &c->graphs.back();
+            g->max_n = c->max_n;
+        }
+        if (g->exec)
+        {
+            // the host-side bookkeeping of run_clustering, then the whole frame as one launch
+            c->clu_pts = c->d_obs.p;
+            c->clu_counts = c->m_no();
+            c->clu_max_m = c->max_n;
+            c->grouped = false;
+            c->hulled = false;
+            c->launches += g->launches;
+            ++c->graph_launches;
+            LB_CUDA(c, cudaGraphLaunch(g->exec, c->stream));
+        }
+        else if (!g->warm || g->bad)
+        {
+            // first frame of this geometry: run it launch by launch (this also makes every lazy allocation and
+            // attribute call of the path happen outside a capture)
+            rc = run_frames(c);
+            if (c->graphs_epoch == c->epoch)
+                g->warm = true;
+            else
+            {
+                drop_graphs(c); // (g dangles from here on)
+                c->graphs_epoch = c->epoch;
+            }
+        }
+        else
+        {
+            const uint64_t launches0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok)
+            {
+                const int rc_cap = run_frames(c);
+                const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+                ok = rc_cap == 0 && e == cudaSuccess && graph != nullptr && c->graphs_epoch == c->epoch;
+            }
+            if (ok)
+                ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+            if (graph)
+                cudaGraphDestroy(graph);
+            if (ok)
+            {
+                g->launches = c->launches - launches0;
+                ++c->graph_launches;
+                LB_CUDA(c, cudaGraphLaunch(g->exec, c->stream));
+            }
+            else
+            {
+                // capture refused (an operation the path performs is not capturable on this driver): this geometry
+                // stays on the launch-by-launch path
+                (void)cudaGetLastError();
+                g->exec = nullptr;
+                g->bad = true;
+                c->launches = launches0;
+                rc = run_frames(c);
+            }
+        }
+    }
     if (rc)
         return rc;
     LB_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
@@ -1715,6 +1842,11 @@ int lidar_b200_last_replay_stats(lidar_b200_ctx *c, uint32_t *stats_out, uint32_
 uint64_t lidar_b200_launch_count(const lidar_b200_ctx *c)
 {
     return c ? c->launches : 0;
+}
+
+uint64_t lidar_b200_graph_launch_count(const lidar_b200_ctx *c)
+{
+    return c ? c->graph_launches : 0;
 }
 
 int lidar_b200_last_run_ms(lidar_b200_ctx *c, float *ms_out)

@@ -27,6 +27,7 @@ for f in frames[6:46]:
     wall.append(1e3 * (time.perf_counter() - t0))
     dev.append(ctx.last_run_ms())
     launches.append(ctx.launch_count() - l0)
+graph_launches = ctx.graph_launch_count()
 ctx.set_profiling(True)
 stages = []
 for f in frames[6:46]:
@@ -34,7 +35,7 @@ for f in frames[6:46]:
     stages.append(ctx.last_stage_ms())
 ctx.close()
 out = {"frames": len(wall), "wall_ms_p50": statistics.median(wall), "device_ms_batch_run_p50": statistics.median(dev),
-       "launches_per_frame_p50": statistics.median(launches),
+       "launches_per_frame_p50": statistics.median(launches), "frames_replayed_as_one_graph_launch": graph_launches,
        "stage_ms_p50": {k: statistics.median(s[k] for s in stages) for k in stages[0]},
        "outside_the_kernels_ms_p50": statistics.median(w - d for w, d in zip(wall, dev))}
 print(json.dumps(out))
