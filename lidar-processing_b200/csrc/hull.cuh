@@ -11,7 +11,8 @@
 //   * the callers' policy: findOrderedConvexOutlines uses CHAN above 1000 points and the monotone chain
 //     otherwise (reference src/polygon_simplification.cpp:55-64); findOrderedConcaveOutlines uses the
 //     monotone chain below 20 points (:100-118) and the Delaunay-based concave hull from 20 points on —
-//     that part stays on the host (BASELINE north star) and such clusters are reported as "host".
+//     in mode kHullModeConcaveSmall that part stays on the host (BASELINE north star) and such clusters are
+//     reported as "host"; in mode kHullModeConcave chi_shape.cuh computes it on the device.
 //
 // Work decomposition: every monotone chain (a cluster up to 1000 points, or one CHAN subset) is a task.
 // Sort: persistent warps pull tasks from a batch-wide counter and run a warp-wide bitonic network over
