@@ -142,6 +142,7 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_chi_meta;   // [bucket counts 32 | bucket fill 32 | cursor]
     DevBuf<unsigned long long> d_chi_stats; // LIDAR_B200_CHI_STATS=1: 8 words per task for the first kChiStatTasks tasks
     bool chi_stats{false};
+    uint32_t chi_ctas_per_sm{8}; // LIDAR_B200_CHI_CTAS_PER_SM: persistent CTAs of chi_outline_kernel per SM (4 are resident)
     uint32_t hull_mode{0};
     DevBuf<uint4> d_color;   // 32-byte PointXYZRGB records (pack.cuh), allocated on first use
     DevBuf<double> d_marker; // marker points, allocated on first use
@@ -1046,6 +1047,8 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     c->device = device;
     c->want_job_stats = std::getenv("LIDAR_B200_REPLAY_STATS") != nullptr;
     c->chi_stats = std::getenv("LIDAR_B200_CHI_STATS") != nullptr;
+    if (const char *e = std::getenv("LIDAR_B200_CHI_CTAS_PER_SM"))
+        c->chi_ctas_per_sm = static_cast<uint32_t>(std::atoi(e) > 0 ? std::atoi(e) : 1);
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
         c->fetch_mode = std::atoi(e);
     if (const char *e = std::getenv("LIDAR_B200_GRAPH"))
@@ -1592,7 +1595,7 @@ int lidar_b200_batch_hull_outlines(lidar_b200_ctx *c, uint32_t mode)
                 return LIDAR_B200_ERR_CUDA;
             LB_CUDA(c, cudaMemsetAsync(c->d_chi_stats.p, 0, static_cast<size_t>(kChiStatTasks) * 64u, s));
         }
-        chi_outline_kernel<<<c->sm_count * 8u, 32 * kChiWarps, 0, s>>>(bv, cv, counts, task_f, task_k, chi_cursor,
+        chi_outline_kernel<<<c->sm_count * c->chi_ctas_per_sm, 32 * kChiWarps, 0, s>>>(bv, cv, counts, task_f, task_k, chi_cursor,
                                                                         c->chi_stats ? c->d_chi_stats.p : nullptr);
         nl += 3u;
     }
