@@ -142,6 +142,7 @@ struct lidar_b200_ctx
     DevBuf<uint32_t> d_chi_meta;   // [bucket counts 32 | bucket fill 32 | cursor]
     DevBuf<unsigned long long> d_chi_stats; // LIDAR_B200_CHI_STATS=1: 8 words per task for the first kChiStatTasks tasks
     bool chi_stats{false};
+    uint32_t replay5_wide_lists{2}, replay5_wide_ctas_per_sm{2}; // LIDAR_B200_REPLAY5_WIDE_LISTS / _WIDE_CTAS_PER_SM
     uint32_t chi_ctas_per_sm{8}; // LIDAR_B200_CHI_CTAS_PER_SM: persistent CTAs of chi_outline_kernel per SM (4 are resident)
     uint32_t hull_mode{0};
     DevBuf<uint4> d_color;   // 32-byte PointXYZRGB records (pack.cuh), allocated on first use
@@ -729,22 +730,24 @@ int run_clustering(lidar_b200_ctx *c, const float4 *pts, const uint32_t *counts,
         }
         else
         {
-            // job lists 0-1 (>= 2048 members) first, with wide CTAs; lists 2-3 beside them
+            // the first `wl` job lists (list 0: >= 8192 members, list 1: >= 2048) first, with wide CTAs; the others beside them
+            const uint32_t wl = c->replay5_wide_lists;
+            const uint32_t wide_grid = c->sm_count * c->replay5_wide_ctas_per_sm;
             if (big_threads >= 1024u)
                 replay_gen_kernel<1024, 1><<<c->sm_count, 1024, smem_normal, c->stream_big>>>(
-                    LB_GEN_ARGS(c->d_biglist.p, big_count, 2u, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
+                    LB_GEN_ARGS(c->d_biglist.p, big_count, wl, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
             else
-                replay_gen_kernel<512, 2><<<c->sm_count * 2u, 512, smem_normal, c->stream_big>>>(
-                    LB_GEN_ARGS(c->d_biglist.p, big_count, 2u, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
+                replay_gen_kernel<512, 2><<<wide_grid, 512, smem_normal, c->stream_big>>>(
+                    LB_GEN_ARGS(c->d_biglist.p, big_count, wl, c->m_cursor() + 2, normal_words, c->d_job_stats.p, 0u));
             LB_CUDA(c, cudaStreamWaitEvent(c->stream_small, c->ev_fork, 0));
             if (three_per_sm)
                 replay_gen_kernel<256, 3><<<c->sm_count * 3u, 256, smem_normal, c->stream_small>>>(
-                    LB_GEN_ARGS(c->d_biglist.p + 2u * static_cast<size_t>(bucket_capacity), big_count + 2, 2u, c->m_cursor() + 14,
-                                normal_words, c->d_job_stats.p, 2u));
+                    LB_GEN_ARGS(c->d_biglist.p + wl * static_cast<size_t>(bucket_capacity), big_count + wl, kBigBuckets - wl,
+                                c->m_cursor() + 14, normal_words, c->d_job_stats.p, wl));
             else
                 replay_gen_kernel<256, 2><<<c->sm_count * 2u, 256, smem_normal, c->stream_small>>>(
-                    LB_GEN_ARGS(c->d_biglist.p + 2u * static_cast<size_t>(bucket_capacity), big_count + 2, 2u, c->m_cursor() + 14,
-                                normal_words, c->d_job_stats.p, 2u));
+                    LB_GEN_ARGS(c->d_biglist.p + wl * static_cast<size_t>(bucket_capacity), big_count + wl, kBigBuckets - wl,
+                                c->m_cursor() + 14, normal_words, c->d_job_stats.p, wl));
             LB_CUDA(c, cudaEventRecord(c->ev_join3, c->stream_small));
             small_launched = true;
             c->launches += 2;
@@ -1047,6 +1050,10 @@ int lidar_b200_create(int device, uint32_t max_points, uint32_t max_frames, lida
     c->device = device;
     c->want_job_stats = std::getenv("LIDAR_B200_REPLAY_STATS") != nullptr;
     c->chi_stats = std::getenv("LIDAR_B200_CHI_STATS") != nullptr;
+    if (const char *e = std::getenv("LIDAR_B200_REPLAY5_WIDE_LISTS"))
+        c->replay5_wide_lists = std::atoi(e) == 1 ? 1u : 2u;
+    if (const char *e = std::getenv("LIDAR_B200_REPLAY5_WIDE_CTAS_PER_SM"))
+        c->replay5_wide_ctas_per_sm = std::atoi(e) == 1 ? 1u : 2u;
     if (const char *e = std::getenv("LIDAR_B200_CHI_CTAS_PER_SM"))
         c->chi_ctas_per_sm = static_cast<uint32_t>(std::atoi(e) > 0 ? std::atoi(e) : 1);
     if (const char *e = std::getenv("LIDAR_B200_FETCH_MODE"))
