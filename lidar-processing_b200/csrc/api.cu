@@ -529,14 +529,26 @@ int stage(lidar_b200_ctx *c, uint32_t n_frames, const void *const *points, const
     std::atomic<uint32_t> next{0u};
     std::vector<std::thread> workers;
     workers.reserve(n_workers);
+    const auto stage_loop = [&]() {
+        for (uint32_t f = next.fetch_add(1u); f < n_frames; f = next.fetch_add(1u))
+        {
+            from[f] = stage_frame(f);
+            done[f].store(1u, std::memory_order_release);
+        }
+    };
     for (uint32_t t = 0; t < n_workers; ++t)
-        workers.emplace_back([&]() {
-            for (uint32_t f = next.fetch_add(1u); f < n_frames; f = next.fetch_add(1u))
-            {
-                from[f] = stage_frame(f);
-                done[f].store(1u, std::memory_order_release);
-            }
-        });
+    {
+        try
+        {
+            workers.emplace_back(stage_loop);
+        }
+        catch (...) // no more threads to be had: the ones that started (or this one, below) do the work
+        {
+            break;
+        }
+    }
+    if (workers.empty())
+        stage_loop();
     cudaError_t first_error = cudaSuccess;
     for (uint32_t f = 0; f < n_frames; ++f)
     {
