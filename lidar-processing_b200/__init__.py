@@ -488,6 +488,19 @@ class Context:
         return float(ms.value)
 
 
+def equal_chunks(n_frames: int, chunk_frames: int):
+    """[(first, end), ...]: the fewest chunks of at most `chunk_frames` frames, sizes differing by at most one."""
+    n_chunks = max(1, -(-n_frames // max(1, chunk_frames)))
+    size, extra = divmod(n_frames, n_chunks)
+    chunks, a = [], 0
+    for k in range(n_chunks):
+        b = a + size + (1 if k < extra else 0)
+        if b > a:
+            chunks.append((a, b))
+        a = b
+    return chunks
+
+
 class FramePipeline:
     """Throughput path: a job of independent frames is cut into chunks that rotate through `depth`
     contexts (lidar_b200_pipe_*), so uploads, kernels and downloads of neighbouring chunks overlap.
@@ -554,14 +567,7 @@ class FramePipeline:
         padded = (counts.astype(np.int64) + 31) & ~31
         # chunks of equal size, at most chunk_frames frames each (a 154-frame job with chunk_frames = 51 is cut into
         # 39 + 39 + 38 + 38, not 51 + 51 + 51 + 1: a short last chunk leaves the pipeline's contexts idle)
-        n_chunks = max(1, -(-nf // self.chunk_frames))
-        size, extra = divmod(nf, n_chunks)
-        chunks, a = [], 0
-        for k in range(n_chunks):
-            b = a + size + (1 if k < extra else 0)
-            if b > a:
-                chunks.append((a, b))
-            a = b
+        chunks = equal_chunks(nf, self.chunk_frames)
         total = int(padded.sum())
         ar = self._arenas.get(arena)
         if ar is None or ar[0].size < max(total, 1) or ar[4].shape[1] < max(nf, 1):

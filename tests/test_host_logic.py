@@ -254,3 +254,16 @@ def test_concave_working_set_fits_its_slot(hc):
     hc.hc_chi_layout_bytes.restype = C.c_ulonglong
     for n in list(range(20, 3000)) + [4095, 4096, 4097, 65535, 65536, 1 << 20, (1 << 24) + 1, (1 << 31) - 1]:
         assert hc.hc_chi_layout_bytes(C.c_uint32(n)) <= 144 * n, n
+
+
+def test_pipeline_chunks_are_equal_sized(pkg):
+    """A job is cut into the fewest chunks of at most chunk_frames frames, sizes differing by at most one."""
+    for nf in (0, 1, 7, 22, 64, 154, 256, 4096):
+        for cf in (1, 11, 22, 51, 77, 154, 1000):
+            ch = pkg.equal_chunks(nf, cf)
+            assert sum(b - a for a, b in ch) == nf and all(0 < b - a <= cf for a, b in ch)
+            assert [a for a, _ in ch] == [0] + [b for _, b in ch][:-1] if ch else nf == 0
+            if ch:
+                sizes = [b - a for a, b in ch]
+                assert max(sizes) - min(sizes) <= 1 and len(ch) == -(-nf // cf)
+    assert pkg.equal_chunks(154, 51) == [(0, 39), (39, 78), (78, 116), (116, 154)]
