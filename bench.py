@@ -463,7 +463,7 @@ def config5_strong(pkg, env, args):
     ctx.close()
     pinned = pkg.pin_frames(distinct)
     src = [pinned[i % 64] for i in mine]
-    pipe = pkg.FramePipeline(device=env.local_rank, depth=args.depth, chunk_frames=args.chunk)
+    pipe = pkg.FramePipeline(device=env.local_rank, depth=args.depth, chunk_frames=args.chunk, gpus_sharing_host=env.world)
     subs = [src[a:a + batch] for a in range(0, len(src), batch)]  # sub-jobs of one batch each, result arenas alternate
     for w_ in range(2):
         pipe.submit(subs[w_ % len(subs)], arena=w_)  # both result arenas and every context exist before the timed region
