@@ -281,8 +281,14 @@ LB_D void kd_fused_level(KdFusedSmem &sm, uint32_t len, uint32_t level, int axis
     }
 }
 
+// fixed_levels = kKdFusedAll: every remaining level, down to the subtrees of at most kKdSubtreeMax nodes, which are
+// finished here too (one frame in flight: the shortest dependent chain). Otherwise exactly that many levels for every
+// range, then the permutation goes back to global memory and kd_subtree_kernel finishes it at full occupancy (batches:
+// the thread-per-subtree tail would keep one warp of every 56 KB CTA busy while the union-find wants the SMs).
+constexpr uint32_t kKdFusedAll = 0xFFFFFFFFu;
+
 __global__ void __launch_bounds__(kKdFusedThreads)
-kd_fused_kernel(float4 *__restrict__ nodes, BatchView bv, uint32_t depth)
+kd_fused_kernel(float4 *__restrict__ nodes, BatchView bv, uint32_t depth, uint32_t fixed_levels)
 {
     extern __shared__ __align__(16) unsigned char kd_fused_raw[];
     KdFusedSmem &sm = *reinterpret_cast<KdFusedSmem *>(kd_fused_raw);
@@ -303,7 +309,7 @@ kd_fused_kernel(float4 *__restrict__ nodes, BatchView bv, uint32_t depth)
     for (;; ++level)
     {
         const uint32_t n_ranges = 1u << level;
-        if (((len + n_ranges - 1u) >> level) <= kKdSubtreeMax)
+        if (fixed_levels == kKdFusedAll ? ((len + n_ranges - 1u) >> level) <= kKdSubtreeMax : level >= fixed_levels)
             break;
         const int axis = static_cast<int>((depth + level) % 3u);
         if (level == 0u)
@@ -317,7 +323,7 @@ kd_fused_kernel(float4 *__restrict__ nodes, BatchView bv, uint32_t depth)
         __syncthreads();
     }
     // one thread per remaining subtree (ranges of at most kKdSubtreeMax nodes), sequential transcription in shared memory
-    for (uint32_t path = threadIdx.x; path < (1u << level); path += kKdFusedThreads)
+    for (uint32_t path = threadIdx.x; fixed_levels == kKdFusedAll && path < (1u << level); path += kKdFusedThreads)
     {
         uint32_t b, e;
         if (!kd_range_at(len, level, path, &b, &e))
@@ -387,8 +393,12 @@ inline int kd_build_launch(cudaStream_t stream, const float4 *pts, BatchView bv,
     // in a large batch the level-synchronous kernels fill the machine anyway and the long-lived 56 KB CTAs of the
     // fused kernel only take SMs away from the union-find running beside them (measured: union_find 3.2 -> 5.9 ms per
     // 154 frames). LIDAR_B200_KD_FUSED=0/1 forces either.
+    // LIDAR_B200_KD_FUSED=2: the levels between 2048 and 64 nodes per range in shared memory, subtrees by kd_subtree_kernel
+    // (measured on 154-frame batches: 10 721 against 11 257 frames/s - the 56 KB CTAs of the shared-memory levels cost the
+    // union-find beside them more than the five level launches they replace; not the default).
     static const int fused_env = std::getenv("LIDAR_B200_KD_FUSED") ? std::atoi(std::getenv("LIDAR_B200_KD_FUSED")) : -1;
     const bool fused = fused_env < 0 ? bv.frames <= 4u : fused_env != 0;
+    const bool fused_middle = fused_env == 2;
     while (((max_m + (1u << depth) - 1u) >> depth) > (fused ? kKdFusedMax : kKdSubtreeMax))
     {
         const uint32_t range = (max_m + (1u << depth) - 1u) >> depth;
@@ -410,8 +420,22 @@ inline int kd_build_launch(cudaStream_t stream, const float4 *pts, BatchView bv,
             cudaFuncSetAttribute(kd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(KdFusedSmem)));
             attr_done = true;
         }
-        kd_fused_kernel<<<dim3(1u << depth, bv.frames), kKdFusedThreads, sizeof(KdFusedSmem), stream>>>(nodes, bv, depth);
+        uint32_t levels = kKdFusedAll;
+        if (fused_middle)
+        {
+            levels = 0u;
+            while (((max_m + (1u << (depth + levels)) - 1u) >> (depth + levels)) > kKdSubtreeMax)
+                ++levels;
+        }
+        kd_fused_kernel<<<dim3(1u << depth, bv.frames), kKdFusedThreads, sizeof(KdFusedSmem), stream>>>(nodes, bv, depth, levels);
         ++launches;
+        if (fused_middle)
+        {
+            depth += levels;
+            const uint32_t paths = 1u << depth;
+            kd_subtree_kernel<<<dim3((paths + 127u) / 128u, bv.frames), 128, 0, stream>>>(nodes, bv, depth);
+            ++launches;
+        }
     }
     else
     {
