@@ -676,6 +676,51 @@ def test_outlines_outside_the_epsilon_envelope_are_reported(pkg):
         c2.close()
 
 
+@pytest.mark.gpu
+def test_single_frame_graph_replay_equals_launch_by_launch(pkg, golden_frames):
+    """One frame in flight goes to the device as ONE CUDA-graph launch from the second frame of a launch geometry on
+    (lidar_b200_batch_run). Same results as launch by launch (LIDAR_B200_GRAPH=0), across frames of different sizes
+    (different graphs), repeated geometries (replays), a reconfiguration and a growing context (both drop the graphs)."""
+    import os
+
+    rng = np.random.default_rng(5)
+    base = golden_frames[0]
+    frames = [base, base[:100_000], base[:99_000], golden_frames[1], base[:100_500], golden_frames[2], base[:60_000], base]
+    old = os.environ.get("LIDAR_B200_GRAPH")
+    try:
+        os.environ["LIDAR_B200_GRAPH"] = "0"
+        plain = pkg.Context(device=0, max_points=70_000, max_frames=1)  # (grows on the way)
+        os.environ["LIDAR_B200_GRAPH"] = "1"
+        graphed = pkg.Context(device=0, max_points=70_000, max_frames=1)
+    finally:
+        if old is None:
+            os.environ.pop("LIDAR_B200_GRAPH", None)
+        else:
+            os.environ["LIDAR_B200_GRAPH"] = old
+    try:
+        for rounds, cfg in ((2, None), (2, pkg.SegmentationConfiguration(number_of_planar_partitions=3, number_of_iterations=2))):
+            if cfg is not None:
+                plain.seg_configure(cfg)
+                graphed.seg_configure(cfg)
+                plain.clu_configure(pkg.ClusteringConfiguration(min_cluster_size=6))
+                graphed.clu_configure(pkg.ClusteringConfiguration(min_cluster_size=6))
+            for _ in range(rounds):
+                for f in frames:
+                    a = plain.process_batch([f])[0]
+                    b = graphed.process_batch([f])[0]
+                    for k in ("seg_labels", "ground_idx", "obstacle_idx", "cluster_labels"):
+                        assert np.array_equal(a[k], b[k]), k
+                    assert a["n_clusters"] == b["n_clusters"]
+        assert plain.graph_launch_count() == 0
+        assert graphed.graph_launch_count() >= 2 * len(frames)  # most frames after the first round are replays
+        # the split / outlines behind a replayed frame see the same state as behind a launch-by-launch one
+        ga, gb = plain.batch_clusters()[0], graphed.batch_clusters()[0]
+        assert np.array_equal(ga["offsets"], gb["offsets"]) and np.array_equal(ga["points"], gb["points"])
+    finally:
+        plain.close()
+        graphed.close()
+
+
 # ---- output packing on the device (SURVEY 8f row 4)
 
 @pytest.mark.gpu
