@@ -253,6 +253,43 @@ def test_batch_pipeline_ragged(ctx, golden_frames, synth_small):
         assert np.array_equal(ctx.cluster(pts[oi]), res["cluster_labels"])
 
 
+def test_batch_of_pageable_clouds_staged_by_threads(pkg, golden_frames):
+    """A batch of pageable clouds above 1 M points is staged into the page-locked buffers by several host threads
+    (api.cu, stage()): same results for 16-byte and 32-byte records, for one staging thread and for page-locked input."""
+    import os
+
+    frames = [golden_frames[i % 3] for i in range(10)]
+    wide = []
+    for pts in frames:
+        w = np.zeros((pts.shape[0], 8), np.float32)  # 32-byte records (PointXYZI layout)
+        w[:, :3] = pts[:, :3]
+        w[:, 3] = 1.0
+        w[:, 4] = pts[:, 3]
+        wide.append(w)
+    cap = sum((f.shape[0] + 31) & ~31 for f in frames)
+    old = os.environ.get("LIDAR_B200_STAGE_THREADS")
+    try:
+        os.environ["LIDAR_B200_STAGE_THREADS"] = "1"
+        one = pkg.Context(device=0, max_points=cap, max_frames=len(frames))
+        os.environ["LIDAR_B200_STAGE_THREADS"] = "6"
+        many = pkg.Context(device=0, max_points=cap, max_frames=len(frames))
+    finally:
+        if old is None:
+            os.environ.pop("LIDAR_B200_STAGE_THREADS", None)
+        else:
+            os.environ["LIDAR_B200_STAGE_THREADS"] = old
+    try:
+        want = one.process_batch(frames)
+        for src in (frames, wide, pkg.pin_frames(frames)):
+            got = many.process_batch(src)
+            for w_, g_ in zip(want, got):
+                for k in ("seg_labels", "ground_idx", "obstacle_idx", "cluster_labels"):
+                    assert np.array_equal(w_[k], g_[k]), k
+    finally:
+        one.close()
+        many.close()
+
+
 def test_batch_is_deterministic(ctx, golden_frames):
     frames = [golden_frames[1]] * 4
     a = ctx.process_batch(frames)
